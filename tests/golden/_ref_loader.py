@@ -1,0 +1,232 @@
+"""Import the reference's OWN hot-path modules in the build container.
+
+Only usable where ``/root/reference`` exists (the build container) -- never
+on the GPU box.  ``make_golden.py`` uses it to run the reference's real
+``fuse_np`` / ``transform_sim`` / ``get_blending_weights`` / ``content_based``
+/ ``phase_correlation_registration`` code and store the results as fixtures.
+
+The reference's data-model dependencies (dask, xarray, zarr, dask-image,
+scikit-image ...) are not installed in this image.  They are replaced by
+inert placeholder modules, and ``multiview_stitcher.spatial_image_utils``
+(the xarray data model, out of scope -- SURVEY.md section 2) by a ~60-line
+fake that carries ``data / dims / origin / spacing``.  The arithmetic that
+runs is the reference's, unmodified.  scikit-image's three functions are
+bound to ``oracle.skimage_restated`` (so registration fixtures pin the
+reference's candidate loop, not scikit-image itself).
+"""
+
+from __future__ import annotations
+
+import importlib
+import importlib.abc
+import importlib.machinery
+import inspect
+import os
+import sys
+import types
+
+import numpy as np
+
+REF_SRC = "/root/reference/src"
+_PLACEHOLDER_ROOTS = {
+    "dask",
+    "dask_image",
+    "xarray",
+    "zarr",
+    "skimage",
+    "spatial_image",
+    "multiscale_spatial_image",
+    "ngff_zarr",
+    "tifffile",
+    "ome_zarr",
+    "fsspec",
+    "aiohttp",
+    "numcodecs",
+    "matplotlib",
+    "ants",
+    "itk",
+}
+
+
+class _Meta(type):
+    """Placeholder classes: any attribute is another placeholder class, any
+    call returns one too, so import-time decorators / annotations work."""
+
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Meta(name, (object,), {})
+
+    def __call__(cls, *a, **k):
+        return _Meta("called_" + cls.__name__, (object,), {})
+
+    def __iter__(cls):
+        return iter(())
+
+
+class _PlaceholderModule(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Meta(name, (object,), {})
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in _PLACEHOLDER_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _PlaceholderModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+class FakeSim:
+    """Minimal stand-in for the reference's xarray 'sim'."""
+
+    def __init__(self, data, dims, origin, spacing):
+        self.data = data
+        self.dims = tuple(dims)
+        self.origin = {d: float(origin[d]) for d in dims}
+        self.spacing = {d: float(spacing[d]) for d in dims}
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def ndim(self):
+        return self.data.ndim
+
+    def astype(self, dtype):
+        return FakeSim(self.data.astype(dtype), self.dims, self.origin, self.spacing)
+
+    def copy(self, data=None):
+        return FakeSim(
+            self.data.copy() if data is None else data,
+            self.dims,
+            self.origin,
+            self.spacing,
+        )
+
+
+def _fake_si_utils():
+    m = types.ModuleType("multiview_stitcher.spatial_image_utils")
+    m.SPATIAL_DIMS = ["z", "y", "x"]
+    m.DEFAULT_TRANSFORM_KEY = "affine_metadata"
+    m.DEFAULT_SPATIAL_CHUNKSIZES_3D = {"z": 256, "y": 256, "x": 256}
+    m.DEFAULT_SPATIAL_CHUNKSIZES_2D = {"y": 2048, "x": 2048}
+    m.get_ndim_from_sim = lambda sim: len(sim.dims)
+    m.get_spatial_dims_from_sim = lambda sim: list(sim.dims)
+
+    def _get(attr):
+        def f(sim, asarray=False):
+            d = getattr(sim, attr)
+            return np.array([d[k] for k in sim.dims]) if asarray else dict(d)
+
+        return f
+
+    m.get_spacing_from_sim = _get("spacing")
+    m.get_origin_from_sim = _get("origin")
+
+    def get_shape_from_sim(sim, asarray=False):
+        if asarray:
+            return np.array(sim.data.shape)
+        return dict(zip(sim.dims, sim.data.shape))
+
+    m.get_shape_from_sim = get_shape_from_sim
+    m._get_backend_data = lambda sim: sim.data
+    m.is_dask_backed_dataarray = lambda sim: False
+
+    def to_spatial_image(data, dims=None, scale=None, translation=None, **kw):
+        dims = list(dims)
+        return FakeSim(data, dims, translation, scale)
+
+    m.to_spatial_image = to_spatial_image
+
+    def __getattr__(name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Meta(name, (object,), {})
+
+    m.__getattr__ = __getattr__
+    return m
+
+
+def _has_keyword(func, keyword):
+    try:
+        return keyword in inspect.signature(func).parameters
+    except Exception:
+        return False
+
+
+_loaded = None
+
+
+def load_reference():
+    """Returns a namespace with the reference's real modules:
+    ``transformation, weights, fusion_core, registration, param_utils``."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not os.path.isdir(REF_SRC):
+        raise RuntimeError("reference tree not present (only in the build container)")
+    repo_root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if repo_root not in sys.path:
+        sys.path.insert(0, repo_root)
+    from oracle import skimage_restated as sk
+
+    sys.meta_path.insert(0, _Finder())
+    # functional pieces of the placeholders
+    import dask.utils  # placeholder
+
+    dask.utils.has_keyword = _has_keyword
+    import skimage.exposure
+    import skimage.metrics
+    import skimage.registration
+
+    skimage.exposure.rescale_intensity = sk.rescale_intensity
+    skimage.metrics.structural_similarity = sk.structural_similarity
+    skimage.registration.phase_cross_correlation = sk.phase_cross_correlation
+
+    pkg = types.ModuleType("multiview_stitcher")
+    pkg.__path__ = [os.path.join(REF_SRC, "multiview_stitcher")]
+    sys.modules["multiview_stitcher"] = pkg
+    sys.modules["multiview_stitcher.spatial_image_utils"] = _fake_si_utils()
+    pkg.spatial_image_utils = sys.modules["multiview_stitcher.spatial_image_utils"]
+    for name in (
+        "msi_utils",
+        "mv_graph",
+        "ngff_utils",
+        "zarr_utils",
+        "param_resolution",
+        "transforms",
+        "_zarr_compat",
+    ):
+        mod = _PlaceholderModule("multiview_stitcher." + name)
+        sys.modules["multiview_stitcher." + name] = mod
+        setattr(pkg, name, mod)
+
+    ns = types.SimpleNamespace()
+    ns.param_utils = importlib.import_module("multiview_stitcher.param_utils")
+    ns.transformation = importlib.import_module("multiview_stitcher.transformation")
+    ns.weights = importlib.import_module("multiview_stitcher.weights")
+    ns.fusion_core = importlib.import_module("multiview_stitcher.fusion._core")
+    ns.registration = importlib.import_module("multiview_stitcher.registration")
+    ns.FakeSim = FakeSim
+    _loaded = ns
+    return ns
+
+
+if __name__ == "__main__":
+    ns = load_reference()
+    print("loaded:", ns.fusion_core.fuse_np, ns.registration.phase_correlation_registration)
