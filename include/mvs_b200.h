@@ -1,0 +1,139 @@
+/*
+ * mvs_b200.h -- C ABI of the B200-native registration-and-fusion engine.
+ *
+ * Drop-in boundary for the hot path of multiview-stitcher (reference commit
+ * 629f72d; paths below are relative to src/multiview_stitcher/).  Plain C:
+ * pointers and sizes only, no torch / C++ types.  All `d_` / "device" pointers
+ * are CUDA device pointers on the current device; `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).  Every entry point returns 0 on
+ * success and a negative mvs_status otherwise; the message of the last failure
+ * on the calling thread is available from mvs_last_error().  Entry points are
+ * thread-safe (the reference calls its hooks from dask worker threads,
+ * registration.py:2680-2692) as long as distinct plans/workspaces are used per
+ * thread; work is enqueued on `stream` and is asynchronous unless stated.
+ *
+ * The reference has no FFI of its own for this path (it is pure Python calling
+ * scipy / scikit-image); each entry point cites the Python interface whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ */
+#ifndef MVS_B200_H
+#define MVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_ABI_VERSION 1
+
+typedef enum {
+  MVS_OK = 0,
+  MVS_ERR_INVALID = -1,     /* bad argument                                  */
+  MVS_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail)   */
+  MVS_ERR_UNSUPPORTED = -3, /* valid request the engine cannot serve         */
+  MVS_ERR_NO_DEVICE = -4    /* no sm_100 device visible                      */
+} mvs_status;
+
+typedef enum { MVS_U8 = 0, MVS_U16 = 1, MVS_F32 = 2 } mvs_dtype;
+
+/* fusion_func selector: fusion/_core.py:61-94, :42-58, :97-131 */
+typedef enum {
+  MVS_FUSE_WAVG = 0, /* weighted_average_fusion with blending weights        */
+  MVS_FUSE_MAX = 1,  /* max_fusion                                            */
+  MVS_FUSE_MEAN = 2  /* simple_average_fusion                                 */
+} mvs_fusion_mode;
+
+const char* mvs_last_error(void);
+int mvs_abi_version(void);
+/* Fills name (<= cap bytes), SM count, compute capability; MVS_ERR_NO_DEVICE
+ * when no CUDA device is usable. */
+int mvs_device_info(char* name, int cap, int* sm_count, int* cc_major, int* cc_minor);
+/* sizeof(mvs_view_xform), sizeof(mvs_chunk) as compiled (binding self-check). */
+int mvs_struct_sizes(int* view_xform_bytes, int* chunk_bytes);
+
+/* ------------------------------------------------------------------------
+ * (ii) fused affine resample + blending weights + weighted accumulation
+ *
+ * Replaces, for a batch of output chunks in ONE launch, what the reference
+ * does per chunk in fuse_np (fusion/_core.py:1513-1733):
+ *   transform_sim -> scipy.ndimage.affine_transform(mode="constant", cval=NaN)
+ *       (transformation.py:15-148)              matrix/offset below
+ *   get_blending_weights (weights.py:391-511)   wmatrix/woffset + table below
+ *   mask + normalize_weights (_core.py:1647-1649, weights.py:325-345)
+ *   fusion_func (_core.py:42-131), trim (:1687-1711), nan_to_num + cast (:1713)
+ *
+ * All index triples are (z, y, x); 2-D problems use z extent 1.
+ * ---------------------------------------------------------------------- */
+
+/* One (chunk, view) pairing: what one transform_sim call sees. */
+typedef struct {
+  const void* data;   /* device ptr to element [0,0,0] of the view window    */
+  int32_t dtype;      /* mvs_dtype of the view                                */
+  int32_t shape[3];   /* window extent                                        */
+  int64_t stride[3];  /* element strides of the window                        */
+  /* sample position in window pixels = matrix * (chunk px + halo) + offset,
+   * exactly the matrix/offset transform_sim hands to scipy (already rounded
+   * to 10 decimals and snapped, transformation.py:72-83); row-major 3x3.     */
+  double matrix[9];
+  double offset[3];
+  /* same for the 5^ndim blending-support table (weights.py:465-481)          */
+  double wmatrix[9];
+  double woffset[3];
+  int32_t table;      /* index of the view's table in `tables`                */
+  int32_t reserved;
+} mvs_view_xform;
+
+/* One output chunk (after trimming). */
+typedef struct {
+  void* out;          /* device ptr to the chunk's first voxel, or NULL       */
+  int32_t out_dtype;  /* mvs_dtype; fused float32 is NaN->0 then C-cast       */
+  int32_t shape[3];   /* trimmed chunk extent                                 */
+  int64_t stride[3];  /* element strides of `out`, `acc_num`, `acc_den`       */
+  int32_t halo[3];    /* trim_overlap_in_pixels: sample index = voxel + halo  */
+  int32_t first_xform;/* this chunk's pairings: xforms[first .. first+n)      */
+  int32_t n_xforms;   /* in view order (order fixes the float32 sums)         */
+  /* optional partial accumulators (multi-GPU partial mode, WAVG only):
+   * acc_num = sum_i v_i*b_i, acc_den = sum_i b_i with UN-normalised blending
+   * weights (overwritten, not accumulated); `out` may then be NULL.         */
+  float* acc_num;
+  float* acc_den;
+} mvs_chunk;
+
+typedef struct mvs_fuse_plan mvs_fuse_plan;
+
+/* Uploads the work list (host arrays; device pointers inside) and builds the
+ * block schedule.  tables: n_tables * 125 floats (5x5x5, z-major; 2-D tables
+ * occupy the first 25 entries of their slot), host pointer.
+ * ndim 2|3; order 0|1 (interpolation_order, _core.py:797). */
+int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunks, int n_chunks,
+                         const mvs_view_xform* xforms, int n_xforms,
+                         const float* tables, int n_tables, int ndim, int order,
+                         int fusion_mode, void* stream);
+/* Enqueues the fused kernel for every chunk of the plan. */
+int mvs_fuse_plan_run(mvs_fuse_plan* plan, void* stream);
+/* Number of kernel launches one mvs_fuse_plan_run issues / blocks scheduled. */
+int mvs_fuse_plan_info(const mvs_fuse_plan* plan, int* launches, int64_t* blocks,
+                       int64_t* out_voxels);
+int mvs_fuse_plan_destroy(mvs_fuse_plan* plan);
+
+/* Finalises partial accumulators: out = cast(nan_to_num(num / (den==0?1:den))).
+ * Used after the NCCL sum of (acc_num, acc_den) across ranks. */
+int mvs_fuse_finalize(const float* acc_num, const float* acc_den, void* out,
+                      int out_dtype, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Synthetic tiles (benchmark / test inputs).  Integer-only
+ * value-noise ground truth sampled at integer global coordinates
+ * origin + index, so overlapping tiles agree exactly.
+ * ---------------------------------------------------------------------- */
+int mvs_synth_tile(void* d_out, int dtype, const int32_t shape[3],
+                   const int64_t stride[3], const int64_t origin[3], uint32_t seed,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVS_B200_H */

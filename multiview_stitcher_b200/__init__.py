@@ -1,0 +1,17 @@
+"""B200-native registration-and-fusion engine behind multiview-stitcher's
+extension API (hot path only).
+
+Public surface mirrors the reference's names for this path:
+
+* ``fusion.fuse`` / ``fusion.fuse_np`` / ``fusion.weighted_average_fusion`` /
+  ``fusion.max_fusion`` / ``fusion.simple_average_fusion``
+* ``registration.phase_correlation_registration`` /
+  ``registration.pairwise_executor``
+
+Everything computes on the GPU through ``libmvs_b200.so`` (C ABI,
+include/mvs_b200.h); there is no CPU fallback.
+"""
+
+from ._lib import EngineError, EngineUnavailable  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,165 @@
+"""ctypes binding of the engine's C ABI (include/mvs_b200.h).
+
+The product path has NO CPU fallback: if ``libmvs_b200.so`` is missing or no
+CUDA device is usable, calls raise ``EngineUnavailable``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmvs_b200.so")
+
+MVS_U8, MVS_U16, MVS_F32 = 0, 1, 2
+MVS_FUSE_WAVG, MVS_FUSE_MAX, MVS_FUSE_MEAN = 0, 1, 2
+
+_NP_TO_MVS = {np.dtype(np.uint8): MVS_U8, np.dtype(np.uint16): MVS_U16, np.dtype(np.float32): MVS_F32}
+_MVS_TO_NP = {v: k for k, v in _NP_TO_MVS.items()}
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA extension is missing / not loadable / has no device."""
+
+
+class EngineError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+# numpy mirrors of the C structs (align=True reproduces the C layout; checked
+# against mvs_struct_sizes() at load time)
+VIEW_XFORM_DTYPE = np.dtype(
+    [
+        ("data", np.uint64),
+        ("dtype", np.int32),
+        ("shape", np.int32, (3,)),
+        ("stride", np.int64, (3,)),
+        ("matrix", np.float64, (9,)),
+        ("offset", np.float64, (3,)),
+        ("wmatrix", np.float64, (9,)),
+        ("woffset", np.float64, (3,)),
+        ("table", np.int32),
+        ("reserved", np.int32),
+    ],
+    align=True,
+)
+
+CHUNK_DTYPE = np.dtype(
+    [
+        ("out", np.uint64),
+        ("out_dtype", np.int32),
+        ("shape", np.int32, (3,)),
+        ("stride", np.int64, (3,)),
+        ("halo", np.int32, (3,)),
+        ("first_xform", np.int32),
+        ("n_xforms", np.int32),
+        ("acc_num", np.uint64),
+        ("acc_den", np.uint64),
+    ],
+    align=True,
+)
+
+
+def mvs_dtype(np_dtype) -> int:
+    try:
+        return _NP_TO_MVS[np.dtype(np_dtype)]
+    except KeyError:
+        raise EngineError(f"unsupported voxel dtype {np_dtype} (uint8, uint16, float32)") from None
+
+
+_lock = threading.Lock()
+_lib = None
+
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "mvs_last_error": (ctypes.c_char_p, []),
+    "mvs_abi_version": (ctypes.c_int, []),
+    "mvs_device_info": (
+        ctypes.c_int,
+        [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)],
+    ),
+    "mvs_struct_sizes": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "mvs_fuse_plan_create": (
+        ctypes.c_int,
+        [ctypes.POINTER(_P), _P, ctypes.c_int, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P],
+    ),
+    "mvs_fuse_plan_run": (ctypes.c_int, [_P, _P]),
+    "mvs_fuse_plan_info": (
+        ctypes.c_int,
+        [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)],
+    ),
+    "mvs_fuse_plan_destroy": (ctypes.c_int, [_P]),
+    "mvs_fuse_finalize": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, _P]),
+    "mvs_synth_tile": (
+        ctypes.c_int,
+        [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.c_uint32, _P],
+    ),
+}
+
+
+def exported_symbols():
+    """Names the header declares (tests check the .so exports each)."""
+    return sorted(_SIGNATURES)
+
+
+def load(require_device=False):
+    """Load libmvs_b200.so (once).  Raises EngineUnavailable if missing."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise EngineUnavailable(
+                    f"{LIB_PATH} not found - build it with `python -m multiview_stitcher_b200.build` "
+                    "(there is no CPU fallback)"
+                )
+            try:
+                lib = ctypes.CDLL(LIB_PATH)
+            except OSError as e:  # pragma: no cover
+                raise EngineUnavailable(f"cannot load {LIB_PATH}: {e}") from e
+            for name, (res, args) in _SIGNATURES.items():
+                try:
+                    fn = getattr(lib, name)
+                except AttributeError as e:
+                    raise EngineUnavailable(f"{LIB_PATH} does not export {name}") from e
+                fn.restype = res
+                fn.argtypes = args
+            a, b = ctypes.c_int(), ctypes.c_int()
+            lib.mvs_struct_sizes(ctypes.byref(a), ctypes.byref(b))
+            if a.value != VIEW_XFORM_DTYPE.itemsize or b.value != CHUNK_DTYPE.itemsize:
+                raise EngineUnavailable(
+                    f"struct layout mismatch: C ({a.value}, {b.value}) vs numpy "
+                    f"({VIEW_XFORM_DTYPE.itemsize}, {CHUNK_DTYPE.itemsize})"
+                )
+            _lib = lib
+    if require_device:
+        device_info()
+    return _lib
+
+
+def last_error() -> str:
+    return load().mvs_last_error().decode("utf-8", "replace")
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise EngineError(f"{what} failed (status {status}): {last_error()}")
+
+
+def device_info():
+    lib = load()
+    name = ctypes.create_string_buffer(256)
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    st = lib.mvs_device_info(name, 256, ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr))
+    if st != 0:
+        raise EngineUnavailable(f"no usable CUDA device: {last_error()}")
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value)}
+
+
+def current_stream_ptr():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,534 @@
+// Fused affine resample + blending weights + weighted accumulation (sm_100a).
+//
+// One launch covers every output chunk of a plan.  Per output voxel and per
+// contributing view the kernel evaluates, in registers:
+//   * the sample position  x = M * o + off  in float64 with scipy's operation
+//     order (ni_interpolation.c NI_GeometricTransform: sequential
+//     multiply-adds over the output coordinates, then the shift), the
+//     "outside" predicate x < 0 || x > len-1 and floor() -- so validity and
+//     nearest-neighbour picks are bit-identical to
+//     scipy.ndimage.affine_transform(mode="constant") as called by
+//     transformation.py:136-139;
+//   * order-0 / order-1 interpolation of the view (float32 arithmetic);
+//   * the blending weight: multilinear lookup in the view's 5^ndim EDT support
+//     table at  u = Mw * o + offw  (weights.py:465-481), cosine ramp and clip
+//     (weights.py:502-509) -- no weight volume ever touches HBM;
+//   * mask, normalisation and the fusion function with the reference's
+//     float32 operation order (fusion/_core.py:1647-1649, weights.py:340-345,
+//     fusion/_core.py:61-94 / :42-58 / :97-131), NaN->0 and the output cast
+//     (fusion/_core.py:1713).
+// HBM traffic is the algorithmic minimum: every contributing view voxel is read
+// (L1/L2 absorb the 2^ndim-tap reuse), every output voxel written once.
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mvs {
+
+constexpr int kBX = 128;      // output block extent along x
+constexpr int kBY = 8;        // ... along y (one warp per row)
+constexpr int kThreads = 256;
+constexpr int kVPT = kBX / 32;  // voxels per thread, strided by 32 along x
+constexpr int kMaxXforms = 1024;  // per chunk
+
+struct ViewEval {
+  float v;  // interpolated value (undefined if !valid)
+  float b;  // blending weight (0 if !valid)
+  bool valid;
+};
+
+__device__ __forceinline__ double affine_coord(const double* __restrict__ m, double off,
+                                               double pre, double cx) {
+  // ((c0*m0 + c1*m1) + c2*m2) + shift, no FMA contraction (matches scipy/C)
+  return __dadd_rn(__dadd_rn(pre, __dmul_rn(cx, m[2])), off);
+}
+
+template <int NDIM>
+__device__ __forceinline__ double affine_pre(const double* __restrict__ m, double cz,
+                                             double cy) {
+  if (NDIM == 3) return __dadd_rn(__dmul_rn(cz, m[0]), __dmul_rn(cy, m[1]));
+  return __dmul_rn(cy, m[1]);
+}
+
+__device__ __forceinline__ float lerp(float a, float b, float t) {
+  return fmaf(t, b, fmaf(-t, a, a));
+}
+
+// Blending weight at table coordinates (uz, uy, ux); table is 5^NDIM, cval 0.
+template <int NDIM>
+__device__ __forceinline__ float blend_weight(const float* __restrict__ tab, double uz,
+                                              double uy, double ux) {
+  if (ux < 0.0 || ux > 4.0 || uy < 0.0 || uy > 4.0) return 0.0f;
+  if (NDIM == 3 && (uz < 0.0 || uz > 4.0)) return 0.0f;
+  double fx = floor(ux), fy = floor(uy);
+  int ix = (int)fx, iy = (int)fy;
+  float tx = (float)(ux - fx), ty = (float)(uy - fy);
+  int ix1 = min(ix + 1, 4), iy1 = min(iy + 1, 4);
+  float w;
+  if (NDIM == 3) {
+    double fz = floor(uz);
+    int iz = (int)fz;
+    float tz = (float)(uz - fz);
+    int iz1 = min(iz + 1, 4);
+    const float* p0 = tab + iz * 25;
+    const float* p1 = tab + iz1 * 25;
+    float a0 = lerp(lerp(__ldg(p0 + iy * 5 + ix), __ldg(p0 + iy * 5 + ix1), tx),
+                    lerp(__ldg(p0 + iy1 * 5 + ix), __ldg(p0 + iy1 * 5 + ix1), tx), ty);
+    float a1 = lerp(lerp(__ldg(p1 + iy * 5 + ix), __ldg(p1 + iy * 5 + ix1), tx),
+                    lerp(__ldg(p1 + iy1 * 5 + ix), __ldg(p1 + iy1 * 5 + ix1), tx), ty);
+    w = lerp(a0, a1, tz);
+  } else {
+    w = lerp(lerp(__ldg(tab + iy * 5 + ix), __ldg(tab + iy * 5 + ix1), tx),
+             lerp(__ldg(tab + iy1 * 5 + ix), __ldg(tab + iy1 * 5 + ix1), tx), ty);
+  }
+  // weights.py:502-507: x<1 -> (cos((1-x)*pi)+1)/2 in float32, then clip
+  if (w < 1.0f) {
+    float a = __fmul_rn(__fsub_rn(1.0f, w), 3.14159274101257324f);
+    w = __fdiv_rn(__fadd_rn(cosf(a), 1.0f), 2.0f);
+  }
+  return fminf(fmaxf(w, 0.0f), 1.0f);
+}
+
+// Evaluates view X at output sample index (cz, cy, cx) (already halo-shifted).
+template <int NDIM, int ORDER, bool WANT_V, bool WANT_B>
+__device__ __forceinline__ ViewEval eval_view(const mvs_view_xform& X,
+                                              const float* __restrict__ tables, double cz,
+                                              double cy, double cx) {
+  ViewEval r;
+  r.v = 0.0f;
+  r.b = 0.0f;
+  const double* m = X.matrix;
+  double xz = 0.0;
+  if (NDIM == 3) xz = affine_coord(m + 0, X.offset[0], affine_pre<NDIM>(m + 0, cz, cy), cx);
+  double xy = affine_coord(m + 3, X.offset[1], affine_pre<NDIM>(m + 3, cz, cy), cx);
+  double xx = affine_coord(m + 6, X.offset[2], affine_pre<NDIM>(m + 6, cz, cy), cx);
+  const int nz = X.shape[0], ny = X.shape[1], nx = X.shape[2];
+  bool valid = !(xx < 0.0 || xx > (double)(nx - 1) || xy < 0.0 || xy > (double)(ny - 1));
+  if (NDIM == 3) valid = valid && !(xz < 0.0 || xz > (double)(nz - 1));
+  r.valid = valid;
+  if (!valid) return r;
+
+  if (WANT_V) {
+    const void* base = X.data;
+    const int dt = X.dtype;
+    const int64_t sz = X.stride[0], sy = X.stride[1], sx = X.stride[2];
+    if (ORDER == 0) {
+      int64_t ix = (int64_t)floor(__dadd_rn(xx, 0.5));
+      int64_t iy = (int64_t)floor(__dadd_rn(xy, 0.5));
+      int64_t iz = NDIM == 3 ? (int64_t)floor(__dadd_rn(xz, 0.5)) : 0;
+      r.v = load_as_float(base, dt, iz * sz + iy * sy + ix * sx);
+    } else {
+      double fx = floor(xx), fy = floor(xy);
+      int64_t ix = (int64_t)fx, iy = (int64_t)fy;
+      float tx = (float)(xx - fx), ty = (float)(xy - fy);
+      int64_t ox0 = ix * sx, ox1 = (ix + 1 > nx - 1 ? ix : ix + 1) * sx;
+      int64_t oy0 = iy * sy, oy1 = (iy + 1 > ny - 1 ? iy : iy + 1) * sy;
+      if (NDIM == 3) {
+        double fz = floor(xz);
+        int64_t iz = (int64_t)fz;
+        float tz = (float)(xz - fz);
+        int64_t oz0 = iz * sz, oz1 = (iz + 1 > nz - 1 ? iz : iz + 1) * sz;
+        float v000 = load_as_float(base, dt, oz0 + oy0 + ox0);
+        float v001 = load_as_float(base, dt, oz0 + oy0 + ox1);
+        float v010 = load_as_float(base, dt, oz0 + oy1 + ox0);
+        float v011 = load_as_float(base, dt, oz0 + oy1 + ox1);
+        float v100 = load_as_float(base, dt, oz1 + oy0 + ox0);
+        float v101 = load_as_float(base, dt, oz1 + oy0 + ox1);
+        float v110 = load_as_float(base, dt, oz1 + oy1 + ox0);
+        float v111 = load_as_float(base, dt, oz1 + oy1 + ox1);
+        float a0 = lerp(lerp(v000, v001, tx), lerp(v010, v011, tx), ty);
+        float a1 = lerp(lerp(v100, v101, tx), lerp(v110, v111, tx), ty);
+        r.v = lerp(a0, a1, tz);
+      } else {
+        float v00 = load_as_float(base, dt, oy0 + ox0);
+        float v01 = load_as_float(base, dt, oy0 + ox1);
+        float v10 = load_as_float(base, dt, oy1 + ox0);
+        float v11 = load_as_float(base, dt, oy1 + ox1);
+        r.v = lerp(lerp(v00, v01, tx), lerp(v10, v11, tx), ty);
+      }
+    }
+  }
+  if (WANT_B) {
+    const double* w = X.wmatrix;
+    double uz = 0.0;
+    if (NDIM == 3)
+      uz = affine_coord(w + 0, X.woffset[0], affine_pre<NDIM>(w + 0, cz, cy), cx);
+    double uy = affine_coord(w + 3, X.woffset[1], affine_pre<NDIM>(w + 3, cz, cy), cx);
+    double ux = affine_coord(w + 6, X.woffset[2], affine_pre<NDIM>(w + 6, cz, cy), cx);
+    r.b = blend_weight<NDIM>(tables + (int64_t)X.table * 125, uz, uy, ux);
+  }
+  return r;
+}
+
+// Conservative test: can view X be valid anywhere in the sample-index box?
+template <int NDIM>
+__device__ bool view_touches_box(const mvs_view_xform& X, const double lo[3],
+                                 const double hi[3]) {
+  for (int d = (NDIM == 3 ? 0 : 1); d < 3; ++d) {
+    double a = X.offset[d], b = X.offset[d];
+    for (int j = (NDIM == 3 ? 0 : 1); j < 3; ++j) {
+      double m = X.matrix[d * 3 + j];
+      double p = m * lo[j], q = m * hi[j];
+      a += fmin(p, q);
+      b += fmax(p, q);
+    }
+    if (b < -1e-6 || a > (double)(X.shape[d] - 1) + 1e-6) return false;
+  }
+  return true;
+}
+
+template <int NDIM, int ORDER, int MODE, bool PARTIAL>
+__global__ void __launch_bounds__(kThreads)
+fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
+            int n_chunks, const mvs_view_xform* __restrict__ xforms,
+            const float* __restrict__ tables) {
+  __shared__ unsigned char s_flag[kMaxXforms];
+  __shared__ int s_nact;
+  __shared__ int s_single;
+
+  const int64_t bid = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+  if (bid >= block_start[n_chunks]) return;
+  int lo = 0, hi = n_chunks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
+  }
+  const mvs_chunk& ck = chunks[lo];
+  const int64_t local = bid - __ldg(block_start + lo);
+  const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
+  const int nbx = (sh_x + kBX - 1) / kBX, nby = (sh_y + kBY - 1) / kBY;
+  const int x0 = (int)(local % nbx) * kBX;
+  const int y0 = (int)((local / nbx) % nby) * kBY;
+  const int z = (int)(local / ((int64_t)nbx * nby));
+  const int first = ck.first_xform, nxf = ck.n_xforms;
+
+  // ---- per-block culling of the chunk's view list (order preserved) ----
+  if (threadIdx.x == 0) { s_nact = 0; s_single = -1; }
+  __syncthreads();
+  {
+    double blo[3], bhi[3];
+    blo[0] = (double)(z + ck.halo[0]);
+    bhi[0] = blo[0];
+    blo[1] = (double)(y0 + ck.halo[1]);
+    bhi[1] = (double)(min(y0 + kBY, sh_y) - 1 + ck.halo[1]);
+    blo[2] = (double)(x0 + ck.halo[2]);
+    bhi[2] = (double)(min(x0 + kBX, sh_x) - 1 + ck.halo[2]);
+    for (int i = threadIdx.x; i < nxf; i += kThreads) {
+      bool t = view_touches_box<NDIM>(xforms[first + i], blo, bhi);
+      s_flag[i] = t ? 1 : 0;
+      if (t) { atomicAdd(&s_nact, 1); atomicMax(&s_single, i); }
+    }
+  }
+  __syncthreads();
+  const int nact = s_nact;
+  const int single = s_single;  // the only active view when nact == 1
+
+  const int lane = threadIdx.x & 31;
+  const int y = y0 + (threadIdx.x >> 5);
+  if (y >= sh_y) return;
+  const double cz = (double)(z + ck.halo[0]);
+  const double cy = (double)(y + ck.halo[1]);
+
+  float res[kVPT];
+  float den[kVPT];
+#pragma unroll
+  for (int k = 0; k < kVPT; ++k) { res[k] = 0.0f; den[k] = 0.0f; }
+
+  if (MODE == MVS_FUSE_WAVG) {
+    if (nact == 1 && !PARTIAL) {
+      // single contributing view: w/w == 1 exactly where b > 0, else 0
+      const mvs_view_xform& X = xforms[first + single];
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) {
+        int x = x0 + lane + 32 * k;
+        if (x < sh_x) {
+          ViewEval e = eval_view<NDIM, ORDER, true, true>(X, tables, cz, cy,
+                                                          (double)(x + ck.halo[2]));
+          res[k] = (e.valid && e.b > 0.0f) ? __fmul_rn(e.v, __fdiv_rn(e.b, e.b)) : 0.0f;
+        }
+      }
+    } else if (nact >= 1) {
+      // pass 1: s = sum_i b_i * valid_i  (sequential float32, view order)
+      float s[kVPT];
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) s[k] = 0.0f;
+      for (int i = 0; i < nxf; ++i) {
+        if (!s_flag[i]) continue;
+        const mvs_view_xform& X = xforms[first + i];
+#pragma unroll
+        for (int k = 0; k < kVPT; ++k) {
+          int x = x0 + lane + 32 * k;
+          if (x < sh_x) {
+            ViewEval e = eval_view<NDIM, ORDER, false, true>(X, tables, cz, cy,
+                                                             (double)(x + ck.halo[2]));
+            s[k] = __fadd_rn(s[k], e.b);
+          }
+        }
+      }
+      if (PARTIAL) {
+#pragma unroll
+        for (int k = 0; k < kVPT; ++k) den[k] = s[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < kVPT; ++k) if (s[k] == 0.0f) s[k] = 1.0f;
+      }
+      // pass 2: sum_i v_i * (b_i / s)
+      for (int i = 0; i < nxf; ++i) {
+        if (!s_flag[i]) continue;
+        const mvs_view_xform& X = xforms[first + i];
+#pragma unroll
+        for (int k = 0; k < kVPT; ++k) {
+          int x = x0 + lane + 32 * k;
+          if (x < sh_x) {
+            ViewEval e = eval_view<NDIM, ORDER, true, true>(X, tables, cz, cy,
+                                                            (double)(x + ck.halo[2]));
+            if (e.valid) {
+              float w = PARTIAL ? e.b : __fdiv_rn(e.b, s[k]);
+              res[k] = __fadd_rn(res[k], __fmul_rn(e.v, w));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    float cnt[kVPT];
+    bool any[kVPT];
+#pragma unroll
+    for (int k = 0; k < kVPT; ++k) { cnt[k] = 0.0f; any[k] = false; }
+    for (int i = 0; i < nxf; ++i) {
+      if (!s_flag[i]) continue;
+      const mvs_view_xform& X = xforms[first + i];
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) {
+        int x = x0 + lane + 32 * k;
+        if (x < sh_x) {
+          ViewEval e = eval_view<NDIM, ORDER, true, false>(X, tables, cz, cy,
+                                                           (double)(x + ck.halo[2]));
+          if (e.valid) {
+            if (MODE == MVS_FUSE_MAX) {
+              res[k] = any[k] ? fmaxf(res[k], e.v) : e.v;
+            } else {
+              res[k] = __fadd_rn(res[k], e.v);
+              cnt[k] = __fadd_rn(cnt[k], 1.0f);
+            }
+            any[k] = true;
+          }
+        }
+      }
+    }
+    if (MODE == MVS_FUSE_MEAN) {
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) res[k] = any[k] ? __fdiv_rn(res[k], cnt[k]) : 0.0f;
+    }
+  }
+
+  const int64_t row = (int64_t)z * ck.stride[0] + (int64_t)y * ck.stride[1];
+#pragma unroll
+  for (int k = 0; k < kVPT; ++k) {
+    int x = x0 + lane + 32 * k;
+    if (x < sh_x) {
+      int64_t o = row + (int64_t)x * ck.stride[2];
+      if (PARTIAL) {
+        ck.acc_num[o] = res[k];
+        ck.acc_den[o] = den[k];
+      } else {
+        store_from_float(ck.out, ck.out_dtype, o, res[k]);
+      }
+    }
+  }
+}
+
+__global__ void finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
+                                void* out, int out_dtype, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    float d = den[i];
+    if (d == 0.0f) d = 1.0f;
+    store_from_float(out, out_dtype, i, __fdiv_rn(num[i], d));
+  }
+}
+
+}  // namespace mvs
+
+struct mvs_fuse_plan {
+  mvs_chunk* d_chunks = nullptr;
+  mvs_view_xform* d_xforms = nullptr;
+  float* d_tables = nullptr;
+  int64_t* d_block_start = nullptr;
+  int n_chunks = 0, n_xforms = 0, n_tables = 0;
+  int ndim = 2, order = 1, mode = 0;
+  bool partial = false;
+  int64_t total_blocks = 0;
+  int64_t out_voxels = 0;
+};
+
+using namespace mvs;
+
+template <int NDIM, int ORDER, int MODE, bool PARTIAL>
+static cudaError_t launch_fuse(const mvs_fuse_plan* p, cudaStream_t st) {
+  const int64_t nb = p->total_blocks;
+  const int64_t gx = std::min<int64_t>(nb, 1 << 30);
+  const int64_t gy = (nb + gx - 1) / gx;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  fuse_kernel<NDIM, ORDER, MODE, PARTIAL><<<grid, kThreads, 0, st>>>(
+      p->d_chunks, p->d_block_start, p->n_chunks, p->d_xforms, p->d_tables);
+  return cudaGetLastError();
+}
+
+template <int NDIM, int ORDER>
+static cudaError_t dispatch_mode(const mvs_fuse_plan* p, cudaStream_t st) {
+  switch (p->mode) {
+    case MVS_FUSE_WAVG:
+      return p->partial ? launch_fuse<NDIM, ORDER, MVS_FUSE_WAVG, true>(p, st)
+                        : launch_fuse<NDIM, ORDER, MVS_FUSE_WAVG, false>(p, st);
+    case MVS_FUSE_MAX:
+      return launch_fuse<NDIM, ORDER, MVS_FUSE_MAX, false>(p, st);
+    default:
+      return launch_fuse<NDIM, ORDER, MVS_FUSE_MEAN, false>(p, st);
+  }
+}
+
+extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunks,
+                                    int n_chunks, const mvs_view_xform* xforms, int n_xforms,
+                                    const float* tables, int n_tables, int ndim, int order,
+                                    int fusion_mode, void* stream) {
+  MVS_REQUIRE(plan != nullptr, MVS_ERR_INVALID, "plan is NULL");
+  *plan = nullptr;
+  MVS_REQUIRE(ndim == 2 || ndim == 3, MVS_ERR_INVALID, "ndim must be 2 or 3, got %d", ndim);
+  MVS_REQUIRE(order == 0 || order == 1, MVS_ERR_UNSUPPORTED,
+              "interpolation order %d not supported (0 or 1)", order);
+  MVS_REQUIRE(fusion_mode >= MVS_FUSE_WAVG && fusion_mode <= MVS_FUSE_MEAN, MVS_ERR_INVALID,
+              "unknown fusion mode %d", fusion_mode);
+  MVS_REQUIRE(n_chunks >= 0 && n_xforms >= 0 && n_tables >= 0, MVS_ERR_INVALID,
+              "negative count");
+  MVS_REQUIRE(n_chunks == 0 || chunks != nullptr, MVS_ERR_INVALID, "chunks is NULL");
+  MVS_REQUIRE(n_xforms == 0 || xforms != nullptr, MVS_ERR_INVALID, "xforms is NULL");
+
+  std::vector<int64_t> block_start(n_chunks + 1, 0);
+  int64_t out_voxels = 0;
+  bool partial = false, any_out = false;
+  for (int c = 0; c < n_chunks; ++c) {
+    const mvs_chunk& ck = chunks[c];
+    for (int d = 0; d < 3; ++d)
+      MVS_REQUIRE(ck.shape[d] >= 0 && ck.halo[d] >= 0, MVS_ERR_INVALID,
+                  "chunk %d: negative extent/halo", c);
+    MVS_REQUIRE(ndim == 3 || ck.shape[0] <= 1, MVS_ERR_INVALID,
+                "chunk %d: 2-D plan with z extent %d", c, ck.shape[0]);
+    MVS_REQUIRE(ck.n_xforms >= 0 && ck.n_xforms <= kMaxXforms, MVS_ERR_UNSUPPORTED,
+                "chunk %d: %d views (max %d per chunk)", c, ck.n_xforms, kMaxXforms);
+    MVS_REQUIRE(ck.first_xform >= 0 && ck.first_xform + ck.n_xforms <= n_xforms,
+                MVS_ERR_INVALID, "chunk %d: xform range out of bounds", c);
+    MVS_REQUIRE(ck.out_dtype >= MVS_U8 && ck.out_dtype <= MVS_F32, MVS_ERR_INVALID,
+                "chunk %d: bad out dtype", c);
+    const bool has_acc = ck.acc_num != nullptr || ck.acc_den != nullptr;
+    if (has_acc) {
+      MVS_REQUIRE(ck.acc_num && ck.acc_den, MVS_ERR_INVALID,
+                  "chunk %d: acc_num and acc_den must both be set", c);
+      MVS_REQUIRE(fusion_mode == MVS_FUSE_WAVG, MVS_ERR_UNSUPPORTED,
+                  "partial accumulators need MVS_FUSE_WAVG");
+      partial = true;
+    } else {
+      MVS_REQUIRE(ck.out != nullptr || ck.shape[0] * ck.shape[1] * ck.shape[2] == 0,
+                  MVS_ERR_INVALID, "chunk %d: out is NULL", c);
+      any_out = true;
+    }
+    const int64_t nbx = (ck.shape[2] + kBX - 1) / kBX, nby = (ck.shape[1] + kBY - 1) / kBY;
+    block_start[c + 1] = block_start[c] + nbx * nby * (int64_t)ck.shape[0];
+    out_voxels += (int64_t)ck.shape[0] * ck.shape[1] * ck.shape[2];
+  }
+  MVS_REQUIRE(!(partial && any_out), MVS_ERR_UNSUPPORTED,
+              "a plan must be all-partial or all-final");
+  for (int i = 0; i < n_xforms; ++i) {
+    const mvs_view_xform& X = xforms[i];
+    MVS_REQUIRE(X.data != nullptr, MVS_ERR_INVALID, "xform %d: data is NULL", i);
+    MVS_REQUIRE(X.dtype >= MVS_U8 && X.dtype <= MVS_F32, MVS_ERR_INVALID,
+                "xform %d: bad dtype %d", i, X.dtype);
+    MVS_REQUIRE(X.shape[0] >= 1 && X.shape[1] >= 1 && X.shape[2] >= 1, MVS_ERR_INVALID,
+                "xform %d: empty window", i);
+    MVS_REQUIRE(fusion_mode != MVS_FUSE_WAVG || (X.table >= 0 && X.table < n_tables),
+                MVS_ERR_INVALID, "xform %d: table index %d out of range", i, X.table);
+  }
+  MVS_REQUIRE(n_tables == 0 || tables != nullptr, MVS_ERR_INVALID, "tables is NULL");
+
+  cudaStream_t st = (cudaStream_t)stream;
+  mvs_fuse_plan* p = new mvs_fuse_plan();
+  p->n_chunks = n_chunks; p->n_xforms = n_xforms; p->n_tables = n_tables;
+  p->ndim = ndim; p->order = order; p->mode = fusion_mode; p->partial = partial;
+  p->total_blocks = block_start[n_chunks]; p->out_voxels = out_voxels;
+  auto fail = [&](cudaError_t e, const char* what) {
+    set_error("%s failed: %s", what, cudaGetErrorString(e));
+    mvs_fuse_plan_destroy(p);
+    return (int)MVS_ERR_CUDA;
+  };
+  cudaError_t e;
+  auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t err = cudaMalloc(dst, bytes);
+    if (err != cudaSuccess) return err;
+    return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  if ((e = upload((void**)&p->d_chunks, chunks, sizeof(mvs_chunk) * n_chunks)) != cudaSuccess)
+    return fail(e, "upload chunks");
+  if ((e = upload((void**)&p->d_xforms, xforms, sizeof(mvs_view_xform) * n_xforms)) !=
+      cudaSuccess)
+    return fail(e, "upload xforms");
+  if ((e = upload((void**)&p->d_tables, tables, sizeof(float) * 125 * n_tables)) != cudaSuccess)
+    return fail(e, "upload tables");
+  if ((e = upload((void**)&p->d_block_start, block_start.data(),
+                  sizeof(int64_t) * (n_chunks + 1))) != cudaSuccess)
+    return fail(e, "upload block schedule");
+  // host staging buffers die with this call: make the copies complete
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+  *plan = p;
+  return MVS_OK;
+}
+
+extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
+  MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
+  if (p->total_blocks == 0) return MVS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (p->ndim == 2)
+    e = p->order == 0 ? dispatch_mode<2, 0>(p, st) : dispatch_mode<2, 1>(p, st);
+  else
+    e = p->order == 0 ? dispatch_mode<3, 0>(p, st) : dispatch_mode<3, 1>(p, st);
+  if (e != cudaSuccess) {
+    set_error("fuse kernel launch failed: %s", cudaGetErrorString(e));
+    return MVS_ERR_CUDA;
+  }
+  return MVS_OK;
+}
+
+extern "C" int mvs_fuse_plan_info(const mvs_fuse_plan* p, int* launches, int64_t* blocks,
+                                  int64_t* out_voxels) {
+  MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
+  if (launches) *launches = p->total_blocks > 0 ? 1 : 0;
+  if (blocks) *blocks = p->total_blocks;
+  if (out_voxels) *out_voxels = p->out_voxels;
+  return MVS_OK;
+}
+
+extern "C" int mvs_fuse_plan_destroy(mvs_fuse_plan* p) {
+  if (!p) return MVS_OK;
+  cudaFree(p->d_chunks);
+  cudaFree(p->d_xforms);
+  cudaFree(p->d_tables);
+  cudaFree(p->d_block_start);
+  delete p;
+  return MVS_OK;
+}
+
+extern "C" int mvs_fuse_finalize(const float* acc_num, const float* acc_den, void* out,
+                                 int out_dtype, int64_t n, void* stream) {
+  MVS_REQUIRE(n >= 0, MVS_ERR_INVALID, "negative n");
+  if (n == 0) return MVS_OK;
+  MVS_REQUIRE(acc_num && acc_den && out, MVS_ERR_INVALID, "NULL pointer");
+  MVS_REQUIRE(out_dtype >= MVS_U8 && out_dtype <= MVS_F32, MVS_ERR_INVALID, "bad out dtype");
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(acc_num, acc_den, out, out_dtype, n);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  return MVS_OK;
+}

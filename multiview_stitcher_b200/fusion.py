@@ -1,0 +1,502 @@
+"""Host side of the fused resample-blend path.
+
+Mirrors the reference's interface for this path (same names, argument meaning
+and defaults) on top of the CUDA engine:
+
+* ``fuse_np``  <- ``fusion._core.fuse_np`` (fusion/_core.py:1513-1733): one
+  output chunk from in-memory view slices (host arrays in, host array out).
+* ``fuse``     <- the arithmetic of ``fusion.fuse`` (fusion/_core.py:782-1501)
+  for in-memory views: output stack properties, chunk grid, per-chunk view
+  lists -- but every chunk of the stack goes to the GPU in ONE launch instead
+  of one dask task per chunk, with the tiles resident in HBM.
+* ``weighted_average_fusion`` / ``max_fusion`` / ``simple_average_fusion`` are
+  the selectors for the fusion function (fusion/_core.py:42-131); the
+  reference's own callables of the same name are recognised too.
+
+There is no CPU fallback: without ``libmvs_b200.so`` and a CUDA device these
+raise ``EngineUnavailable``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import inspect
+
+import numpy as np
+
+from . import _lib, geometry
+from ._lib import EngineError
+
+__all__ = [
+    "fuse",
+    "fuse_np",
+    "FusionPlan",
+    "DeviceView",
+    "weighted_average_fusion",
+    "max_fusion",
+    "simple_average_fusion",
+]
+
+
+# --- fusion-function selectors (same names/signatures as the reference) ------
+
+
+def weighted_average_fusion(transformed_views, blending_weights, fusion_weights=None):
+    """Selector for the engine's weighted-average mode (fusion/_core.py:61-94).
+    Called directly with (V, *chunk) stacks it runs the same arithmetic on the
+    GPU (post-resample hook level)."""
+    from . import hooks
+
+    return hooks.weighted_average_fusion(transformed_views, blending_weights, fusion_weights)
+
+
+def max_fusion(transformed_views):
+    """Selector for max fusion (fusion/_core.py:42-58)."""
+    from . import hooks
+
+    return hooks.max_fusion(transformed_views)
+
+
+def simple_average_fusion(transformed_views):
+    """Selector for valid-count average fusion (fusion/_core.py:97-131)."""
+    from . import hooks
+
+    return hooks.simple_average_fusion(transformed_views)
+
+
+_MODE_BY_NAME = {
+    "weighted_average_fusion": _lib.MVS_FUSE_WAVG,
+    "max_fusion": _lib.MVS_FUSE_MAX,
+    "simple_average_fusion": _lib.MVS_FUSE_MEAN,
+}
+
+
+def _fusion_mode(fusion_func):
+    if fusion_func is None:
+        return _lib.MVS_FUSE_WAVG
+    name = getattr(fusion_func, "__name__", None)
+    if name in _MODE_BY_NAME:
+        return _MODE_BY_NAME[name]
+    raise EngineError(
+        f"fusion_func {fusion_func!r} has no fused CUDA implementation "
+        "(weighted_average_fusion, max_fusion, simple_average_fusion)"
+    )
+
+
+# --- views --------------------------------------------------------------------
+
+
+class DeviceView:
+    """A view (tile) resident in HBM: a CUDA tensor (z,)y,x plus its physical
+    origin / spacing (what the reference keeps in the xarray coords)."""
+
+    def __init__(self, tensor, origin, spacing):
+        import torch
+
+        if not isinstance(tensor, torch.Tensor) or not tensor.is_cuda:
+            raise EngineError("DeviceView needs a CUDA tensor")
+        self.tensor = tensor
+        self.ndim = tensor.ndim
+        self.dims = geometry.spatial_dims(self.ndim)
+        self.origin = {d: float(origin[d]) for d in self.dims}
+        self.spacing = {d: float(spacing[d]) for d in self.dims}
+        self.mvs_dtype = _lib.mvs_dtype(_torch_to_np(tensor.dtype))
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    def bb(self):
+        return {
+            "origin": dict(self.origin),
+            "spacing": dict(self.spacing),
+            "shape": dict(zip(self.dims, map(int, self.tensor.shape))),
+        }
+
+
+def _torch_to_np(dt):
+    import torch
+
+    return {torch.uint8: np.uint8, torch.uint16: np.uint16, torch.float32: np.float32}.get(dt, None) or _bad_dtype(dt)
+
+
+def _bad_dtype(dt):
+    raise EngineError(f"unsupported voxel dtype {dt} (uint8, uint16, float32)")
+
+
+def _np_to_torch(dt):
+    import torch
+
+    return {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16, np.dtype(np.float32): torch.float32}[np.dtype(dt)]
+
+
+def _view_fields(view):
+    """(data, origin dict, spacing dict) of a view dict or an xarray-like
+    spatial image (``.data`` + 1-D coords per spatial dim, like the reference's
+    sims: origin = first coordinate, spacing = coordinate step)."""
+    if isinstance(view, DeviceView):
+        return view.tensor, view.origin, view.spacing
+    if isinstance(view, dict):
+        return view["data"], view["origin"], view["spacing"]
+    if hasattr(view, "coords") and hasattr(view, "dims"):
+        dims = [d for d in view.dims if d in geometry.SPATIAL_DIMS]
+        origin, spacing = {}, {}
+        for d in dims:
+            c = np.asarray(view.coords[d].values if hasattr(view.coords[d], "values") else view.coords[d])
+            origin[d] = float(c[0])
+            spacing[d] = float(c[1] - c[0]) if len(c) > 1 else 1.0
+        return np.asarray(view.data), origin, spacing
+    raise EngineError(f"cannot interpret view of type {type(view)}")
+
+
+def to_device_view(view, device="cuda", non_blocking=True):
+    """Upload a host view (dict / xarray-like) -- or pass a DeviceView through."""
+    import torch
+
+    if isinstance(view, DeviceView):
+        return view
+    data, origin, spacing = _view_fields(view)
+    if isinstance(data, torch.Tensor):
+        t = data.to(device, non_blocking=non_blocking)
+    else:
+        data = np.ascontiguousarray(data)
+        _lib.mvs_dtype(data.dtype)
+        t = torch.from_numpy(data).to(device, non_blocking=non_blocking)
+    return DeviceView(t, origin, spacing)
+
+
+# --- planning -----------------------------------------------------------------
+
+
+def _required_overlap(func, kwargs):
+    """Halo a hook asks for via its ``required_overlap`` attribute
+    (misc_utils.py:69-105, consumed at fusion/_core.py:1199-1222)."""
+    if func is None or not hasattr(func, "required_overlap"):
+        return 0
+    defaults = {
+        k: v.default
+        for k, v in inspect.signature(func).parameters.items()
+        if v.default is not inspect.Parameter.empty
+    }
+    ov = func.required_overlap({**defaults, **(kwargs or {})})
+    if isinstance(ov, dict):
+        return {d: int(np.ceil(v)) for d, v in ov.items()}
+    return int(np.ceil(ov))
+
+
+class FusionPlan:
+    """Device work list for fusing ``views`` onto ``output_stack_properties``.
+
+    Building the plan does the O(chunks x views) host geometry once and uploads
+    it; ``run()`` then is a single kernel launch over all chunks.  ``out`` is
+    the fused stack as a CUDA tensor.
+    """
+
+    def __init__(
+        self,
+        views,
+        params,
+        output_stack_properties,
+        output_chunksize=None,
+        fusion_func=None,
+        interpolation_order=1,
+        blending_widths=None,
+        shrink_distance=0,
+        full_view_bbs=None,
+        spacings=None,
+        chunk_subset=None,
+        out=None,
+        out_dtype=None,
+        partial=False,
+        halo=0,
+        sample_origin=None,
+        device="cuda",
+    ):
+        import torch
+
+        lib = _lib.load(require_device=True)
+        self._lib = lib
+        self.views = [to_device_view(v, device) for v in views]
+        if not self.views:
+            raise EngineError("no views to fuse")
+        ndim = self.views[0].ndim
+        if ndim not in (2, 3):
+            raise EngineError(f"views must be 2-D or 3-D, got {ndim}-D")
+        self.ndim = ndim
+        dims = geometry.spatial_dims(ndim)
+        self.dims = dims
+        self.params = [np.asarray(p, dtype=np.float64) for p in params]
+        if len(self.params) != len(self.views):
+            raise EngineError("need one affine per view")
+        self.mode = _fusion_mode(fusion_func)
+        self.order = int(interpolation_order)
+        osp = output_stack_properties
+        self.osp = osp
+        full_shape = tuple(int(osp["shape"][d]) for d in dims)
+        if output_chunksize is None:
+            output_chunksize = (
+                geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
+            )
+        self.chunksize = {d: int(output_chunksize[d]) for d in dims}
+        if not isinstance(halo, dict):
+            halo = {d: int(halo) for d in dims}
+        self.halo = halo
+
+        in_dtype = _torch_to_np(self.views[0].tensor.dtype)
+        self.out_np_dtype = np.dtype(out_dtype or in_dtype)
+        self.partial = bool(partial)
+        if out is None and not partial:
+            out = torch.zeros(full_shape, dtype=_np_to_torch(self.out_np_dtype), device=device)
+        self.out = out
+        if partial:
+            self.acc_num = torch.zeros(full_shape, dtype=torch.float32, device=device)
+            self.acc_den = torch.zeros(full_shape, dtype=torch.float32, device=device)
+            ref = self.acc_num
+        else:
+            if tuple(out.shape) != full_shape:
+                raise EngineError(f"out has shape {tuple(out.shape)}, expected {full_shape}")
+            ref = out
+        ostride = [0] * (3 - ndim) + [int(s) for s in ref.stride()]
+        elem = ref.element_size()
+
+        if full_view_bbs is None:
+            full_view_bbs = [v.bb() for v in self.views]
+        if spacings is None:
+            spacings = [bb["spacing"] for bb in full_view_bbs]
+
+        o_org, o_sp, _ = geometry.bb_arrays(osp, dims)
+        halo_v = np.array([halo[d] for d in dims], dtype=np.int64)
+
+        # per-view constants
+        tables = np.zeros((len(self.views), 125), dtype=np.float32)
+        tab_org, tab_sp, inv_params, aabbs = [], [], [], []
+        for i, (v, p) in enumerate(zip(self.views, self.params)):
+            t, to, ts = geometry.blending_table(full_view_bbs[i], blending_widths, shrink_distance)
+            tables[i, : t.size] = t.reshape(-1)
+            tab_org.append(to)
+            tab_sp.append(ts)
+            inv_params.append(np.linalg.inv(p))
+            aabbs.append(geometry.transformed_aabb(v.bb(), p, dims))
+
+        chunks = geometry.chunk_grid(osp, self.chunksize)
+        if sample_origin is not None and len(chunks) != 1:
+            raise EngineError("sample_origin needs a single-chunk plan")
+        if chunk_subset is not None:
+            chunks = [chunks[i] for i in chunk_subset]
+        n_chunks = len(chunks)
+        carr = np.zeros(n_chunks, dtype=_lib.CHUNK_DTYPE)
+        xrows = []
+        eps = 1e-6
+        for ci, (start, shape) in enumerate(chunks):
+            start = np.array(start, dtype=np.int64)
+            shape_a = np.array(shape, dtype=np.int64)
+            # halo'd chunk origin = what transform_sim sees as output origin;
+            # same operation order as mv_graph.py:965-971 + fusion/_core.py:1237-1243
+            if sample_origin is not None:
+                c_org = np.asarray(sample_origin, dtype=np.float64)
+            else:
+                c_org = (o_org + o_sp * start) - halo_v * o_sp
+            lo = c_org
+            hi = c_org + (shape_a + 2 * halo_v - 1) * o_sp
+            first = len(xrows)
+            for vi, v in enumerate(self.views):
+                alo, ahi = aabbs[vi]
+                if np.any(ahi < lo - eps) or np.any(alo > hi + eps):
+                    continue
+                in_org = np.array([v.origin[d] for d in dims])
+                in_sp = np.array([spacings[vi][d] for d in dims])
+                m, off = geometry.pixel_affine(inv_params[vi], c_org, o_sp, in_org, in_sp)
+                wm, woff = geometry.pixel_affine(inv_params[vi], c_org, o_sp, tab_org[vi], tab_sp[vi])
+                xrows.append((vi, m, off, wm, woff))
+            c = carr[ci]
+            off_elems = int(np.dot(start, ostride[3 - ndim :]))
+            if partial:
+                c["out"] = 0
+                c["acc_num"] = self.acc_num.data_ptr() + off_elems * 4
+                c["acc_den"] = self.acc_den.data_ptr() + off_elems * 4
+            else:
+                c["out"] = out.data_ptr() + off_elems * elem
+            c["out_dtype"] = _lib.mvs_dtype(self.out_np_dtype)
+            c["shape"] = [1] * (3 - ndim) + list(map(int, shape))
+            c["stride"] = ostride
+            c["halo"] = [0] * (3 - ndim) + [int(h) for h in halo_v]
+            c["first_xform"] = first
+            c["n_xforms"] = len(xrows) - first
+
+        xarr = np.zeros(len(xrows), dtype=_lib.VIEW_XFORM_DTYPE)
+        for r, (vi, m, off, wm, woff) in enumerate(xrows):
+            v = self.views[vi]
+            x = xarr[r]
+            x["data"] = v.tensor.data_ptr()
+            x["dtype"] = v.mvs_dtype
+            x["shape"] = [1] * (3 - ndim) + list(map(int, v.tensor.shape))
+            x["stride"] = [0] * (3 - ndim) + [int(s) for s in v.tensor.stride()]
+            x["matrix"], x["offset"] = geometry.embed3(m, off)
+            x["wmatrix"], x["woffset"] = geometry.embed3(wm, woff)
+            x["table"] = vi
+        self._chunks, self._xforms, self._tables = carr, xarr, tables
+        self.n_chunks, self.n_xforms = n_chunks, len(xrows)
+
+        handle = ctypes.c_void_p()
+        st = lib.mvs_fuse_plan_create(
+            ctypes.byref(handle),
+            carr.ctypes.data_as(ctypes.c_void_p),
+            n_chunks,
+            xarr.ctypes.data_as(ctypes.c_void_p),
+            len(xrows),
+            tables.ctypes.data_as(ctypes.c_void_p),
+            len(self.views),
+            ndim,
+            self.order,
+            self.mode,
+            _lib.current_stream_ptr(),
+        )
+        _lib.check(st, "mvs_fuse_plan_create")
+        self._handle = handle
+        launches, blocks, vox = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+        lib.mvs_fuse_plan_info(handle, ctypes.byref(launches), ctypes.byref(blocks), ctypes.byref(vox))
+        self.launches_per_run = launches.value
+        self.blocks = blocks.value
+        self.out_voxels = vox.value
+
+    def run(self):
+        """Enqueue the fused kernel on torch's current stream."""
+        _lib.check(self._lib.mvs_fuse_plan_run(self._handle, _lib.current_stream_ptr()), "mvs_fuse_plan_run")
+        return self.out
+
+    def algorithmic_bytes(self):
+        """B_fuse = sum of view bytes + output bytes."""
+        b_in = sum(v.tensor.numel() * v.tensor.element_size() for v in self.views)
+        return b_in + self.out_voxels * self.out_np_dtype.itemsize
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.mvs_fuse_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --- reference-facing entry points --------------------------------------------
+
+
+def fuse_np(
+    sims,
+    params,
+    output_properties,
+    fusion_func=weighted_average_fusion,
+    fusion_func_kwargs=None,
+    weights_func=None,
+    weights_func_kwargs=None,
+    trim_overlap_in_pixels=0,
+    interpolation_order=1,
+    full_view_bbs=None,
+    spacings=None,
+    origins=None,
+    blending_widths=None,
+    shrink_distance=0,
+    backend=None,
+    output_on_backend=False,
+):
+    """GPU replacement for ``fusion._core.fuse_np`` (fusion/_core.py:1513-1733):
+    same arguments; ``sims`` are view dicts / xarray-like slices (host or
+    device), the result is the fused, trimmed chunk as a host array in the input
+    dtype (or a CUDA tensor with ``output_on_backend=True``)."""
+    if weights_func is not None:
+        from . import content
+
+        return content.fuse_np_with_weights(
+            sims, params, output_properties, fusion_func, fusion_func_kwargs, weights_func,
+            weights_func_kwargs, trim_overlap_in_pixels, interpolation_order, full_view_bbs,
+            spacings, blending_widths, shrink_distance, output_on_backend,
+        )
+    dviews = [to_device_view(s) for s in sims]
+    dims = dviews[0].dims
+    if not isinstance(trim_overlap_in_pixels, dict):
+        trim_overlap_in_pixels = {d: int(trim_overlap_in_pixels) for d in dims}
+    trim = {d: int(trim_overlap_in_pixels[d]) for d in dims}
+    # plan for the trimmed chunk, sampling with the halo'd origin
+    inner = {
+        "origin": {
+            d: output_properties["origin"][d] + trim[d] * output_properties["spacing"][d]
+            for d in dims
+        },
+        "spacing": output_properties["spacing"],
+        "shape": {d: int(output_properties["shape"][d]) - 2 * trim[d] for d in dims},
+    }
+    plan = FusionPlan(
+        dviews,
+        params,
+        inner,
+        output_chunksize=inner["shape"],
+        fusion_func=fusion_func,
+        interpolation_order=interpolation_order,
+        blending_widths=blending_widths,
+        shrink_distance=shrink_distance,
+        full_view_bbs=full_view_bbs,
+        spacings=spacings,
+        halo=trim,
+        sample_origin=[output_properties["origin"][d] for d in dims],
+    )
+    out = plan.run()
+    plan.close()
+    if output_on_backend:
+        return out
+    return out.cpu().numpy()
+
+
+def fuse(
+    views,
+    params,
+    output_stack_properties=None,
+    output_spacing=None,
+    output_stack_mode="union",
+    output_chunksize=None,
+    fusion_func=weighted_average_fusion,
+    weights_func=None,
+    weights_func_kwargs=None,
+    interpolation_order=1,
+    blending_widths=None,
+    output_on_backend=False,
+):
+    """Fuse whole in-memory views (host or device) into one stack.
+
+    Follows ``fusion.fuse`` (fusion/_core.py:782-1501) for the in-memory case:
+    output spacing defaults to the first view's (:316-325), the stack is the
+    union of the transformed views (:1821-1992), chunks default to 2048^2 /
+    256^3 (spatial_image_utils.py:21-22).  Returns ``(fused, stack_props)``.
+    """
+    dviews = [to_device_view(v) for v in views]
+    bbs = [v.bb() for v in dviews]
+    if output_spacing is None:
+        output_spacing = bbs[0]["spacing"]
+    if output_stack_properties is None:
+        output_stack_properties = geometry.union_stack_props(
+            bbs, params, output_spacing, mode=output_stack_mode
+        )
+    if weights_func is not None:
+        from . import content
+
+        out = content.fuse_with_weights(
+            dviews, params, output_stack_properties, output_chunksize, fusion_func, weights_func,
+            weights_func_kwargs, interpolation_order, blending_widths,
+        )
+    else:
+        plan = FusionPlan(
+            dviews,
+            params,
+            output_stack_properties,
+            output_chunksize=output_chunksize,
+            fusion_func=fusion_func,
+            interpolation_order=interpolation_order,
+            blending_widths=blending_widths,
+        )
+        out = plan.run()
+        plan.close()
+    if not output_on_backend:
+        out = out.cpu().numpy()
+    return out, output_stack_properties
