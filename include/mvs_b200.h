@@ -125,6 +125,68 @@ int mvs_fuse_finalize(const float* acc_num, const float* acc_den, void* out,
                       int out_dtype, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------
+ * (i) batched 2-D/3-D phase-correlation pairwise registration
+ *
+ * Replaces registration.phase_correlation_registration
+ * (registration.py:353-565) and the scikit-image / scipy calls inside it:
+ *   rescale_intensity (:382-389), two phase_cross_correlation calls with
+ *   normalization "phase" / None and upsample_factor (:410-431), candidate
+ *   resampling with scipy.ndimage.affine_transform order 1 (:494-500), mask
+ *   statistics (:501-528), structural_similarity (:535-548) and
+ *   scipy.stats.spearmanr (:109-111, :551-553).
+ * A plan serves pairs of ONE crop shape (z, y, x; z = 1 in 2-D); the stages
+ * are batched over pairs / candidates.  The small data-dependent decisions in
+ * between (candidate expansion :461-477, the 10 % overlap rule :503, window
+ * size :535-536, list semantics :530-533, argmax :558) stay on the host.
+ * Outputs are written to HOST arrays; each stage synchronises `stream`.
+ * ---------------------------------------------------------------------- */
+typedef struct mvs_pc_plan mvs_pc_plan;
+
+/* upsample_factor: 10 (2-D) / 2 (3-D) are the reference defaults (:410-411). */
+int mvs_pc_plan_create(mvs_pc_plan** plan, int ndim, const int32_t shape[3], int max_pairs,
+                       int upsample_factor);
+int mvs_pc_plan_destroy(mvs_pc_plan* plan);
+/* region = ceil(1.5 * upsample) samples per axis of the upsampled DFT. */
+int mvs_pc_plan_info(const mvs_pc_plan* plan, int* region, int64_t* voxels,
+                     int* launches_per_correlate);
+
+/* Stage A: per-image statistics and rescale_intensity to [0,1] (NaN kept).
+ * fixed/moving: n device pointers to contiguous float32 crops of the plan's
+ * shape (NaN = outside).  stats_host[2n][9] (image 2i = fixed i, 2i+1 =
+ * moving i): nanmin, nanmax, NaN count, bbox lo z,y,x, bbox hi z,y,x (inclusive)
+ * of the non-NaN voxels.  nanmin == nanmax is the caller's constant-image
+ * guard (registration.py:1504-1530). */
+int mvs_pc_load_pairs(mvs_pc_plan* plan, int n, const float* const* fixed,
+                      const float* const* moving, double* stats_host, void* stream);
+
+/* Stage B: forward FFT, normalised / plain cross-power spectrum, inverse FFT,
+ * integer peaks and upsampled-DFT samples for the n loaded pairs.
+ * peaks_host[n][2][3]: wrapped integer peak (z,y,x); slot 0 = normalization
+ * None, slot 1 = "phase".  updft_host[n][2][region^ndim][2]: complex128
+ * cross-correlation samples around each peak, C order (z,y,x); sample index
+ * argmax |.| minus fix(region/2), divided by upsample, refines the peak. */
+int mvs_pc_correlate(mvs_pc_plan* plan, int n, int32_t* peaks_host, double* updft_host,
+                     void* stream);
+
+/* Stage C: for each candidate translation t (z,y,x; fixed px -> moving px) of
+ * pair cand_pair[i]: stats_host[i][8] = count(mask), count(~isnan(im1t)),
+ * bbox lo z,y,x and hi z,y,x (inclusive) of ~isnan(im1t). */
+int mvs_pc_candidate_stats(mvs_pc_plan* plan, int n_cand, const int32_t* cand_pair,
+                           const double* cand_t, int64_t* stats_host, void* stream);
+
+/* Stage D: SSIM of nan_to_num(im0) vs nan_to_num(im1t) on slices[i] =
+ * lo z,y,x, hi z,y,x (exclusive) with an odd window win[i] in 3..7.
+ * out_host[i][2] = mean SSIM, nanmax(im1t[slices]) (NaN if all-NaN). */
+int mvs_pc_candidate_ssim(mvs_pc_plan* plan, int n_cand, const int32_t* cand_pair,
+                          const double* cand_t, const int32_t* slices, const int32_t* win,
+                          double* out_host, void* stream);
+
+/* Stage E: Spearman rank correlation of im0[mask] vs im1t[mask] for one
+ * (pair, t); NaN when fewer than two samples or a constant input. */
+int mvs_pc_spearman(mvs_pc_plan* plan, int pair, const double t[3], double* rho_host,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
  * Synthetic tiles (benchmark / test inputs).  Integer-only
  * value-noise ground truth sampled at integer global coordinates
  * origin + index, so overlapping tiles agree exactly.

@@ -1,0 +1,573 @@
+// Candidate disambiguation for phase-correlation registration (sm_100a):
+// the loop of registration.phase_correlation_registration over translation
+// candidates (registration.py:493-556), batched over (pair, candidate):
+//   im1t   = scipy.ndimage.affine_transform(im1, translation, order=1,
+//            mode="constant", cval=NaN)                                  (:494-500)
+//   mask   = ~isnan(im1t) & ~isnan(im0), its count, bbox of ~isnan(im1t) (:501-528)
+//   SSIM   = skimage.metrics.structural_similarity on the bbox slices    (:535-548)
+//   quality= scipy.stats.spearmanr(im0[mask], im1t[mask])                (:551-553)
+// im1t is recomputed on the fly wherever it is needed (never stored), with
+// scipy's float64 tap arithmetic so masks and values are bit-identical.
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct mvs_pc_plan;
+
+namespace mvs {
+const float* pc_r0(const mvs_pc_plan* p, int pair);
+const float* pc_r1(const mvs_pc_plan* p, int pair);
+int pc_ndim(const mvs_pc_plan* p);
+const int* pc_shape(const mvs_pc_plan* p);
+int pc_loaded(const mvs_pc_plan* p);
+int pc_scratch(mvs_pc_plan* p, size_t bytes, void** out);
+
+struct Cand {
+  const float* r0;
+  const float* r1;
+  double t[3];
+  int lo[3];   // slice start (SSIM)
+  int len[3];  // slice extent
+  int win;
+  int tiles[3];
+  long long tile_base;  // first tile index of this candidate in the flat tile list
+};
+
+// scipy's mirrored tap index for mode="constant" splines (ni_interpolation.c)
+__device__ __forceinline__ int mirror_idx(int idx, int len) {
+  if (len <= 1) return 0;
+  const int s2 = 2 * len - 2;
+  if (idx < 0) {
+    idx = s2 * (-idx / s2) + idx;
+    return idx <= 1 - len ? idx + s2 : -idx;
+  }
+  if (idx >= len) {
+    idx -= s2 * (idx / s2);
+    if (idx >= len) idx = s2 - idx;
+  }
+  return idx;
+}
+
+// im1t at integer voxel (z, y, x): order-1 spline of r1 at (o + t), NaN outside
+// [0, len-1]; float64 tap products in scipy's order, result rounded to float32.
+template <int NDIM>
+__device__ __forceinline__ float shifted_value(const float* __restrict__ r1, int n0, int n1,
+                                               int n2, const double* t, int z, int y, int x) {
+  const double cx = (double)x + t[2], cy = (double)y + t[1];
+  const double cz = NDIM == 3 ? (double)z + t[0] : 0.0;
+  if (cx < 0.0 || cx > (double)(n2 - 1) || cy < 0.0 || cy > (double)(n1 - 1)) return NAN;
+  if (NDIM == 3 && (cz < 0.0 || cz > (double)(n0 - 1))) return NAN;
+  const double fx = floor(cx), fy = floor(cy), fz = floor(cz);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  double wx[2], wy[2], wz[2];
+  wx[0] = 1.0 - (cx - fx); wx[1] = 1.0 - wx[0];
+  wy[0] = 1.0 - (cy - fy); wy[1] = 1.0 - wy[0];
+  wz[0] = 1.0 - (cz - fz); wz[1] = 1.0 - wz[0];
+  int xs[2] = {ix, ix + 1 < n2 ? ix + 1 : mirror_idx(ix + 1, n2)};
+  int ys[2] = {iy, iy + 1 < n1 ? iy + 1 : mirror_idx(iy + 1, n1)};
+  int zs[2] = {iz, iz + 1 < n0 ? iz + 1 : mirror_idx(iz + 1, n0)};
+  double acc = 0.0;
+  if (NDIM == 3) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double v = (double)__ldg(r1 + ((long long)zs[a] * n1 + ys[b]) * n2 + xs[c]);
+          v = __dmul_rn(__dmul_rn(__dmul_rn(v, wz[a]), wy[b]), wx[c]);
+          acc = __dadd_rn(acc, v);
+        }
+  } else {
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double v = (double)__ldg(r1 + (long long)ys[b] * n2 + xs[c]);
+        v = __dmul_rn(__dmul_rn(v, wy[b]), wx[c]);
+        acc = __dadd_rn(acc, v);
+      }
+  }
+  return (float)acc;
+}
+
+// ---- stage C: mask statistics ------------------------------------------------
+
+constexpr int kStatBlocks = 32;
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+cand_stats_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
+                  long long* __restrict__ partial /* [cand][block][8] */) {
+  const Cand c = cands[blockIdx.y];
+  const long long N = (long long)n0 * n1 * n2;
+  long long nmask = 0, nvalid = 0;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % n2), y = (int)((i / n2) % n1), z = (int)(i / ((long long)n1 * n2));
+    float v = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, z, y, x);
+    if (v == v) {
+      ++nvalid;
+      lo[0] = min(lo[0], z); lo[1] = min(lo[1], y); lo[2] = min(lo[2], x);
+      hi[0] = max(hi[0], z); hi[1] = max(hi[1], y); hi[2] = max(hi[2], x);
+      float f = __ldg(c.r0 + i);
+      if (f == f) ++nmask;
+    }
+  }
+  __shared__ long long s_cnt[2][256];
+  __shared__ int s_lo[3][256], s_hi[3][256];
+  const int t = threadIdx.x;
+  s_cnt[0][t] = nmask; s_cnt[1][t] = nvalid;
+  for (int d = 0; d < 3; ++d) { s_lo[d][t] = lo[d]; s_hi[d][t] = hi[d]; }
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) {
+      s_cnt[0][t] += s_cnt[0][t + s]; s_cnt[1][t] += s_cnt[1][t + s];
+      for (int d = 0; d < 3; ++d) {
+        s_lo[d][t] = min(s_lo[d][t], s_lo[d][t + s]);
+        s_hi[d][t] = max(s_hi[d][t], s_hi[d][t + s]);
+      }
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    long long* p = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    p[0] = s_cnt[0][0]; p[1] = s_cnt[1][0];
+    for (int d = 0; d < 3; ++d) { p[2 + d] = s_lo[d][0]; p[5 + d] = s_hi[d][0]; }
+  }
+}
+
+// ---- stage D: SSIM -------------------------------------------------------------
+// Uniform win^ndim window, sample covariance, K1 = 0.01, K2 = 0.03, data_range 1
+// (images are rescaled to [0,1]); scipy.ndimage.uniform_filter semantics: one
+// pass per axis (z, y, x), float64 line sums, float32 between passes.
+
+constexpr int kTX = 32, kTY = 16, kTZ3 = 4, kTY3 = 8;
+constexpr int kMaxWin = 7;
+
+template <int NDIM>
+struct SsimTile {
+  static constexpr int TZ = NDIM == 3 ? kTZ3 : 1;
+  static constexpr int TY = NDIM == 3 ? kTY3 : kTY;
+  static constexpr int TX = kTX;
+  static constexpr int WZ = NDIM == 3 ? TZ + kMaxWin - 1 : 1;
+  static constexpr int WY = TY + kMaxWin - 1;
+  static constexpr int WX = TX + kMaxWin - 1;
+  static constexpr int WVOL = WZ * WY * WX;
+  static constexpr int OUT = TZ * TY * TX;
+  static constexpr int PER_THREAD = OUT / 256;
+};
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+ssim_kernel(const Cand* __restrict__ cands, int n_cand, int n0, int n1, int n2,
+            double* __restrict__ tile_sum, float* __restrict__ tile_max) {
+  using T = SsimTile<NDIM>;
+  extern __shared__ float ssim_smem[];
+  float* W0 = ssim_smem;
+  float* W1 = W0 + T::WVOL;
+  float* S1 = W1 + T::WVOL;
+  float* S2 = S1 + T::WVOL;
+  __shared__ double s_red[256];
+  __shared__ float s_max[256];
+
+  // locate the candidate this tile belongs to
+  const long long tile = blockIdx.x;
+  int ci = 0, chi = n_cand - 1;
+  while (ci < chi) {
+    const int mid = (ci + chi + 1) >> 1;
+    if (cands[mid].tile_base <= tile) ci = mid; else chi = mid - 1;
+  }
+  const Cand c = cands[ci];
+  long long local = tile - c.tile_base;
+  const int tx_i = (int)(local % c.tiles[2]);
+  const int ty_i = (int)((local / c.tiles[2]) % c.tiles[1]);
+  const int tz_i = (int)(local / ((long long)c.tiles[2] * c.tiles[1]));
+  const int ox = tx_i * T::TX, oy = ty_i * T::TY, oz = tz_i * T::TZ;  // output origin in slice
+  const int win = c.win;
+  const int wz = NDIM == 3 ? T::TZ + win - 1 : 1, wy = T::TY + win - 1, wx = T::TX + win - 1;
+
+  // ---- load windows (nan_to_num) and track nanmax of im1t inside the slice ----
+  float vmax = -INFINITY;
+  for (int i = threadIdx.x; i < wz * wy * wx; i += 256) {
+    const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
+    const int sx = ox + lx, sy = oy + ly, sz = oz + lz;  // slice-local
+    float a = 0.f, b = 0.f;
+    if (sx < c.len[2] && sy < c.len[1] && sz < c.len[0]) {
+      const int gx = c.lo[2] + sx, gy = c.lo[1] + sy, gz = c.lo[0] + sz;
+      a = __ldg(c.r0 + ((long long)gz * n1 + gy) * n2 + gx);
+      b = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, gz, gy, gx);
+      if (b == b) vmax = fmaxf(vmax, b); else b = 0.f;
+      if (a != a) a = 0.f;
+    }
+    const int w = (lz * T::WY + ly) * T::WX + lx;
+    W0[w] = a; W1[w] = b;
+  }
+  __syncthreads();
+
+  float U[5][T::PER_THREAD];
+  const double dwin = (double)win;
+  for (int q = 0; q < 5; ++q) {
+    for (int i = threadIdx.x; i < wz * wy * wx; i += 256) {
+      const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
+      const int w = (lz * T::WY + ly) * T::WX + lx;
+      const float a = W0[w], b = W1[w];
+      float v;
+      switch (q) {
+        case 0: v = a; break;
+        case 1: v = b; break;
+        case 2: v = __fmul_rn(a, a); break;
+        case 3: v = __fmul_rn(b, b); break;
+        default: v = __fmul_rn(a, b); break;
+      }
+      S1[w] = v;
+    }
+    __syncthreads();
+    float* src = S1;
+    float* dst = S2;
+    int cz = wz, cy = wy;
+    if (NDIM == 3) {  // filter along z
+      for (int i = threadIdx.x; i < T::TZ * wy * wx; i += 256) {
+        const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
+        double s = 0.0;
+        for (int k = 0; k < win; ++k) s += (double)src[((lz + k) * T::WY + ly) * T::WX + lx];
+        dst[(lz * T::WY + ly) * T::WX + lx] = (float)(s / dwin);
+      }
+      __syncthreads();
+      float* tmp = src; src = dst; dst = tmp;
+      cz = T::TZ;
+    }
+    // filter along y
+    for (int i = threadIdx.x; i < cz * T::TY * wx; i += 256) {
+      const int lx = i % wx, ly = (i / wx) % T::TY, lz = i / (wx * T::TY);
+      double s = 0.0;
+      for (int k = 0; k < win; ++k) s += (double)src[(lz * T::WY + ly + k) * T::WX + lx];
+      dst[(lz * T::WY + ly) * T::WX + lx] = (float)(s / dwin);
+    }
+    __syncthreads();
+    { float* tmp = src; src = dst; dst = tmp; }
+    cy = T::TY;
+    (void)cy;
+    // filter along x -> registers
+#pragma unroll
+    for (int r = 0; r < T::PER_THREAD; ++r) {
+      const int i = threadIdx.x + r * 256;
+      const int lx = i % T::TX, ly = (i / T::TX) % T::TY, lz = i / (T::TX * T::TY);
+      double s = 0.0;
+      for (int k = 0; k < win; ++k) s += (double)src[(lz * T::WY + ly) * T::WX + lx + k];
+      U[q][r] = (float)(s / dwin);
+    }
+    __syncthreads();
+  }
+
+  // ---- SSIM map on this tile's interior outputs ----
+  int np = win * win * (NDIM == 3 ? win : 1);
+  const float cov_norm = (float)((double)np / (double)(np - 1));
+  const float C1 = __fmul_rn(0.01f, 0.01f);  // (K1 * R)^2 with R = 1 in float32
+  const float C2 = __fmul_rn(0.03f, 0.03f);
+  const int nout_x = c.len[2] - win + 1, nout_y = c.len[1] - win + 1,
+            nout_z = NDIM == 3 ? c.len[0] - win + 1 : 1;
+  double sum = 0.0;
+#pragma unroll
+  for (int r = 0; r < T::PER_THREAD; ++r) {
+    const int i = threadIdx.x + r * 256;
+    const int lx = i % T::TX, ly = (i / T::TX) % T::TY, lz = i / (T::TX * T::TY);
+    if (ox + lx < nout_x && oy + ly < nout_y && oz + lz < nout_z) {
+      const float ux = U[0][r], uy = U[1][r], uxx = U[2][r], uyy = U[3][r], uxy = U[4][r];
+      const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
+      const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
+      const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
+      const float A1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, ux), uy), C1);
+      const float A2 = __fadd_rn(__fmul_rn(2.f, vxy), C2);
+      const float B1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), C1);
+      const float B2 = __fadd_rn(__fadd_rn(vx, vy), C2);
+      const float S = __fdiv_rn(__fmul_rn(A1, A2), __fmul_rn(B1, B2));
+      sum += (double)S;
+    }
+  }
+  s_red[threadIdx.x] = sum;
+  s_max[threadIdx.x] = vmax;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      s_red[threadIdx.x] += s_red[threadIdx.x + s];
+      s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { tile_sum[tile] = s_red[0]; tile_max[tile] = s_max[0]; }
+}
+
+// ---- stage E: Spearman ---------------------------------------------------------
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+spearman_keys_kernel(Cand c, int n0, int n1, int n2, float* __restrict__ ka,
+                     float* __restrict__ kb, unsigned* __restrict__ idx) {
+  const long long N = (long long)n0 * n1 * n2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % n2), y = (int)((i / n2) % n1), z = (int)(i / ((long long)n1 * n2));
+    float b = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, z, y, x);
+    float a = __ldg(c.r0 + i);
+    const bool m = (a == a) && (b == b);
+    ka[i] = m ? a : INFINITY;
+    // the reference ranks `im1t[mask] - 1` in float32 (registration.py:551-553):
+    // the subtraction merges values below ~3e-8 into ties, which changes ranks
+    kb[i] = m ? __fsub_rn(b, 1.0f) : INFINITY;
+    idx[i] = (unsigned)i;
+  }
+}
+
+// average ranks (ties share the mean rank, scipy.stats.rankdata "average")
+__global__ void __launch_bounds__(256)
+rank_kernel(const float* __restrict__ sorted, const unsigned* __restrict__ sidx, long long n,
+            double* __restrict__ rank_out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const float v = sorted[j];
+    long long lo = 0, hi = j;  // first index with sorted[idx] == v (>= v)
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (sorted[mid] < v) lo = mid + 1; else hi = mid; }
+    const long long first = lo;
+    lo = j; hi = n;            // first index with sorted[idx] > v
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (sorted[mid] <= v) lo = mid + 1; else hi = mid; }
+    const long long last = lo;  // exclusive
+    rank_out[sidx[j]] = 0.5 * (double)(first + last - 1) + 1.0;
+  }
+}
+
+constexpr int kPearsonBlocks = 128;
+
+__global__ void __launch_bounds__(256)
+pearson_kernel(const float* __restrict__ ka, const double* __restrict__ ra,
+               const double* __restrict__ rb, long long N, double mean,
+               double* __restrict__ partial /* [block][3] */) {
+  double sab = 0.0, saa = 0.0, sbb = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (ka[i] != INFINITY) {
+      const double a = ra[i] - mean, b = rb[i] - mean;
+      sab += a * b; saa += a * a; sbb += b * b;
+    }
+  }
+  __shared__ double s[3][256];
+  const int t = threadIdx.x;
+  s[0][t] = sab; s[1][t] = saa; s[2][t] = sbb;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (t < k) { s[0][t] += s[0][t + k]; s[1][t] += s[1][t + k]; s[2][t] += s[2][t + k]; }
+    __syncthreads();
+  }
+  if (t == 0) { partial[blockIdx.x * 3] = s[0][0]; partial[blockIdx.x * 3 + 1] = s[1][0]; partial[blockIdx.x * 3 + 2] = s[2][0]; }
+}
+
+}  // namespace mvs
+
+using namespace mvs;
+
+static int fill_cands(mvs_pc_plan* p, int n_cand, const int32_t* cand_pair, const double* cand_t,
+                      std::vector<Cand>& out) {
+  MVS_REQUIRE(p && cand_pair && cand_t, MVS_ERR_INVALID, "NULL pointer");
+  MVS_REQUIRE(n_cand >= 1, MVS_ERR_INVALID, "n_cand = %d", n_cand);
+  out.resize(n_cand);
+  for (int i = 0; i < n_cand; ++i) {
+    MVS_REQUIRE(cand_pair[i] >= 0 && cand_pair[i] < pc_loaded(p), MVS_ERR_INVALID,
+                "candidate %d: pair %d not loaded", i, cand_pair[i]);
+    Cand& c = out[i];
+    memset(&c, 0, sizeof(c));
+    c.r0 = pc_r0(p, cand_pair[i]);
+    c.r1 = pc_r1(p, cand_pair[i]);
+    for (int d = 0; d < 3; ++d) c.t[d] = cand_t[3 * i + d];
+  }
+  return MVS_OK;
+}
+
+extern "C" int mvs_pc_candidate_stats(mvs_pc_plan* p, int n_cand, const int32_t* cand_pair,
+                                      const double* cand_t, int64_t* stats_host, void* stream) {
+  MVS_REQUIRE(stats_host, MVS_ERR_INVALID, "NULL pointer");
+  std::vector<Cand> cands;
+  int rc = fill_cands(p, n_cand, cand_pair, cand_t, cands);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* sh = pc_shape(p);
+  const size_t cbytes = sizeof(Cand) * n_cand;
+  const size_t pbytes = sizeof(long long) * 8 * kStatBlocks * n_cand;
+  void* scratch;
+  if ((rc = pc_scratch(p, cbytes + pbytes + 256, &scratch))) return rc;
+  Cand* d_c = (Cand*)scratch;
+  long long* d_p = (long long*)((char*)scratch + ((cbytes + 255) / 256) * 256);
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data(), cbytes, cudaMemcpyHostToDevice, st));
+  dim3 grid(kStatBlocks, n_cand);
+  if (pc_ndim(p) == 3)
+    cand_stats_kernel<3><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], d_p);
+  else
+    cand_stats_kernel<2><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], d_p);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  std::vector<long long> part((size_t)8 * kStatBlocks * n_cand);
+  MVS_CHECK_CUDA(cudaMemcpyAsync(part.data(), d_p, pbytes, cudaMemcpyDeviceToHost, st));
+  MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int c = 0; c < n_cand; ++c) {
+    int64_t* s = stats_host + (size_t)c * 8;
+    s[0] = s[1] = 0;
+    for (int d = 0; d < 3; ++d) { s[2 + d] = INT_MAX; s[5 + d] = -1; }
+    for (int b = 0; b < kStatBlocks; ++b) {
+      const long long* q = part.data() + ((size_t)c * kStatBlocks + b) * 8;
+      s[0] += q[0]; s[1] += q[1];
+      for (int d = 0; d < 3; ++d) {
+        s[2 + d] = std::min<int64_t>(s[2 + d], q[2 + d]);
+        s[5 + d] = std::max<int64_t>(s[5 + d], q[5 + d]);
+      }
+    }
+  }
+  return MVS_OK;
+}
+
+extern "C" int mvs_pc_candidate_ssim(mvs_pc_plan* p, int n_cand, const int32_t* cand_pair,
+                                     const double* cand_t, const int32_t* slices,
+                                     const int32_t* win, double* out_host, void* stream) {
+  MVS_REQUIRE(slices && win && out_host, MVS_ERR_INVALID, "NULL pointer");
+  std::vector<Cand> cands;
+  int rc = fill_cands(p, n_cand, cand_pair, cand_t, cands);
+  if (rc) return rc;
+  const int ndim = pc_ndim(p);
+  const int* sh = pc_shape(p);
+  const int TZ = ndim == 3 ? kTZ3 : 1, TY = ndim == 3 ? kTY3 : kTY, TX = kTX;
+  long long total_tiles = 0;
+  for (int i = 0; i < n_cand; ++i) {
+    Cand& c = cands[i];
+    c.win = win[i];
+    MVS_REQUIRE(c.win >= 3 && c.win <= kMaxWin && (c.win & 1), MVS_ERR_INVALID,
+                "candidate %d: SSIM window %d (odd, 3..7)", i, c.win);
+    for (int d = 0; d < 3; ++d) {
+      c.lo[d] = slices[6 * i + d];
+      c.len[d] = slices[6 * i + 3 + d] - slices[6 * i + d];
+      MVS_REQUIRE(c.lo[d] >= 0 && c.len[d] >= 1 && c.lo[d] + c.len[d] <= sh[d], MVS_ERR_INVALID,
+                  "candidate %d: slice out of range on axis %d", i, d);
+      MVS_REQUIRE(d < 3 - ndim || c.len[d] >= c.win, MVS_ERR_INVALID,
+                  "candidate %d: window exceeds slice extent", i);
+    }
+    const int T[3] = {TZ, TY, TX};
+    for (int d = 0; d < 3; ++d) {
+      int nout = (d < 3 - ndim) ? 1 : c.len[d] - c.win + 1;
+      c.tiles[d] = (nout + T[d] - 1) / T[d];
+    }
+    c.tile_base = total_tiles;
+    total_tiles += (long long)c.tiles[0] * c.tiles[1] * c.tiles[2];
+  }
+  MVS_REQUIRE(total_tiles < (1LL << 31), MVS_ERR_UNSUPPORTED, "too many SSIM tiles");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t cbytes = ((sizeof(Cand) * n_cand + 255) / 256) * 256;
+  const size_t sbytes = ((sizeof(double) * total_tiles + 255) / 256) * 256;
+  const size_t mbytes = sizeof(float) * total_tiles;
+  void* scratch;
+  if ((rc = pc_scratch(p, cbytes + sbytes + mbytes + 256, &scratch))) return rc;
+  Cand* d_c = (Cand*)scratch;
+  double* d_sum = (double*)((char*)scratch + cbytes);
+  float* d_max = (float*)((char*)scratch + cbytes + sbytes);
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data(), sizeof(Cand) * n_cand,
+                                 cudaMemcpyHostToDevice, st));
+  if (ndim == 3) {
+    const int smem = (int)(sizeof(float) * 4 * SsimTile<3>::WVOL);
+    MVS_CHECK_CUDA(cudaFuncSetAttribute(ssim_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ssim_kernel<3><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_sum, d_max);
+  } else {
+    const int smem = (int)(sizeof(float) * 4 * SsimTile<2>::WVOL);
+    ssim_kernel<2><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_sum, d_max);
+  }
+  MVS_CHECK_CUDA(cudaGetLastError());
+  std::vector<double> hs(total_tiles);
+  std::vector<float> hm(total_tiles);
+  MVS_CHECK_CUDA(cudaMemcpyAsync(hs.data(), d_sum, sizeof(double) * total_tiles,
+                                 cudaMemcpyDeviceToHost, st));
+  MVS_CHECK_CUDA(cudaMemcpyAsync(hm.data(), d_max, sizeof(float) * total_tiles,
+                                 cudaMemcpyDeviceToHost, st));
+  MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n_cand; ++i) {
+    const Cand& c = cands[i];
+    const long long nt = (long long)c.tiles[0] * c.tiles[1] * c.tiles[2];
+    double s = 0.0;
+    float m = -INFINITY;
+    for (long long k = 0; k < nt; ++k) {
+      s += hs[c.tile_base + k];
+      m = std::max(m, hm[c.tile_base + k]);
+    }
+    double cnt = 1.0;
+    for (int d = 3 - ndim; d < 3; ++d) cnt *= (double)(c.len[d] - c.win + 1);
+    out_host[2 * i] = s / cnt;
+    out_host[2 * i + 1] = (m == -INFINITY) ? NAN : (double)m;
+  }
+  return MVS_OK;
+}
+
+extern "C" int mvs_pc_spearman(mvs_pc_plan* p, int pair, const double t[3], double* rho_host,
+                               void* stream) {
+  MVS_REQUIRE(p && t && rho_host, MVS_ERR_INVALID, "NULL pointer");
+  int32_t cp = pair;
+  std::vector<Cand> cands;
+  int rc = fill_cands(p, 1, &cp, t, cands);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ndim = pc_ndim(p);
+  const int* sh = pc_shape(p);
+  const long long N = (long long)sh[0] * sh[1] * sh[2];
+  MVS_REQUIRE(N < (1LL << 31), MVS_ERR_UNSUPPORTED, "pair volume too large for the rank sort");
+  size_t temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const float*)nullptr, (float*)nullptr,
+                                  (const unsigned*)nullptr, (unsigned*)nullptr, (int)N, 0, 32, st);
+  auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
+  const size_t fb = al(sizeof(float) * N), ub = al(sizeof(unsigned) * N),
+               db = al(sizeof(double) * N), pb = al(sizeof(double) * 3 * kPearsonBlocks);
+  void* scratch;
+  if ((rc = pc_scratch(p, 3 * fb + 2 * ub + 2 * db + pb + al(temp_bytes), &scratch))) return rc;
+  char* w = (char*)scratch;
+  float* ka = (float*)w; w += fb;
+  float* kb = (float*)w; w += fb;
+  float* ks = (float*)w; w += fb;
+  unsigned* idx = (unsigned*)w; w += ub;
+  unsigned* sidx = (unsigned*)w; w += ub;
+  double* ra = (double*)w; w += db;
+  double* rb = (double*)w; w += db;
+  double* part = (double*)w; w += pb;
+  void* temp = w;
+  const int grid = (int)std::min<long long>((N + 255) / 256, 148 * 8);
+  if (ndim == 3)
+    spearman_keys_kernel<3><<<grid, 256, 0, st>>>(cands[0], sh[0], sh[1], sh[2], ka, kb, idx);
+  else
+    spearman_keys_kernel<2><<<grid, 256, 0, st>>>(cands[0], sh[0], sh[1], sh[2], ka, kb, idx);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  // number of masked voxels = number of finite keys; count on the host from stats
+  // (cheap alternative: count after sort by a binary search kernel) -> use a reduction
+  // through the rank kernel bound: sort first, then find n on the host.
+  MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ka, ks, idx, sidx, (int)N, 0,
+                                                 32, st));
+  // n = first index whose key is +inf: binary search on the device-resident sorted keys
+  long long lo = 0, hi = N;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    float v;
+    MVS_CHECK_CUDA(cudaMemcpyAsync(&v, ks + mid, sizeof(float), cudaMemcpyDeviceToHost, st));
+    MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (v < INFINITY) lo = mid + 1; else hi = mid;
+  }
+  const long long n = lo;
+  if (n < 2) { *rho_host = NAN; return MVS_OK; }
+  rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, n, ra);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, ks, idx, sidx, (int)N, 0,
+                                                 32, st));
+  rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, n, rb);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  pearson_kernel<<<kPearsonBlocks, 256, 0, st>>>(ka, ra, rb, N, 0.5 * (double)(n + 1), part);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  double hp[3 * kPearsonBlocks];
+  MVS_CHECK_CUDA(cudaMemcpyAsync(hp, part, sizeof(hp), cudaMemcpyDeviceToHost, st));
+  MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+  double sab = 0, saa = 0, sbb = 0;
+  for (int b = 0; b < kPearsonBlocks; ++b) { sab += hp[3 * b]; saa += hp[3 * b + 1]; sbb += hp[3 * b + 2]; }
+  *rho_host = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
+  return MVS_OK;
+}

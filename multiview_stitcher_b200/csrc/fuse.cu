@@ -197,7 +197,7 @@ fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ bl
   }
   const mvs_chunk& ck = chunks[lo];
   const int64_t local = bid - __ldg(block_start + lo);
-  const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
+  const int sh_y = ck.shape[1], sh_x = ck.shape[2];
   const int nbx = (sh_x + kBX - 1) / kBX, nby = (sh_y + kBY - 1) / kBY;
   const int x0 = (int)(local % nbx) * kBX;
   const int y0 = (int)((local / nbx) % nby) * kBY;

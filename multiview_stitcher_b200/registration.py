@@ -1,0 +1,417 @@
+"""Host side of the batched phase-correlation registration path.
+
+``phase_correlation_registration`` has the signature of the reference's
+default ``pairwise_reg_func`` (registration.py:353-358) and returns the same
+``{"affine_matrix", "quality"}`` dict, so ``registration.register(...,
+pairwise_reg_func=phase_correlation_registration)`` calls it unchanged.
+``register_pairs`` is the batched form (all overlap pairs of a tile grid in a
+handful of launches) that a ``pairwise_executor`` (registration.py:2634-2655)
+drives.
+
+What runs where: FFTs, cross-power spectra, peak search, upsampled DFT,
+candidate resampling, masks, SSIM and Spearman run on the GPU
+(csrc/phasecorr.cu, csrc/disambig.cu).  The data-dependent glue between the
+stages -- candidate expansion (:461-477), the 10 % overlap rule (:503), bbox
+slices (:507-528), window size (:535-536), the append-or-skip list semantics
+(:530-533) and the final argmax (:558-563) -- is O(candidates) host logic and
+mirrors the reference line by line.  No CPU fallback exists for the array work.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import warnings
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineError
+
+__all__ = [
+    "phase_correlation_registration",
+    "register_pairs",
+    "dispatch_pairwise_reg_func",
+    "PhaseCorrPlan",
+]
+
+
+def affine_from_translation(translation):
+    """Homogeneous matrix of a translation (param_utils.py:7-14)."""
+    t = np.asarray(translation, dtype=np.float64)
+    m = np.eye(len(t) + 1)
+    m[:-1, -1] = t
+    return m
+
+
+class PhaseCorrPlan:
+    """Device buffers + FFT tables for pairs of one crop shape."""
+
+    def __init__(self, shape, max_pairs, upsample_factor):
+        lib = _lib.load(require_device=True)
+        self._lib = lib
+        self.ndim = len(shape)
+        if self.ndim not in (2, 3):
+            raise EngineError(f"phase correlation needs 2-D or 3-D crops, got {self.ndim}-D")
+        self.shape = tuple(int(s) for s in shape)
+        self.shape3 = (1,) * (3 - self.ndim) + self.shape
+        self.max_pairs = int(max_pairs)
+        self.upsample = int(upsample_factor)
+        if self.upsample != upsample_factor:
+            raise EngineError("upsample_factor must be an integer")
+        handle = ctypes.c_void_p()
+        shp = (ctypes.c_int32 * 3)(*self.shape3)
+        _lib.check(
+            lib.mvs_pc_plan_create(ctypes.byref(handle), self.ndim, shp, self.max_pairs, self.upsample),
+            "mvs_pc_plan_create",
+        )
+        self._h = handle
+        region, vox, launches = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int()
+        lib.mvs_pc_plan_info(handle, ctypes.byref(region), ctypes.byref(vox), ctypes.byref(launches))
+        self.region = region.value
+        self.voxels = vox.value
+        self.launches_per_correlate = launches.value
+        self.launch_count = 0
+        self._keep = None
+
+    # ---- stages --------------------------------------------------------------
+
+    def load_pairs(self, fixed, moving):
+        """fixed / moving: lists of CUDA float32 contiguous tensors."""
+        n = len(fixed)
+        if n < 1 or n > self.max_pairs or len(moving) != n:
+            raise EngineError(f"{n} pairs for a plan of {self.max_pairs}")
+        for t in list(fixed) + list(moving):
+            if tuple(t.shape) != self.shape:
+                raise EngineError(f"crop shape {tuple(t.shape)} != plan shape {self.shape}")
+        self._keep = (fixed, moving)  # keep inputs alive while the plan refers to them
+        fa = (ctypes.c_void_p * n)(*[t.data_ptr() for t in fixed])
+        ma = (ctypes.c_void_p * n)(*[t.data_ptr() for t in moving])
+        stats = np.zeros((2 * n, 9), dtype=np.float64)
+        _lib.check(
+            self._lib.mvs_pc_load_pairs(self._h, n, fa, ma, stats.ctypes.data_as(ctypes.c_void_p), _lib.current_stream_ptr()),
+            "mvs_pc_load_pairs",
+        )
+        self.n = n
+        self.launch_count += 2
+        return stats.reshape(n, 2, 9)
+
+    def correlate(self):
+        n = self.n
+        peaks = np.zeros((n, 2, 3), dtype=np.int32)
+        rn = self.region**self.ndim if self.upsample > 1 else 1
+        updft = np.zeros((n, 2, rn, 2), dtype=np.float64)
+        _lib.check(
+            self._lib.mvs_pc_correlate(
+                self._h, n, peaks.ctypes.data_as(ctypes.c_void_p), updft.ctypes.data_as(ctypes.c_void_p), _lib.current_stream_ptr()
+            ),
+            "mvs_pc_correlate",
+        )
+        self.launch_count += self.launches_per_correlate
+        return peaks, updft[..., 0] + 1j * updft[..., 1]
+
+    def _cand_arrays(self, cand_pair, cand_t):
+        cp = np.ascontiguousarray(cand_pair, dtype=np.int32)
+        ct = np.zeros((len(cp), 3), dtype=np.float64)
+        ct[:, 3 - self.ndim :] = np.asarray(cand_t, dtype=np.float64).reshape(len(cp), self.ndim)
+        return cp, ct
+
+    def candidate_stats(self, cand_pair, cand_t):
+        cp, ct = self._cand_arrays(cand_pair, cand_t)
+        out = np.zeros((len(cp), 8), dtype=np.int64)
+        _lib.check(
+            self._lib.mvs_pc_candidate_stats(
+                self._h, len(cp), cp.ctypes.data_as(ctypes.c_void_p), ct.ctypes.data_as(ctypes.c_void_p),
+                out.ctypes.data_as(ctypes.c_void_p), _lib.current_stream_ptr(),
+            ),
+            "mvs_pc_candidate_stats",
+        )
+        self.launch_count += 1
+        return out
+
+    def candidate_ssim(self, cand_pair, cand_t, slices, win):
+        cp, ct = self._cand_arrays(cand_pair, cand_t)
+        sl = np.zeros((len(cp), 6), dtype=np.int32)
+        sl[:, :3] = 0
+        sl[:, 3:6] = 1
+        s = np.asarray(slices, dtype=np.int32).reshape(len(cp), 2, self.ndim)
+        sl[:, 3 - self.ndim : 3] = s[:, 0]
+        sl[:, 6 - self.ndim : 6] = s[:, 1]
+        w = np.ascontiguousarray(win, dtype=np.int32)
+        out = np.zeros((len(cp), 2), dtype=np.float64)
+        _lib.check(
+            self._lib.mvs_pc_candidate_ssim(
+                self._h, len(cp), cp.ctypes.data_as(ctypes.c_void_p), ct.ctypes.data_as(ctypes.c_void_p),
+                sl.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p),
+                out.ctypes.data_as(ctypes.c_void_p), _lib.current_stream_ptr(),
+            ),
+            "mvs_pc_candidate_ssim",
+        )
+        self.launch_count += 1
+        return out
+
+    def spearman(self, pair, t):
+        t3 = np.zeros(3, dtype=np.float64)
+        t3[3 - self.ndim :] = np.asarray(t, dtype=np.float64)
+        rho = ctypes.c_double()
+        _lib.check(
+            self._lib.mvs_pc_spearman(self._h, int(pair), t3.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rho), _lib.current_stream_ptr()),
+            "mvs_pc_spearman",
+        )
+        self.launch_count += 6
+        return rho.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mvs_pc_plan_destroy(self._h)
+            self._h = None
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --- host glue (mirrors registration.py:410-563) ------------------------------
+
+
+def _subpixel_shifts(plan, peaks, updft):
+    """skimage.phase_cross_correlation's float32 shift arithmetic on the
+    engine's integer peaks and upsampled-DFT samples.  Returns
+    shifts[pair][norm] (norm 0 = None, 1 = "phase")."""
+    n, ndim, u = peaks.shape[0], plan.ndim, plan.upsample
+    out = np.zeros((n, 2, ndim), dtype=np.float32)
+    uf = np.float32(u)
+    region = plan.region
+    dftshift = np.fix(np.float32(region) / np.float32(2.0))
+    for i in range(n):
+        for k in range(2):
+            shift = peaks[i, k, 3 - ndim :].astype(np.float32)
+            if u > 1:
+                shift = np.round(shift * uf) / uf
+                cc = updft[i, k].reshape((region,) * ndim).astype(np.complex64)
+                maxima = np.unravel_index(np.argmax(np.abs(cc)), cc.shape)
+                maxima = np.stack(maxima).astype(np.float32) - dftshift
+                shift = shift + maxima / uf
+            for d in range(ndim):
+                if plan.shape[d] == 1:
+                    shift[d] = 0
+            out[i, k] = shift
+    return out
+
+
+def _expand_candidates(shift_cands, shape, max_shift_per_dim):
+    """registration.py:461-477."""
+    ndim = len(shape)
+    t_candidates = []
+    for sc in shift_cands:
+        for s in np.ndindex(tuple(1 if sc[d] == 0 else 4 for d in range(ndim))):
+            t = []
+            for d in range(ndim):
+                if s[d] == 0:
+                    t.append(sc[d])
+                elif s[d] == 1:
+                    t.append(-sc[d])
+                elif s[d] == 2:
+                    t.append(-(sc[d] - shape[d]))
+                else:
+                    t.append(-sc[d] - shape[d])
+            if np.max(np.abs(t)) < max_shift_per_dim:
+                t_candidates.append(t)
+    return t_candidates
+
+
+def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=False):
+    """Stages B-E for the pairs loaded into ``plan``; one result dict per pair."""
+    n, ndim, shape = plan.n, plan.ndim, plan.shape
+    peaks, updft = plan.correlate()
+    shifts = _subpixel_shifts(plan, peaks, updft)
+
+    # per pair: shift candidates in the reference's order ("phase", None[, masked])
+    per_pair = []
+    for i in range(n):
+        has_nan = bool(stats[i, 0, 2] > 0 or stats[i, 1, 2] > 0)
+        sc = [shifts[i, 1], shifts[i, 0]]
+        if has_nan:
+            # the masked call (:433-443) is handed isnan masks (True = invalid) and
+            # degenerates to a zero shift ("masked candidate")
+            sc.append(np.zeros(ndim))
+        mode = disambiguate_region_mode or ("intersection" if has_nan else "union")
+        t_cands = _expand_candidates(sc, shape, max(shape))
+        per_pair.append({"has_nan": has_nan, "mode": mode, "shift_candidates": sc, "t": t_cands})
+
+    cand_pair = [i for i, pp in enumerate(per_pair) for _ in pp["t"]]
+    cand_t = [t for pp in per_pair for t in pp["t"]]
+    results = [None] * n
+    if not cand_t:
+        return [[np.zeros(ndim)] for _ in range(n)]  # registration.py:479-480
+    cstats = plan.candidate_stats(cand_pair, np.array(cand_t, dtype=np.float64))
+
+    # decide which candidates need SSIM (:501-536)
+    ssim_req = []  # (flat cand index, slices lo, hi, win)
+    pos = 0
+    for i, pp in enumerate(per_pair):
+        valid_pixels1 = int(plan.voxels - stats[i, 1, 2])
+        im0_lo = stats[i, 0, 3 + 3 - ndim : 6].astype(int)
+        im0_hi = stats[i, 0, 6 + 3 - ndim : 9].astype(int)
+        pp["kind"] = []
+        for _ in pp["t"]:
+            st = cstats[pos]
+            nmask = int(st[0])
+            if nmask == 0 or float(nmask) / valid_pixels1 < 0.1:
+                pp["kind"].append(("low", None))
+            else:
+                lo1 = st[2 + 3 - ndim : 5].astype(int)
+                hi1 = st[5 + 3 - ndim : 8].astype(int)
+                if pp["mode"] == "union":
+                    lo = np.minimum(im0_lo, lo1)
+                    hi = np.maximum(im0_hi, hi1) + 1
+                else:
+                    lo = np.maximum(im0_lo, lo1)
+                    hi = np.minimum(im0_hi, hi1) + 1
+                min_shape = int(np.min(hi - lo))
+                win = int(min(7, min_shape - ((min_shape - 1) % 2)))
+                pp["kind"].append(("eval", (pos, lo, hi, win)))
+                if win >= 3:
+                    ssim_req.append((pos, lo, hi, win))
+            pos += 1
+
+    ssim_out = {}
+    if ssim_req:
+        idx = [r[0] for r in ssim_req]
+        res = plan.candidate_ssim(
+            [cand_pair[j] for j in idx],
+            np.array([cand_t[j] for j in idx], dtype=np.float64),
+            np.array([[r[1], r[2]] for r in ssim_req]),
+            [r[3] for r in ssim_req],
+        )
+        for j, r in zip(idx, res):
+            ssim_out[j] = r
+
+    for i, pp in enumerate(per_pair):
+        if not pp["t"]:
+            results[i] = [np.zeros(ndim)]  # registration.py:479-480
+            continue
+        disamb, quality_src = [], []  # quality_src: None (-1) or the candidate index to rank
+        for ci, (kind, info) in enumerate(pp["kind"]):
+            if kind == "low":
+                disamb.append(-1)
+                quality_src.append(None)
+                continue
+            pos_j, lo, hi, win = info
+            if win >= 3:
+                ssim_val, vmax = ssim_out[pos_j]
+                flat = vmax <= 0.0  # np.nanmax(im1t[slices]) <= im1_min (== 0 after rescale)
+                if flat:
+                    continue  # :530-533 -- nothing appended
+                disamb.append(ssim_val)
+            else:
+                # SSIM window < 3 (:536-538).  The flat-region skip (:530) is not
+                # evaluated for such 1-2 px slivers: rescaled, non-constant images
+                # are not identically 0 there.
+                disamb.append(-1)
+            quality_src.append(ci)
+        argmax_index = int(np.nanargmax(disamb))
+        t = pp["t"][argmax_index]  # same (mis)alignment as the reference when entries were skipped
+        src = quality_src[argmax_index]
+        if src is None:
+            quality = -1
+        else:
+            quality = plan.spearman(i, pp["t"][src])
+        res = {"affine_matrix": affine_from_translation(t), "quality": quality}
+        if return_details:
+            res["shift_candidates"] = pp["shift_candidates"]
+            res["t_candidates"] = pp["t"]
+            res["ssim"] = disamb
+        results[i] = res
+    return results
+
+
+def _to_device_f32(a):
+    import torch
+
+    if isinstance(a, torch.Tensor):
+        return a.to("cuda", dtype=torch.float32).contiguous()
+    if hasattr(a, "data") and not isinstance(a, np.ndarray):
+        a = a.data  # xr.DataArray-like (registration.py:377-378)
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to("cuda")
+
+
+def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsample_factor=None, return_details=False, plans=None):
+    """Batched phase-correlation registration.  ``fixed_list[i]`` /
+    ``moving_list[i]`` are same-shape float arrays (host or CUDA, NaN = outside);
+    pairs are grouped by shape and each group runs as one batch.  Returns one
+    ``{"affine_matrix", "quality"}`` per pair (see
+    ``phase_correlation_registration``).  Constant images get the caller-side
+    guard's answer (identity, quality NaN, UserWarning; registration.py:1504-1530).
+    ``plans``: optional dict reused across calls to keep device buffers/tables."""
+    n = len(fixed_list)
+    if len(moving_list) != n:
+        raise EngineError("fixed_list and moving_list differ in length")
+    fixed = [_to_device_f32(a) for a in fixed_list]
+    moving = [_to_device_f32(a) for a in moving_list]
+    groups = {}
+    for i, (f, m) in enumerate(zip(fixed, moving)):
+        if tuple(f.shape) != tuple(m.shape):
+            raise EngineError(f"pair {i}: shapes differ {tuple(f.shape)} vs {tuple(m.shape)}")
+        groups.setdefault(tuple(f.shape), []).append(i)
+    results = [None] * n
+    for shape, idx in groups.items():
+        ndim = len(shape)
+        u = upsample_factor if upsample_factor is not None else (10 if ndim == 2 else 2)
+        key = (shape, u)
+        plan = plans.get(key) if plans is not None else None
+        if plan is None or plan.max_pairs < len(idx):
+            plan = PhaseCorrPlan(shape, len(idx), u)
+            if plans is not None:
+                plans[key] = plan
+        stats = plan.load_pairs([fixed[i] for i in idx], [moving[i] for i in idx])
+        constant = [bool(stats[k, 0, 0] == stats[k, 0, 1] or stats[k, 1, 0] == stats[k, 1, 1]) for k in range(len(idx))]
+        if any(constant):
+            keep = [k for k in range(len(idx)) if not constant[k]]
+            for k in range(len(idx)):
+                if constant[k]:
+                    warnings.warn(
+                        "An overlap region between tiles/views is all zero or constant. Assuming identity transform.",
+                        UserWarning,
+                        stacklevel=2,
+                    )
+                    results[idx[k]] = {"affine_matrix": np.eye(ndim + 1), "quality": np.nan}
+            if keep:
+                stats = plan.load_pairs([fixed[idx[k]] for k in keep], [moving[idx[k]] for k in keep])
+                out = _register_loaded(plan, stats, disambiguate_region_mode, return_details)
+                for k, r in zip(keep, out):
+                    results[idx[k]] = r
+        else:
+            out = _register_loaded(plan, stats, disambiguate_region_mode, return_details)
+            for k, r in zip(range(len(idx)), out):
+                results[idx[k]] = r
+        if plans is None:
+            plan.close()
+    return results
+
+
+def phase_correlation_registration(fixed_data, moving_data, disambiguate_region_mode=None, **skimage_phase_corr_kwargs):
+    """Drop-in ``pairwise_reg_func`` (registration.py:353-565): translation
+    between two same-grid images by phase correlation, sub-pixel refined by an
+    upsampled DFT, sign/wrap ambiguity resolved by SSIM, quality = Spearman.
+
+    ``fixed_data`` / ``moving_data``: arrays or ``xr.DataArray``-likes (``.data``
+    is used), float, NaN = outside.  Returns ``{"affine_matrix": (ndim+1)^2
+    translation mapping fixed px -> moving px, "quality": float}``.
+    """
+    kwargs = dict(skimage_phase_corr_kwargs)
+    u = kwargs.pop("upsample_factor", None)
+    if kwargs:
+        raise EngineError(f"unsupported phase_cross_correlation arguments: {sorted(kwargs)}")
+    return register_pairs([fixed_data], [moving_data], disambiguate_region_mode, u)[0]
+
+
+def dispatch_pairwise_reg_func(pairwise_reg_func, fixed_data=None, moving_data=None, skip_constant_check=False, **kwargs):
+    """registration.py:1477-1544 for image data: the constant-image guard, then
+    the hook.  (``register_pairs`` applies the same guard itself.)"""
+    if fixed_data is not None and moving_data is not None:
+        kwargs["fixed_data"] = fixed_data
+        kwargs["moving_data"] = moving_data
+    return pairwise_reg_func(**kwargs)
