@@ -21,6 +21,10 @@
 // (L1/L2 absorb the 2^ndim-tap reuse), every output voxel written once.
 
 #include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -32,6 +36,10 @@ constexpr int kBY = 8;        // ... along y (one warp per row)
 constexpr int kThreads = 256;
 constexpr int kVPT = kBX / 32;  // voxels per thread, strided by 32 along x
 constexpr int kMaxXforms = 1024;  // per chunk
+
+}  // namespace mvs
+#include "fuse_stencil.cuh"
+namespace mvs {
 
 struct ViewEval {
   float v;  // interpolated value (undefined if !valid)
@@ -354,18 +362,146 @@ __global__ void finalize_kernel(const float* __restrict__ num, const float* __re
 }  // namespace mvs
 
 struct mvs_fuse_plan {
+  // general-affine schedule
   mvs_chunk* d_chunks = nullptr;
+  int64_t* d_block_start = nullptr;
+  int n_chunks = 0;
+  int64_t total_blocks = 0;
+  // translation (stencil) schedule
+  mvs_chunk* d_chunks_st = nullptr;
+  int64_t* d_block_start_st = nullptr;
+  int n_chunks_st = 0;
+  int64_t total_blocks_st = 0;
+  mvs::StencilXform* d_sxf = nullptr;
+  int stencil_dtype = MVS_F32;
   mvs_view_xform* d_xforms = nullptr;
   float* d_tables = nullptr;
-  int64_t* d_block_start = nullptr;
-  int n_chunks = 0, n_xforms = 0, n_tables = 0;
+  int n_xforms = 0, n_tables = 0;
   int ndim = 2, order = 1, mode = 0;
   bool partial = false;
-  int64_t total_blocks = 0;
   int64_t out_voxels = 0;
 };
 
 using namespace mvs;
+
+// ---- translation fast path: host-side classification ---------------------------
+
+static float host_table_interp(const float* tab, int ndim, const double u[3]) {
+  // multilinear lookup (float64) in the 5^ndim table, cval 0 outside [0,4]
+  double w[3][2];
+  int i0[3], i1[3];
+  for (int d = 3 - ndim; d < 3; ++d) {
+    if (u[d] < 0.0 || u[d] > 4.0) return 0.f;
+    double f = floor(u[d]);
+    i0[d] = (int)f; i1[d] = std::min(i0[d] + 1, 4);
+    w[d][1] = u[d] - f; w[d][0] = 1.0 - w[d][1];
+  }
+  double acc = 0.0;
+  for (int a = 0; a < (ndim == 3 ? 2 : 1); ++a)
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < 2; ++c) {
+        int iz = ndim == 3 ? (a ? i1[0] : i0[0]) : 0;
+        int iy = b ? i1[1] : i0[1], ix = c ? i1[2] : i0[2];
+        double wt = (ndim == 3 ? w[0][a] : 1.0) * w[1][b] * w[2][c];
+        float v = ndim == 3 ? tab[iz * 25 + iy * 5 + ix] : tab[iy * 5 + ix];
+        acc += wt * v;
+      }
+  return (float)acc;
+}
+
+// Fills S and returns true when pairing X is a pure translation that the
+// bulk-copy stencil kernel can serve.
+static bool make_stencil(const mvs_view_xform& X, int ndim, int order, int dtype,
+                         const float* tables, StencilXform& S) {
+  memset(&S, 0, sizeof(S));
+  for (int d = 0; d < 3; ++d)
+    for (int j = 0; j < 3; ++j) {
+      if (X.matrix[d * 3 + j] != (d == j ? 1.0 : 0.0)) return false;
+      if (d != j && X.wmatrix[d * 3 + j] != 0.0) return false;
+    }
+  if (X.dtype != dtype || X.stride[2] != 1) return false;
+  const int64_t esize = (int64_t)dtype_size(dtype);
+  const int A = (int)(16 / esize);
+  if (((uintptr_t)X.data) % 16 || (X.stride[1] * esize) % 16 || X.shape[2] % A) return false;
+  if (ndim == 3 && (X.stride[0] * esize) % 16) return false;
+  for (int d = 0; d < 3; ++d) {
+    S.omin[d] = INT_MIN / 2; S.omax[d] = INT_MAX / 2;
+    S.wm[d] = X.wmatrix[d * 3 + d]; S.woff[d] = X.woffset[d];
+  }
+  for (int d = 3 - ndim; d < 3; ++d) {
+    const double off = X.offset[d];
+    const int n = X.shape[d];
+    if (!(fabs(off) < 1e9)) return false;
+    if (order == 0) {
+      S.shift[d] = (int)floor(off + 0.5); S.t[d] = 0.f; S.d1[d] = 0;
+    } else {
+      const double f = floor(off);
+      S.shift[d] = (int)f; S.t[d] = (float)(off - f);
+      if (S.t[d] >= 1.0f) return false;  // cannot happen after the 1e-6 snap
+      S.d1[d] = S.t[d] != 0.f ? 1 : 0;
+    }
+    // valid sample range: scipy's predicate is fl(o + off) < 0 || fl(o + off) > n - 1
+    long long lo = (long long)ceil(-off), hi = (long long)floor((double)(n - 1) - off);
+    while ((double)lo + off < 0.0) ++lo;
+    while ((double)(lo - 1) + off >= 0.0) --lo;
+    while ((double)hi + off > (double)(n - 1)) --hi;
+    while ((double)(hi + 1) + off <= (double)(n - 1)) ++hi;
+    if (lo < INT_MIN / 2 || hi > INT_MAX / 2) return false;
+    S.omin[d] = (int)lo; S.omax[d] = (int)hi;
+    // order 0 picks floor(o + off + 0.5): must stay inside the window
+  }
+  // blending weight strictly positive on the valid box? (corners carry the minimum)
+  S.always_pos = 0;
+  if (tables && X.table >= 0) {
+    float mn = INFINITY;
+    for (int c = 0; c < (1 << ndim); ++c) {
+      double u[3] = {0, 0, 0};
+      bool empty = false;
+      for (int d = 3 - ndim; d < 3; ++d) {
+        if (S.omax[d] < S.omin[d]) { empty = true; break; }
+        const int o = ((c >> (2 - d)) & 1) ? S.omax[d] : S.omin[d];
+        u[d] = (double)o * S.wm[d] + S.woff[d];
+      }
+      if (empty) { mn = 1.f; break; }
+      mn = std::min(mn, host_table_interp(tables + (int64_t)X.table * 125, ndim, u));
+    }
+    S.always_pos = mn >= 1e-3f ? 1 : 0;
+  }
+  return true;
+}
+
+template <int NDIM, typename T, int MODE, bool PARTIAL>
+static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
+  const int64_t nb = p->total_blocks_st;
+  const int64_t gx = std::min<int64_t>(nb, 1 << 30);
+  const int64_t gy = (nb + gx - 1) / gx;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  fuse_stencil_kernel<NDIM, T, MODE, PARTIAL><<<grid, 256, 0, st>>>(
+      p->d_chunks_st, p->d_block_start_st, p->n_chunks_st, p->d_xforms, p->d_sxf, p->d_tables);
+  return cudaGetLastError();
+}
+
+template <int NDIM, typename T>
+static cudaError_t dispatch_stencil_mode(const mvs_fuse_plan* p, cudaStream_t st) {
+  switch (p->mode) {
+    case MVS_FUSE_WAVG:
+      return p->partial ? launch_stencil<NDIM, T, MVS_FUSE_WAVG, true>(p, st)
+                        : launch_stencil<NDIM, T, MVS_FUSE_WAVG, false>(p, st);
+    case MVS_FUSE_MAX:
+      return launch_stencil<NDIM, T, MVS_FUSE_MAX, false>(p, st);
+    default:
+      return launch_stencil<NDIM, T, MVS_FUSE_MEAN, false>(p, st);
+  }
+}
+
+template <int NDIM>
+static cudaError_t dispatch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
+  switch (p->stencil_dtype) {
+    case MVS_U8: return dispatch_stencil_mode<NDIM, unsigned char>(p, st);
+    case MVS_U16: return dispatch_stencil_mode<NDIM, unsigned short>(p, st);
+    default: return dispatch_stencil_mode<NDIM, float>(p, st);
+  }
+}
 
 template <int NDIM, int ORDER, int MODE, bool PARTIAL>
 static cudaError_t launch_fuse(const mvs_fuse_plan* p, cudaStream_t st) {
@@ -407,7 +543,6 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   MVS_REQUIRE(n_chunks == 0 || chunks != nullptr, MVS_ERR_INVALID, "chunks is NULL");
   MVS_REQUIRE(n_xforms == 0 || xforms != nullptr, MVS_ERR_INVALID, "xforms is NULL");
 
-  std::vector<int64_t> block_start(n_chunks + 1, 0);
   int64_t out_voxels = 0;
   bool partial = false, any_out = false;
   for (int c = 0; c < n_chunks; ++c) {
@@ -435,8 +570,6 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
                   MVS_ERR_INVALID, "chunk %d: out is NULL", c);
       any_out = true;
     }
-    const int64_t nbx = (ck.shape[2] + kBX - 1) / kBX, nby = (ck.shape[1] + kBY - 1) / kBY;
-    block_start[c + 1] = block_start[c] + nbx * nby * (int64_t)ck.shape[0];
     out_voxels += (int64_t)ck.shape[0] * ck.shape[1] * ck.shape[2];
   }
   MVS_REQUIRE(!(partial && any_out), MVS_ERR_UNSUPPORTED,
@@ -453,11 +586,41 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   }
   MVS_REQUIRE(n_tables == 0 || tables != nullptr, MVS_ERR_INVALID, "tables is NULL");
 
+  // classify pairings / chunks: translation stencil path vs general affine path
+  const bool allow_stencil = getenv("MVS_FUSE_GENERIC") == nullptr;
+  const int stencil_dtype = n_xforms ? xforms[0].dtype : MVS_F32;
+  std::vector<StencilXform> sxf(n_xforms);
+  std::vector<char> xf_ok(n_xforms, 0);
+  for (int i = 0; i < n_xforms; ++i)
+    xf_ok[i] = allow_stencil && make_stencil(xforms[i], ndim, order, stencil_dtype,
+                                             fusion_mode == MVS_FUSE_WAVG ? tables : nullptr, sxf[i]);
+  std::vector<mvs_chunk> ch_st, ch_gen;
+  std::vector<int64_t> bs_st(1, 0), bs_gen(1, 0);
+  for (int c = 0; c < n_chunks; ++c) {
+    const mvs_chunk& ck = chunks[c];
+    bool ok = allow_stencil;
+    for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
+    if (ok) {
+      const int BX = 128, BY = ndim == 3 ? 8 : 32, BZ = ndim == 3 ? 4 : 1;
+      const int64_t nb = (int64_t)((ck.shape[2] + BX - 1) / BX) * ((ck.shape[1] + BY - 1) / BY) *
+                         ((ck.shape[0] + BZ - 1) / BZ);
+      ch_st.push_back(ck);
+      bs_st.push_back(bs_st.back() + nb);
+    } else {
+      const int64_t nbx = (ck.shape[2] + kBX - 1) / kBX, nby = (ck.shape[1] + kBY - 1) / kBY;
+      ch_gen.push_back(ck);
+      bs_gen.push_back(bs_gen.back() + nbx * nby * (int64_t)ck.shape[0]);
+    }
+  }
+
   cudaStream_t st = (cudaStream_t)stream;
   mvs_fuse_plan* p = new mvs_fuse_plan();
-  p->n_chunks = n_chunks; p->n_xforms = n_xforms; p->n_tables = n_tables;
+  p->n_chunks = (int)ch_gen.size(); p->n_chunks_st = (int)ch_st.size();
+  p->n_xforms = n_xforms; p->n_tables = n_tables;
   p->ndim = ndim; p->order = order; p->mode = fusion_mode; p->partial = partial;
-  p->total_blocks = block_start[n_chunks]; p->out_voxels = out_voxels;
+  p->total_blocks = bs_gen.back(); p->total_blocks_st = bs_st.back();
+  p->stencil_dtype = stencil_dtype;
+  p->out_voxels = out_voxels;
   auto fail = [&](cudaError_t e, const char* what) {
     set_error("%s failed: %s", what, cudaGetErrorString(e));
     mvs_fuse_plan_destroy(p);
@@ -470,15 +633,25 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
     if (err != cudaSuccess) return err;
     return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
   };
-  if ((e = upload((void**)&p->d_chunks, chunks, sizeof(mvs_chunk) * n_chunks)) != cudaSuccess)
+  if ((e = upload((void**)&p->d_chunks, ch_gen.data(), sizeof(mvs_chunk) * ch_gen.size())) !=
+      cudaSuccess)
     return fail(e, "upload chunks");
+  if ((e = upload((void**)&p->d_chunks_st, ch_st.data(), sizeof(mvs_chunk) * ch_st.size())) !=
+      cudaSuccess)
+    return fail(e, "upload stencil chunks");
+  if ((e = upload((void**)&p->d_sxf, sxf.data(), sizeof(StencilXform) * sxf.size())) !=
+      cudaSuccess)
+    return fail(e, "upload stencil constants");
+  if ((e = upload((void**)&p->d_block_start_st, bs_st.data(), sizeof(int64_t) * bs_st.size())) !=
+      cudaSuccess)
+    return fail(e, "upload stencil block schedule");
   if ((e = upload((void**)&p->d_xforms, xforms, sizeof(mvs_view_xform) * n_xforms)) !=
       cudaSuccess)
     return fail(e, "upload xforms");
   if ((e = upload((void**)&p->d_tables, tables, sizeof(float) * 125 * n_tables)) != cudaSuccess)
     return fail(e, "upload tables");
-  if ((e = upload((void**)&p->d_block_start, block_start.data(),
-                  sizeof(int64_t) * (n_chunks + 1))) != cudaSuccess)
+  if ((e = upload((void**)&p->d_block_start, bs_gen.data(), sizeof(int64_t) * bs_gen.size())) !=
+      cudaSuccess)
     return fail(e, "upload block schedule");
   // host staging buffers die with this call: make the copies complete
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
@@ -488,13 +661,16 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
 
 extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
   MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
-  if (p->total_blocks == 0) return MVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e;
-  if (p->ndim == 2)
-    e = p->order == 0 ? dispatch_mode<2, 0>(p, st) : dispatch_mode<2, 1>(p, st);
-  else
-    e = p->order == 0 ? dispatch_mode<3, 0>(p, st) : dispatch_mode<3, 1>(p, st);
+  cudaError_t e = cudaSuccess;
+  if (p->total_blocks_st > 0)
+    e = p->ndim == 2 ? dispatch_stencil<2>(p, st) : dispatch_stencil<3>(p, st);
+  if (e == cudaSuccess && p->total_blocks > 0) {
+    if (p->ndim == 2)
+      e = p->order == 0 ? dispatch_mode<2, 0>(p, st) : dispatch_mode<2, 1>(p, st);
+    else
+      e = p->order == 0 ? dispatch_mode<3, 0>(p, st) : dispatch_mode<3, 1>(p, st);
+  }
   if (e != cudaSuccess) {
     set_error("fuse kernel launch failed: %s", cudaGetErrorString(e));
     return MVS_ERR_CUDA;
@@ -505,8 +681,8 @@ extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
 extern "C" int mvs_fuse_plan_info(const mvs_fuse_plan* p, int* launches, int64_t* blocks,
                                   int64_t* out_voxels) {
   MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
-  if (launches) *launches = p->total_blocks > 0 ? 1 : 0;
-  if (blocks) *blocks = p->total_blocks;
+  if (launches) *launches = (p->total_blocks > 0 ? 1 : 0) + (p->total_blocks_st > 0 ? 1 : 0);
+  if (blocks) *blocks = p->total_blocks + p->total_blocks_st;
   if (out_voxels) *out_voxels = p->out_voxels;
   return MVS_OK;
 }
@@ -514,6 +690,9 @@ extern "C" int mvs_fuse_plan_info(const mvs_fuse_plan* p, int* launches, int64_t
 extern "C" int mvs_fuse_plan_destroy(mvs_fuse_plan* p) {
   if (!p) return MVS_OK;
   cudaFree(p->d_chunks);
+  cudaFree(p->d_chunks_st);
+  cudaFree(p->d_block_start_st);
+  cudaFree(p->d_sxf);
   cudaFree(p->d_xforms);
   cudaFree(p->d_tables);
   cudaFree(p->d_block_start);

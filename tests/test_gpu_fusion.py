@@ -217,3 +217,78 @@ def test_synthetic_grid_full_size_properties(eng):
     fused2, _ = eng.fuse(views, true, interpolation_order=1)
     d = np.abs(fused2.astype(np.int64) - g.astype(np.int64))[covered]
     assert d.max() <= 1
+
+
+# ---- translation fast path (bulk-copy stencil kernel) vs general kernel / oracle ----
+
+
+def _grid_views(rng, ndim, dtype, tile, grid, ov, jitter):
+    import itertools
+
+    views, params = [], []
+    pitch = [t - o for t, o in zip(tile, ov)]
+    full = [p * (g - 1) + t + 8 for p, g, t in zip(pitch, grid, tile)]
+    gt = ndimage_smooth(rng, full)
+    if np.dtype(dtype).kind == "u":
+        gt = (gt * (250 if dtype == np.uint8 else 4000)).astype(dtype)
+    else:
+        gt = gt.astype(dtype)
+    for idx in itertools.product(*[range(g) for g in grid]):
+        org = [4 + i * p for i, p in zip(idx, pitch)]
+        sl = tuple(slice(o, o + t) for o, t in zip(org, tile))
+        views.append(_v(np.ascontiguousarray(gt[sl]), [float(o) for o in org], [1.0] * ndim))
+        p = np.eye(ndim + 1)
+        p[:ndim, ndim] = jitter(rng, ndim)
+        params.append(p)
+    return views, params
+
+
+def ndimage_smooth(rng, shape):
+    from scipy import ndimage
+
+    im = ndimage.gaussian_filter(rng.random(shape), 1.2)
+    return (im - im.min()) / (im.max() - im.min())
+
+
+STENCIL_CASES = [
+    (2, np.float32, (72, 136), (2, 3), (20, 24)),
+    (2, np.uint16, (64, 144), (3, 2), (16, 40)),
+    (2, np.uint8, (48, 160), (2, 2), (12, 32)),
+    (3, np.uint16, (12, 20, 136), (2, 2, 2), (4, 6, 24)),
+    (3, np.float32, (10, 24, 132), (1, 2, 2), (2, 8, 20)),
+]
+
+
+@pytest.mark.parametrize("ndim,dtype,tile,grid,ov", STENCIL_CASES)
+@pytest.mark.parametrize("order,func", [(1, "weighted_average_fusion"), (0, "weighted_average_fusion"), (0, "max_fusion"), (1, "simple_average_fusion")])
+@pytest.mark.parametrize("integer_shift", [False, True])
+def test_stencil_path_matches_general_and_oracle(eng, monkeypatch, ndim, dtype, tile, grid, ov, order, func, integer_shift):
+    rng = np.random.default_rng(ndim * 100 + np.dtype(dtype).itemsize + order)
+    jit = (lambda r, n: r.integers(-2, 3, n).astype(float)) if integer_shift else (lambda r, n: np.round(r.uniform(-2, 2, n), 3))
+    views, params = _grid_views(rng, ndim, dtype, tile, grid, ov, jit)
+    cs = {d: c for d, c in zip(DIMS[-ndim:], (7, 40, 200)[-ndim:])}
+    kw = dict(interpolation_order=order, output_chunksize=cs)
+    monkeypatch.delenv("MVS_FUSE_GENERIC", raising=False)
+    fast, _ = eng.fuse(views, params, fusion_func=getattr(eng, func), **kw)
+    monkeypatch.setenv("MVS_FUSE_GENERIC", "1")
+    slow, _ = eng.fuse(views, params, fusion_func=getattr(eng, func), **kw)
+    monkeypatch.delenv("MVS_FUSE_GENERIC", raising=False)
+    if order == 0 and func == "max_fusion":
+        assert np.array_equal(fast, slow)
+    else:
+        assert_fused_close(fast, slow)
+    ref, _ = of.fuse(views, params, fusion_func=getattr(of, func), interpolation_order=order)
+    assert_fused_close(fast, ref, exact=(order == 0 and func == "max_fusion"))
+
+
+def test_stencil_path_is_taken(eng):
+    """The plan schedules translation-only, aligned views on the stencil kernel."""
+    import ctypes
+
+    from multiview_stitcher_b200 import synthetic
+
+    views, stage, true = synthetic.make_grid((2, 2), (256, 256), (40, 40), np.float32, jitter=2, seed=9)
+    osp = of.calc_stack_properties([v.bb() for v in views], true, views[0].spacing)
+    plan = eng.FusionPlan(views, true, osp)
+    assert plan.launches_per_run == 1
+    plan.close()
