@@ -112,40 +112,52 @@ __device__ __forceinline__ void fill_weight_axes(const StencilXform& S, int x0s,
   }
 }
 
+// raw (pre-cosine) table value at float64 table coordinates; 0 outside [0,4]
 template <int NDIM>
-__device__ __forceinline__ float stencil_weight(const float* __restrict__ tab, const int* s_wi,
-                                                const float* s_wt, int ix_, int iy_, int iz_) {
-  using B = SBlock<NDIM>;
-  const int ix = s_wi[ix_], iy = s_wi[B::BX + iy_];
-  if (ix < 0 || iy < 0) return 0.f;
-  const float tx = s_wt[ix_], ty = s_wt[B::BX + iy_];
-  const int ix1 = min(ix + 1, 4), iy1 = min(iy + 1, 4);
-  float w;
+__device__ float raw_table_value(const float* __restrict__ tab, double uz, double uy, double ux) {
+  if (ux < 0.0 || ux > 4.0 || uy < 0.0 || uy > 4.0) return 0.f;
+  if (NDIM == 3 && (uz < 0.0 || uz > 4.0)) return 0.f;
+  const double fx = floor(ux), fy = floor(uy), fz = floor(uz);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const float tx = (float)(ux - fx), ty = (float)(uy - fy), tz = (float)(uz - fz);
+  const int ix1 = min(ix + 1, 4), iy1 = min(iy + 1, 4), iz1 = min(iz + 1, 4);
   if (NDIM == 3) {
-    const int iz = s_wi[B::BX + B::BY + iz_];
-    if (iz < 0) return 0.f;
-    const float tz = s_wt[B::BX + B::BY + iz_];
-    const int iz1 = min(iz + 1, 4);
     const float* p0 = tab + iz * 25;
     const float* p1 = tab + iz1 * 25;
-    float a0 = lerp_s(lerp_s(p0[iy * 5 + ix], p0[iy * 5 + ix1], tx),
-                      lerp_s(p0[iy1 * 5 + ix], p0[iy1 * 5 + ix1], tx), ty);
-    float a1 = lerp_s(lerp_s(p1[iy * 5 + ix], p1[iy * 5 + ix1], tx),
-                      lerp_s(p1[iy1 * 5 + ix], p1[iy1 * 5 + ix1], tx), ty);
-    w = lerp_s(a0, a1, tz);
-  } else {
-    w = lerp_s(lerp_s(tab[iy * 5 + ix], tab[iy * 5 + ix1], tx),
-               lerp_s(tab[iy1 * 5 + ix], tab[iy1 * 5 + ix1], tx), ty);
+    float a0 = lerp_s(lerp_s(__ldg(p0 + iy * 5 + ix), __ldg(p0 + iy * 5 + ix1), tx),
+                      lerp_s(__ldg(p0 + iy1 * 5 + ix), __ldg(p0 + iy1 * 5 + ix1), tx), ty);
+    float a1 = lerp_s(lerp_s(__ldg(p1 + iy * 5 + ix), __ldg(p1 + iy * 5 + ix1), tx),
+                      lerp_s(__ldg(p1 + iy1 * 5 + ix), __ldg(p1 + iy1 * 5 + ix1), tx), ty);
+    return lerp_s(a0, a1, tz);
   }
-  if (w < 1.0f) {
-    float a = __fmul_rn(__fsub_rn(1.0f, w), 3.14159274101257324f);
-    w = __fdiv_rn(__fadd_rn(cosf(a), 1.0f), 2.0f);
-  }
-  return fminf(fmaxf(w, 0.0f), 1.0f);
+  return lerp_s(lerp_s(__ldg(tab + iy * 5 + ix), __ldg(tab + iy * 5 + ix1), tx),
+                lerp_s(__ldg(tab + iy1 * 5 + ix), __ldg(tab + iy1 * 5 + ix1), tx), ty);
+}
+
+// Smallest pre-cosine table value x for which (cos((1-x)*pi)+1)/2 is safely > 0
+// in float32 (delta^2/2 >= ~3 ulp of 2^-24 with delta = pi*x).
+#define MVS_POSITIVE_X 1.8e-4f
+
+// s_flag codes
+enum { VIEW_OFF = 0, VIEW_GENERAL = 1, VIEW_POSITIVE = 2, VIEW_UNIT = 3 };
+
+template <typename OUT_T>
+__device__ __forceinline__ OUT_T cast_out(float v);
+template <>
+__device__ __forceinline__ float cast_out<float>(float v) { return v != v ? 0.f : v; }
+template <>
+__device__ __forceinline__ unsigned short cast_out<unsigned short>(float v) {
+  int q = __float2int_rz(v != v ? 0.f : v);
+  return (unsigned short)(q < 0 ? 0 : (q > 65535 ? 65535 : q));
+}
+template <>
+__device__ __forceinline__ unsigned char cast_out<unsigned char>(float v) {
+  int q = __float2int_rz(v != v ? 0.f : v);
+  return (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NDIM == 3 ? 2 : 3)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables) {
@@ -156,7 +168,6 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   __shared__ int s_wi[B::NW];
   __shared__ float s_wt[B::NW];
   __shared__ unsigned char s_flag[kMaxXforms];
-  __shared__ int s_nact, s_single;
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int64_t bid = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
@@ -167,12 +178,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
   }
   const mvs_chunk& ck = chunks[lo];
-  const int64_t local = bid - __ldg(block_start + lo);
+  const int local = (int)(bid - __ldg(block_start + lo));
   const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
   const int nbx = (sh_x + B::BX - 1) / B::BX, nby = (sh_y + B::BY - 1) / B::BY;
-  const int x0 = (int)(local % nbx) * B::BX;
-  const int y0 = (int)((local / nbx) % nby) * B::BY;
-  const int z0 = (int)(local / ((int64_t)nbx * nby)) * B::BZ;
+  const int bz = local / (nbx * nby);
+  const int rem = local - bz * (nbx * nby);
+  const int by = rem / nbx;
+  const int x0 = (rem - by * nbx) * B::BX, y0 = by * B::BY, z0 = bz * B::BZ;
   const int first = ck.first_xform, nxf = ck.n_xforms;
   // block origin / extent in sample-index space
   const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
@@ -181,66 +193,86 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   const int z1s = min(z0 + B::BZ, sh_z) - 1 + ck.halo[0];
 
   if (threadIdx.x == 0) {
-    s_nact = 0; s_single = -1;
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nxf; i += blockDim.x) {
-    const StencilXform& S = sxf[first + i];
-    bool t = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
-    if (NDIM == 3) t = t && S.omax[0] >= z0s && S.omin[0] <= z1s;
-    s_flag[i] = t ? 1 : 0;
-    if (t) { atomicAdd(&s_nact, 1); atomicMax(&s_single, i); }
+  // ---- cull the chunk's views against this block and classify their weights ----
+  // 8 lanes per view: each evaluates the (pre-cosine) blending weight at one
+  // corner of block x valid-box; the weight is smallest at a corner, so
+  //   min >= 1          -> every weight in the block is exactly 1    (VIEW_UNIT)
+  //   min >= POSITIVE_X -> every weight in the block is > 0          (VIEW_POSITIVE)
+  for (int idx = threadIdx.x; idx < ((nxf * 8 + 31) & ~31); idx += blockDim.x) {
+    const int vi = idx >> 3, c = idx & 7;
+    float raw = INFINITY;
+    bool active = false;
+    if (vi < nxf) {
+      const StencilXform& S = sxf[first + vi];
+      active = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
+      if (NDIM == 3) active = active && S.omax[0] >= z0s && S.omin[0] <= z1s;
+      if (active && MODE == MVS_FUSE_WAVG) {
+        const int ox = (c & 1) ? min(x1s, S.omax[2]) : max(x0s, S.omin[2]);
+        const int oy = (c & 2) ? min(y1s, S.omax[1]) : max(y0s, S.omin[1]);
+        const int oz = NDIM == 3 ? ((c & 4) ? min(z1s, S.omax[0]) : max(z0s, S.omin[0])) : 0;
+        const double ux = __dadd_rn(__dmul_rn((double)ox, S.wm[2]), S.woff[2]);
+        const double uy = __dadd_rn(__dmul_rn((double)oy, S.wm[1]), S.woff[1]);
+        const double uz = NDIM == 3 ? __dadd_rn(__dmul_rn((double)oz, S.wm[0]), S.woff[0]) : 0.0;
+        raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)xforms[first + vi].table * 125, uz, uy, ux), 0.f);
+      }
+    }
+    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 1));
+    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 2));
+    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 4));
+    if (c == 0 && vi < nxf) {
+      unsigned char code = VIEW_OFF;
+      if (active) {
+        code = VIEW_GENERAL;
+        if (MODE == MVS_FUSE_WAVG) {
+          if (raw >= 1.0f) code = VIEW_UNIT;
+          else if (raw >= MVS_POSITIVE_X) code = VIEW_POSITIVE;
+        }
+      }
+      s_flag[vi] = code;
+    }
   }
   __syncthreads();
-  const int nact = s_nact;
-  const int single = s_single;
+  int nact = 0;
+  for (int i = 0; i < nxf; ++i) nact += s_flag[i] != VIEW_OFF;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = warp & 3, half = warp >> 2;
   const int jx = cg * 32 + lane;  // block-local output column
   uint32_t phase = 0;
 
-  float acc[B::OUTS], s[B::OUTS];
-  unsigned anymask = 0;  // MAX / MEAN: bit k set once a valid view was seen
+  float acc[B::OUTS], den[B::OUTS];
+  unsigned anymask = 0;    // bit k: a valid view was seen for output k
+  unsigned multimask = 0;  // bit k: at least two valid views (WAVG: acc is weighted)
 #pragma unroll
-  for (int k = 0; k < B::OUTS; ++k) { acc[k] = 0.f; s[k] = 0.f; }
+  for (int k = 0; k < B::OUTS; ++k) { acc[k] = 0.f; den[k] = 0.f; }
 
-  // block-local (jz, jy) of output k of this thread
+  // output k of this thread sits at block-local row out_y(k), plane out_z(k)
   auto out_y = [&](int k) { return NDIM == 3 ? (k & 7) : half * 16 + k; };
   auto out_z = [&](int k) { return NDIM == 3 ? half * 2 + (k >> 3) : 0; };
 
-  // valid bits of this thread's outputs for view S
-  auto valid_bits = [&](const StencilXform& S) -> unsigned {
-    unsigned m = 0;
-    const int sx = x0s + jx;
-    if (sx < S.omin[2] || sx > S.omax[2] || x0 + jx >= sh_x) return 0u;
-#pragma unroll
-    for (int k = 0; k < B::OUTS; ++k) {
-      const int sy = y0s + out_y(k), sz = z0s + out_z(k);
-      bool v = sy >= S.omin[1] && sy <= S.omax[1] && y0 + out_y(k) < sh_y;
-      if (NDIM == 3) v = v && sz >= S.omin[0] && sz <= S.omax[0] && z0 + out_z(k) < sh_z;
-      m |= v ? (1u << k) : 0u;
+  for (int i = 0; i < nxf; ++i) {
+    const int code = s_flag[i];
+    if (code == VIEW_OFF) continue;
+    const mvs_view_xform& X = xforms[first + i];
+    const StencilXform& S = sxf[first + i];
+    // weights: 0 = not needed (out = v), 1 = all ones, 2 = table lookup
+    int wmode = 0;
+    if (MODE == MVS_FUSE_WAVG) {
+      if (nact == 1 && !PARTIAL && code >= VIEW_POSITIVE) wmode = 0;
+      else wmode = code == VIEW_UNIT ? 1 : 2;
     }
-    return m;
-  };
+    const int shx = S.shift[2], shy = S.shift[1], shz = NDIM == 3 ? S.shift[0] : 0;
 
-  // stages the footprint of view `xi` (and its weight axes / table when WANT_W)
-  auto stage_view = [&](int xi, bool want_w, bool want_data) {
-    const mvs_view_xform& X = xforms[first + xi];
-    const StencilXform& S = sxf[first + xi];
+    // ---- stage the footprint (bulk async copies) and the weight axes ----
     __syncthreads();  // previous consumers of stage / weight axes are done
-    if (want_w) {
-      fill_weight_axes<NDIM>(S, x0s, y0s, z0s, s_wi, s_wt);
-      const float* tab = tables + (int64_t)X.table * 125;
-      for (int i = threadIdx.x; i < (NDIM == 3 ? 125 : 25); i += blockDim.x) s_tab[i] = __ldg(tab + i);
-    }
-    uint32_t total = 0;
-    if (want_data) {
+    const int x0g = x0s + shx, y0g = y0s + shy, z0g = z0s + shz;
+    const int xa_u = floor_div(x0g, A) * A;
+    uint32_t total;
+    {
       const int nx = X.shape[2], ny = X.shape[1], nz = X.shape[0];
-      const int x0g = x0s + S.shift[2], y0g = y0s + S.shift[1], z0g = z0s + S.shift[0];
-      const int xa_u = floor_div(x0g, A) * A;
       const int xb_u = floor_div(x0g + B::BX + 1 + A - 1, A) * A;
       const int xa = max(xa_u, 0), xb = min(xb_u, nx);
       const int row_bytes = xb > xa ? (xb - xa) * (int)sizeof(T) : 0;
@@ -264,21 +296,46 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         }
       }
     }
-    __syncthreads();  // weight axes / table visible
-    if (total) { mbar_wait(&s_bar, phase); phase ^= 1; }
-  };
+    if (wmode == 2) {
+      fill_weight_axes<NDIM>(S, x0s, y0s, z0s, s_wi, s_wt);
+      const float* tab = tables + (int64_t)X.table * 125;
+      for (int q = threadIdx.x; q < (NDIM == 3 ? 125 : 25); q += blockDim.x) s_tab[q] = __ldg(tab + q);
+    }
 
-  // interpolated values of this thread's outputs from the staged footprint
-  auto values = [&](const StencilXform& S, float* val) {
-    const int x0g = x0s + S.shift[2];
-    const int xa_u = floor_div(x0g, A) * A;
+    // ---- valid bits of this thread's outputs (ranges -> masks) ----
+    unsigned vm;
+    {
+      const int sx = x0s + jx;
+      const bool vx = sx >= S.omin[2] && sx <= S.omax[2] && x0 + jx < sh_x;
+      // rows: block-local y in [ya, yb]
+      const int ya = max(S.omin[1] - y0s, 0), yb = min(min(S.omax[1] - y0s, sh_y - 1 - y0), B::BY - 1);
+      if (NDIM == 2) {
+        const int ka = max(ya - half * 16, 0), kb = min(yb - half * 16, 15);
+        vm = (vx && kb >= ka) ? ((0xffffu >> (15 - kb)) & (0xffffu << ka)) : 0u;
+      } else {
+        const int ka = max(ya, 0), kb = min(yb, 7);
+        const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
+        const int za = max(S.omin[0] - z0s, 0), zb = min(min(S.omax[0] - z0s, sh_z - 1 - z0), B::BZ - 1);
+        const int p0 = half * 2, p1 = half * 2 + 1;
+        vm = 0u;
+        if (vx) {
+          if (p0 >= za && p0 <= zb) vm |= ym;
+          if (p1 >= za && p1 <= zb) vm |= ym << 8;
+        }
+      }
+    }
+    const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
     const int c0 = (x0g - xa_u) + jx;
     const int c1 = c0 + S.d1[2];
-    const float tx = S.t[2], ty = S.t[1], tz = S.t[0];
-    const bool dy = S.d1[1] != 0, dz = S.d1[0] != 0;
+    const bool dy = S.d1[1] != 0, dz = NDIM == 3 && S.d1[0] != 0;
+
+    __syncthreads();  // weight axes / table visible
+    if (total) { mbar_wait(&s_bar, phase); phase ^= 1; }
+
+    // ---- interpolate this thread's outputs from shared memory ----
+    float val[B::OUTS];
     if (NDIM == 2) {
-      const int rb = half * 16;
-      const T* p = stage + rb * B::ROWP;
+      const T* p = stage + (half * 16) * B::ROWP;
       float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
@@ -310,63 +367,72 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         for (int y = 0; y < 8; ++y) gprev[y] = g[y];
       }
     }
-  };
 
-  auto weight_of = [&](int k) {
-    return stencil_weight<NDIM>(s_tab, s_wi, s_wt, jx, out_y(k), out_z(k));
-  };
-
-  if (MODE == MVS_FUSE_WAVG) {
-    const bool fast_single = (nact == 1) && !PARTIAL && sxf[first + max(single, 0)].always_pos;
-    if (nact >= 1 && fast_single) {
-      const StencilXform& S = sxf[first + single];
-      stage_view(single, false, true);
-      float val[B::OUTS];
-      values(S, val);
-      const unsigned vm = valid_bits(S);
+    // ---- combine ----
+    if (MODE == MVS_FUSE_WAVG) {
+      if (wmode == 0) {
+        // the block's only view and its weight is positive everywhere: out = v
 #pragma unroll
-      for (int k = 0; k < B::OUTS; ++k) acc[k] = (vm >> k) & 1 ? val[k] : 0.f;
-    } else if (nact >= 1) {
-      // pass A: s = sum_i b_i * valid_i (float32, view order)
-      for (int i = 0; i < nxf; ++i) {
-        if (!s_flag[i]) continue;
-        const StencilXform& S = sxf[first + i];
-        stage_view(i, true, false);
-        const unsigned vm = valid_bits(S);
-#pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
-          if ((vm >> k) & 1) s[k] = __fadd_rn(s[k], weight_of(k));
-      }
-      if (!PARTIAL) {
-#pragma unroll
-        for (int k = 0; k < B::OUTS; ++k) if (s[k] == 0.f) s[k] = 1.f;
-      }
-      // pass B: sum_i v_i * (b_i / s)
-      for (int i = 0; i < nxf; ++i) {
-        if (!s_flag[i]) continue;
-        const StencilXform& S = sxf[first + i];
-        stage_view(i, true, true);
-        float val[B::OUTS];
-        values(S, val);
-        const unsigned vm = valid_bits(S);
+        for (int k = 0; k < B::OUTS; ++k) { acc[k] = val[k]; den[k] = 1.f; }
+        anymask = vm;
+      } else {
+        int ix = 0, ixc = 0, ix1 = 0;
+        float wtx = 0.f;
+        if (wmode == 2) {
+          ix = s_wi[jx]; wtx = s_wt[jx];
+          ixc = max(ix, 0); ix1 = min(ixc + 1, 4);
+        }
 #pragma unroll
         for (int k = 0; k < B::OUTS; ++k) {
-          if ((vm >> k) & 1) {
-            const float b = weight_of(k);
-            const float w = PARTIAL ? b : __fdiv_rn(b, s[k]);
-            acc[k] = __fadd_rn(acc[k], __fmul_rn(val[k], w));
+          const bool valid = (vm >> k) & 1;
+          float b = valid ? 1.f : 0.f;
+          if (wmode == 2) {
+            const int iy = s_wi[B::BX + out_y(k)];
+            const float wty = s_wt[B::BX + out_y(k)];
+            const int iyc = max(iy, 0), iy1 = min(iyc + 1, 4);
+            bool inside = ix >= 0 && iy >= 0;
+            float w;
+            if (NDIM == 3) {
+              const int iz = s_wi[B::BX + B::BY + out_z(k)];
+              const float wtz = s_wt[B::BX + B::BY + out_z(k)];
+              const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
+              inside = inside && iz >= 0;
+              const float* p0 = s_tab + izc * 25;
+              const float* p1 = s_tab + iz1 * 25;
+              const float a0 = lerp_s(lerp_s(p0[iyc * 5 + ixc], p0[iyc * 5 + ix1], wtx),
+                                      lerp_s(p0[iy1 * 5 + ixc], p0[iy1 * 5 + ix1], wtx), wty);
+              const float a1 = lerp_s(lerp_s(p1[iyc * 5 + ixc], p1[iyc * 5 + ix1], wtx),
+                                      lerp_s(p1[iy1 * 5 + ixc], p1[iy1 * 5 + ix1], wtx), wty);
+              w = lerp_s(a0, a1, wtz);
+            } else {
+              w = lerp_s(lerp_s(s_tab[iyc * 5 + ixc], s_tab[iyc * 5 + ix1], wtx),
+                         lerp_s(s_tab[iy1 * 5 + ixc], s_tab[iy1 * 5 + ix1], wtx), wty);
+            }
+            if (__any_sync(0xffffffffu, valid && w < 1.0f)) {
+              // weights.py:502-507 cosine ramp (float32), only near view borders
+              const float a = __fmul_rn(__fsub_rn(1.0f, w), 3.14159274101257324f);
+              const float cw = __fmul_rn(__fadd_rn(cosf(a), 1.0f), 0.5f);
+              w = w < 1.0f ? cw : w;
+            }
+            w = fminf(fmaxf(w, 0.0f), 1.0f);
+            b = (valid && inside) ? w : 0.f;
+          }
+          // acc holds the raw value while only one view has contributed (its
+          // normalised weight is exactly 1); the first view is weighted
+          // retroactively once a second one arrives.
+          if (valid) {
+            if (!((anymask >> k) & 1)) { acc[k] = val[k]; den[k] = b; }
+            else {
+              const float first_term = ((multimask >> k) & 1) ? acc[k] : __fmul_rn(acc[k], den[k]);
+              acc[k] = __fadd_rn(first_term, __fmul_rn(val[k], b));
+              den[k] = __fadd_rn(den[k], b);
+              multimask |= 1u << k;
+            }
           }
         }
+        anymask |= vm;
       }
-    }
-  } else {
-    for (int i = 0; i < nxf; ++i) {
-      if (!s_flag[i]) continue;
-      const StencilXform& S = sxf[first + i];
-      stage_view(i, false, true);
-      float val[B::OUTS];
-      values(S, val);
-      const unsigned vm = valid_bits(S);
+    } else {
 #pragma unroll
       for (int k = 0; k < B::OUTS; ++k) {
         if ((vm >> k) & 1) {
@@ -374,35 +440,62 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
             acc[k] = (anymask >> k) & 1 ? fmaxf(acc[k], val[k]) : val[k];
           } else {
             acc[k] = __fadd_rn(acc[k], val[k]);
-            s[k] = __fadd_rn(s[k], 1.0f);
+            den[k] = __fadd_rn(den[k], 1.0f);
           }
-          anymask |= 1u << k;
         }
       }
-    }
-    if (MODE == MVS_FUSE_MEAN) {
-#pragma unroll
-      for (int k = 0; k < B::OUTS; ++k)
-        acc[k] = (anymask >> k) & 1 ? __fdiv_rn(acc[k], s[k]) : 0.f;
+      anymask |= vm;
     }
   }
 
-  const int xo = x0 + jx;
-  if (xo < sh_x) {
+  // ---- finalise ----
 #pragma unroll
-    for (int k = 0; k < B::OUTS; ++k) {
-      const int yo = y0 + out_y(k), zo = z0 + out_z(k);
-      if (yo < sh_y && zo < sh_z) {
-        const int64_t o = (int64_t)zo * ck.stride[0] + (int64_t)yo * ck.stride[1] +
-                          (int64_t)xo * ck.stride[2];
-        if (PARTIAL) {
-          ck.acc_num[o] = acc[k];
-          ck.acc_den[o] = s[k];
-        } else {
-          store_from_float(ck.out, ck.out_dtype, o, acc[k]);
-        }
-      }
+  for (int k = 0; k < B::OUTS; ++k) {
+    const bool had = (anymask >> k) & 1, multi = (multimask >> k) & 1;
+    if (MODE == MVS_FUSE_WAVG && PARTIAL) {
+      acc[k] = !had ? 0.f : (multi ? acc[k] : __fmul_rn(acc[k], den[k]));
+    } else if (MODE == MVS_FUSE_WAVG) {
+      float r = (had && den[k] > 0.f) ? acc[k] : 0.f;
+      if (multimask) r = multi ? __fdiv_rn(acc[k], den[k] == 0.f ? 1.f : den[k]) : r;
+      acc[k] = r;
+    } else if (MODE == MVS_FUSE_MEAN) {
+      acc[k] = had ? __fdiv_rn(acc[k], den[k]) : 0.f;
+    } else {
+      acc[k] = had ? acc[k] : 0.f;
     }
+  }
+
+  // ---- store (lanes along x: coalesced rows) ----
+  const int xo = x0 + jx;
+  if (xo >= sh_x) return;
+  const int64_t sy = ck.stride[1], sz = ck.stride[0];
+  const int64_t o0 = (int64_t)(z0 + out_z(0)) * sz + (int64_t)(y0 + out_y(0)) * sy + (int64_t)xo * ck.stride[2];
+  // offset of output k relative to output 0
+  auto off_k = [&](int k) -> int64_t {
+    return NDIM == 3 ? (int64_t)(k >> 3) * sz + (int64_t)(k & 7) * sy : (int64_t)k * sy;
+  };
+  auto in_chunk = [&](int k) { return y0 + out_y(k) < sh_y && z0 + out_z(k) < sh_z; };
+  if (PARTIAL) {
+    float* pn = ck.acc_num + o0;
+    float* pd = ck.acc_den + o0;
+#pragma unroll
+    for (int k = 0; k < B::OUTS; ++k)
+      if (in_chunk(k)) { pn[off_k(k)] = acc[k]; pd[off_k(k)] = den[k]; }
+  } else if (ck.out_dtype == MVS_F32) {
+    float* po = reinterpret_cast<float*>(ck.out) + o0;
+#pragma unroll
+    for (int k = 0; k < B::OUTS; ++k)
+      if (in_chunk(k)) po[off_k(k)] = cast_out<float>(acc[k]);
+  } else if (ck.out_dtype == MVS_U16) {
+    unsigned short* po = reinterpret_cast<unsigned short*>(ck.out) + o0;
+#pragma unroll
+    for (int k = 0; k < B::OUTS; ++k)
+      if (in_chunk(k)) po[off_k(k)] = cast_out<unsigned short>(acc[k]);
+  } else {
+    unsigned char* po = reinterpret_cast<unsigned char*>(ck.out) + o0;
+#pragma unroll
+    for (int k = 0; k < B::OUTS; ++k)
+      if (in_chunk(k)) po[off_k(k)] = cast_out<unsigned char>(acc[k]);
   }
 }
 
