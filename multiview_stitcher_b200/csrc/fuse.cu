@@ -374,6 +374,7 @@ struct mvs_fuse_plan {
   int64_t total_blocks_st = 0;
   mvs::StencilXform* d_sxf = nullptr;
   int stencil_dtype = MVS_F32;
+  int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
   float* d_tables = nullptr;
   int n_xforms = 0, n_tables = 0;
@@ -473,11 +474,14 @@ static bool make_stencil(const mvs_view_xform& X, int ndim, int order, int dtype
 template <int NDIM, typename T, int MODE, bool PARTIAL>
 static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   const int64_t nb = p->total_blocks_st;
-  const int64_t gx = std::min<int64_t>(nb, 1 << 30);
-  const int64_t gy = (nb + gx - 1) / gx;
-  dim3 grid((unsigned)gx, (unsigned)gy);
-  fuse_stencil_kernel<NDIM, T, MODE, PARTIAL><<<grid, 256, 0, st>>>(
-      p->d_chunks_st, p->d_block_start_st, p->n_chunks_st, p->d_xforms, p->d_sxf, p->d_tables);
+  auto kern = fuse_stencil_kernel<NDIM, T, MODE, PARTIAL>;
+  const size_t smem = stencil_smem_bytes<NDIM, T>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // persistent: two CTAs per SM, each walks blocks bid, bid + grid, ...
+  const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * 2);
+  kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
+                                            p->d_xforms, p->d_sxf, p->d_tables);
   return cudaGetLastError();
 }
 
@@ -598,7 +602,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   std::vector<int64_t> bs_st(1, 0), bs_gen(1, 0);
   for (int c = 0; c < n_chunks; ++c) {
     const mvs_chunk& ck = chunks[c];
-    bool ok = allow_stencil;
+    bool ok = allow_stencil && ck.n_xforms <= 32;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
     if (ok) {
       const int BX = 128, BY = ndim == 3 ? 8 : 32, BZ = ndim == 3 ? 4 : 1;
@@ -620,6 +624,12 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   p->ndim = ndim; p->order = order; p->mode = fusion_mode; p->partial = partial;
   p->total_blocks = bs_gen.back(); p->total_blocks_st = bs_st.back();
   p->stencil_dtype = stencil_dtype;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (p->sm_count <= 0) p->sm_count = 148;
+  }
   p->out_voxels = out_voxels;
   auto fail = [&](cudaError_t e, const char* what) {
     set_error("%s failed: %s", what, cudaGetErrorString(e));

@@ -138,8 +138,10 @@ __device__ float raw_table_value(const float* __restrict__ tab, double uz, doubl
 // in float32 (delta^2/2 >= ~3 ulp of 2^-24 with delta = pi*x).
 #define MVS_POSITIVE_X 1.8e-4f
 
-// s_flag codes
-enum { VIEW_OFF = 0, VIEW_GENERAL = 1, VIEW_POSITIVE = 2, VIEW_UNIT = 3 };
+// weight classes of a (block, view) pairing
+enum { VIEW_GENERAL = 1, VIEW_POSITIVE = 2, VIEW_UNIT = 3 };
+// item flags
+enum { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_STOP = 8, ITEM_SIMPLE = 16 };
 
 template <typename OUT_T>
 __device__ __forceinline__ OUT_T cast_out(float v);
@@ -156,230 +158,345 @@ __device__ __forceinline__ unsigned char cast_out<unsigned char>(float v) {
   return (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One pipeline slot: the staged footprint of one (block, view) item plus what the
+// consumer warps need to blend it.
+template <int NDIM, typename T>
+struct alignas(128) StencilSlot {
+  using B = SBlock<NDIM>;
+  T stage[B::NROWS * B::ROWP];
+  float tab[128];
+  int wi[B::NW];
+  float wt[B::NW];
+  StencilXform sx;
+  int chunk, x0, y0, z0;  // block origin (chunk-local voxels)
+  int flags, wmode, xa_u, pad;
+};
+
+constexpr int kStencilConsumerWarps = 8;
+constexpr int kStencilThreads = (kStencilConsumerWarps + 1) * 32;
+
+template <int NDIM, typename T>
+struct StencilStages {
+  static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 4;
+};
+
+// Persistent, warp-specialised kernel: warp 8 is the producer (block decode,
+// view culling + weight classification, bulk async copies into a ring of shared
+// memory slots); warps 0-7 consume the slots (interpolate, blend, store).
 template <int NDIM, typename T, int MODE, bool PARTIAL>
-__global__ void __launch_bounds__(256, NDIM == 3 ? 2 : 3)
+__global__ void __launch_bounds__(kStencilThreads, 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables) {
   using B = SBlock<NDIM>;
+  using Slot = StencilSlot<NDIM, T>;
+  constexpr int NS = StencilStages<NDIM, T>::value;
   constexpr int A = 16 / (int)sizeof(T);  // elements per 16 bytes
-  __shared__ __align__(128) T stage[B::NROWS * B::ROWP];
-  __shared__ float s_tab[125];
-  __shared__ int s_wi[B::NW];
-  __shared__ float s_wt[B::NW];
-  __shared__ unsigned char s_flag[kMaxXforms];
-  __shared__ __align__(8) unsigned long long s_bar;
-
-  const int64_t bid = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
-  if (bid >= block_start[n_chunks]) return;
-  int lo = 0, hi = n_chunks - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
-  }
-  const mvs_chunk& ck = chunks[lo];
-  const int local = (int)(bid - __ldg(block_start + lo));
-  const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
-  const int nbx = (sh_x + B::BX - 1) / B::BX, nby = (sh_y + B::BY - 1) / B::BY;
-  const int bz = local / (nbx * nby);
-  const int rem = local - bz * (nbx * nby);
-  const int by = rem / nbx;
-  const int x0 = (rem - by * nbx) * B::BX, y0 = by * B::BY, z0 = bz * B::BZ;
-  const int first = ck.first_xform, nxf = ck.n_xforms;
-  // block origin / extent in sample-index space
-  const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
-  const int x1s = min(x0 + B::BX, sh_x) - 1 + ck.halo[2];
-  const int y1s = min(y0 + B::BY, sh_y) - 1 + ck.halo[1];
-  const int z1s = min(z0 + B::BZ, sh_z) - 1 + ck.halo[0];
-
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // ---- cull the chunk's views against this block and classify their weights ----
-  // 8 lanes per view: each evaluates the (pre-cosine) blending weight at one
-  // corner of block x valid-box; the weight is smallest at a corner, so
-  //   min >= 1          -> every weight in the block is exactly 1    (VIEW_UNIT)
-  //   min >= POSITIVE_X -> every weight in the block is > 0          (VIEW_POSITIVE)
-  for (int idx = threadIdx.x; idx < ((nxf * 8 + 31) & ~31); idx += blockDim.x) {
-    const int vi = idx >> 3, c = idx & 7;
-    float raw = INFINITY;
-    bool active = false;
-    if (vi < nxf) {
-      const StencilXform& S = sxf[first + vi];
-      active = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
-      if (NDIM == 3) active = active && S.omax[0] >= z0s && S.omin[0] <= z1s;
-      if (active && MODE == MVS_FUSE_WAVG) {
-        const int ox = (c & 1) ? min(x1s, S.omax[2]) : max(x0s, S.omin[2]);
-        const int oy = (c & 2) ? min(y1s, S.omax[1]) : max(y0s, S.omin[1]);
-        const int oz = NDIM == 3 ? ((c & 4) ? min(z1s, S.omax[0]) : max(z0s, S.omin[0])) : 0;
-        const double ux = __dadd_rn(__dmul_rn((double)ox, S.wm[2]), S.woff[2]);
-        const double uy = __dadd_rn(__dmul_rn((double)oy, S.wm[1]), S.woff[1]);
-        const double uz = NDIM == 3 ? __dadd_rn(__dmul_rn((double)oz, S.wm[0]), S.woff[0]) : 0.0;
-        raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)xforms[first + vi].table * 125, uz, uy, ux), 0.f);
-      }
-    }
-    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 1));
-    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 2));
-    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 4));
-    if (c == 0 && vi < nxf) {
-      unsigned char code = VIEW_OFF;
-      if (active) {
-        code = VIEW_GENERAL;
-        if (MODE == MVS_FUSE_WAVG) {
-          if (raw >= 1.0f) code = VIEW_UNIT;
-          else if (raw >= MVS_POSITIVE_X) code = VIEW_POSITIVE;
-        }
-      }
-      s_flag[vi] = code;
-    }
-  }
-  __syncthreads();
-  int nact = 0;
-  for (int i = 0; i < nxf; ++i) nact += s_flag[i] != VIEW_OFF;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Slot* slots = reinterpret_cast<Slot*>(smem_raw);
+  __shared__ __align__(8) unsigned long long full_bar[NS], empty_bar[NS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kStencilConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nblocks = block_start[n_chunks];
+
+  if (warp == kStencilConsumerWarps) {
+    // =========================== producer warp ===========================
+    int it = 0;  // item counter (slot = it % NS)
+    auto acquire = [&]() -> Slot& {
+      const int s = it % NS;
+      mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
+      return slots[s];
+    };
+    for (int64_t bid = blockIdx.x; bid < nblocks; bid += gridDim.x) {
+      int lo = 0, hi = n_chunks - 1;
+      while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
+      }
+      const mvs_chunk& ck = chunks[lo];
+      const int local = (int)(bid - __ldg(block_start + lo));
+      const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
+      const int nbx = (sh_x + B::BX - 1) / B::BX, nby = (sh_y + B::BY - 1) / B::BY;
+      const int bz = local / (nbx * nby);
+      const int rem = local - bz * (nbx * nby);
+      const int by = rem / nbx;
+      const int x0 = (rem - by * nbx) * B::BX, y0 = by * B::BY, z0 = bz * B::BZ;
+      const int first = ck.first_xform, nxf = ck.n_xforms;
+      const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
+      const int x1s = min(x0 + B::BX, sh_x) - 1 + ck.halo[2];
+      const int y1s = min(y0 + B::BY, sh_y) - 1 + ck.halo[1];
+      const int z1s = min(z0 + B::BZ, sh_z) - 1 + ck.halo[0];
+
+      // ---- cull the chunk's views against this block, classify their weights:
+      // 8 lanes per view evaluate the (pre-cosine) blending weight at the corners
+      // of block x valid-box, where it is smallest:
+      //   min >= 1          -> every weight in the block is exactly 1   (UNIT)
+      //   min >= POSITIVE_X -> every weight in the block is > 0         (POSITIVE)
+      unsigned active = 0;            // bit per view (nxf <= 32, checked on the host)
+      unsigned long long codes = 0;   // 2 bits per view
+      for (int base = 0; base < nxf; base += 4) {
+        const int vi = base + (lane >> 3), c = lane & 7;
+        float raw = INFINITY;
+        bool act = false;
+        if (vi < nxf) {
+          const StencilXform& S = sxf[first + vi];
+          act = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
+          if (NDIM == 3) act = act && S.omax[0] >= z0s && S.omin[0] <= z1s;
+          if (act && MODE == MVS_FUSE_WAVG) {
+            const int ox = (c & 1) ? min(x1s, S.omax[2]) : max(x0s, S.omin[2]);
+            const int oy = (c & 2) ? min(y1s, S.omax[1]) : max(y0s, S.omin[1]);
+            const int oz = NDIM == 3 ? ((c & 4) ? min(z1s, S.omax[0]) : max(z0s, S.omin[0])) : 0;
+            const double ux = __dadd_rn(__dmul_rn((double)ox, S.wm[2]), S.woff[2]);
+            const double uy = __dadd_rn(__dmul_rn((double)oy, S.wm[1]), S.woff[1]);
+            const double uz = NDIM == 3 ? __dadd_rn(__dmul_rn((double)oz, S.wm[0]), S.woff[0]) : 0.0;
+            raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)xforms[first + vi].table * 125, uz, uy, ux), 0.f);
+          }
+        }
+        raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 1));
+        raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 2));
+        raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 4));
+        int code = 0;
+        if (act) {
+          code = VIEW_GENERAL;
+          if (MODE == MVS_FUSE_WAVG) {
+            if (raw >= 1.0f) code = VIEW_UNIT;
+            else if (raw >= MVS_POSITIVE_X) code = VIEW_POSITIVE;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg_ = __shfl_sync(0xffffffffu, code, g * 8);
+          if (base + g < nxf && cg_) {
+            active |= 1u << (base + g);
+            codes |= (unsigned long long)cg_ << (2 * (base + g));
+          }
+        }
+      }
+      const int nact = __popc(active);
+      // every active view has unit weights (or the mode needs no weights): the
+      // consumers can use plain sums (acc = sum v, den = count)
+      bool simple = true;
+      if (MODE == MVS_FUSE_WAVG)
+        for (unsigned rest = active; rest; rest &= rest - 1)
+          simple = simple && ((codes >> (2 * (__ffs(rest) - 1))) & 3) == VIEW_UNIT;
+
+      if (nact == 0) {
+        Slot& sl = acquire();
+        if (lane == 0) {
+          sl.chunk = lo; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
+          sl.flags = ITEM_FIRST | ITEM_LAST | ITEM_EMPTY; sl.wmode = 0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[it % NS]);
+        ++it;
+        continue;
+      }
+      int seen = 0;
+      for (unsigned rest = active; rest; rest &= rest - 1) {
+        const int vi = __ffs(rest) - 1;
+        const int code = (int)((codes >> (2 * vi)) & 3);
+        const mvs_view_xform& X = xforms[first + vi];
+        const StencilXform& S = sxf[first + vi];
+        // weights: 0 = not needed (out = v), 1 = all ones, 2 = table lookup
+        int wmode = 0;
+        if (MODE == MVS_FUSE_WAVG) {
+          if (nact == 1 && !PARTIAL && code >= VIEW_POSITIVE) wmode = 0;
+          else wmode = code == VIEW_UNIT ? 1 : 2;
+        }
+        Slot& sl = acquire();
+        const int shx = S.shift[2], shy = S.shift[1], shz = NDIM == 3 ? S.shift[0] : 0;
+        const int x0g = x0s + shx, y0g = y0s + shy, z0g = z0s + shz;
+        const int xa_u = floor_div(x0g, A) * A;
+        // descriptor
+        {
+          const int* src = reinterpret_cast<const int*>(&S);
+          int* dst = reinterpret_cast<int*>(&sl.sx);
+          for (int q = lane; q < (int)(sizeof(StencilXform) / 4); q += 32) dst[q] = src[q];
+          if (lane == 0) {
+            sl.chunk = lo; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
+            sl.flags = (seen == 0 ? ITEM_FIRST : 0) | (seen == nact - 1 ? ITEM_LAST : 0) |
+                       (simple ? ITEM_SIMPLE : 0);
+            sl.wmode = wmode; sl.xa_u = xa_u;
+          }
+        }
+        if (wmode == 2) {
+          for (int q = lane; q < B::NW; q += 32) {
+            int d, o;
+            if (q < B::BX) { d = 2; o = x0s + q; }
+            else if (q < B::BX + B::BY) { d = 1; o = y0s + (q - B::BX); }
+            else { d = 0; o = z0s + (q - B::BX - B::BY); }
+            const double u = __dadd_rn(__dmul_rn((double)o, S.wm[d]), S.woff[d]);
+            int cell = -1;
+            float fr = 0.f;
+            if (!(u < 0.0 || u > 4.0)) { const double f = floor(u); cell = (int)f; fr = (float)(u - f); }
+            sl.wi[q] = cell; sl.wt[q] = fr;
+          }
+          const float* tab = tables + (int64_t)X.table * 125;
+          for (int q = lane; q < (NDIM == 3 ? 125 : 25); q += 32) sl.tab[q] = __ldg(tab + q);
+        }
+        // footprint rows
+        const int nx = X.shape[2], ny = X.shape[1], nz = X.shape[0];
+        const int xb_u = floor_div(x0g + B::BX + 1 + A - 1, A) * A;
+        const int xa = max(xa_u, 0), xb = min(xb_u, nx);
+        const int row_bytes = xb > xa ? (xb - xa) * (int)sizeof(T) : 0;
+        const int nyv = max(0, min(y0g + B::ROWS_Y - 1, ny - 1) - max(y0g, 0) + 1);
+        const int nzv = NDIM == 3 ? max(0, min(z0g + B::ROWS_Z - 1, nz - 1) - max(z0g, 0) + 1) : 1;
+        const uint32_t total = (uint32_t)row_bytes * nyv * nzv;
+        __syncwarp();
+        unsigned long long* fb = &full_bar[it % NS];
+        if (lane == 0) {
+          if (total) mbar_expect_tx(fb, total); else mbar_arrive(fb);
+        }
+        if (total) {
+          for (int r = lane; r < B::NROWS; r += 32) {
+            const int rz = r / B::ROWS_Y, ry = r - rz * B::ROWS_Y;
+            const int gy = y0g + ry, gz = NDIM == 3 ? z0g + rz : 0;
+            if (gy >= 0 && gy < ny && gz >= 0 && gz < nz) {
+              const T* src = reinterpret_cast<const T*>(X.data) + (int64_t)gz * X.stride[0] +
+                             (int64_t)gy * X.stride[1] + xa;
+              bulk_g2s(sl.stage + r * B::ROWP + (xa - xa_u), src, (uint32_t)row_bytes, fb);
+            }
+          }
+        }
+        ++it;
+        ++seen;
+      }
+    }
+    // stop item
+    {
+      Slot& sl = acquire();
+      if (lane == 0) sl.flags = ITEM_STOP;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[it % NS]);
+    }
+    return;
+  }
+
+  // ============================ consumer warps ============================
   const int cg = warp & 3, half = warp >> 2;
   const int jx = cg * 32 + lane;  // block-local output column
-  uint32_t phase = 0;
+  auto out_y = [&](int k) { return NDIM == 3 ? (k & 7) : half * 16 + k; };
+  auto out_z = [&](int k) { return NDIM == 3 ? half * 2 + (k >> 3) : 0; };
 
   float acc[B::OUTS], den[B::OUTS];
   unsigned anymask = 0;    // bit k: a valid view was seen for output k
   unsigned multimask = 0;  // bit k: at least two valid views (WAVG: acc is weighted)
+
+  for (int it = 0;; ++it) {
+    const int s = it % NS;
+    Slot& sl = slots[s];
+    mbar_wait(&full_bar[s], (it / NS) & 1);
+    const int flags = sl.flags;
+    if (flags & ITEM_STOP) break;
+    const int last_wmode = sl.wmode;
+    const mvs_chunk& ck = chunks[sl.chunk];
+    const int x0 = sl.x0, y0 = sl.y0, z0 = sl.z0;
+    const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
+    if (flags & ITEM_FIRST) {
+      anymask = 0; multimask = 0;
 #pragma unroll
-  for (int k = 0; k < B::OUTS; ++k) { acc[k] = 0.f; den[k] = 0.f; }
-
-  // output k of this thread sits at block-local row out_y(k), plane out_z(k)
-  auto out_y = [&](int k) { return NDIM == 3 ? (k & 7) : half * 16 + k; };
-  auto out_z = [&](int k) { return NDIM == 3 ? half * 2 + (k >> 3) : 0; };
-
-  for (int i = 0; i < nxf; ++i) {
-    const int code = s_flag[i];
-    if (code == VIEW_OFF) continue;
-    const mvs_view_xform& X = xforms[first + i];
-    const StencilXform& S = sxf[first + i];
-    // weights: 0 = not needed (out = v), 1 = all ones, 2 = table lookup
-    int wmode = 0;
-    if (MODE == MVS_FUSE_WAVG) {
-      if (nact == 1 && !PARTIAL && code >= VIEW_POSITIVE) wmode = 0;
-      else wmode = code == VIEW_UNIT ? 1 : 2;
+      for (int k = 0; k < B::OUTS; ++k) { acc[k] = 0.f; den[k] = 0.f; }
     }
-    const int shx = S.shift[2], shy = S.shift[1], shz = NDIM == 3 ? S.shift[0] : 0;
-
-    // ---- stage the footprint (bulk async copies) and the weight axes ----
-    __syncthreads();  // previous consumers of stage / weight axes are done
-    const int x0g = x0s + shx, y0g = y0s + shy, z0g = z0s + shz;
-    const int xa_u = floor_div(x0g, A) * A;
-    uint32_t total;
-    {
-      const int nx = X.shape[2], ny = X.shape[1], nz = X.shape[0];
-      const int xb_u = floor_div(x0g + B::BX + 1 + A - 1, A) * A;
-      const int xa = max(xa_u, 0), xb = min(xb_u, nx);
-      const int row_bytes = xb > xa ? (xb - xa) * (int)sizeof(T) : 0;
-      const int nyv = max(0, min(y0g + B::ROWS_Y - 1, ny - 1) - max(y0g, 0) + 1);
-      const int nzv = NDIM == 3 ? max(0, min(z0g + B::ROWS_Z - 1, nz - 1) - max(z0g, 0) + 1) : 1;
-      total = (uint32_t)row_bytes * nyv * nzv;
-      if (total) {
-        if (threadIdx.x == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(&s_bar, total);
-        }
-        if (threadIdx.x < B::NROWS) {
-          const int r = threadIdx.x;
-          const int rz = r / B::ROWS_Y, ry = r - rz * B::ROWS_Y;
-          const int gy = y0g + ry, gz = NDIM == 3 ? z0g + rz : 0;
-          if (gy >= 0 && gy < ny && gz >= 0 && gz < nz) {
-            const T* src = reinterpret_cast<const T*>(X.data) + (int64_t)gz * X.stride[0] +
-                           (int64_t)gy * X.stride[1] + xa;
-            bulk_g2s(stage + r * B::ROWP + (xa - xa_u), src, (uint32_t)row_bytes, &s_bar);
+    if (!(flags & ITEM_EMPTY)) {
+      const StencilXform& S = sl.sx;
+      const int wmode = sl.wmode;
+      const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
+      // ---- valid bits of this thread's outputs (ranges -> masks) ----
+      unsigned vm;
+      {
+        const int sx = x0s + jx;
+        const bool vx = sx >= S.omin[2] && sx <= S.omax[2] && x0 + jx < sh_x;
+        const int ya = max(S.omin[1] - y0s, 0), yb = min(min(S.omax[1] - y0s, sh_y - 1 - y0), B::BY - 1);
+        if (NDIM == 2) {
+          const int ka = max(ya - half * 16, 0), kb = min(yb - half * 16, 15);
+          vm = (vx && kb >= ka) ? ((0xffffu >> (15 - kb)) & (0xffffu << ka)) : 0u;
+        } else {
+          const int ka = max(ya, 0), kb = min(yb, 7);
+          const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
+          const int za = max(S.omin[0] - z0s, 0), zb = min(min(S.omax[0] - z0s, sh_z - 1 - z0), B::BZ - 1);
+          const int p0 = half * 2, p1 = half * 2 + 1;
+          vm = 0u;
+          if (vx) {
+            if (p0 >= za && p0 <= zb) vm |= ym;
+            if (p1 >= za && p1 <= zb) vm |= ym << 8;
           }
         }
       }
-    }
-    if (wmode == 2) {
-      fill_weight_axes<NDIM>(S, x0s, y0s, z0s, s_wi, s_wt);
-      const float* tab = tables + (int64_t)X.table * 125;
-      for (int q = threadIdx.x; q < (NDIM == 3 ? 125 : 25); q += blockDim.x) s_tab[q] = __ldg(tab + q);
-    }
+      const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
+      const int c0 = (x0s + S.shift[2] - sl.xa_u) + jx;
+      const int c1 = c0 + S.d1[2];
+      const bool dy = S.d1[1] != 0, dz = NDIM == 3 && S.d1[0] != 0;
 
-    // ---- valid bits of this thread's outputs (ranges -> masks) ----
-    unsigned vm;
-    {
-      const int sx = x0s + jx;
-      const bool vx = sx >= S.omin[2] && sx <= S.omax[2] && x0 + jx < sh_x;
-      // rows: block-local y in [ya, yb]
-      const int ya = max(S.omin[1] - y0s, 0), yb = min(min(S.omax[1] - y0s, sh_y - 1 - y0), B::BY - 1);
+      // ---- interpolate this thread's outputs from shared memory ----
+      float val[B::OUTS];
       if (NDIM == 2) {
-        const int ka = max(ya - half * 16, 0), kb = min(yb - half * 16, 15);
-        vm = (vx && kb >= ka) ? ((0xffffu >> (15 - kb)) & (0xffffu << ka)) : 0u;
-      } else {
-        const int ka = max(ya, 0), kb = min(yb, 7);
-        const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
-        const int za = max(S.omin[0] - z0s, 0), zb = min(min(S.omax[0] - z0s, sh_z - 1 - z0), B::BZ - 1);
-        const int p0 = half * 2, p1 = half * 2 + 1;
-        vm = 0u;
-        if (vx) {
-          if (p0 >= za && p0 <= zb) vm |= ym;
-          if (p1 >= za && p1 <= zb) vm |= ym << 8;
-        }
-      }
-    }
-    const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
-    const int c0 = (x0g - xa_u) + jx;
-    const int c1 = c0 + S.d1[2];
-    const bool dy = S.d1[1] != 0, dz = NDIM == 3 && S.d1[0] != 0;
-
-    __syncthreads();  // weight axes / table visible
-    if (total) { mbar_wait(&s_bar, phase); phase ^= 1; }
-
-    // ---- interpolate this thread's outputs from shared memory ----
-    float val[B::OUTS];
-    if (NDIM == 2) {
-      const T* p = stage + (half * 16) * B::ROWP;
-      float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        p += B::ROWP;
-        const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
-        val[k] = dy ? lerp_s(hprev, hn, ty) : hprev;
-        hprev = hn;
-      }
-    } else {
-      float gprev[8];
-#pragma unroll
-      for (int pz = 0; pz < 3; ++pz) {
-        const T* p = stage + ((half * 2 + pz) * B::ROWS_Y) * B::ROWP;
-        float g[8];
+        const T* p = sl.stage + (half * 16) * B::ROWP;
         float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {
+        for (int k = 0; k < 16; ++k) {
           p += B::ROWP;
           const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
-          g[y] = dy ? lerp_s(hprev, hn, ty) : hprev;
+          val[k] = dy ? lerp_s(hprev, hn, ty) : hprev;
           hprev = hn;
         }
-        if (pz > 0) {
+      } else {
+        float gprev[8];
 #pragma unroll
-          for (int y = 0; y < 8; ++y)
-            val[(pz - 1) * 8 + y] = dz ? lerp_s(gprev[y], g[y], tz) : gprev[y];
+        for (int pz = 0; pz < 3; ++pz) {
+          const T* p = sl.stage + ((half * 2 + pz) * B::ROWS_Y) * B::ROWP;
+          float g[8];
+          float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
+#pragma unroll
+          for (int y = 0; y < 8; ++y) {
+            p += B::ROWP;
+            const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
+            g[y] = dy ? lerp_s(hprev, hn, ty) : hprev;
+            hprev = hn;
+          }
+          if (pz > 0) {
+#pragma unroll
+            for (int y = 0; y < 8; ++y)
+              val[(pz - 1) * 8 + y] = dz ? lerp_s(gprev[y], g[y], tz) : gprev[y];
+          }
+#pragma unroll
+          for (int y = 0; y < 8; ++y) gprev[y] = g[y];
         }
-#pragma unroll
-        for (int y = 0; y < 8; ++y) gprev[y] = g[y];
       }
-    }
 
-    // ---- combine ----
-    if (MODE == MVS_FUSE_WAVG) {
-      if (wmode == 0) {
-        // the block's only view and its weight is positive everywhere: out = v
+      // ---- combine ----
+      const bool lone = (flags & (ITEM_FIRST | ITEM_LAST)) == (ITEM_FIRST | ITEM_LAST) &&
+                        (MODE != MVS_FUSE_WAVG || (wmode == 0 && !PARTIAL));
+      if (lone) {
+        // the block's only view (weight positive everywhere): out = v, stored below
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k) { acc[k] = val[k]; den[k] = 1.f; }
-        anymask = vm;
+        for (int k = 0; k < B::OUTS; ++k) acc[k] = (vm >> k) & 1 ? val[k] : 0.f;
+      } else if (MODE == MVS_FUSE_MAX) {
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if ((vm >> k) & 1) acc[k] = (anymask >> k) & 1 ? fmaxf(acc[k], val[k]) : val[k];
+        anymask |= vm;
+      } else if (MODE == MVS_FUSE_MEAN || (flags & ITEM_SIMPLE)) {
+        // unit weights: acc = sum of valid values, den = number of valid views
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k) {
+          const bool valid = (vm >> k) & 1;
+          acc[k] = __fadd_rn(acc[k], valid ? val[k] : 0.f);
+          den[k] = __fadd_rn(den[k], valid ? 1.f : 0.f);
+        }
       } else {
         int ix = 0, ixc = 0, ix1 = 0;
         float wtx = 0.f;
         if (wmode == 2) {
-          ix = s_wi[jx]; wtx = s_wt[jx];
+          ix = sl.wi[jx]; wtx = sl.wt[jx];
           ixc = max(ix, 0); ix1 = min(ixc + 1, 4);
         }
 #pragma unroll
@@ -387,26 +504,26 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           const bool valid = (vm >> k) & 1;
           float b = valid ? 1.f : 0.f;
           if (wmode == 2) {
-            const int iy = s_wi[B::BX + out_y(k)];
-            const float wty = s_wt[B::BX + out_y(k)];
+            const int iy = sl.wi[B::BX + out_y(k)];
+            const float wty = sl.wt[B::BX + out_y(k)];
             const int iyc = max(iy, 0), iy1 = min(iyc + 1, 4);
             bool inside = ix >= 0 && iy >= 0;
             float w;
             if (NDIM == 3) {
-              const int iz = s_wi[B::BX + B::BY + out_z(k)];
-              const float wtz = s_wt[B::BX + B::BY + out_z(k)];
+              const int iz = sl.wi[B::BX + B::BY + out_z(k)];
+              const float wtz = sl.wt[B::BX + B::BY + out_z(k)];
               const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
               inside = inside && iz >= 0;
-              const float* p0 = s_tab + izc * 25;
-              const float* p1 = s_tab + iz1 * 25;
+              const float* p0 = sl.tab + izc * 25;
+              const float* p1 = sl.tab + iz1 * 25;
               const float a0 = lerp_s(lerp_s(p0[iyc * 5 + ixc], p0[iyc * 5 + ix1], wtx),
                                       lerp_s(p0[iy1 * 5 + ixc], p0[iy1 * 5 + ix1], wtx), wty);
               const float a1 = lerp_s(lerp_s(p1[iyc * 5 + ixc], p1[iyc * 5 + ix1], wtx),
                                       lerp_s(p1[iy1 * 5 + ixc], p1[iy1 * 5 + ix1], wtx), wty);
               w = lerp_s(a0, a1, wtz);
             } else {
-              w = lerp_s(lerp_s(s_tab[iyc * 5 + ixc], s_tab[iyc * 5 + ix1], wtx),
-                         lerp_s(s_tab[iy1 * 5 + ixc], s_tab[iy1 * 5 + ix1], wtx), wty);
+              w = lerp_s(lerp_s(sl.tab[iyc * 5 + ixc], sl.tab[iyc * 5 + ix1], wtx),
+                         lerp_s(sl.tab[iy1 * 5 + ixc], sl.tab[iy1 * 5 + ix1], wtx), wty);
             }
             if (__any_sync(0xffffffffu, valid && w < 1.0f)) {
               // weights.py:502-507 cosine ramp (float32), only near view borders
@@ -432,71 +549,84 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         }
         anymask |= vm;
       }
+    }
+    // slot fully consumed by this warp
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (!(flags & ITEM_LAST)) continue;
+
+    // ---- finalise (registers only) ----
+    if (flags & ITEM_EMPTY) {
+      // acc / den are zero
+    } else if ((flags & ITEM_FIRST) && (MODE != MVS_FUSE_WAVG || (last_wmode == 0 && !PARTIAL))) {
+      // lone view: acc already holds the result
+    } else if (MODE == MVS_FUSE_MAX) {
+#pragma unroll
+      for (int k = 0; k < B::OUTS; ++k) acc[k] = (anymask >> k) & 1 ? acc[k] : 0.f;
+    } else if (MODE == MVS_FUSE_MEAN || (flags & ITEM_SIMPLE)) {
+      if (!PARTIAL) {
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if (__any_sync(0xffffffffu, den[k] > 1.f))
+            acc[k] = den[k] > 1.f ? __fdiv_rn(acc[k], den[k]) : acc[k];
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < B::OUTS; ++k) {
-        if ((vm >> k) & 1) {
-          if (MODE == MVS_FUSE_MAX) {
-            acc[k] = (anymask >> k) & 1 ? fmaxf(acc[k], val[k]) : val[k];
-          } else {
-            acc[k] = __fadd_rn(acc[k], val[k]);
-            den[k] = __fadd_rn(den[k], 1.0f);
-          }
+        const bool had = (anymask >> k) & 1, multi = (multimask >> k) & 1;
+        if (PARTIAL) {
+          acc[k] = !had ? 0.f : (multi ? acc[k] : __fmul_rn(acc[k], den[k]));
+        } else {
+          float r = (had && den[k] > 0.f) ? acc[k] : 0.f;
+          if (__any_sync(0xffffffffu, multi))
+            r = multi ? __fdiv_rn(acc[k], den[k] == 0.f ? 1.f : den[k]) : r;
+          acc[k] = r;
         }
       }
-      anymask |= vm;
+    }
+
+    // ---- store (lanes along x: coalesced rows) ----
+    const int xo = x0 + jx;
+    if (xo < sh_x) {
+      const int64_t sy = ck.stride[1], sz = ck.stride[0];
+      const int64_t o0 = (int64_t)(z0 + out_z(0)) * sz + (int64_t)(y0 + out_y(0)) * sy +
+                         (int64_t)xo * ck.stride[2];
+      // rows / planes of this thread that lie inside the chunk
+      const int ylim = sh_y - y0 - (NDIM == 3 ? 0 : half * 16);
+      const int zlim = NDIM == 3 ? sh_z - z0 - half * 2 : 1;
+      auto keep = [&](int k) { return NDIM == 3 ? ((k & 7) < ylim && (k >> 3) < zlim) : k < ylim; };
+      auto off = [&](int k) -> int64_t {
+        return NDIM == 3 ? (int64_t)(k >> 3) * sz + (int64_t)(k & 7) * sy : (int64_t)k * sy;
+      };
+      if (PARTIAL) {
+        float* pn = ck.acc_num + o0;
+        float* pd = ck.acc_den + o0;
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if (keep(k)) { pn[off(k)] = acc[k]; pd[off(k)] = den[k]; }
+      } else if (ck.out_dtype == MVS_F32) {
+        float* po = reinterpret_cast<float*>(ck.out) + o0;
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if (keep(k)) po[off(k)] = cast_out<float>(acc[k]);
+      } else if (ck.out_dtype == MVS_U16) {
+        unsigned short* po = reinterpret_cast<unsigned short*>(ck.out) + o0;
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if (keep(k)) po[off(k)] = cast_out<unsigned short>(acc[k]);
+      } else {
+        unsigned char* po = reinterpret_cast<unsigned char*>(ck.out) + o0;
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if (keep(k)) po[off(k)] = cast_out<unsigned char>(acc[k]);
+      }
     }
   }
+}
 
-  // ---- finalise ----
-#pragma unroll
-  for (int k = 0; k < B::OUTS; ++k) {
-    const bool had = (anymask >> k) & 1, multi = (multimask >> k) & 1;
-    if (MODE == MVS_FUSE_WAVG && PARTIAL) {
-      acc[k] = !had ? 0.f : (multi ? acc[k] : __fmul_rn(acc[k], den[k]));
-    } else if (MODE == MVS_FUSE_WAVG) {
-      float r = (had && den[k] > 0.f) ? acc[k] : 0.f;
-      if (multimask) r = multi ? __fdiv_rn(acc[k], den[k] == 0.f ? 1.f : den[k]) : r;
-      acc[k] = r;
-    } else if (MODE == MVS_FUSE_MEAN) {
-      acc[k] = had ? __fdiv_rn(acc[k], den[k]) : 0.f;
-    } else {
-      acc[k] = had ? acc[k] : 0.f;
-    }
-  }
-
-  // ---- store (lanes along x: coalesced rows) ----
-  const int xo = x0 + jx;
-  if (xo >= sh_x) return;
-  const int64_t sy = ck.stride[1], sz = ck.stride[0];
-  const int64_t o0 = (int64_t)(z0 + out_z(0)) * sz + (int64_t)(y0 + out_y(0)) * sy + (int64_t)xo * ck.stride[2];
-  // offset of output k relative to output 0
-  auto off_k = [&](int k) -> int64_t {
-    return NDIM == 3 ? (int64_t)(k >> 3) * sz + (int64_t)(k & 7) * sy : (int64_t)k * sy;
-  };
-  auto in_chunk = [&](int k) { return y0 + out_y(k) < sh_y && z0 + out_z(k) < sh_z; };
-  if (PARTIAL) {
-    float* pn = ck.acc_num + o0;
-    float* pd = ck.acc_den + o0;
-#pragma unroll
-    for (int k = 0; k < B::OUTS; ++k)
-      if (in_chunk(k)) { pn[off_k(k)] = acc[k]; pd[off_k(k)] = den[k]; }
-  } else if (ck.out_dtype == MVS_F32) {
-    float* po = reinterpret_cast<float*>(ck.out) + o0;
-#pragma unroll
-    for (int k = 0; k < B::OUTS; ++k)
-      if (in_chunk(k)) po[off_k(k)] = cast_out<float>(acc[k]);
-  } else if (ck.out_dtype == MVS_U16) {
-    unsigned short* po = reinterpret_cast<unsigned short*>(ck.out) + o0;
-#pragma unroll
-    for (int k = 0; k < B::OUTS; ++k)
-      if (in_chunk(k)) po[off_k(k)] = cast_out<unsigned short>(acc[k]);
-  } else {
-    unsigned char* po = reinterpret_cast<unsigned char*>(ck.out) + o0;
-#pragma unroll
-    for (int k = 0; k < B::OUTS; ++k)
-      if (in_chunk(k)) po[off_k(k)] = cast_out<unsigned char>(acc[k]);
-  }
+template <int NDIM, typename T>
+constexpr size_t stencil_smem_bytes() {
+  return sizeof(StencilSlot<NDIM, T>) * StencilStages<NDIM, T>::value;
 }
 
 }  // namespace mvs
