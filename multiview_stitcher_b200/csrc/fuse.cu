@@ -373,6 +373,7 @@ struct mvs_fuse_plan {
   int n_chunks_st = 0;
   int64_t total_blocks_st = 0;
   mvs::StencilXform* d_sxf = nullptr;
+  CUtensorMap* d_tmaps = nullptr;
   int stencil_dtype = MVS_F32;
   int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
@@ -387,33 +388,50 @@ using namespace mvs;
 
 // ---- translation fast path: host-side classification ---------------------------
 
-static float host_table_interp(const float* tab, int ndim, const double u[3]) {
-  // multilinear lookup (float64) in the 5^ndim table, cval 0 outside [0,4]
-  double w[3][2];
-  int i0[3], i1[3];
-  for (int d = 3 - ndim; d < 3; ++d) {
-    if (u[d] < 0.0 || u[d] > 4.0) return 0.f;
-    double f = floor(u[d]);
-    i0[d] = (int)f; i1[d] = std::min(i0[d] + 1, 4);
-    w[d][1] = u[d] - f; w[d][0] = 1.0 - w[d][1];
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                             const cuuint64_t*, const cuuint64_t*,
+                                             const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tensorMapEncodeTiled get_tensor_map_encoder() {
+  static PFN_tensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tensorMapEncodeTiled)p;
   }
-  double acc = 0.0;
-  for (int a = 0; a < (ndim == 3 ? 2 : 1); ++a)
-    for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < 2; ++c) {
-        int iz = ndim == 3 ? (a ? i1[0] : i0[0]) : 0;
-        int iy = b ? i1[1] : i0[1], ix = c ? i1[2] : i0[2];
-        double wt = (ndim == 3 ? w[0][a] : 1.0) * w[1][b] * w[2][c];
-        float v = ndim == 3 ? tab[iz * 25 + iy * 5 + ix] : tab[iy * 5 + ix];
-        acc += wt * v;
-      }
-  return (float)acc;
+  return fn;
+}
+
+// TMA descriptor of one view window: box = one stencil block footprint.
+static bool make_tensor_map(const mvs_view_xform& X, int ndim, CUtensorMap* out) {
+  PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t es = (cuuint64_t)dtype_size(X.dtype);
+  const CUtensorMapDataType dt = X.dtype == MVS_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : X.dtype == MVS_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                                      : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  const cuuint32_t bw = (cuuint32_t)(128 + 16 / es);
+  cuuint64_t gdim[3] = {(cuuint64_t)X.shape[2], (cuuint64_t)X.shape[1], (cuuint64_t)X.shape[0]};
+  cuuint64_t gstr[2] = {(cuuint64_t)X.stride[1] * es, (cuuint64_t)X.stride[0] * es};
+  cuuint32_t box[3] = {bw, (cuuint32_t)(ndim == 3 ? 9 : 33), (cuuint32_t)(ndim == 3 ? 5 : 1)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  // a rank-2 map needs a sane stride even for single-row windows
+  if (X.shape[1] == 1) gstr[0] = ((gdim[0] * es + 15) / 16) * 16;
+  if (ndim == 3 && X.shape[0] == 1) gstr[1] = gstr[0] * gdim[1];
+  CUresult r = enc(out, dt, (cuuint32_t)ndim, const_cast<void*>(X.data), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
 }
 
 // Fills S and returns true when pairing X is a pure translation that the
 // bulk-copy stencil kernel can serve.
 static bool make_stencil(const mvs_view_xform& X, int ndim, int order, int dtype,
-                         const float* tables, StencilXform& S) {
+                         StencilXform& S) {
   memset(&S, 0, sizeof(S));
   for (int d = 0; d < 3; ++d)
     for (int j = 0; j < 3; ++j) {
@@ -422,8 +440,7 @@ static bool make_stencil(const mvs_view_xform& X, int ndim, int order, int dtype
     }
   if (X.dtype != dtype || X.stride[2] != 1) return false;
   const int64_t esize = (int64_t)dtype_size(dtype);
-  const int A = (int)(16 / esize);
-  if (((uintptr_t)X.data) % 16 || (X.stride[1] * esize) % 16 || X.shape[2] % A) return false;
+  if (((uintptr_t)X.data) % 16 || (X.stride[1] * esize) % 16) return false;
   if (ndim == 3 && (X.stride[0] * esize) % 16) return false;
   for (int d = 0; d < 3; ++d) {
     S.omin[d] = INT_MIN / 2; S.omax[d] = INT_MAX / 2;
@@ -451,23 +468,6 @@ static bool make_stencil(const mvs_view_xform& X, int ndim, int order, int dtype
     S.omin[d] = (int)lo; S.omax[d] = (int)hi;
     // order 0 picks floor(o + off + 0.5): must stay inside the window
   }
-  // blending weight strictly positive on the valid box? (corners carry the minimum)
-  S.always_pos = 0;
-  if (tables && X.table >= 0) {
-    float mn = INFINITY;
-    for (int c = 0; c < (1 << ndim); ++c) {
-      double u[3] = {0, 0, 0};
-      bool empty = false;
-      for (int d = 3 - ndim; d < 3; ++d) {
-        if (S.omax[d] < S.omin[d]) { empty = true; break; }
-        const int o = ((c >> (2 - d)) & 1) ? S.omax[d] : S.omin[d];
-        u[d] = (double)o * S.wm[d] + S.woff[d];
-      }
-      if (empty) { mn = 1.f; break; }
-      mn = std::min(mn, host_table_interp(tables + (int64_t)X.table * 125, ndim, u));
-    }
-    S.always_pos = mn >= 1e-3f ? 1 : 0;
-  }
   return true;
 }
 
@@ -481,7 +481,7 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   // persistent: two CTAs per SM, each walks blocks bid, bid + grid, ...
   const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * 2);
   kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
-                                            p->d_xforms, p->d_sxf, p->d_tables);
+                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps);
   return cudaGetLastError();
 }
 
@@ -596,13 +596,35 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   std::vector<StencilXform> sxf(n_xforms);
   std::vector<char> xf_ok(n_xforms, 0);
   for (int i = 0; i < n_xforms; ++i)
-    xf_ok[i] = allow_stencil && make_stencil(xforms[i], ndim, order, stencil_dtype,
-                                             fusion_mode == MVS_FUSE_WAVG ? tables : nullptr, sxf[i]);
+    xf_ok[i] = allow_stencil && make_stencil(xforms[i], ndim, order, stencil_dtype, sxf[i]);
+  std::vector<CUtensorMap> tmaps;
+  {
+    std::vector<int> owner;  // xform index that created tmaps[k]
+    for (int i = 0; i < n_xforms; ++i) {
+      if (!xf_ok[i]) continue;
+      int found = -1;
+      for (size_t k = 0; k < owner.size() && found < 0; ++k) {
+        const mvs_view_xform& Y = xforms[owner[k]];
+        const mvs_view_xform& X = xforms[i];
+        if (Y.data == X.data && !memcmp(Y.shape, X.shape, sizeof(X.shape)) &&
+            !memcmp(Y.stride, X.stride, sizeof(X.stride)) && Y.dtype == X.dtype)
+          found = (int)k;
+      }
+      if (found < 0) {
+        CUtensorMap m;
+        if (!make_tensor_map(xforms[i], ndim, &m)) { xf_ok[i] = 0; continue; }
+        tmaps.push_back(m);
+        owner.push_back(i);
+        found = (int)tmaps.size() - 1;
+      }
+      sxf[i].tmap = found;
+    }
+  }
   std::vector<mvs_chunk> ch_st, ch_gen;
   std::vector<int64_t> bs_st(1, 0), bs_gen(1, 0);
   for (int c = 0; c < n_chunks; ++c) {
     const mvs_chunk& ck = chunks[c];
-    bool ok = allow_stencil && ck.n_xforms <= 32;
+    bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
     if (ok) {
       const int BX = 128, BY = ndim == 3 ? 8 : 32, BZ = ndim == 3 ? 4 : 1;
@@ -655,6 +677,9 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   if ((e = upload((void**)&p->d_block_start_st, bs_st.data(), sizeof(int64_t) * bs_st.size())) !=
       cudaSuccess)
     return fail(e, "upload stencil block schedule");
+  if ((e = upload((void**)&p->d_tmaps, tmaps.data(), sizeof(CUtensorMap) * tmaps.size())) !=
+      cudaSuccess)
+    return fail(e, "upload tensor maps");
   if ((e = upload((void**)&p->d_xforms, xforms, sizeof(mvs_view_xform) * n_xforms)) !=
       cudaSuccess)
     return fail(e, "upload xforms");
@@ -703,6 +728,7 @@ extern "C" int mvs_fuse_plan_destroy(mvs_fuse_plan* p) {
   cudaFree(p->d_chunks_st);
   cudaFree(p->d_block_start_st);
   cudaFree(p->d_sxf);
+  cudaFree(p->d_tmaps);
   cudaFree(p->d_xforms);
   cudaFree(p->d_tables);
   cudaFree(p->d_block_start);

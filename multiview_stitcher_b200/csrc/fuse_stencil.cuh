@@ -4,19 +4,23 @@
 // identity (transformation.py:56 with equal spacings), so the order-1 resample
 // of a view is a constant-coefficient 2^ndim-tap stencil on a shifted window:
 //   x_in = o + off,  floor(x_in) = o + floor(off),  frac = off - floor(off).
-// A CTA owns an output block (BZ x BY x 128).  For every contributing view it
-//   1. pulls the block's input footprint (rows of <= 160 elements) into shared
-//      memory with 1-D bulk async copies (cp.async.bulk -> UBLKCP, 16-byte
-//      aligned, completion on an mbarrier) -- HBM is read in full coalesced
-//      row segments, never gathered;
-//   2. meanwhile evaluates the separable parts of the blending weight (table
-//      cell + fraction per column / row / plane, float64) into shared memory;
-//   3. interpolates from shared memory (lanes along x: conflict-free), reusing
-//      the x-interpolated rows between neighbouring output rows / planes;
-//   4. blends with the reference's float32 operation order.
-// Results are bit-identical to the general kernel except for the last ulp of
-// the interpolation fraction.
+//
+// Persistent, warp-specialised kernel.  Output blocks (BZ x BY x 128 voxels) are
+// dealt round-robin to the CTAs:
+//   * warp 8, the producer, culls the chunk's views against the block,
+//     classifies their blending weights (all ones / all positive / general) from
+//     the weight at the corners of block x valid-box, and pulls each contributing
+//     view's input footprint into a ring of shared-memory slots with ONE TMA
+//     tensor copy (cp.async.bulk.tensor -> UTMALDG; out-of-bounds elements are
+//     zero-filled by the hardware), completion signalled on an mbarrier;
+//   * warps 0-7 consume the slots: lanes along x (conflict-free shared-memory
+//     reads whatever the sub-vector misalignment of the box), x-interpolated
+//     rows reused between neighbouring output rows / planes, blending with the
+//     reference's float32 semantics, coalesced 128-byte row-segment stores.
+// HBM is read in full row segments through TMA and written once.
 #pragma once
+
+#include <cuda.h>
 
 #include "common.cuh"
 
@@ -28,7 +32,7 @@ struct StencilXform {
   int d1[3];      // offset of the second tap (0 when the fraction is 0 / order 0)
   int omin[3];    // valid sample-index range per axis (inclusive)
   int omax[3];
-  int always_pos; // blending weight > 0 on every valid voxel (single-view shortcut)
+  int tmap;       // index of the view's tensor map
   double wm[3];   // diagonal of wmatrix
   double woff[3];
 };
@@ -38,13 +42,16 @@ struct SBlock {
   static constexpr int BX = 128;
   static constexpr int BY = NDIM == 3 ? 8 : 32;
   static constexpr int BZ = NDIM == 3 ? 4 : 1;
-  static constexpr int ROWP = 160;  // staged row pitch in elements (>= BX + 1 + 2*15)
   static constexpr int ROWS_Y = BY + 1;
   static constexpr int ROWS_Z = NDIM == 3 ? BZ + 1 : 1;
   static constexpr int NROWS = ROWS_Y * ROWS_Z;
-  static constexpr int OUTS = 16;  // outputs per thread
+  static constexpr int OUTS = 16;  // outputs per thread: 4 rows x 4 columns
   static constexpr int NW = BX + BY + BZ;
 };
+
+// staged row pitch in elements: >= BX + 1 and a multiple of 16 bytes
+template <typename T>
+struct BoxW { static constexpr int value = 128 + 16 / (int)sizeof(T); };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -57,13 +64,8 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                         unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t done = 0;
@@ -79,6 +81,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
     if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU on a lost copy
   }
 }
+// TMA tile copy global -> shared, 2-D / 3-D (coordinates innermost first)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int cx, int cy,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(cx), "r"(cy), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int cx, int cy,
+                                            int cz, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(cx), "r"(cy), "r"(cz), "r"(smem_u32(bar))
+      : "memory");
+}
 
 __device__ __forceinline__ float lerp_s(float a, float b, float t) {
   return fmaf(t, b, fmaf(-t, a, a));
@@ -87,29 +106,6 @@ __device__ __forceinline__ float lerp_s(float a, float b, float t) {
 __device__ __forceinline__ int floor_div(int a, int b) {
   int q = a / b;
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
-}
-
-// Separable blending-weight coordinates of this block for one view.
-template <int NDIM>
-__device__ __forceinline__ void fill_weight_axes(const StencilXform& S, int x0s, int y0s, int z0s,
-                                                 int* s_wi, float* s_wt) {
-  using B = SBlock<NDIM>;
-  for (int i = threadIdx.x; i < B::NW; i += blockDim.x) {
-    int d, o;
-    if (i < B::BX) { d = 2; o = x0s + i; }
-    else if (i < B::BX + B::BY) { d = 1; o = y0s + (i - B::BX); }
-    else { d = 0; o = z0s + (i - B::BX - B::BY); }
-    const double u = __dadd_rn(__dmul_rn((double)o, S.wm[d]), S.woff[d]);
-    int cell = -1;
-    float fr = 0.f;
-    if (!(u < 0.0 || u > 4.0)) {
-      const double f = floor(u);
-      cell = (int)f;
-      fr = (float)(u - f);
-    }
-    s_wi[i] = cell;
-    s_wt[i] = fr;
-  }
 }
 
 // raw (pre-cosine) table value at float64 table coordinates; 0 outside [0,4]
@@ -143,23 +139,66 @@ enum { VIEW_GENERAL = 1, VIEW_POSITIVE = 2, VIEW_UNIT = 3 };
 // item flags
 enum { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_STOP = 8, ITEM_SIMPLE = 16 };
 
-template <typename OUT_T>
-__device__ __forceinline__ OUT_T cast_out(float v);
-template <>
-__device__ __forceinline__ float cast_out<float>(float v) { return v != v ? 0.f : v; }
-template <>
-__device__ __forceinline__ unsigned short cast_out<unsigned short>(float v) {
-  int q = __float2int_rz(v != v ? 0.f : v);
-  return (unsigned short)(q < 0 ? 0 : (q > 65535 ? 65535 : q));
+// four consecutive staged elements as floats (16-byte aligned for every T)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const unsigned short* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4((float)(v.x & 0xffffu), (float)(v.x >> 16), (float)(v.y & 0xffffu),
+                     (float)(v.y >> 16));
 }
-template <>
-__device__ __forceinline__ unsigned char cast_out<unsigned char>(float v) {
-  int q = __float2int_rz(v != v ? 0.f : v);
-  return (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
+__device__ __forceinline__ float4 load4(const unsigned char* p) {
+  const unsigned v = *reinterpret_cast<const unsigned*>(p);
+  return make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu),
+                     (float)(v >> 24));
 }
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// float32 -> output dtype like np.nan_to_num(x).astype(dtype) for in-range values
+__device__ __forceinline__ float fix_nan(float v) { return v != v ? 0.f : v; }
+__device__ __forceinline__ unsigned to_u16(float v) {
+  int q = __float2int_rz(fix_nan(v));
+  return (unsigned)(q < 0 ? 0 : (q > 65535 ? 65535 : q));
+}
+__device__ __forceinline__ unsigned to_u8(float v) {
+  int q = __float2int_rz(fix_nan(v));
+  return (unsigned)(q < 0 ? 0 : (q > 255 ? 255 : q));
+}
+
+// stores 4 consecutive outputs of one row; `nvalid` = how many lie inside the chunk
+__device__ __forceinline__ void store_row4(void* out, int dtype, int64_t o, const float* v,
+                                           int nvalid) {
+  if (dtype == MVS_F32) {
+    float* p = reinterpret_cast<float*>(out) + o;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      *reinterpret_cast<float4*>(p) = make_float4(fix_nan(v[0]), fix_nan(v[1]), fix_nan(v[2]), fix_nan(v[3]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < nvalid) p[c] = fix_nan(v[c]);
+    }
+  } else if (dtype == MVS_U16) {
+    unsigned short* p = reinterpret_cast<unsigned short*>(out) + o;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+      *reinterpret_cast<uint2*>(p) = make_uint2(to_u16(v[0]) | (to_u16(v[1]) << 16), to_u16(v[2]) | (to_u16(v[3]) << 16));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < nvalid) p[c] = (unsigned short)to_u16(v[c]);
+    }
+  } else {
+    unsigned char* p = reinterpret_cast<unsigned char*>(out) + o;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+      *reinterpret_cast<unsigned*>(p) = to_u8(v[0]) | (to_u8(v[1]) << 8) | (to_u8(v[2]) << 16) | (to_u8(v[3]) << 24);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < nvalid) p[c] = (unsigned char)to_u8(v[c]);
+    }
+  }
+}
+__device__ __forceinline__ void store_row4_f32(float* p, const float* v, int nvalid) {
+  if (nvalid == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (c < nvalid) p[c] = v[c];
+  }
 }
 
 // One pipeline slot: the staged footprint of one (block, view) item plus what the
@@ -167,38 +206,41 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 template <int NDIM, typename T>
 struct alignas(128) StencilSlot {
   using B = SBlock<NDIM>;
-  T stage[B::NROWS * B::ROWP];
+  T stage[B::NROWS * BoxW<T>::value];
   float tab[128];
   int wi[B::NW];
   float wt[B::NW];
   StencilXform sx;
   int chunk, x0, y0, z0;  // block origin (chunk-local voxels)
-  int flags, wmode, xa_u, pad;
+  int flags, wmode, xoff, pad1;  // xoff: staged column of the block's first tap
 };
 
 constexpr int kStencilConsumerWarps = 8;
 constexpr int kStencilThreads = (kStencilConsumerWarps + 1) * 32;
+constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 
 template <int NDIM, typename T>
 struct StencilStages {
   static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 4;
 };
 
-// Persistent, warp-specialised kernel: warp 8 is the producer (block decode,
-// view culling + weight classification, bulk async copies into a ring of shared
-// memory slots); warps 0-7 consume the slots (interpolate, blend, store).
 template <int NDIM, typename T, int MODE, bool PARTIAL>
 __global__ void __launch_bounds__(kStencilThreads, 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
-                    const StencilXform* __restrict__ sxf, const float* __restrict__ tables) {
+                    const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
+                    const CUtensorMap* __restrict__ tmaps) {
   using B = SBlock<NDIM>;
   using Slot = StencilSlot<NDIM, T>;
   constexpr int NS = StencilStages<NDIM, T>::value;
+  constexpr int BW = BoxW<T>::value;
   constexpr int A = 16 / (int)sizeof(T);  // elements per 16 bytes
+  constexpr uint32_t kBoxBytes = (uint32_t)(B::NROWS * BW * sizeof(T));
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Slot* slots = reinterpret_cast<Slot*>(smem_raw);
   __shared__ __align__(8) unsigned long long full_bar[NS], empty_bar[NS];
+  __shared__ StencilXform s_sx[kStencilMaxViews];  // producer's per-chunk cache
+  __shared__ int s_table[kStencilMaxViews];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -216,39 +258,56 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
       return slots[s];
     };
+    int ci = -1;  // current chunk
+    int64_t c_begin = 0, c_end = 0;
+    int sh_z = 0, sh_y = 0, sh_x = 0, nbx = 1, nby = 1, first = 0, nxf = 0, hz = 0, hy = 0, hx = 0;
+    // blocks are dealt round-robin to the CTAs: overlap-heavy regions spread evenly
     for (int64_t bid = blockIdx.x; bid < nblocks; bid += gridDim.x) {
-      int lo = 0, hi = n_chunks - 1;
-      while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
+      if (ci < 0 || bid >= c_end) {
+        // (re)locate the chunk and cache its view constants in shared memory
+        int lo = max(ci, 0), hi = n_chunks - 1;
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
+        }
+        ci = lo;
+        c_begin = __ldg(block_start + ci);
+        c_end = __ldg(block_start + ci + 1);
+        const mvs_chunk& ck = chunks[ci];
+        sh_z = ck.shape[0]; sh_y = ck.shape[1]; sh_x = ck.shape[2];
+        hz = ck.halo[0]; hy = ck.halo[1]; hx = ck.halo[2];
+        nbx = (sh_x + B::BX - 1) / B::BX; nby = (sh_y + B::BY - 1) / B::BY;
+        first = ck.first_xform; nxf = ck.n_xforms;
+        __syncwarp();
+        constexpr int W = (int)(sizeof(StencilXform) / 4);
+        for (int q = lane; q < nxf * W; q += 32)
+          reinterpret_cast<int*>(s_sx)[q] = __ldg(reinterpret_cast<const int*>(sxf + first) + q);
+        for (int q = lane; q < nxf; q += 32) s_table[q] = xforms[first + q].table;
+        __syncwarp();
       }
-      const mvs_chunk& ck = chunks[lo];
-      const int local = (int)(bid - __ldg(block_start + lo));
-      const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
-      const int nbx = (sh_x + B::BX - 1) / B::BX, nby = (sh_y + B::BY - 1) / B::BY;
+      const int local = (int)(bid - c_begin);
       const int bz = local / (nbx * nby);
       const int rem = local - bz * (nbx * nby);
       const int by = rem / nbx;
       const int x0 = (rem - by * nbx) * B::BX, y0 = by * B::BY, z0 = bz * B::BZ;
-      const int first = ck.first_xform, nxf = ck.n_xforms;
-      const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
-      const int x1s = min(x0 + B::BX, sh_x) - 1 + ck.halo[2];
-      const int y1s = min(y0 + B::BY, sh_y) - 1 + ck.halo[1];
-      const int z1s = min(z0 + B::BZ, sh_z) - 1 + ck.halo[0];
+      const int x0s = x0 + hx, y0s = y0 + hy, z0s = z0 + hz;
+      const int x1s = min(x0 + B::BX, sh_x) - 1 + hx;
+      const int y1s = min(y0 + B::BY, sh_y) - 1 + hy;
+      const int z1s = min(z0 + B::BZ, sh_z) - 1 + hz;
 
       // ---- cull the chunk's views against this block, classify their weights:
       // 8 lanes per view evaluate the (pre-cosine) blending weight at the corners
       // of block x valid-box, where it is smallest:
       //   min >= 1          -> every weight in the block is exactly 1   (UNIT)
       //   min >= POSITIVE_X -> every weight in the block is > 0         (POSITIVE)
-      unsigned active = 0;            // bit per view (nxf <= 32, checked on the host)
-      unsigned long long codes = 0;   // 2 bits per view
+      unsigned active = 0;           // bit per view
+      unsigned long long codes = 0;  // 2 bits per view
       for (int base = 0; base < nxf; base += 4) {
         const int vi = base + (lane >> 3), c = lane & 7;
         float raw = INFINITY;
         bool act = false;
         if (vi < nxf) {
-          const StencilXform& S = sxf[first + vi];
+          const StencilXform& S = s_sx[vi];
           act = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
           if (NDIM == 3) act = act && S.omax[0] >= z0s && S.omin[0] <= z1s;
           if (act && MODE == MVS_FUSE_WAVG) {
@@ -258,7 +317,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
             const double ux = __dadd_rn(__dmul_rn((double)ox, S.wm[2]), S.woff[2]);
             const double uy = __dadd_rn(__dmul_rn((double)oy, S.wm[1]), S.woff[1]);
             const double uz = NDIM == 3 ? __dadd_rn(__dmul_rn((double)oz, S.wm[0]), S.woff[0]) : 0.0;
-            raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)xforms[first + vi].table * 125, uz, uy, ux), 0.f);
+            raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)s_table[vi] * 125, uz, uy, ux), 0.f);
           }
         }
         raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 1));
@@ -292,7 +351,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       if (nact == 0) {
         Slot& sl = acquire();
         if (lane == 0) {
-          sl.chunk = lo; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
+          sl.chunk = ci; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
           sl.flags = ITEM_FIRST | ITEM_LAST | ITEM_EMPTY; sl.wmode = 0;
         }
         __syncwarp();
@@ -304,8 +363,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       for (unsigned rest = active; rest; rest &= rest - 1) {
         const int vi = __ffs(rest) - 1;
         const int code = (int)((codes >> (2 * vi)) & 3);
-        const mvs_view_xform& X = xforms[first + vi];
-        const StencilXform& S = sxf[first + vi];
+        const StencilXform& S = s_sx[vi];
         // weights: 0 = not needed (out = v), 1 = all ones, 2 = table lookup
         int wmode = 0;
         if (MODE == MVS_FUSE_WAVG) {
@@ -313,19 +371,15 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           else wmode = code == VIEW_UNIT ? 1 : 2;
         }
         Slot& sl = acquire();
-        const int shx = S.shift[2], shy = S.shift[1], shz = NDIM == 3 ? S.shift[0] : 0;
-        const int x0g = x0s + shx, y0g = y0s + shy, z0g = z0s + shz;
-        const int xa_u = floor_div(x0g, A) * A;
-        // descriptor
         {
           const int* src = reinterpret_cast<const int*>(&S);
           int* dst = reinterpret_cast<int*>(&sl.sx);
           for (int q = lane; q < (int)(sizeof(StencilXform) / 4); q += 32) dst[q] = src[q];
           if (lane == 0) {
-            sl.chunk = lo; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
+            sl.chunk = ci; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
             sl.flags = (seen == 0 ? ITEM_FIRST : 0) | (seen == nact - 1 ? ITEM_LAST : 0) |
                        (simple ? ITEM_SIMPLE : 0);
-            sl.wmode = wmode; sl.xa_u = xa_u;
+            sl.wmode = wmode;
           }
         }
         if (wmode == 2) {
@@ -334,38 +388,30 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
             if (q < B::BX) { d = 2; o = x0s + q; }
             else if (q < B::BX + B::BY) { d = 1; o = y0s + (q - B::BX); }
             else { d = 0; o = z0s + (q - B::BX - B::BY); }
-            const double u = __dadd_rn(__dmul_rn((double)o, S.wm[d]), S.woff[d]);
+            const double wm = d == 2 ? S.wm[2] : (d == 1 ? S.wm[1] : S.wm[0]);
+            const double wo = d == 2 ? S.woff[2] : (d == 1 ? S.woff[1] : S.woff[0]);
+            const double u = __dadd_rn(__dmul_rn((double)o, wm), wo);
             int cell = -1;
             float fr = 0.f;
             if (!(u < 0.0 || u > 4.0)) { const double f = floor(u); cell = (int)f; fr = (float)(u - f); }
             sl.wi[q] = cell; sl.wt[q] = fr;
           }
-          const float* tab = tables + (int64_t)X.table * 125;
+          const float* tab = tables + (int64_t)s_table[vi] * 125;
           for (int q = lane; q < (NDIM == 3 ? 125 : 25); q += 32) sl.tab[q] = __ldg(tab + q);
         }
-        // footprint rows
-        const int nx = X.shape[2], ny = X.shape[1], nz = X.shape[0];
-        const int xb_u = floor_div(x0g + B::BX + 1 + A - 1, A) * A;
-        const int xa = max(xa_u, 0), xb = min(xb_u, nx);
-        const int row_bytes = xb > xa ? (xb - xa) * (int)sizeof(T) : 0;
-        const int nyv = max(0, min(y0g + B::ROWS_Y - 1, ny - 1) - max(y0g, 0) + 1);
-        const int nzv = NDIM == 3 ? max(0, min(z0g + B::ROWS_Z - 1, nz - 1) - max(z0g, 0) + 1) : 1;
-        const uint32_t total = (uint32_t)row_bytes * nyv * nzv;
+        // TMA needs a 16-byte aligned innermost start coordinate
+        const int x0g = x0s + S.shift[2];
+        const int xa = floor_div(x0g, A) * A;
+        if (lane == 0) sl.xoff = x0g - xa;
         __syncwarp();
-        unsigned long long* fb = &full_bar[it % NS];
         if (lane == 0) {
-          if (total) mbar_expect_tx(fb, total); else mbar_arrive(fb);
-        }
-        if (total) {
-          for (int r = lane; r < B::NROWS; r += 32) {
-            const int rz = r / B::ROWS_Y, ry = r - rz * B::ROWS_Y;
-            const int gy = y0g + ry, gz = NDIM == 3 ? z0g + rz : 0;
-            if (gy >= 0 && gy < ny && gz >= 0 && gz < nz) {
-              const T* src = reinterpret_cast<const T*>(X.data) + (int64_t)gz * X.stride[0] +
-                             (int64_t)gy * X.stride[1] + xa;
-              bulk_g2s(sl.stage + r * B::ROWP + (xa - xa_u), src, (uint32_t)row_bytes, fb);
-            }
-          }
+          unsigned long long* fb = &full_bar[it % NS];
+          mbar_expect_tx(fb, kBoxBytes);
+          const CUtensorMap* map = tmaps + S.tmap;
+          if (NDIM == 3)
+            tma_load_3d(sl.stage, map, xa, y0s + S.shift[1], z0s + S.shift[0], fb);
+          else
+            tma_load_2d(sl.stage, map, xa, y0s + S.shift[1], fb);
         }
         ++it;
         ++seen;
@@ -382,12 +428,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   }
 
   // ============================ consumer warps ============================
+  // lanes run along x (conflict-free shared-memory reads for any sub-vector
+  // misalignment of the staged box): thread = one column x 16 rows.
+  // 2-D: column (w&3)*32 + lane, rows (w>>2)*16 + k.   3-D: planes (w>>2)*2 + (k>>3), rows k&7.
   const int cg = warp & 3, half = warp >> 2;
-  const int jx = cg * 32 + lane;  // block-local output column
-  auto out_y = [&](int k) { return NDIM == 3 ? (k & 7) : half * 16 + k; };
-  auto out_z = [&](int k) { return NDIM == 3 ? half * 2 + (k >> 3) : 0; };
+  const int jx = cg * 32 + lane;
 
-  float acc[B::OUTS], den[B::OUTS];
+  float acc[16], den[16];
   unsigned anymask = 0;    // bit k: a valid view was seen for output k
   unsigned multimask = 0;  // bit k: at least two valid views (WAVG: acc is weighted)
 
@@ -397,32 +444,33 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     mbar_wait(&full_bar[s], (it / NS) & 1);
     const int flags = sl.flags;
     if (flags & ITEM_STOP) break;
-    const int last_wmode = sl.wmode;
+    const int wmode = sl.wmode;
     const mvs_chunk& ck = chunks[sl.chunk];
     const int x0 = sl.x0, y0 = sl.y0, z0 = sl.z0;
     const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
     if (flags & ITEM_FIRST) {
       anymask = 0; multimask = 0;
 #pragma unroll
-      for (int k = 0; k < B::OUTS; ++k) { acc[k] = 0.f; den[k] = 0.f; }
+      for (int k = 0; k < 16; ++k) { acc[k] = 0.f; den[k] = 0.f; }
     }
+    const bool lone = (flags & (ITEM_FIRST | ITEM_LAST | ITEM_EMPTY)) == (ITEM_FIRST | ITEM_LAST) &&
+                      (MODE != MVS_FUSE_WAVG || (wmode == 0 && !PARTIAL));
     if (!(flags & ITEM_EMPTY)) {
       const StencilXform& S = sl.sx;
-      const int wmode = sl.wmode;
       const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
-      // ---- valid bits of this thread's outputs (ranges -> masks) ----
+      // ---- valid bits of this thread's 16 outputs (ranges -> masks) ----
       unsigned vm;
       {
         const int sx = x0s + jx;
         const bool vx = sx >= S.omin[2] && sx <= S.omax[2] && x0 + jx < sh_x;
-        const int ya = max(S.omin[1] - y0s, 0), yb = min(min(S.omax[1] - y0s, sh_y - 1 - y0), B::BY - 1);
+        const int ya = max(S.omin[1] - y0s, 0), yb = min(S.omax[1] - y0s, sh_y - 1 - y0);
         if (NDIM == 2) {
           const int ka = max(ya - half * 16, 0), kb = min(yb - half * 16, 15);
           vm = (vx && kb >= ka) ? ((0xffffu >> (15 - kb)) & (0xffffu << ka)) : 0u;
         } else {
           const int ka = max(ya, 0), kb = min(yb, 7);
           const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
-          const int za = max(S.omin[0] - z0s, 0), zb = min(min(S.omax[0] - z0s, sh_z - 1 - z0), B::BZ - 1);
+          const int za = max(S.omin[0] - z0s, 0), zb = min(S.omax[0] - z0s, sh_z - 1 - z0);
           const int p0 = half * 2, p1 = half * 2 + 1;
           vm = 0u;
           if (vx) {
@@ -432,18 +480,18 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         }
       }
       const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
-      const int c0 = (x0s + S.shift[2] - sl.xa_u) + jx;
+      const int c0 = sl.xoff + jx;
       const int c1 = c0 + S.d1[2];
       const bool dy = S.d1[1] != 0, dz = NDIM == 3 && S.d1[0] != 0;
 
       // ---- interpolate this thread's outputs from shared memory ----
-      float val[B::OUTS];
+      float val[16];
       if (NDIM == 2) {
-        const T* p = sl.stage + (half * 16) * B::ROWP;
+        const T* p = sl.stage + (half * 16) * BW;
         float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          p += B::ROWP;
+          p += BW;
           const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
           val[k] = dy ? lerp_s(hprev, hn, ty) : hprev;
           hprev = hn;
@@ -452,12 +500,12 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         float gprev[8];
 #pragma unroll
         for (int pz = 0; pz < 3; ++pz) {
-          const T* p = sl.stage + ((half * 2 + pz) * B::ROWS_Y) * B::ROWP;
+          const T* p = sl.stage + ((half * 2 + pz) * B::ROWS_Y) * BW;
           float g[8];
           float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
           for (int y = 0; y < 8; ++y) {
-            p += B::ROWP;
+            p += BW;
             const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
             g[y] = dy ? lerp_s(hprev, hn, ty) : hprev;
             hprev = hn;
@@ -473,21 +521,19 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       }
 
       // ---- combine ----
-      const bool lone = (flags & (ITEM_FIRST | ITEM_LAST)) == (ITEM_FIRST | ITEM_LAST) &&
-                        (MODE != MVS_FUSE_WAVG || (wmode == 0 && !PARTIAL));
       if (lone) {
-        // the block's only view (weight positive everywhere): out = v, stored below
+        // the block's only view (weight positive everywhere): out = v
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k) acc[k] = (vm >> k) & 1 ? val[k] : 0.f;
+        for (int k = 0; k < 16; ++k) acc[k] = (vm >> k) & 1 ? val[k] : 0.f;
       } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
+        for (int k = 0; k < 16; ++k)
           if ((vm >> k) & 1) acc[k] = (anymask >> k) & 1 ? fmaxf(acc[k], val[k]) : val[k];
         anymask |= vm;
       } else if (MODE == MVS_FUSE_MEAN || (flags & ITEM_SIMPLE)) {
         // unit weights: acc = sum of valid values, den = number of valid views
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k) {
+        for (int k = 0; k < 16; ++k) {
           const bool valid = (vm >> k) & 1;
           acc[k] = __fadd_rn(acc[k], valid ? val[k] : 0.f);
           den[k] = __fadd_rn(den[k], valid ? 1.f : 0.f);
@@ -500,18 +546,20 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           ixc = max(ix, 0); ix1 = min(ixc + 1, 4);
         }
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k) {
+        for (int k = 0; k < 16; ++k) {
+          const int ky = NDIM == 3 ? (k & 7) : half * 16 + k;
+          const int kz = NDIM == 3 ? half * 2 + (k >> 3) : 0;
           const bool valid = (vm >> k) & 1;
           float b = valid ? 1.f : 0.f;
           if (wmode == 2) {
-            const int iy = sl.wi[B::BX + out_y(k)];
-            const float wty = sl.wt[B::BX + out_y(k)];
+            const int iy = sl.wi[B::BX + ky];
+            const float wty = sl.wt[B::BX + ky];
             const int iyc = max(iy, 0), iy1 = min(iyc + 1, 4);
             bool inside = ix >= 0 && iy >= 0;
             float w;
             if (NDIM == 3) {
-              const int iz = sl.wi[B::BX + B::BY + out_z(k)];
-              const float wtz = sl.wt[B::BX + B::BY + out_z(k)];
+              const int iz = sl.wi[B::BX + B::BY + kz];
+              const float wtz = sl.wt[B::BX + B::BY + kz];
               const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
               inside = inside && iz >= 0;
               const float* p0 = sl.tab + izc * 25;
@@ -556,23 +604,21 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     if (!(flags & ITEM_LAST)) continue;
 
     // ---- finalise (registers only) ----
-    if (flags & ITEM_EMPTY) {
-      // acc / den are zero
-    } else if ((flags & ITEM_FIRST) && (MODE != MVS_FUSE_WAVG || (last_wmode == 0 && !PARTIAL))) {
-      // lone view: acc already holds the result
+    if ((flags & ITEM_EMPTY) || lone) {
+      // acc already holds the result (zeros for an empty block)
     } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll
-      for (int k = 0; k < B::OUTS; ++k) acc[k] = (anymask >> k) & 1 ? acc[k] : 0.f;
+      for (int k = 0; k < 16; ++k) acc[k] = (anymask >> k) & 1 ? acc[k] : 0.f;
     } else if (MODE == MVS_FUSE_MEAN || (flags & ITEM_SIMPLE)) {
       if (!PARTIAL) {
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
+        for (int k = 0; k < 16; ++k)
           if (__any_sync(0xffffffffu, den[k] > 1.f))
             acc[k] = den[k] > 1.f ? __fdiv_rn(acc[k], den[k]) : acc[k];
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < B::OUTS; ++k) {
+      for (int k = 0; k < 16; ++k) {
         const bool had = (anymask >> k) & 1, multi = (multimask >> k) & 1;
         if (PARTIAL) {
           acc[k] = !had ? 0.f : (multi ? acc[k] : __fmul_rn(acc[k], den[k]));
@@ -585,15 +631,16 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       }
     }
 
-    // ---- store (lanes along x: coalesced rows) ----
+    // ---- store: lanes along x -> every warp store instruction writes one
+    // contiguous 128-byte (float32) row segment ----
     const int xo = x0 + jx;
     if (xo < sh_x) {
       const int64_t sy = ck.stride[1], sz = ck.stride[0];
-      const int64_t o0 = (int64_t)(z0 + out_z(0)) * sz + (int64_t)(y0 + out_y(0)) * sy +
-                         (int64_t)xo * ck.stride[2];
+      const int zrow0 = NDIM == 3 ? half * 2 : 0, yrow0 = NDIM == 3 ? 0 : half * 16;
+      const int64_t o0 = (int64_t)(z0 + zrow0) * sz + (int64_t)(y0 + yrow0) * sy + (int64_t)xo;
       // rows / planes of this thread that lie inside the chunk
-      const int ylim = sh_y - y0 - (NDIM == 3 ? 0 : half * 16);
-      const int zlim = NDIM == 3 ? sh_z - z0 - half * 2 : 1;
+      const int ylim = sh_y - y0 - yrow0;
+      const int zlim = NDIM == 3 ? sh_z - z0 - zrow0 : 1;
       auto keep = [&](int k) { return NDIM == 3 ? ((k & 7) < ylim && (k >> 3) < zlim) : k < ylim; };
       auto off = [&](int k) -> int64_t {
         return NDIM == 3 ? (int64_t)(k >> 3) * sz + (int64_t)(k & 7) * sy : (int64_t)k * sy;
@@ -602,23 +649,23 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         float* pn = ck.acc_num + o0;
         float* pd = ck.acc_den + o0;
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
+        for (int k = 0; k < 16; ++k)
           if (keep(k)) { pn[off(k)] = acc[k]; pd[off(k)] = den[k]; }
       } else if (ck.out_dtype == MVS_F32) {
         float* po = reinterpret_cast<float*>(ck.out) + o0;
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
-          if (keep(k)) po[off(k)] = cast_out<float>(acc[k]);
+        for (int k = 0; k < 16; ++k)
+          if (keep(k)) po[off(k)] = fix_nan(acc[k]);
       } else if (ck.out_dtype == MVS_U16) {
         unsigned short* po = reinterpret_cast<unsigned short*>(ck.out) + o0;
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
-          if (keep(k)) po[off(k)] = cast_out<unsigned short>(acc[k]);
+        for (int k = 0; k < 16; ++k)
+          if (keep(k)) po[off(k)] = (unsigned short)to_u16(acc[k]);
       } else {
         unsigned char* po = reinterpret_cast<unsigned char*>(ck.out) + o0;
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
-          if (keep(k)) po[off(k)] = cast_out<unsigned char>(acc[k]);
+        for (int k = 0; k < 16; ++k)
+          if (keep(k)) po[off(k)] = (unsigned char)to_u8(acc[k]);
       }
     }
   }
