@@ -125,6 +125,51 @@ int mvs_fuse_finalize(const float* acc_num, const float* acc_den, void* out,
                       int out_dtype, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Post-resample stage on (V, *chunk) float32 stacks (NaN = outside): the
+ * arithmetic behind the reference's fusion_func / weights_func hooks
+ * (docs/extension_api_fusion.md; fusion/_core.py:1653-1685) and the multi-pass
+ * half of content-weighted fusion.  A stack is V contiguous volumes of
+ * shape[0]*shape[1]*shape[2] voxels on the device.
+ * ---------------------------------------------------------------------- */
+
+/* transform_sim of n_views views onto one chunk grid (fusion/_core.py:1621-1632)
+ * and, if d_weights != NULL, the un-normalised blending weights masked by
+ * validity (weights.py:391-511, _core.py:1636-1648).  xforms / tables are HOST
+ * arrays (device pointers inside); shape / halo as in mvs_chunk. */
+int mvs_resample_views(const mvs_view_xform* xforms, int n_views, const float* tables,
+                       int n_tables, const int32_t shape[3], const int32_t halo[3], int ndim,
+                       int order, float* d_views, float* d_weights, void* stream);
+
+/* weights.normalize_weights (weights.py:325-345), in place. */
+int mvs_normalize_weights(float* d_weights, int V, int64_t N, void* stream);
+
+/* scipy.ndimage.gaussian_filter(mode="reflect") of `batch` volumes with the
+ * symmetric kernel weights[0..radius] (HOST float64, weights[j] = weight at
+ * distance j; scipy's own normalised kernel for sigma, truncate 4). */
+int mvs_gaussian_filter(const float* d_in, float* d_out, int batch, const int32_t shape[3],
+                        int ndim, const double* weights, int radius, void* stream);
+
+/* weights.content_based (weights.py:22-74): views whose normalised blending
+ * weight is < 1e-7 are ignored, W = G2 ~* (v - G1 ~* v)^2 with NaN-normalised
+ * Gaussians (weights.py:293-322), then normalised over V.  w1/r1, w2/r2: the two
+ * kernels as in mvs_gaussian_filter. */
+int mvs_content_based(const float* d_views, const float* d_blending, int V,
+                      const int32_t shape[3], int ndim, const double* w1, int r1,
+                      const double* w2, int r2, float* d_out_weights, void* stream);
+
+/* fusion_func on stacks: MVS_FUSE_WAVG = weighted_average_fusion(views, blending,
+ * fusion_weights or NULL) (_core.py:61-94), MVS_FUSE_MAX (_core.py:42-58),
+ * MVS_FUSE_MEAN (_core.py:97-131).  d_out: float32 volume (NaN where the
+ * reference yields NaN). */
+int mvs_fuse_stack(const float* d_views, const float* d_blending, const float* d_fusion_weights,
+                   int V, int64_t N, int fusion_mode, float* d_out, void* stream);
+
+/* fused[trim:-trim] -> nan_to_num -> astype(out_dtype) (_core.py:1687-1713);
+ * out_stride in elements. */
+int mvs_trim_cast(const float* d_in, const int32_t shape[3], const int32_t trim[3], void* d_out,
+                  int out_dtype, const int64_t out_stride[3], void* stream);
+
+/* ------------------------------------------------------------------------
  * (i) batched 2-D/3-D phase-correlation pairwise registration
  *
  * Replaces registration.phase_correlation_registration

@@ -348,6 +348,33 @@ fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ bl
   }
 }
 
+// transform_sim of every view of one chunk (NaN outside) plus the un-normalised
+// blending weights (cosine ramp x validity): the (V, *chunk) stacks fuse_np hands
+// to weights_func / fusion_func (fusion/_core.py:1621-1651).
+template <int NDIM, int ORDER>
+__global__ void __launch_bounds__(256)
+resample_views_kernel(mvs_chunk ck, const mvs_view_xform* __restrict__ xforms, int n_views,
+                      const float* __restrict__ tables, float* __restrict__ out_views,
+                      float* __restrict__ out_weights) {
+  const long long N = (long long)ck.shape[0] * ck.shape[1] * ck.shape[2];
+  const int v = blockIdx.y;
+  const mvs_view_xform& X = xforms[v];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % ck.shape[2]), y = (int)((i / ck.shape[2]) % ck.shape[1]),
+              z = (int)(i / ((long long)ck.shape[2] * ck.shape[1]));
+    ViewEval e;
+    if (out_weights)
+      e = eval_view<NDIM, ORDER, true, true>(X, tables, (double)(z + ck.halo[0]),
+                                             (double)(y + ck.halo[1]), (double)(x + ck.halo[2]));
+    else
+      e = eval_view<NDIM, ORDER, true, false>(X, tables, (double)(z + ck.halo[0]),
+                                              (double)(y + ck.halo[1]), (double)(x + ck.halo[2]));
+    out_views[(long long)v * N + i] = e.valid ? e.v : NAN;
+    if (out_weights) out_weights[(long long)v * N + i] = e.valid ? e.b : 0.f;
+  }
+}
+
 __global__ void finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
                                 void* out, int out_dtype, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -745,5 +772,49 @@ extern "C" int mvs_fuse_finalize(const float* acc_num, const float* acc_den, voi
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(acc_num, acc_den, out, out_dtype, n);
   MVS_CHECK_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+extern "C" int mvs_resample_views(const mvs_view_xform* xforms, int n_views, const float* tables,
+                                  int n_tables, const int32_t shape[3], const int32_t halo[3],
+                                  int ndim, int order, float* d_views, float* d_weights,
+                                  void* stream) {
+  MVS_REQUIRE(xforms && shape && halo && d_views, MVS_ERR_INVALID, "NULL pointer");
+  MVS_REQUIRE(n_views >= 1, MVS_ERR_INVALID, "n_views = %d", n_views);
+  MVS_REQUIRE(ndim == 2 || ndim == 3, MVS_ERR_INVALID, "ndim must be 2 or 3");
+  MVS_REQUIRE(order == 0 || order == 1, MVS_ERR_UNSUPPORTED, "interpolation order %d", order);
+  MVS_REQUIRE(!d_weights || (tables && n_tables >= 1), MVS_ERR_INVALID, "weights need tables");
+  for (int i = 0; i < n_views; ++i) {
+    MVS_REQUIRE(xforms[i].data != nullptr, MVS_ERR_INVALID, "xform %d: data is NULL", i);
+    MVS_REQUIRE(!d_weights || (xforms[i].table >= 0 && xforms[i].table < n_tables),
+                MVS_ERR_INVALID, "xform %d: table index out of range", i);
+  }
+  mvs_chunk ck{};
+  for (int d = 0; d < 3; ++d) { ck.shape[d] = shape[d]; ck.halo[d] = halo[d]; }
+  const long long N = (long long)shape[0] * shape[1] * shape[2];
+  if (N <= 0) return MVS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  mvs_view_xform* d_x = nullptr;
+  float* d_t = nullptr;
+  MVS_CHECK_CUDA(cudaMalloc(&d_x, sizeof(mvs_view_xform) * n_views));
+  if (d_weights) {
+    cudaError_t e = cudaMalloc(&d_t, sizeof(float) * 125 * n_tables);
+    if (e != cudaSuccess) { cudaFree(d_x); set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
+    cudaMemcpyAsync(d_t, tables, sizeof(float) * 125 * n_tables, cudaMemcpyHostToDevice, st);
+  }
+  cudaMemcpyAsync(d_x, xforms, sizeof(mvs_view_xform) * n_views, cudaMemcpyHostToDevice, st);
+  dim3 grid((unsigned)std::min<long long>((N + 255) / 256, 148 * 16), n_views);
+  if (ndim == 2) {
+    if (order == 0) resample_views_kernel<2, 0><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
+    else resample_views_kernel<2, 1><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
+  } else {
+    if (order == 0) resample_views_kernel<3, 0><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
+    else resample_views_kernel<3, 1><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(st);
+  cudaFree(d_x);
+  cudaFree(d_t);
+  if (e != cudaSuccess) { set_error("resample launch: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
   return MVS_OK;
 }

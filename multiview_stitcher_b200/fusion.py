@@ -35,6 +35,8 @@ __all__ = [
     "weighted_average_fusion",
     "max_fusion",
     "simple_average_fusion",
+    "content_based",
+    "build_work_list",
 ]
 
 
@@ -62,6 +64,16 @@ def simple_average_fusion(transformed_views):
     from . import hooks
 
     return hooks.simple_average_fusion(transformed_views)
+
+
+def content_based(transformed_views, blending_weights, sigma_1=5, sigma_2=11):
+    """weights.content_based (weights.py:22-74) on the GPU; pass as ``weights_func``."""
+    from . import hooks
+
+    return hooks.content_based(transformed_views, blending_weights, sigma_1, sigma_2)
+
+
+content_based.required_overlap = lambda kwargs: 2 * kwargs["sigma_2"]
 
 
 _MODE_BY_NAME = {
@@ -184,6 +196,84 @@ def _required_overlap(func, kwargs):
     return int(np.ceil(ov))
 
 
+def build_work_list(
+    views, params, osp, chunksize, halo=0, sample_origin=None, full_view_bbs=None, spacings=None,
+    blending_widths=None, shrink_distance=0, chunk_subset=None,
+):
+    """Host geometry of a fusion job: for every output chunk the views that can
+    touch it and, per (chunk, view) pairing, exactly the matrix / offset
+    ``transform_sim`` would hand to scipy for the view (transformation.py:31-83)
+    and for its blending-support table (weights.py:465-481).
+
+    Returns ``{"chunks": [(start, shape, first_xform, n_xforms)], "xforms":
+    VIEW_XFORM_DTYPE array, "tables": (V, 125) float32, "halo": int array}``.
+    """
+    ndim = views[0].ndim
+    dims = geometry.spatial_dims(ndim)
+    if not isinstance(halo, dict):
+        halo = {d: int(halo) for d in dims}
+    if full_view_bbs is None:
+        full_view_bbs = [v.bb() for v in views]
+    if spacings is None:
+        spacings = [bb["spacing"] for bb in full_view_bbs]
+    spacings = [sp if sp is not None else bb["spacing"] for sp, bb in zip(spacings, full_view_bbs)]
+    o_org, o_sp, _ = geometry.bb_arrays(osp, dims)
+    halo_v = np.array([halo[d] for d in dims], dtype=np.int64)
+
+    tables = np.zeros((len(views), 125), dtype=np.float32)
+    tab_org, tab_sp, inv_params, aabbs = [], [], [], []
+    for i, (v, p) in enumerate(zip(views, params)):
+        t, to, ts = geometry.blending_table(full_view_bbs[i], blending_widths, shrink_distance)
+        tables[i, : t.size] = t.reshape(-1)
+        tab_org.append(to)
+        tab_sp.append(ts)
+        inv_params.append(np.linalg.inv(np.asarray(p, dtype=np.float64)))
+        aabbs.append(geometry.transformed_aabb(v.bb(), p, dims))
+
+    grid = geometry.chunk_grid(osp, chunksize)
+    if sample_origin is not None and len(grid) != 1:
+        raise EngineError("sample_origin needs a single-chunk plan")
+    if chunk_subset is not None:
+        grid = [grid[i] for i in chunk_subset]
+    chunks, xrows = [], []
+    eps = 1e-6
+    for start, shape in grid:
+        start = np.array(start, dtype=np.int64)
+        shape_a = np.array(shape, dtype=np.int64)
+        # halo'd chunk origin = what transform_sim sees as output origin; same
+        # operation order as mv_graph.py:965-971 + fusion/_core.py:1237-1243
+        if sample_origin is not None:
+            c_org = np.asarray(sample_origin, dtype=np.float64)
+        else:
+            c_org = (o_org + o_sp * start) - halo_v * o_sp
+        lo = c_org
+        hi = c_org + (shape_a + 2 * halo_v - 1) * o_sp
+        first = len(xrows)
+        for vi, v in enumerate(views):
+            alo, ahi = aabbs[vi]
+            if np.any(ahi < lo - eps) or np.any(alo > hi + eps):
+                continue
+            in_org = np.array([v.origin[d] for d in dims])
+            in_sp = np.array([spacings[vi][d] for d in dims])
+            m, off = geometry.pixel_affine(inv_params[vi], c_org, o_sp, in_org, in_sp)
+            wm, woff = geometry.pixel_affine(inv_params[vi], c_org, o_sp, tab_org[vi], tab_sp[vi])
+            xrows.append((vi, m, off, wm, woff))
+        chunks.append((start, tuple(int(s) for s in shape), first, len(xrows) - first))
+
+    xarr = np.zeros(len(xrows), dtype=_lib.VIEW_XFORM_DTYPE)
+    for r, (vi, m, off, wm, woff) in enumerate(xrows):
+        v = views[vi]
+        x = xarr[r]
+        x["data"] = v.tensor.data_ptr()
+        x["dtype"] = v.mvs_dtype
+        x["shape"] = [1] * (3 - ndim) + list(map(int, v.tensor.shape))
+        x["stride"] = [0] * (3 - ndim) + [int(st) for st in v.tensor.stride()]
+        x["matrix"], x["offset"] = geometry.embed3(m, off)
+        x["wmatrix"], x["woffset"] = geometry.embed3(wm, woff)
+        x["table"] = vi
+    return {"chunks": chunks, "xforms": xarr, "tables": tables, "halo": halo_v, "view_index": [r[0] for r in xrows]}
+
+
 class FusionPlan:
     """Device work list for fusing ``views`` onto ``output_stack_properties``.
 
@@ -259,55 +349,15 @@ class FusionPlan:
         ostride = [0] * (3 - ndim) + [int(s) for s in ref.stride()]
         elem = ref.element_size()
 
-        if full_view_bbs is None:
-            full_view_bbs = [v.bb() for v in self.views]
-        if spacings is None:
-            spacings = [bb["spacing"] for bb in full_view_bbs]
-
-        o_org, o_sp, _ = geometry.bb_arrays(osp, dims)
-        halo_v = np.array([halo[d] for d in dims], dtype=np.int64)
-
-        # per-view constants
-        tables = np.zeros((len(self.views), 125), dtype=np.float32)
-        tab_org, tab_sp, inv_params, aabbs = [], [], [], []
-        for i, (v, p) in enumerate(zip(self.views, self.params)):
-            t, to, ts = geometry.blending_table(full_view_bbs[i], blending_widths, shrink_distance)
-            tables[i, : t.size] = t.reshape(-1)
-            tab_org.append(to)
-            tab_sp.append(ts)
-            inv_params.append(np.linalg.inv(p))
-            aabbs.append(geometry.transformed_aabb(v.bb(), p, dims))
-
-        chunks = geometry.chunk_grid(osp, self.chunksize)
-        if sample_origin is not None and len(chunks) != 1:
-            raise EngineError("sample_origin needs a single-chunk plan")
-        if chunk_subset is not None:
-            chunks = [chunks[i] for i in chunk_subset]
-        n_chunks = len(chunks)
+        work = build_work_list(
+            self.views, self.params, osp, self.chunksize, halo, sample_origin, full_view_bbs,
+            spacings, blending_widths, shrink_distance, chunk_subset,
+        )
+        tables, xarr = work["tables"], work["xforms"]
+        n_chunks = len(work["chunks"])
         carr = np.zeros(n_chunks, dtype=_lib.CHUNK_DTYPE)
-        xrows = []
-        eps = 1e-6
-        for ci, (start, shape) in enumerate(chunks):
-            start = np.array(start, dtype=np.int64)
-            shape_a = np.array(shape, dtype=np.int64)
-            # halo'd chunk origin = what transform_sim sees as output origin;
-            # same operation order as mv_graph.py:965-971 + fusion/_core.py:1237-1243
-            if sample_origin is not None:
-                c_org = np.asarray(sample_origin, dtype=np.float64)
-            else:
-                c_org = (o_org + o_sp * start) - halo_v * o_sp
-            lo = c_org
-            hi = c_org + (shape_a + 2 * halo_v - 1) * o_sp
-            first = len(xrows)
-            for vi, v in enumerate(self.views):
-                alo, ahi = aabbs[vi]
-                if np.any(ahi < lo - eps) or np.any(alo > hi + eps):
-                    continue
-                in_org = np.array([v.origin[d] for d in dims])
-                in_sp = np.array([spacings[vi][d] for d in dims])
-                m, off = geometry.pixel_affine(inv_params[vi], c_org, o_sp, in_org, in_sp)
-                wm, woff = geometry.pixel_affine(inv_params[vi], c_org, o_sp, tab_org[vi], tab_sp[vi])
-                xrows.append((vi, m, off, wm, woff))
+        halo_v = work["halo"]
+        for ci, (start, shape, first, count) in enumerate(work["chunks"]):
             c = carr[ci]
             off_elems = int(np.dot(start, ostride[3 - ndim :]))
             if partial:
@@ -321,19 +371,8 @@ class FusionPlan:
             c["stride"] = ostride
             c["halo"] = [0] * (3 - ndim) + [int(h) for h in halo_v]
             c["first_xform"] = first
-            c["n_xforms"] = len(xrows) - first
-
-        xarr = np.zeros(len(xrows), dtype=_lib.VIEW_XFORM_DTYPE)
-        for r, (vi, m, off, wm, woff) in enumerate(xrows):
-            v = self.views[vi]
-            x = xarr[r]
-            x["data"] = v.tensor.data_ptr()
-            x["dtype"] = v.mvs_dtype
-            x["shape"] = [1] * (3 - ndim) + list(map(int, v.tensor.shape))
-            x["stride"] = [0] * (3 - ndim) + [int(s) for s in v.tensor.stride()]
-            x["matrix"], x["offset"] = geometry.embed3(m, off)
-            x["wmatrix"], x["woffset"] = geometry.embed3(wm, woff)
-            x["table"] = vi
+            c["n_xforms"] = count
+        xrows = xarr
         self._chunks, self._xforms, self._tables = carr, xarr, tables
         self.n_chunks, self.n_xforms = n_chunks, len(xrows)
 
@@ -406,7 +445,7 @@ def fuse_np(
     same arguments; ``sims`` are view dicts / xarray-like slices (host or
     device), the result is the fused, trimmed chunk as a host array in the input
     dtype (or a CUDA tensor with ``output_on_backend=True``)."""
-    if weights_func is not None:
+    if weights_func is not None or getattr(fusion_func, "__name__", None) not in _MODE_BY_NAME:
         from . import content
 
         return content.fuse_np_with_weights(
@@ -478,7 +517,7 @@ def fuse(
         output_stack_properties = geometry.union_stack_props(
             bbs, params, output_spacing, mode=output_stack_mode
         )
-    if weights_func is not None:
+    if weights_func is not None or getattr(fusion_func, "__name__", None) not in _MODE_BY_NAME:
         from . import content
 
         out = content.fuse_with_weights(
