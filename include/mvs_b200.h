@@ -226,10 +226,12 @@ int mvs_pc_candidate_ssim(mvs_pc_plan* plan, int n_cand, const int32_t* cand_pai
                           const double* cand_t, const int32_t* slices, const int32_t* win,
                           double* out_host, void* stream);
 
-/* Stage E: Spearman rank correlation of im0[mask] vs im1t[mask] for one
- * (pair, t); NaN when fewer than two samples or a constant input. */
-int mvs_pc_spearman(mvs_pc_plan* plan, int pair, const double t[3], double* rho_host,
-                    void* stream);
+/* Stage E: Spearman rank correlation (average ranks for ties) of im0[mask] vs
+ * (im1t[mask] - 1 in float32, registration.py:551-553) for n (pair, t) items;
+ * n_mask[i] = count(mask) from stage C.  rho_host[i] is NaN when fewer than two
+ * samples or a constant input. */
+int mvs_pc_spearman_batch(mvs_pc_plan* plan, int n, const int32_t* pairs, const double* ts,
+                          const int64_t* n_mask, double* rho_host, void* stream);
 
 /* ------------------------------------------------------------------------
  * Synthetic tiles (benchmark / test inputs).  Integer-only

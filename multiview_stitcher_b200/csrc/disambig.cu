@@ -503,12 +503,12 @@ extern "C" int mvs_pc_candidate_ssim(mvs_pc_plan* p, int n_cand, const int32_t* 
   return MVS_OK;
 }
 
-extern "C" int mvs_pc_spearman(mvs_pc_plan* p, int pair, const double t[3], double* rho_host,
-                               void* stream) {
-  MVS_REQUIRE(p && t && rho_host, MVS_ERR_INVALID, "NULL pointer");
-  int32_t cp = pair;
+extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs, const double* ts,
+                                     const int64_t* n_mask, double* rho_host, void* stream) {
+  MVS_REQUIRE(p && pairs && ts && n_mask && rho_host, MVS_ERR_INVALID, "NULL pointer");
+  MVS_REQUIRE(n >= 1, MVS_ERR_INVALID, "n = %d", n);
   std::vector<Cand> cands;
-  int rc = fill_cands(p, 1, &cp, t, cands);
+  int rc = fill_cands(p, n, pairs, ts, cands);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int ndim = pc_ndim(p);
@@ -520,7 +520,7 @@ extern "C" int mvs_pc_spearman(mvs_pc_plan* p, int pair, const double t[3], doub
                                   (const unsigned*)nullptr, (unsigned*)nullptr, (int)N, 0, 32, st);
   auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
   const size_t fb = al(sizeof(float) * N), ub = al(sizeof(unsigned) * N),
-               db = al(sizeof(double) * N), pb = al(sizeof(double) * 3 * kPearsonBlocks);
+               db = al(sizeof(double) * N), pb = al(sizeof(double) * 3 * kPearsonBlocks * n);
   void* scratch;
   if ((rc = pc_scratch(p, 3 * fb + 2 * ub + 2 * db + pb + al(temp_bytes), &scratch))) return rc;
   char* w = (char*)scratch;
@@ -534,40 +534,34 @@ extern "C" int mvs_pc_spearman(mvs_pc_plan* p, int pair, const double t[3], doub
   double* part = (double*)w; w += pb;
   void* temp = w;
   const int grid = (int)std::min<long long>((N + 255) / 256, 148 * 8);
-  if (ndim == 3)
-    spearman_keys_kernel<3><<<grid, 256, 0, st>>>(cands[0], sh[0], sh[1], sh[2], ka, kb, idx);
-  else
-    spearman_keys_kernel<2><<<grid, 256, 0, st>>>(cands[0], sh[0], sh[1], sh[2], ka, kb, idx);
-  MVS_CHECK_CUDA(cudaGetLastError());
-  // number of masked voxels = number of finite keys; count on the host from stats
-  // (cheap alternative: count after sort by a binary search kernel) -> use a reduction
-  // through the rank kernel bound: sort first, then find n on the host.
-  MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ka, ks, idx, sidx, (int)N, 0,
-                                                 32, st));
-  // n = first index whose key is +inf: binary search on the device-resident sorted keys
-  long long lo = 0, hi = N;
-  while (lo < hi) {
-    long long mid = (lo + hi) >> 1;
-    float v;
-    MVS_CHECK_CUDA(cudaMemcpyAsync(&v, ks + mid, sizeof(float), cudaMemcpyDeviceToHost, st));
-    MVS_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (v < INFINITY) lo = mid + 1; else hi = mid;
+  // pairs run back to back on the stream (shared scratch), one sync at the end
+  for (int i = 0; i < n; ++i) {
+    const long long nm = n_mask[i];
+    if (nm < 2) continue;
+    if (ndim == 3)
+      spearman_keys_kernel<3><<<grid, 256, 0, st>>>(cands[i], sh[0], sh[1], sh[2], ka, kb, idx);
+    else
+      spearman_keys_kernel<2><<<grid, 256, 0, st>>>(cands[i], sh[0], sh[1], sh[2], ka, kb, idx);
+    MVS_CHECK_CUDA(cudaGetLastError());
+    // masked-out voxels carry +inf keys and sort to the end: ranks of the first
+    // nm sorted entries are the ranks within the mask
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ka, ks, idx, sidx, (int)N, 0, 32, st));
+    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, nm, ra);
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, ks, idx, sidx, (int)N, 0, 32, st));
+    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, nm, rb);
+    pearson_kernel<<<kPearsonBlocks, 256, 0, st>>>(ka, ra, rb, N, 0.5 * (double)(nm + 1),
+                                                   part + (size_t)3 * kPearsonBlocks * i);
+    MVS_CHECK_CUDA(cudaGetLastError());
   }
-  const long long n = lo;
-  if (n < 2) { *rho_host = NAN; return MVS_OK; }
-  rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, n, ra);
-  MVS_CHECK_CUDA(cudaGetLastError());
-  MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, ks, idx, sidx, (int)N, 0,
-                                                 32, st));
-  rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, n, rb);
-  MVS_CHECK_CUDA(cudaGetLastError());
-  pearson_kernel<<<kPearsonBlocks, 256, 0, st>>>(ka, ra, rb, N, 0.5 * (double)(n + 1), part);
-  MVS_CHECK_CUDA(cudaGetLastError());
-  double hp[3 * kPearsonBlocks];
-  MVS_CHECK_CUDA(cudaMemcpyAsync(hp, part, sizeof(hp), cudaMemcpyDeviceToHost, st));
+  std::vector<double> hp((size_t)3 * kPearsonBlocks * n);
+  MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, st));
   MVS_CHECK_CUDA(cudaStreamSynchronize(st));
-  double sab = 0, saa = 0, sbb = 0;
-  for (int b = 0; b < kPearsonBlocks; ++b) { sab += hp[3 * b]; saa += hp[3 * b + 1]; sbb += hp[3 * b + 2]; }
-  *rho_host = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
+  for (int i = 0; i < n; ++i) {
+    if (n_mask[i] < 2) { rho_host[i] = NAN; continue; }
+    double sab = 0, saa = 0, sbb = 0;
+    const double* q = hp.data() + (size_t)3 * kPearsonBlocks * i;
+    for (int b = 0; b < kPearsonBlocks; ++b) { sab += q[3 * b]; saa += q[3 * b + 1]; sbb += q[3 * b + 2]; }
+    rho_host[i] = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
+  }
   return MVS_OK;
 }

@@ -149,16 +149,24 @@ class PhaseCorrPlan:
         self.launch_count += 1
         return out
 
-    def spearman(self, pair, t):
-        t3 = np.zeros(3, dtype=np.float64)
-        t3[3 - self.ndim :] = np.asarray(t, dtype=np.float64)
-        rho = ctypes.c_double()
+    def spearman_batch(self, pairs, ts, n_mask):
+        """Spearman of im0[mask] vs im1t[mask] for each (pair, t); one sync."""
+        n = len(pairs)
+        cp, ct = self._cand_arrays(pairs, ts)
+        nm = np.ascontiguousarray(n_mask, dtype=np.int64)
+        rho = np.zeros(n, dtype=np.float64)
         _lib.check(
-            self._lib.mvs_pc_spearman(self._h, int(pair), t3.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rho), _lib.current_stream_ptr()),
-            "mvs_pc_spearman",
+            self._lib.mvs_pc_spearman_batch(
+                self._h, n, cp.ctypes.data_as(ctypes.c_void_p), ct.ctypes.data_as(ctypes.c_void_p),
+                nm.ctypes.data_as(ctypes.c_void_p), rho.ctypes.data_as(ctypes.c_void_p), _lib.current_stream_ptr(),
+            ),
+            "mvs_pc_spearman_batch",
         )
-        self.launch_count += 6
-        return rho.value
+        self.launch_count += 10 * n  # keys, 2 x (radix sort ~3 kernels + rank), pearson
+        return rho
+
+    def spearman(self, pair, t, n_mask):
+        return float(self.spearman_batch([pair], [t], [n_mask])[0])
 
     def close(self):
         if getattr(self, "_h", None):
@@ -289,6 +297,7 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
         for j, r in zip(idx, res):
             ssim_out[j] = r
 
+    winners = []  # (pair, candidate index whose ranks are needed)
     for i, pp in enumerate(per_pair):
         if not pp["t"]:
             results[i] = [np.zeros(ndim)]  # registration.py:479-480
@@ -315,16 +324,24 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
         argmax_index = int(np.nanargmax(disamb))
         t = pp["t"][argmax_index]  # same (mis)alignment as the reference when entries were skipped
         src = quality_src[argmax_index]
-        if src is None:
-            quality = -1
-        else:
-            quality = plan.spearman(i, pp["t"][src])
-        res = {"affine_matrix": affine_from_translation(t), "quality": quality}
+        res = {"affine_matrix": affine_from_translation(t), "quality": -1}
+        if src is not None:
+            winners.append((i, src))
         if return_details:
             res["shift_candidates"] = pp["shift_candidates"]
             res["t_candidates"] = pp["t"]
             res["ssim"] = disamb
         results[i] = res
+    if winners:
+        # quality is read only at the argmax (:558-563): rank just those candidates
+        first_pos = np.cumsum([0] + [len(pp["t"]) for pp in per_pair])
+        rho = plan.spearman_batch(
+            [w[0] for w in winners],
+            np.array([per_pair[w[0]]["t"][w[1]] for w in winners], dtype=np.float64),
+            [int(cstats[first_pos[w[0]] + w[1]][0]) for w in winners],
+        )
+        for (i, _), r in zip(winners, rho):
+            results[i]["quality"] = float(r)
     return results
 
 

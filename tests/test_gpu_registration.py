@@ -109,7 +109,7 @@ def test_candidate_stages_match_scipy(reg, name):
                 got_s = plan.candidate_ssim([0], np.array([t]), np.array([[lo, hi]]), [7])[0]
                 assert abs(got_s[0] - ref) < 2e-5, (t, got_s, ref)
                 assert got_s[1] == np.nanmax(im1t[sl])
-            rho = plan.spearman(0, t)
+            rho = plan.spearman(0, t, int(mask.sum()))
             ref_rho = stats.spearmanr(r0[mask], im1t[mask] - 1).correlation
             assert abs(rho - ref_rho) < 1e-9, (t, rho, ref_rho)
     plan.close()
