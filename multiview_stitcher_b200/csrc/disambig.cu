@@ -34,6 +34,7 @@ struct Cand {
   int win;
   int tiles[3];
   long long tile_base;  // first tile index of this candidate in the flat tile list
+  long long mat_off;    // offset of this candidate's materialised im1t[slices]
 };
 
 // scipy's mirrored tap index for mode="constant" splines (ni_interpolation.c)
@@ -145,6 +146,8 @@ cand_stats_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
 // Uniform win^ndim window, sample covariance, K1 = 0.01, K2 = 0.03, data_range 1
 // (images are rescaled to [0,1]); scipy.ndimage.uniform_filter semantics: one
 // pass per axis (z, y, x), float64 line sums, float32 between passes.
+// im1t is materialised once per candidate (slice region only) by
+// materialize_kernel; the tiles then read plain float32 windows.
 
 constexpr int kTX = 32, kTY = 16, kTZ3 = 4, kTY3 = 8;
 constexpr int kMaxWin = 7;
@@ -162,16 +165,31 @@ struct SsimTile {
   static constexpr int PER_THREAD = OUT / 256;
 };
 
+// im1t[slices] of every candidate, packed one after the other (offset mat_off)
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+materialize_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
+                   float* __restrict__ mat) {
+  const Cand c = cands[blockIdx.y];
+  const long long n = (long long)c.len[0] * c.len[1] * c.len[2];
+  float* out = mat + c.mat_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % c.len[2]), y = (int)((i / c.len[2]) % c.len[1]),
+              z = (int)(i / ((long long)c.len[2] * c.len[1]));
+    out[i] = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, c.lo[0] + z, c.lo[1] + y, c.lo[2] + x);
+  }
+}
+
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 ssim_kernel(const Cand* __restrict__ cands, int n_cand, int n0, int n1, int n2,
-            double* __restrict__ tile_sum, float* __restrict__ tile_max) {
+            const float* __restrict__ mat, double* __restrict__ tile_sum,
+            float* __restrict__ tile_max) {
   using T = SsimTile<NDIM>;
   extern __shared__ float ssim_smem[];
-  float* W0 = ssim_smem;
-  float* W1 = W0 + T::WVOL;
-  float* S1 = W1 + T::WVOL;
-  float* S2 = S1 + T::WVOL;
+  float* Q = ssim_smem;                 // 5 quantity windows: a, b, aa, bb, ab
+  float* R = ssim_smem + 5 * T::WVOL;   // 5 filtered windows (ping-pong partner)
   __shared__ double s_red[256];
   __shared__ float s_max[256];
 
@@ -190,8 +208,9 @@ ssim_kernel(const Cand* __restrict__ cands, int n_cand, int n0, int n1, int n2,
   const int ox = tx_i * T::TX, oy = ty_i * T::TY, oz = tz_i * T::TZ;  // output origin in slice
   const int win = c.win;
   const int wz = NDIM == 3 ? T::TZ + win - 1 : 1, wy = T::TY + win - 1, wx = T::TX + win - 1;
+  const float* m1 = mat + c.mat_off;
 
-  // ---- load windows (nan_to_num) and track nanmax of im1t inside the slice ----
+  // ---- load windows (nan_to_num), build the five products, track nanmax(im1t) ----
   float vmax = -INFINITY;
   for (int i = threadIdx.x; i < wz * wy * wx; i += 256) {
     const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
@@ -200,68 +219,71 @@ ssim_kernel(const Cand* __restrict__ cands, int n_cand, int n0, int n1, int n2,
     if (sx < c.len[2] && sy < c.len[1] && sz < c.len[0]) {
       const int gx = c.lo[2] + sx, gy = c.lo[1] + sy, gz = c.lo[0] + sz;
       a = __ldg(c.r0 + ((long long)gz * n1 + gy) * n2 + gx);
-      b = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, gz, gy, gx);
+      b = __ldg(m1 + ((long long)sz * c.len[1] + sy) * c.len[2] + sx);
       if (b == b) vmax = fmaxf(vmax, b); else b = 0.f;
       if (a != a) a = 0.f;
     }
     const int w = (lz * T::WY + ly) * T::WX + lx;
-    W0[w] = a; W1[w] = b;
+    Q[w] = a;
+    Q[T::WVOL + w] = b;
+    Q[2 * T::WVOL + w] = __fmul_rn(a, a);
+    Q[3 * T::WVOL + w] = __fmul_rn(b, b);
+    Q[4 * T::WVOL + w] = __fmul_rn(a, b);
   }
   __syncthreads();
 
-  float U[5][T::PER_THREAD];
   const double dwin = (double)win;
-  for (int q = 0; q < 5; ++q) {
-    for (int i = threadIdx.x; i < wz * wy * wx; i += 256) {
-      const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
-      const int w = (lz * T::WY + ly) * T::WX + lx;
-      const float a = W0[w], b = W1[w];
-      float v;
-      switch (q) {
-        case 0: v = a; break;
-        case 1: v = b; break;
-        case 2: v = __fmul_rn(a, a); break;
-        case 3: v = __fmul_rn(b, b); break;
-        default: v = __fmul_rn(a, b); break;
+  float* src = Q;
+  float* dst = R;
+  if (NDIM == 3) {
+    // z pass: running sums down each (y, x) column of the 5 windows
+    for (int i = threadIdx.x; i < 5 * wy * wx; i += 256) {
+      const int q = i / (wy * wx), r = i - q * (wy * wx);
+      const int ly = r / wx, lx = r - ly * wx;
+      const float* p = src + q * T::WVOL + ly * T::WX + lx;
+      float* o = dst + q * T::WVOL + ly * T::WX + lx;
+      double sum = 0.0;
+      for (int k = 0; k < win; ++k) sum += (double)p[k * T::WY * T::WX];
+      for (int lz = 0; lz < T::TZ; ++lz) {
+        o[lz * T::WY * T::WX] = (float)(sum / dwin);
+        if (lz + 1 < T::TZ)
+          sum += (double)p[(lz + win) * T::WY * T::WX] - (double)p[lz * T::WY * T::WX];
       }
-      S1[w] = v;
     }
     __syncthreads();
-    float* src = S1;
-    float* dst = S2;
-    int cz = wz, cy = wy;
-    if (NDIM == 3) {  // filter along z
-      for (int i = threadIdx.x; i < T::TZ * wy * wx; i += 256) {
-        const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
-        double s = 0.0;
-        for (int k = 0; k < win; ++k) s += (double)src[((lz + k) * T::WY + ly) * T::WX + lx];
-        dst[(lz * T::WY + ly) * T::WX + lx] = (float)(s / dwin);
+    float* tmp = src; src = dst; dst = tmp;
+  }
+  {
+    // y pass: running sums down each column (per plane, per quantity)
+    const int nzp = NDIM == 3 ? T::TZ : 1;
+    for (int i = threadIdx.x; i < 5 * nzp * wx; i += 256) {
+      const int q = i / (nzp * wx), r = i - q * (nzp * wx);
+      const int lz = r / wx, lx = r - lz * wx;
+      const float* p = src + q * T::WVOL + lz * T::WY * T::WX + lx;
+      float* o = dst + q * T::WVOL + lz * T::WY * T::WX + lx;
+      double sum = 0.0;
+      for (int k = 0; k < win; ++k) sum += (double)p[k * T::WX];
+      for (int ly = 0; ly < T::TY; ++ly) {
+        o[ly * T::WX] = (float)(sum / dwin);
+        if (ly + 1 < T::TY) sum += (double)p[(ly + win) * T::WX] - (double)p[ly * T::WX];
       }
-      __syncthreads();
-      float* tmp = src; src = dst; dst = tmp;
-      cz = T::TZ;
-    }
-    // filter along y
-    for (int i = threadIdx.x; i < cz * T::TY * wx; i += 256) {
-      const int lx = i % wx, ly = (i / wx) % T::TY, lz = i / (wx * T::TY);
-      double s = 0.0;
-      for (int k = 0; k < win; ++k) s += (double)src[(lz * T::WY + ly + k) * T::WX + lx];
-      dst[(lz * T::WY + ly) * T::WX + lx] = (float)(s / dwin);
     }
     __syncthreads();
-    { float* tmp = src; src = dst; dst = tmp; }
-    cy = T::TY;
-    (void)cy;
-    // filter along x -> registers
+    float* tmp = src; src = dst; dst = tmp;
+  }
+  // x pass into registers: every thread owns PER_THREAD outputs
+  float U[5][T::PER_THREAD];
 #pragma unroll
-    for (int r = 0; r < T::PER_THREAD; ++r) {
-      const int i = threadIdx.x + r * 256;
-      const int lx = i % T::TX, ly = (i / T::TX) % T::TY, lz = i / (T::TX * T::TY);
-      double s = 0.0;
-      for (int k = 0; k < win; ++k) s += (double)src[(lz * T::WY + ly) * T::WX + lx + k];
-      U[q][r] = (float)(s / dwin);
+  for (int r = 0; r < T::PER_THREAD; ++r) {
+    const int i = threadIdx.x + r * 256;
+    const int lx = i % T::TX, ly = (i / T::TX) % T::TY, lz = i / (T::TX * T::TY);
+    const float* p = src + (lz * T::WY + ly) * T::WX + lx;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      double sum = 0.0;
+      for (int k = 0; k < win; ++k) sum += (double)p[q * T::WVOL + k];
+      U[q][r] = (float)(sum / dwin);
     }
-    __syncthreads();
   }
 
   // ---- SSIM map on this tile's interior outputs ----
@@ -459,24 +481,37 @@ extern "C" int mvs_pc_candidate_ssim(mvs_pc_plan* p, int n_cand, const int32_t* 
     total_tiles += (long long)c.tiles[0] * c.tiles[1] * c.tiles[2];
   }
   MVS_REQUIRE(total_tiles < (1LL << 31), MVS_ERR_UNSUPPORTED, "too many SSIM tiles");
+  long long mat_total = 0;
+  for (int i = 0; i < n_cand; ++i) {
+    cands[i].mat_off = mat_total;
+    mat_total += (long long)cands[i].len[0] * cands[i].len[1] * cands[i].len[2];
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t cbytes = ((sizeof(Cand) * n_cand + 255) / 256) * 256;
   const size_t sbytes = ((sizeof(double) * total_tiles + 255) / 256) * 256;
-  const size_t mbytes = sizeof(float) * total_tiles;
+  const size_t mbytes = ((sizeof(float) * total_tiles + 255) / 256) * 256;
+  const size_t matbytes = sizeof(float) * (size_t)mat_total;
   void* scratch;
-  if ((rc = pc_scratch(p, cbytes + sbytes + mbytes + 256, &scratch))) return rc;
+  if ((rc = pc_scratch(p, cbytes + sbytes + mbytes + matbytes + 256, &scratch))) return rc;
   Cand* d_c = (Cand*)scratch;
   double* d_sum = (double*)((char*)scratch + cbytes);
   float* d_max = (float*)((char*)scratch + cbytes + sbytes);
+  float* d_mat = (float*)((char*)scratch + cbytes + sbytes + mbytes);
   MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data(), sizeof(Cand) * n_cand,
                                  cudaMemcpyHostToDevice, st));
+  {
+    dim3 g(148 * 2, n_cand);
+    if (ndim == 3) materialize_kernel<3><<<g, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], d_mat);
+    else materialize_kernel<2><<<g, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], d_mat);
+    MVS_CHECK_CUDA(cudaGetLastError());
+  }
   if (ndim == 3) {
-    const int smem = (int)(sizeof(float) * 4 * SsimTile<3>::WVOL);
+    const int smem = (int)(sizeof(float) * 10 * SsimTile<3>::WVOL);
     MVS_CHECK_CUDA(cudaFuncSetAttribute(ssim_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ssim_kernel<3><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_sum, d_max);
+    ssim_kernel<3><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_mat, d_sum, d_max);
   } else {
-    const int smem = (int)(sizeof(float) * 4 * SsimTile<2>::WVOL);
-    ssim_kernel<2><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_sum, d_max);
+    const int smem = (int)(sizeof(float) * 10 * SsimTile<2>::WVOL);
+    ssim_kernel<2><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_mat, d_sum, d_max);
   }
   MVS_CHECK_CUDA(cudaGetLastError());
   std::vector<double> hs(total_tiles);

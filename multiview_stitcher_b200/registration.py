@@ -254,7 +254,15 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
     results = [None] * n
     if not cand_t:
         return [[np.zeros(ndim)] for _ in range(n)]  # registration.py:479-480
-    cstats = plan.candidate_stats(cand_pair, np.array(cand_t, dtype=np.float64))
+    # identical (pair, t) candidates (both normalisations often agree) are evaluated
+    # once; the reference evaluates them twice with identical results
+    uniq, umap = {}, []
+    for cp_, ct_ in zip(cand_pair, cand_t):
+        key = (cp_,) + tuple(float(x) for x in ct_)
+        umap.append(uniq.setdefault(key, len(uniq)))
+    ukeys = list(uniq.keys())
+    cstats_u = plan.candidate_stats([k[0] for k in ukeys], np.array([k[1:] for k in ukeys], dtype=np.float64))
+    cstats = cstats_u[np.array(umap)]
 
     # decide which candidates need SSIM (:501-536)
     ssim_req = []  # (flat cand index, slices lo, hi, win)
@@ -287,15 +295,20 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
 
     ssim_out = {}
     if ssim_req:
-        idx = [r[0] for r in ssim_req]
+        first_req = {}
+        for r in ssim_req:
+            first_req.setdefault(umap[r[0]], r)
+        reqs = list(first_req.values())
+        idx = [r[0] for r in reqs]
         res = plan.candidate_ssim(
             [cand_pair[j] for j in idx],
             np.array([cand_t[j] for j in idx], dtype=np.float64),
-            np.array([[r[1], r[2]] for r in ssim_req]),
-            [r[3] for r in ssim_req],
+            np.array([[r[1], r[2]] for r in reqs]),
+            [r[3] for r in reqs],
         )
-        for j, r in zip(idx, res):
-            ssim_out[j] = r
+        by_u = {umap[j]: r for j, r in zip(idx, res)}
+        for r in ssim_req:
+            ssim_out[r[0]] = by_u[umap[r[0]]]
 
     winners = []  # (pair, candidate index whose ranks are needed)
     for i, pp in enumerate(per_pair):
