@@ -39,11 +39,12 @@ __device__ inline float2* stockham_lines(float2* a, float2* b, int m, int mp, in
   for (int Ns = 1; Ns < m;) {
     const int R = (Ns * 4 <= m) ? 4 : 2;
     const int q = m / R;
+    const int qshift = 31 - __clz(q);  // m, q are powers of two
     const int tstep = m / (Ns * R);
     const int total = L * q;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int line = idx / q;
-      const int j = idx - line * q;
+      const int line = idx >> qshift;
+      const int j = idx & (q - 1);
       const int k = j & (Ns - 1);
       const float2* in = a + line * mp;
       float2* out = b + line * mp;

@@ -115,10 +115,10 @@ const AxisFft* get_axis_fft(int n) {
 }
 
 int fft_lines_per_cta(const AxisFft& ax, bool contiguous) {
-  int L = 8192 / ax.m;           // ~64 KB of float2 per buffer at most
+  int L = 2048 / ax.m;           // 32 KB for the two buffers -> several CTAs per SM
   if (L < 1) L = 1;
   if (L > 16) L = 16;
-  if (!contiguous && L < 4 && ax.m <= 2048) L = 4;  // 32-byte runs on strided axes
+  if (!contiguous && L < 4 && ax.m <= 1024) L = 4;  // 32-byte runs on strided axes
   if (!contiguous && L < 2 && ax.m <= 4096) L = 2;
   return L;
 }
