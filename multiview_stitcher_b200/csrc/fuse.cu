@@ -505,8 +505,8 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   const size_t smem = stencil_smem_bytes<NDIM, T>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  // persistent: two CTAs per SM, each walks blocks bid, bid + grid, ...
-  const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * 2);
+  // persistent: 2-3 CTAs per SM, each walks blocks bid, bid + grid, ...
+  const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 3 : 2));
   kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
                                             p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps);
   return cudaGetLastError();

@@ -201,6 +201,45 @@ __device__ __forceinline__ void store_row4_f32(float* p, const float* v, int nva
   }
 }
 
+// Stores the 16 outputs of one consumer thread (one column; 2-D: 16 consecutive
+// rows, 3-D: 2 planes x 8 rows).  Lanes run along x, so every warp store
+// instruction writes one contiguous row segment.  CHECK_NAN: float inputs may
+// carry NaN data (-> 0 like np.nan_to_num); integer inputs cannot.
+template <int NDIM, typename OT, bool CHECK_NAN>
+__device__ __forceinline__ void store_column(OT* __restrict__ p, int64_t sy, int64_t sz, int ylim,
+                                             int zlim, const float* v) {
+  auto conv = [](float x) -> OT {
+    if (CHECK_NAN) x = fix_nan(x);
+    if (sizeof(OT) == 4) return (OT)x;
+    int q = __float2int_rz(x);
+    const int hi = sizeof(OT) == 2 ? 65535 : 255;
+    return (OT)(q < 0 ? 0 : (q > hi ? hi : q));
+  };
+  if (NDIM == 2) {
+    if (ylim >= 16) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { *p = conv(v[k]); p += sy; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { if (k < ylim) *p = conv(v[k]); p += sy; }
+    }
+  } else {
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz) {
+      if (pz < zlim) {
+        OT* q = p + pz * sz;
+        if (ylim >= 8) {
+#pragma unroll
+          for (int y = 0; y < 8; ++y) { *q = conv(v[pz * 8 + y]); q += sy; }
+        } else {
+#pragma unroll
+          for (int y = 0; y < 8; ++y) { if (y < ylim) *q = conv(v[pz * 8 + y]); q += sy; }
+        }
+      }
+    }
+  }
+}
+
 // One pipeline slot: the staged footprint of one (block, view) item plus what the
 // consumer warps need to blend it.
 template <int NDIM, typename T>
@@ -221,11 +260,11 @@ constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 
 template <int NDIM, typename T>
 struct StencilStages {
-  static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 4;
+  static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 3;
 };
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
-__global__ void __launch_bounds__(kStencilThreads, 2)
+__global__ void __launch_bounds__(kStencilThreads, NDIM == 2 ? 3 : 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
@@ -434,6 +473,28 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   const int cg = warp & 3, half = warp >> 2;
   const int jx = cg * 32 + lane;
 
+  // writes this thread's 16 outputs of the block at (x0, y0, z0)
+  auto store_block = [&](const mvs_chunk& ck, int x0, int y0, int z0, const float* v, const float* d) {
+    const int xo = x0 + jx;
+    if (xo >= ck.shape[2]) return;
+    const int64_t sy = ck.stride[1], sz = ck.stride[0];
+    const int zrow0 = NDIM == 3 ? half * 2 : 0, yrow0 = NDIM == 3 ? 0 : half * 16;
+    const int64_t o0 = (int64_t)(z0 + zrow0) * sz + (int64_t)(y0 + yrow0) * sy + (int64_t)xo;
+    const int ylim = ck.shape[1] - y0 - yrow0;
+    const int zlim = NDIM == 3 ? ck.shape[0] - z0 - zrow0 : 1;
+    constexpr bool kNan = sizeof(T) == 4;  // float32 views may hold NaN data
+    if (PARTIAL) {
+      store_column<NDIM, float, false>(ck.acc_num + o0, sy, sz, ylim, zlim, v);
+      store_column<NDIM, float, false>(ck.acc_den + o0, sy, sz, ylim, zlim, d);
+    } else if (ck.out_dtype == MVS_F32) {
+      store_column<NDIM, float, kNan>(reinterpret_cast<float*>(ck.out) + o0, sy, sz, ylim, zlim, v);
+    } else if (ck.out_dtype == MVS_U16) {
+      store_column<NDIM, unsigned short, kNan>(reinterpret_cast<unsigned short*>(ck.out) + o0, sy, sz, ylim, zlim, v);
+    } else {
+      store_column<NDIM, unsigned char, kNan>(reinterpret_cast<unsigned char*>(ck.out) + o0, sy, sz, ylim, zlim, v);
+    }
+  };
+
   float acc[16], den[16];
   unsigned anymask = 0;    // bit k: a valid view was seen for output k
   unsigned multimask = 0;  // bit k: at least two valid views (WAVG: acc is weighted)
@@ -523,8 +584,14 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       // ---- combine ----
       if (lone) {
         // the block's only view (weight positive everywhere): out = v
+        if (!__all_sync(0xffffffffu, vm == 0xffffu)) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = (vm >> k) & 1 ? val[k] : 0.f;
+          for (int k = 0; k < 16; ++k) val[k] = (vm >> k) & 1 ? val[k] : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // slot consumed
+        store_block(ck, x0, y0, z0, val, nullptr);
+        continue;
       } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll
         for (int k = 0; k < 16; ++k)
@@ -604,8 +671,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     if (!(flags & ITEM_LAST)) continue;
 
     // ---- finalise (registers only) ----
-    if ((flags & ITEM_EMPTY) || lone) {
-      // acc already holds the result (zeros for an empty block)
+    if (flags & ITEM_EMPTY) {
+      // acc holds zeros
     } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc[k] = (anymask >> k) & 1 ? acc[k] : 0.f;
@@ -631,43 +698,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       }
     }
 
-    // ---- store: lanes along x -> every warp store instruction writes one
-    // contiguous 128-byte (float32) row segment ----
-    const int xo = x0 + jx;
-    if (xo < sh_x) {
-      const int64_t sy = ck.stride[1], sz = ck.stride[0];
-      const int zrow0 = NDIM == 3 ? half * 2 : 0, yrow0 = NDIM == 3 ? 0 : half * 16;
-      const int64_t o0 = (int64_t)(z0 + zrow0) * sz + (int64_t)(y0 + yrow0) * sy + (int64_t)xo;
-      // rows / planes of this thread that lie inside the chunk
-      const int ylim = sh_y - y0 - yrow0;
-      const int zlim = NDIM == 3 ? sh_z - z0 - zrow0 : 1;
-      auto keep = [&](int k) { return NDIM == 3 ? ((k & 7) < ylim && (k >> 3) < zlim) : k < ylim; };
-      auto off = [&](int k) -> int64_t {
-        return NDIM == 3 ? (int64_t)(k >> 3) * sz + (int64_t)(k & 7) * sy : (int64_t)k * sy;
-      };
-      if (PARTIAL) {
-        float* pn = ck.acc_num + o0;
-        float* pd = ck.acc_den + o0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (keep(k)) { pn[off(k)] = acc[k]; pd[off(k)] = den[k]; }
-      } else if (ck.out_dtype == MVS_F32) {
-        float* po = reinterpret_cast<float*>(ck.out) + o0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (keep(k)) po[off(k)] = fix_nan(acc[k]);
-      } else if (ck.out_dtype == MVS_U16) {
-        unsigned short* po = reinterpret_cast<unsigned short*>(ck.out) + o0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (keep(k)) po[off(k)] = (unsigned short)to_u16(acc[k]);
-      } else {
-        unsigned char* po = reinterpret_cast<unsigned char*>(ck.out) + o0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (keep(k)) po[off(k)] = (unsigned char)to_u8(acc[k]);
-      }
-    }
+    store_block(ck, x0, y0, z0, acc, den);
   }
 }
 
