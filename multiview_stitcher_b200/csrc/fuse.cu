@@ -444,7 +444,7 @@ static bool make_tensor_map(const mvs_view_xform& X, int ndim, CUtensorMap* out)
   const cuuint32_t bw = (cuuint32_t)(128 + 16 / es);
   cuuint64_t gdim[3] = {(cuuint64_t)X.shape[2], (cuuint64_t)X.shape[1], (cuuint64_t)X.shape[0]};
   cuuint64_t gstr[2] = {(cuuint64_t)X.stride[1] * es, (cuuint64_t)X.stride[0] * es};
-  cuuint32_t box[3] = {bw, (cuuint32_t)(ndim == 3 ? 9 : 33), (cuuint32_t)(ndim == 3 ? 5 : 1)};
+  cuuint32_t box[3] = {bw, (cuuint32_t)(ndim == 3 ? 9 : 17), (cuuint32_t)(ndim == 3 ? 5 : 1)};
   cuuint32_t estr[3] = {1, 1, 1};
   // a rank-2 map needs a sane stride even for single-row windows
   if (X.shape[1] == 1) gstr[0] = ((gdim[0] * es + 15) / 16) * 16;
@@ -506,7 +506,7 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // persistent: 2-3 CTAs per SM, each walks blocks bid, bid + grid, ...
-  const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 3 : 2));
+  const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 4 : 2));
   kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
                                             p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps);
   return cudaGetLastError();
@@ -654,7 +654,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
     bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
     if (ok) {
-      const int BX = 128, BY = ndim == 3 ? 8 : 32, BZ = ndim == 3 ? 4 : 1;
+      const int BX = 128, BY = ndim == 3 ? 8 : 16, BZ = ndim == 3 ? 4 : 1;
       const int64_t nb = (int64_t)((ck.shape[2] + BX - 1) / BX) * ((ck.shape[1] + BY - 1) / BY) *
                          ((ck.shape[0] + BZ - 1) / BZ);
       ch_st.push_back(ck);

@@ -40,12 +40,13 @@ struct StencilXform {
 template <int NDIM>
 struct SBlock {
   static constexpr int BX = 128;
-  static constexpr int BY = NDIM == 3 ? 8 : 32;
+  static constexpr int BY = NDIM == 3 ? 8 : 16;
   static constexpr int BZ = NDIM == 3 ? 4 : 1;
   static constexpr int ROWS_Y = BY + 1;
   static constexpr int ROWS_Z = NDIM == 3 ? BZ + 1 : 1;
   static constexpr int NROWS = ROWS_Y * ROWS_Z;
-  static constexpr int OUTS = 16;  // outputs per thread: 4 rows x 4 columns
+  static constexpr int OUTS = NDIM == 3 ? 16 : 8;  // outputs per thread (one column)
+  static constexpr int ROWS2D = 8;                 // 2-D: rows per consumer warp group
   static constexpr int NW = BX + BY + BZ;
 };
 
@@ -216,12 +217,13 @@ __device__ __forceinline__ void store_column(OT* __restrict__ p, int64_t sy, int
     return (OT)(q < 0 ? 0 : (q > hi ? hi : q));
   };
   if (NDIM == 2) {
-    if (ylim >= 16) {
+    constexpr int NR = SBlock<2>::OUTS;
+    if (ylim >= NR) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { *p = conv(v[k]); p += sy; }
+      for (int k = 0; k < NR; ++k) { *p = conv(v[k]); p += sy; }
     } else {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { if (k < ylim) *p = conv(v[k]); p += sy; }
+      for (int k = 0; k < NR; ++k) { if (k < ylim) *p = conv(v[k]); p += sy; }
     }
   } else {
 #pragma unroll
@@ -260,11 +262,11 @@ constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 
 template <int NDIM, typename T>
 struct StencilStages {
-  static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 3;
+  static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 4;
 };
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
-__global__ void __launch_bounds__(kStencilThreads, NDIM == 2 ? 3 : 2)
+__global__ void __launch_bounds__(kStencilThreads, NDIM == 2 ? 4 : 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
@@ -478,7 +480,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     const int xo = x0 + jx;
     if (xo >= ck.shape[2]) return;
     const int64_t sy = ck.stride[1], sz = ck.stride[0];
-    const int zrow0 = NDIM == 3 ? half * 2 : 0, yrow0 = NDIM == 3 ? 0 : half * 16;
+    const int zrow0 = NDIM == 3 ? half * 2 : 0, yrow0 = NDIM == 3 ? 0 : half * B::OUTS;
     const int64_t o0 = (int64_t)(z0 + zrow0) * sz + (int64_t)(y0 + yrow0) * sy + (int64_t)xo;
     const int ylim = ck.shape[1] - y0 - yrow0;
     const int zlim = NDIM == 3 ? ck.shape[0] - z0 - zrow0 : 1;
@@ -495,7 +497,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     }
   };
 
-  float acc[16], den[16];
+  constexpr unsigned kAll = (1u << B::OUTS) - 1u;
+  float acc[B::OUTS], den[B::OUTS];
   unsigned anymask = 0;    // bit k: a valid view was seen for output k
   unsigned multimask = 0;  // bit k: at least two valid views (WAVG: acc is weighted)
 
@@ -512,7 +515,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     if (flags & ITEM_FIRST) {
       anymask = 0; multimask = 0;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { acc[k] = 0.f; den[k] = 0.f; }
+      for (int k = 0; k < B::OUTS; ++k) { acc[k] = 0.f; den[k] = 0.f; }
     }
     const bool lone = (flags & (ITEM_FIRST | ITEM_LAST | ITEM_EMPTY)) == (ITEM_FIRST | ITEM_LAST) &&
                       (MODE != MVS_FUSE_WAVG || (wmode == 0 && !PARTIAL));
@@ -526,8 +529,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         const bool vx = sx >= S.omin[2] && sx <= S.omax[2] && x0 + jx < sh_x;
         const int ya = max(S.omin[1] - y0s, 0), yb = min(S.omax[1] - y0s, sh_y - 1 - y0);
         if (NDIM == 2) {
-          const int ka = max(ya - half * 16, 0), kb = min(yb - half * 16, 15);
-          vm = (vx && kb >= ka) ? ((0xffffu >> (15 - kb)) & (0xffffu << ka)) : 0u;
+          const int ka = max(ya - half * B::OUTS, 0), kb = min(yb - half * B::OUTS, B::OUTS - 1);
+          vm = (vx && kb >= ka) ? ((kAll >> (B::OUTS - 1 - kb)) & (kAll << ka) & kAll) : 0u;
         } else {
           const int ka = max(ya, 0), kb = min(yb, 7);
           const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
@@ -546,12 +549,12 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       const bool dy = S.d1[1] != 0, dz = NDIM == 3 && S.d1[0] != 0;
 
       // ---- interpolate this thread's outputs from shared memory ----
-      float val[16];
+      float val[B::OUTS];
       if (NDIM == 2) {
-        const T* p = sl.stage + (half * 16) * BW;
+        const T* p = sl.stage + (half * B::OUTS) * BW;
         float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < B::OUTS; ++k) {
           p += BW;
           const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
           val[k] = dy ? lerp_s(hprev, hn, ty) : hprev;
@@ -584,9 +587,9 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       // ---- combine ----
       if (lone) {
         // the block's only view (weight positive everywhere): out = v
-        if (!__all_sync(0xffffffffu, vm == 0xffffu)) {
+        if (!__all_sync(0xffffffffu, vm == kAll)) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) val[k] = (vm >> k) & 1 ? val[k] : 0.f;
+          for (int k = 0; k < B::OUTS; ++k) val[k] = (vm >> k) & 1 ? val[k] : 0.f;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);  // slot consumed
@@ -594,13 +597,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         continue;
       } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
+        for (int k = 0; k < B::OUTS; ++k)
           if ((vm >> k) & 1) acc[k] = (anymask >> k) & 1 ? fmaxf(acc[k], val[k]) : val[k];
         anymask |= vm;
       } else if (MODE == MVS_FUSE_MEAN || (flags & ITEM_SIMPLE)) {
         // unit weights: acc = sum of valid values, den = number of valid views
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < B::OUTS; ++k) {
           const bool valid = (vm >> k) & 1;
           acc[k] = __fadd_rn(acc[k], valid ? val[k] : 0.f);
           den[k] = __fadd_rn(den[k], valid ? 1.f : 0.f);
@@ -613,8 +616,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           ixc = max(ix, 0); ix1 = min(ixc + 1, 4);
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int ky = NDIM == 3 ? (k & 7) : half * 16 + k;
+        for (int k = 0; k < B::OUTS; ++k) {
+          const int ky = NDIM == 3 ? (k & 7) : half * B::OUTS + k;
           const int kz = NDIM == 3 ? half * 2 + (k >> 3) : 0;
           const bool valid = (vm >> k) & 1;
           float b = valid ? 1.f : 0.f;
@@ -675,17 +678,17 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       // acc holds zeros
     } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] = (anymask >> k) & 1 ? acc[k] : 0.f;
+      for (int k = 0; k < B::OUTS; ++k) acc[k] = (anymask >> k) & 1 ? acc[k] : 0.f;
     } else if (MODE == MVS_FUSE_MEAN || (flags & ITEM_SIMPLE)) {
       if (!PARTIAL) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
+        for (int k = 0; k < B::OUTS; ++k)
           if (__any_sync(0xffffffffu, den[k] > 1.f))
             acc[k] = den[k] > 1.f ? __fdiv_rn(acc[k], den[k]) : acc[k];
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
+      for (int k = 0; k < B::OUTS; ++k) {
         const bool had = (anymask >> k) & 1, multi = (multimask >> k) & 1;
         if (PARTIAL) {
           acc[k] = !had ? 0.f : (multi ? acc[k] : __fmul_rn(acc[k], den[k]));
