@@ -401,6 +401,7 @@ struct mvs_fuse_plan {
   int64_t total_blocks_st = 0;
   mvs::StencilXform* d_sxf = nullptr;
   CUtensorMap* d_tmaps = nullptr;
+  mvs::BlockRec* d_recs = nullptr;  // per-block schedule of the stencil path
   int stencil_dtype = MVS_F32;
   int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
@@ -508,7 +509,7 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   // persistent: 2-3 CTAs per SM, each walks blocks bid, bid + grid, ...
   const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 4 : 2));
   kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
-                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps);
+                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs);
   return cudaGetLastError();
 }
 
@@ -715,6 +716,20 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   if ((e = upload((void**)&p->d_block_start, bs_gen.data(), sizeof(int64_t) * bs_gen.size())) !=
       cudaSuccess)
     return fail(e, "upload block schedule");
+  // per-block schedule of the stencil path (views touching each block + weight classes)
+  if (p->total_blocks_st > 0) {
+    if ((e = cudaMalloc((void**)&p->d_recs, sizeof(BlockRec) * p->total_blocks_st)) != cudaSuccess)
+      return fail(e, "allocate block schedule");
+    const float* tabs = fusion_mode == MVS_FUSE_WAVG ? p->d_tables : nullptr;
+    const unsigned grid = (unsigned)((p->total_blocks_st + 7) / 8);
+    if (ndim == 3)
+      stencil_classify_kernel<3><<<grid, 256, 0, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
+                                                     p->d_xforms, p->d_sxf, tabs, p->d_recs);
+    else
+      stencil_classify_kernel<2><<<grid, 256, 0, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
+                                                     p->d_xforms, p->d_sxf, tabs, p->d_recs);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "classify launch");
+  }
   // host staging buffers die with this call: make the copies complete
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
   *plan = p;
@@ -756,6 +771,7 @@ extern "C" int mvs_fuse_plan_destroy(mvs_fuse_plan* p) {
   cudaFree(p->d_block_start_st);
   cudaFree(p->d_sxf);
   cudaFree(p->d_tmaps);
+  cudaFree(p->d_recs);
   cudaFree(p->d_xforms);
   cudaFree(p->d_tables);
   cudaFree(p->d_block_start);

@@ -202,6 +202,97 @@ __device__ __forceinline__ void store_row4_f32(float* p, const float* v, int nva
   }
 }
 
+// Per-block schedule record, computed once per plan by stencil_classify_kernel:
+// which of the chunk's views touch the block and how their weights behave there.
+struct BlockRec {
+  int chunk, first;     // chunk index, its first_xform
+  int x0, y0, z0;       // block origin (chunk-local voxels)
+  unsigned active;      // bit per view of the chunk (<= 32 views on this path)
+  unsigned codes_lo, codes_hi;  // 2 bits per view: VIEW_GENERAL / POSITIVE / UNIT
+};
+
+// One warp per output block: cull the chunk's views against the block and
+// classify their blending weights.  8 lanes per view evaluate the (pre-cosine)
+// weight at the corners of block x valid-box, where it is smallest:
+//   min >= 1          -> every weight in the block is exactly 1   (VIEW_UNIT)
+//   min >= POSITIVE_X -> every weight in the block is > 0         (VIEW_POSITIVE)
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+stencil_classify_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
+                        int n_chunks, const mvs_view_xform* __restrict__ xforms,
+                        const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
+                        BlockRec* __restrict__ recs) {
+  using B = SBlock<NDIM>;
+  const int lane = threadIdx.x & 31;
+  const int64_t nblocks = block_start[n_chunks];
+  const int64_t bid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bid >= nblocks) return;
+  int lo = 0, hi = n_chunks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
+  }
+  const mvs_chunk& ck = chunks[lo];
+  const int local = (int)(bid - __ldg(block_start + lo));
+  const int sh_z = ck.shape[0], sh_y = ck.shape[1], sh_x = ck.shape[2];
+  const int nbx = (sh_x + B::BX - 1) / B::BX, nby = (sh_y + B::BY - 1) / B::BY;
+  const int bz = local / (nbx * nby);
+  const int rem = local - bz * (nbx * nby);
+  const int by = rem / nbx;
+  const int x0 = (rem - by * nbx) * B::BX, y0 = by * B::BY, z0 = bz * B::BZ;
+  const int first = ck.first_xform, nxf = ck.n_xforms;
+  const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
+  const int x1s = min(x0 + B::BX, sh_x) - 1 + ck.halo[2];
+  const int y1s = min(y0 + B::BY, sh_y) - 1 + ck.halo[1];
+  const int z1s = min(z0 + B::BZ, sh_z) - 1 + ck.halo[0];
+  unsigned active = 0;
+  unsigned long long codes = 0;
+  for (int base = 0; base < nxf; base += 4) {
+    const int vi = base + (lane >> 3), c = lane & 7;
+    float raw = INFINITY;
+    bool act = false;
+    if (vi < nxf) {
+      const StencilXform& S = sxf[first + vi];
+      act = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
+      if (NDIM == 3) act = act && S.omax[0] >= z0s && S.omin[0] <= z1s;
+      if (act && tables != nullptr) {
+        const int ox = (c & 1) ? min(x1s, S.omax[2]) : max(x0s, S.omin[2]);
+        const int oy = (c & 2) ? min(y1s, S.omax[1]) : max(y0s, S.omin[1]);
+        const int oz = NDIM == 3 ? ((c & 4) ? min(z1s, S.omax[0]) : max(z0s, S.omin[0])) : 0;
+        const double ux = __dadd_rn(__dmul_rn((double)ox, S.wm[2]), S.woff[2]);
+        const double uy = __dadd_rn(__dmul_rn((double)oy, S.wm[1]), S.woff[1]);
+        const double uz = NDIM == 3 ? __dadd_rn(__dmul_rn((double)oz, S.wm[0]), S.woff[0]) : 0.0;
+        raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)xforms[first + vi].table * 125, uz, uy, ux), 0.f);
+      }
+    }
+    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 1));
+    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 2));
+    raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 4));
+    int code = 0;
+    if (act) {
+      code = VIEW_GENERAL;
+      if (tables != nullptr) {
+        if (raw >= 1.0f) code = VIEW_UNIT;
+        else if (raw >= MVS_POSITIVE_X) code = VIEW_POSITIVE;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int cg_ = __shfl_sync(0xffffffffu, code, g * 8);
+      if (base + g < nxf && cg_) {
+        active |= 1u << (base + g);
+        codes |= (unsigned long long)cg_ << (2 * (base + g));
+      }
+    }
+  }
+  if (lane == 0) {
+    BlockRec r;
+    r.chunk = lo; r.first = first; r.x0 = x0; r.y0 = y0; r.z0 = z0;
+    r.active = active; r.codes_lo = (unsigned)codes; r.codes_hi = (unsigned)(codes >> 32);
+    recs[bid] = r;
+  }
+}
+
 // Stores the 16 outputs of one consumer thread (one column; 2-D: 16 consecutive
 // rows, 3-D: 2 planes x 8 rows).  Lanes run along x, so every warp store
 // instruction writes one contiguous row segment.  CHECK_NAN: float inputs may
@@ -270,7 +361,7 @@ __global__ void __launch_bounds__(kStencilThreads, NDIM == 2 ? 4 : 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
-                    const CUtensorMap* __restrict__ tmaps) {
+                    const CUtensorMap* __restrict__ tmaps, const BlockRec* __restrict__ recs) {
   using B = SBlock<NDIM>;
   using Slot = StencilSlot<NDIM, T>;
   constexpr int NS = StencilStages<NDIM, T>::value;
@@ -280,8 +371,6 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Slot* slots = reinterpret_cast<Slot*>(smem_raw);
   __shared__ __align__(8) unsigned long long full_bar[NS], empty_bar[NS];
-  __shared__ StencilXform s_sx[kStencilMaxViews];  // producer's per-chunk cache
-  __shared__ int s_table[kStencilMaxViews];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -299,88 +388,15 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
       return slots[s];
     };
-    int ci = -1;  // current chunk
-    int64_t c_begin = 0, c_end = 0;
-    int sh_z = 0, sh_y = 0, sh_x = 0, nbx = 1, nby = 1, first = 0, nxf = 0, hz = 0, hy = 0, hx = 0;
     // blocks are dealt round-robin to the CTAs: overlap-heavy regions spread evenly
+    const int4* recs4 = reinterpret_cast<const int4*>(recs);
     for (int64_t bid = blockIdx.x; bid < nblocks; bid += gridDim.x) {
-      if (ci < 0 || bid >= c_end) {
-        // (re)locate the chunk and cache its view constants in shared memory
-        int lo = max(ci, 0), hi = n_chunks - 1;
-        while (lo < hi) {
-          int mid = (lo + hi + 1) >> 1;
-          if (__ldg(block_start + mid) <= bid) lo = mid; else hi = mid - 1;
-        }
-        ci = lo;
-        c_begin = __ldg(block_start + ci);
-        c_end = __ldg(block_start + ci + 1);
-        const mvs_chunk& ck = chunks[ci];
-        sh_z = ck.shape[0]; sh_y = ck.shape[1]; sh_x = ck.shape[2];
-        hz = ck.halo[0]; hy = ck.halo[1]; hx = ck.halo[2];
-        nbx = (sh_x + B::BX - 1) / B::BX; nby = (sh_y + B::BY - 1) / B::BY;
-        first = ck.first_xform; nxf = ck.n_xforms;
-        __syncwarp();
-        constexpr int W = (int)(sizeof(StencilXform) / 4);
-        for (int q = lane; q < nxf * W; q += 32)
-          reinterpret_cast<int*>(s_sx)[q] = __ldg(reinterpret_cast<const int*>(sxf + first) + q);
-        for (int q = lane; q < nxf; q += 32) s_table[q] = xforms[first + q].table;
-        __syncwarp();
-      }
-      const int local = (int)(bid - c_begin);
-      const int bz = local / (nbx * nby);
-      const int rem = local - bz * (nbx * nby);
-      const int by = rem / nbx;
-      const int x0 = (rem - by * nbx) * B::BX, y0 = by * B::BY, z0 = bz * B::BZ;
-      const int x0s = x0 + hx, y0s = y0 + hy, z0s = z0 + hz;
-      const int x1s = min(x0 + B::BX, sh_x) - 1 + hx;
-      const int y1s = min(y0 + B::BY, sh_y) - 1 + hy;
-      const int z1s = min(z0 + B::BZ, sh_z) - 1 + hz;
-
-      // ---- cull the chunk's views against this block, classify their weights:
-      // 8 lanes per view evaluate the (pre-cosine) blending weight at the corners
-      // of block x valid-box, where it is smallest:
-      //   min >= 1          -> every weight in the block is exactly 1   (UNIT)
-      //   min >= POSITIVE_X -> every weight in the block is > 0         (POSITIVE)
-      unsigned active = 0;           // bit per view
-      unsigned long long codes = 0;  // 2 bits per view
-      for (int base = 0; base < nxf; base += 4) {
-        const int vi = base + (lane >> 3), c = lane & 7;
-        float raw = INFINITY;
-        bool act = false;
-        if (vi < nxf) {
-          const StencilXform& S = s_sx[vi];
-          act = S.omax[2] >= x0s && S.omin[2] <= x1s && S.omax[1] >= y0s && S.omin[1] <= y1s;
-          if (NDIM == 3) act = act && S.omax[0] >= z0s && S.omin[0] <= z1s;
-          if (act && MODE == MVS_FUSE_WAVG) {
-            const int ox = (c & 1) ? min(x1s, S.omax[2]) : max(x0s, S.omin[2]);
-            const int oy = (c & 2) ? min(y1s, S.omax[1]) : max(y0s, S.omin[1]);
-            const int oz = NDIM == 3 ? ((c & 4) ? min(z1s, S.omax[0]) : max(z0s, S.omin[0])) : 0;
-            const double ux = __dadd_rn(__dmul_rn((double)ox, S.wm[2]), S.woff[2]);
-            const double uy = __dadd_rn(__dmul_rn((double)oy, S.wm[1]), S.woff[1]);
-            const double uz = NDIM == 3 ? __dadd_rn(__dmul_rn((double)oz, S.wm[0]), S.woff[0]) : 0.0;
-            raw = fmaxf(raw_table_value<NDIM>(tables + (int64_t)s_table[vi] * 125, uz, uy, ux), 0.f);
-          }
-        }
-        raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 1));
-        raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 2));
-        raw = fminf(raw, __shfl_xor_sync(0xffffffffu, raw, 4));
-        int code = 0;
-        if (act) {
-          code = VIEW_GENERAL;
-          if (MODE == MVS_FUSE_WAVG) {
-            if (raw >= 1.0f) code = VIEW_UNIT;
-            else if (raw >= MVS_POSITIVE_X) code = VIEW_POSITIVE;
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cg_ = __shfl_sync(0xffffffffu, code, g * 8);
-          if (base + g < nxf && cg_) {
-            active |= 1u << (base + g);
-            codes |= (unsigned long long)cg_ << (2 * (base + g));
-          }
-        }
-      }
+      const int4 ra = __ldg(recs4 + 2 * bid), rb = __ldg(recs4 + 2 * bid + 1);
+      const int ci = ra.x, first = ra.y, x0 = ra.z, y0 = ra.w, z0 = rb.x;
+      const unsigned active = (unsigned)rb.y;
+      const unsigned long long codes = (unsigned long long)(unsigned)rb.z | ((unsigned long long)(unsigned)rb.w << 32);
+      const mvs_chunk& ck = chunks[ci];
+      const int x0s = x0 + ck.halo[2], y0s = y0 + ck.halo[1], z0s = z0 + ck.halo[0];
       const int nact = __popc(active);
       // every active view has unit weights (or the mode needs no weights): the
       // consumers can use plain sums (acc = sum v, den = count)
@@ -404,7 +420,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       for (unsigned rest = active; rest; rest &= rest - 1) {
         const int vi = __ffs(rest) - 1;
         const int code = (int)((codes >> (2 * vi)) & 3);
-        const StencilXform& S = s_sx[vi];
+        const StencilXform& S = sxf[first + vi];
         // weights: 0 = not needed (out = v), 1 = all ones, 2 = table lookup
         int wmode = 0;
         if (MODE == MVS_FUSE_WAVG) {
@@ -437,7 +453,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
             if (!(u < 0.0 || u > 4.0)) { const double f = floor(u); cell = (int)f; fr = (float)(u - f); }
             sl.wi[q] = cell; sl.wt[q] = fr;
           }
-          const float* tab = tables + (int64_t)s_table[vi] * 125;
+          const float* tab = tables + (int64_t)xforms[first + vi].table * 125;
           for (int q = lane; q < (NDIM == 3 ? 125 : 25); q += 32) sl.tab[q] = __ldg(tab + q);
         }
         // TMA needs a 16-byte aligned innermost start coordinate
