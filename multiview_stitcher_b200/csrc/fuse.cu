@@ -402,6 +402,7 @@ struct mvs_fuse_plan {
   mvs::StencilXform* d_sxf = nullptr;
   CUtensorMap* d_tmaps = nullptr;
   mvs::BlockRec* d_recs = nullptr;  // per-block schedule of the stencil path
+  unsigned long long* d_counter = nullptr;  // dynamic block scheduler
   int stencil_dtype = MVS_F32;
   int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
@@ -506,10 +507,11 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   const size_t smem = stencil_smem_bytes<NDIM, T>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
   // persistent: 2-3 CTAs per SM, each walks blocks bid, bid + grid, ...
   const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 4 : 2));
   kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
-                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs);
+                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs, p->d_counter);
   return cudaGetLastError();
 }
 
@@ -720,6 +722,8 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   if (p->total_blocks_st > 0) {
     if ((e = cudaMalloc((void**)&p->d_recs, sizeof(BlockRec) * p->total_blocks_st)) != cudaSuccess)
       return fail(e, "allocate block schedule");
+    if ((e = cudaMalloc((void**)&p->d_counter, sizeof(unsigned long long))) != cudaSuccess)
+      return fail(e, "allocate block counter");
     const float* tabs = fusion_mode == MVS_FUSE_WAVG ? p->d_tables : nullptr;
     const unsigned grid = (unsigned)((p->total_blocks_st + 7) / 8);
     if (ndim == 3)
@@ -772,6 +776,7 @@ extern "C" int mvs_fuse_plan_destroy(mvs_fuse_plan* p) {
   cudaFree(p->d_sxf);
   cudaFree(p->d_tmaps);
   cudaFree(p->d_recs);
+  cudaFree(p->d_counter);
   cudaFree(p->d_xforms);
   cudaFree(p->d_tables);
   cudaFree(p->d_block_start);

@@ -5,8 +5,8 @@
 // of a view is a constant-coefficient 2^ndim-tap stencil on a shifted window:
 //   x_in = o + off,  floor(x_in) = o + floor(off),  frac = off - floor(off).
 //
-// Persistent, warp-specialised kernel.  Output blocks (BZ x BY x 128 voxels) are
-// dealt round-robin to the CTAs:
+// Persistent, warp-specialised kernel.  CTAs pull output blocks (BZ x BY x 128
+// voxels) from a global counter:
 //   * warp 8, the producer, culls the chunk's views against the block,
 //     classifies their blending weights (all ones / all positive / general) from
 //     the weight at the corners of block x valid-box, and pulls each contributing
@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(kStencilThreads, NDIM == 2 ? 4 : 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
-                    const CUtensorMap* __restrict__ tmaps, const BlockRec* __restrict__ recs) {
+                    const CUtensorMap* __restrict__ tmaps, const BlockRec* __restrict__ recs,
+                    unsigned long long* __restrict__ next_block) {
   using B = SBlock<NDIM>;
   using Slot = StencilSlot<NDIM, T>;
   constexpr int NS = StencilStages<NDIM, T>::value;
@@ -388,9 +389,15 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
       return slots[s];
     };
-    // blocks are dealt round-robin to the CTAs: overlap-heavy regions spread evenly
+    // dynamic schedule: every producer pulls the next block from a global counter,
+    // so CTAs stay busy whatever the mix of single- and multi-view blocks, and
+    // concurrently processed blocks are neighbours (halo rows hit in L2)
     const int4* recs4 = reinterpret_cast<const int4*>(recs);
-    for (int64_t bid = blockIdx.x; bid < nblocks; bid += gridDim.x) {
+    for (;;) {
+      unsigned long long nb = 0;
+      if (lane == 0) nb = atomicAdd(next_block, 1ull);
+      const int64_t bid = (int64_t)__shfl_sync(0xffffffffu, nb, 0);
+      if (bid >= nblocks) break;
       const int4 ra = __ldg(recs4 + 2 * bid), rb = __ldg(recs4 + 2 * bid + 1);
       const int ci = ra.x, first = ra.y, x0 = ra.z, y0 = ra.w, z0 = rb.x;
       const unsigned active = (unsigned)rb.y;
