@@ -510,7 +510,7 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   if ((e = cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
   // persistent: 2-3 CTAs per SM, each walks blocks bid, bid + grid, ...
   const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 4 : 2));
-  kern<<<grid, kStencilThreads, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
+  kern<<<grid, SBlock<NDIM>::THREADS, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
                                             p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs, p->d_counter);
   return cudaGetLastError();
 }

@@ -45,8 +45,10 @@ struct SBlock {
   static constexpr int ROWS_Y = BY + 1;
   static constexpr int ROWS_Z = NDIM == 3 ? BZ + 1 : 1;
   static constexpr int NROWS = ROWS_Y * ROWS_Z;
-  static constexpr int OUTS = NDIM == 3 ? 16 : 8;  // outputs per thread (one column)
-  static constexpr int ROWS2D = 8;                 // 2-D: rows per consumer warp group
+  static constexpr int OUTS = 8;  // outputs per thread: one column x 8 rows
+  // consumer warps: 4 column groups x (2 row groups in 2-D | 4 planes in 3-D)
+  static constexpr int CWARPS = NDIM == 3 ? 16 : 8;
+  static constexpr int THREADS = (CWARPS + 1) * 32;
   static constexpr int NW = BX + BY + BZ;
 };
 
@@ -317,18 +319,13 @@ __device__ __forceinline__ void store_column(OT* __restrict__ p, int64_t sy, int
       for (int k = 0; k < NR; ++k) { if (k < ylim) *p = conv(v[k]); p += sy; }
     }
   } else {
+    // 3-D: this thread owns one plane (zlim > 0 checked by the caller) x 8 rows
+    if (ylim >= 8) {
 #pragma unroll
-    for (int pz = 0; pz < 2; ++pz) {
-      if (pz < zlim) {
-        OT* q = p + pz * sz;
-        if (ylim >= 8) {
+      for (int y = 0; y < 8; ++y) { *p = conv(v[y]); p += sy; }
+    } else {
 #pragma unroll
-          for (int y = 0; y < 8; ++y) { *q = conv(v[pz * 8 + y]); q += sy; }
-        } else {
-#pragma unroll
-          for (int y = 0; y < 8; ++y) { if (y < ylim) *q = conv(v[pz * 8 + y]); q += sy; }
-        }
-      }
+      for (int y = 0; y < 8; ++y) { if (y < ylim) *p = conv(v[y]); p += sy; }
     }
   }
 }
@@ -347,17 +344,15 @@ struct alignas(128) StencilSlot {
   int flags, wmode, xoff, pad1;  // xoff: staged column of the block's first tap
 };
 
-constexpr int kStencilConsumerWarps = 8;
-constexpr int kStencilThreads = (kStencilConsumerWarps + 1) * 32;
 constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 
 template <int NDIM, typename T>
 struct StencilStages {
-  static constexpr int value = NDIM == 3 ? (sizeof(T) == 4 ? 3 : 4) : 4;
+  static constexpr int value = NDIM == 3 ? 3 : 4;
 };
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
-__global__ void __launch_bounds__(kStencilThreads, NDIM == 2 ? 4 : 2)
+__global__ void __launch_bounds__(SBlock<NDIM>::THREADS, NDIM == 2 ? 4 : 2)
 fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
@@ -375,13 +370,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kStencilConsumerWarps); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], B::CWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int64_t nblocks = block_start[n_chunks];
 
-  if (warp == kStencilConsumerWarps) {
+  if (warp == B::CWARPS) {
     // =========================== producer warp ===========================
     int it = 0;  // item counter (slot = it % NS)
     auto acquire = [&]() -> Slot& {
@@ -494,7 +489,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   // ============================ consumer warps ============================
   // lanes run along x (conflict-free shared-memory reads for any sub-vector
   // misalignment of the staged box): thread = one column x 16 rows.
-  // 2-D: column (w&3)*32 + lane, rows (w>>2)*16 + k.   3-D: planes (w>>2)*2 + (k>>3), rows k&7.
+  // 2-D: column (w&3)*32 + lane, rows (w>>2)*8 + k.   3-D: plane w>>2, rows k.
   const int cg = warp & 3, half = warp >> 2;
   const int jx = cg * 32 + lane;
 
@@ -503,10 +498,11 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     const int xo = x0 + jx;
     if (xo >= ck.shape[2]) return;
     const int64_t sy = ck.stride[1], sz = ck.stride[0];
-    const int zrow0 = NDIM == 3 ? half * 2 : 0, yrow0 = NDIM == 3 ? 0 : half * B::OUTS;
+    const int zrow0 = NDIM == 3 ? half : 0, yrow0 = NDIM == 3 ? 0 : half * B::OUTS;
     const int64_t o0 = (int64_t)(z0 + zrow0) * sz + (int64_t)(y0 + yrow0) * sy + (int64_t)xo;
     const int ylim = ck.shape[1] - y0 - yrow0;
     const int zlim = NDIM == 3 ? ck.shape[0] - z0 - zrow0 : 1;
+    if (zlim <= 0) return;
     constexpr bool kNan = sizeof(T) == 4;  // float32 views may hold NaN data
     if (PARTIAL) {
       store_column<NDIM, float, false>(ck.acc_num + o0, sy, sz, ylim, zlim, v);
@@ -558,12 +554,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           const int ka = max(ya, 0), kb = min(yb, 7);
           const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
           const int za = max(S.omin[0] - z0s, 0), zb = min(S.omax[0] - z0s, sh_z - 1 - z0);
-          const int p0 = half * 2, p1 = half * 2 + 1;
-          vm = 0u;
-          if (vx) {
-            if (p0 >= za && p0 <= zb) vm |= ym;
-            if (p1 >= za && p1 <= zb) vm |= ym << 8;
-          }
+          vm = (vx && half >= za && half <= zb) ? ym : 0u;
         }
       }
       const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
@@ -584,26 +575,21 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           hprev = hn;
         }
       } else {
-        float gprev[8];
+        // plane `half` and the one above it: 2 x 9 staged rows -> 8 outputs
+        float g0[8];
 #pragma unroll
-        for (int pz = 0; pz < 3; ++pz) {
-          const T* p = sl.stage + ((half * 2 + pz) * B::ROWS_Y) * BW;
-          float g[8];
+        for (int pz = 0; pz < 2; ++pz) {
+          const T* p = sl.stage + ((half + pz) * B::ROWS_Y) * BW;
           float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
           for (int y = 0; y < 8; ++y) {
             p += BW;
             const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
-            g[y] = dy ? lerp_s(hprev, hn, ty) : hprev;
+            const float g = dy ? lerp_s(hprev, hn, ty) : hprev;
+            if (pz == 0) g0[y] = g;
+            else val[y] = dz ? lerp_s(g0[y], g, tz) : g0[y];
             hprev = hn;
           }
-          if (pz > 0) {
-#pragma unroll
-            for (int y = 0; y < 8; ++y)
-              val[(pz - 1) * 8 + y] = dz ? lerp_s(gprev[y], g[y], tz) : gprev[y];
-          }
-#pragma unroll
-          for (int y = 0; y < 8; ++y) gprev[y] = g[y];
         }
       }
 
@@ -640,8 +626,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         }
 #pragma unroll
         for (int k = 0; k < B::OUTS; ++k) {
-          const int ky = NDIM == 3 ? (k & 7) : half * B::OUTS + k;
-          const int kz = NDIM == 3 ? half * 2 + (k >> 3) : 0;
+          const int ky = NDIM == 3 ? k : half * B::OUTS + k;
+          const int kz = NDIM == 3 ? half : 0;
           const bool valid = (vm >> k) & 1;
           float b = valid ? 1.f : 0.f;
           if (wmode == 2) {
