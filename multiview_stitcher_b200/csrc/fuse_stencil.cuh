@@ -618,39 +618,66 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           den[k] = __fadd_rn(den[k], valid ? 1.f : 0.f);
         }
       } else {
-        int ix = 0, ixc = 0, ix1 = 0;
-        float wtx = 0.f;
+        // General weights.  A thread owns one column (and plane): the x (and z)
+        // parts of the multilinear table lookup are constant for its 8 outputs, so
+        // the table is first reduced to the <= 3 y-nodes the block can touch
+        // (A[0..2]); each output then costs one lerp (+ the cosine near borders).
+        int ix = 0, iz = 0, iyA = 0;
+        float A0 = 0.f, A1 = 0.f, A2 = 0.f;
+        bool colin = true;
         if (wmode == 2) {
-          ix = sl.wi[jx]; wtx = sl.wt[jx];
-          ixc = max(ix, 0); ix1 = min(ixc + 1, 4);
+          ix = sl.wi[jx];
+          const float wtx = sl.wt[jx];
+          const int ixc = max(ix, 0), ix1 = min(ixc + 1, 4);
+          const int ky0 = NDIM == 3 ? 0 : half * B::OUTS;
+          iyA = max(sl.wi[B::BX + ky0], 0);
+          const int n0 = min(iyA, 4), n1 = min(iyA + 1, 4), n2 = min(iyA + 2, 4);
+          if (NDIM == 3) {
+            iz = sl.wi[B::BX + B::BY + half];
+            const float wtz = sl.wt[B::BX + B::BY + half];
+            const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
+            const float* p0 = sl.tab + izc * 25;
+            const float* p1 = sl.tab + iz1 * 25;
+            A0 = lerp_s(lerp_s(p0[n0 * 5 + ixc], p0[n0 * 5 + ix1], wtx), lerp_s(p1[n0 * 5 + ixc], p1[n0 * 5 + ix1], wtx), wtz);
+            A1 = lerp_s(lerp_s(p0[n1 * 5 + ixc], p0[n1 * 5 + ix1], wtx), lerp_s(p1[n1 * 5 + ixc], p1[n1 * 5 + ix1], wtx), wtz);
+            A2 = lerp_s(lerp_s(p0[n2 * 5 + ixc], p0[n2 * 5 + ix1], wtx), lerp_s(p1[n2 * 5 + ixc], p1[n2 * 5 + ix1], wtx), wtz);
+          } else {
+            A0 = lerp_s(sl.tab[n0 * 5 + ixc], sl.tab[n0 * 5 + ix1], wtx);
+            A1 = lerp_s(sl.tab[n1 * 5 + ixc], sl.tab[n1 * 5 + ix1], wtx);
+            A2 = lerp_s(sl.tab[n2 * 5 + ixc], sl.tab[n2 * 5 + ix1], wtx);
+          }
+          colin = ix >= 0 && iz >= 0;
         }
 #pragma unroll
         for (int k = 0; k < B::OUTS; ++k) {
           const int ky = NDIM == 3 ? k : half * B::OUTS + k;
-          const int kz = NDIM == 3 ? half : 0;
           const bool valid = (vm >> k) & 1;
           float b = valid ? 1.f : 0.f;
           if (wmode == 2) {
             const int iy = sl.wi[B::BX + ky];
             const float wty = sl.wt[B::BX + ky];
-            const int iyc = max(iy, 0), iy1 = min(iyc + 1, 4);
-            bool inside = ix >= 0 && iy >= 0;
-            float w;
-            if (NDIM == 3) {
-              const int iz = sl.wi[B::BX + B::BY + kz];
-              const float wtz = sl.wt[B::BX + B::BY + kz];
-              const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
-              inside = inside && iz >= 0;
-              const float* p0 = sl.tab + izc * 25;
-              const float* p1 = sl.tab + iz1 * 25;
-              const float a0 = lerp_s(lerp_s(p0[iyc * 5 + ixc], p0[iyc * 5 + ix1], wtx),
-                                      lerp_s(p0[iy1 * 5 + ixc], p0[iy1 * 5 + ix1], wtx), wty);
-              const float a1 = lerp_s(lerp_s(p1[iyc * 5 + ixc], p1[iyc * 5 + ix1], wtx),
-                                      lerp_s(p1[iy1 * 5 + ixc], p1[iy1 * 5 + ix1], wtx), wty);
-              w = lerp_s(a0, a1, wtz);
-            } else {
-              w = lerp_s(lerp_s(sl.tab[iyc * 5 + ixc], sl.tab[iyc * 5 + ix1], wtx),
-                         lerp_s(sl.tab[iy1 * 5 + ixc], sl.tab[iy1 * 5 + ix1], wtx), wty);
+            const int d = max(iy, 0) - iyA;  // 0 or 1 (table cells are wider than a block)
+            const bool inside = colin && iy >= 0;
+            float w = d == 0 ? lerp_s(A0, A1, wty) : lerp_s(A1, A2, wty);
+            if (d > 1 || d < 0) {
+              // tiny views (table cell narrower than the block): full lookup
+              const float wtx = sl.wt[jx];
+              const int ixc = max(ix, 0), ix1 = min(ixc + 1, 4);
+              const int iyc = max(iy, 0), iy1 = min(iyc + 1, 4);
+              if (NDIM == 3) {
+                const float wtz = sl.wt[B::BX + B::BY + half];
+                const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
+                const float* p0 = sl.tab + izc * 25;
+                const float* p1 = sl.tab + iz1 * 25;
+                const float a0 = lerp_s(lerp_s(p0[iyc * 5 + ixc], p0[iyc * 5 + ix1], wtx),
+                                        lerp_s(p1[iyc * 5 + ixc], p1[iyc * 5 + ix1], wtx), wtz);
+                const float a1 = lerp_s(lerp_s(p0[iy1 * 5 + ixc], p0[iy1 * 5 + ix1], wtx),
+                                        lerp_s(p1[iy1 * 5 + ixc], p1[iy1 * 5 + ix1], wtx), wtz);
+                w = lerp_s(a0, a1, wty);
+              } else {
+                w = lerp_s(lerp_s(sl.tab[iyc * 5 + ixc], sl.tab[iyc * 5 + ix1], wtx),
+                           lerp_s(sl.tab[iy1 * 5 + ixc], sl.tab[iy1 * 5 + ix1], wtx), wty);
+              }
             }
             if (__any_sync(0xffffffffu, valid && w < 1.0f)) {
               // weights.py:502-507 cosine ramp (float32), only near view borders
