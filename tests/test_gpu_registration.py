@@ -176,3 +176,26 @@ def test_synthetic_grid_pairs_recover_jitter(reg):
     # moving tile content at stage position is displaced by its jitter difference
     assert np.allclose(res["affine_matrix"][:2, 2], -d, atol=0.11), (res["affine_matrix"][:2, 2], d)
     assert res["quality"] > 0.9
+
+
+def test_synthetic_3d_pair_matches_oracle(reg):
+    """3-D face pair cut from the synthetic ground truth (integer jitter, default
+    upsample_factor 2): engine == oracle within the half-pixel grid."""
+    from multiview_stitcher_b200 import synthetic
+
+    tile, ov = (40, 96, 64), (8, 16, 21)
+    true, stage, idx = synthetic.grid_layout((1, 1, 2), tile, ov, jitter=2, seed=11)
+    tiles = [synthetic.make_tile(tile, o, np.float32, seed=11) for o in true]
+    fixed = tiles[0][:, :, tile[2] - ov[2]:].contiguous()
+    moving = tiles[1][:, :, : ov[2]].contiguous()
+    res = reg.register_pairs([fixed], [moving], return_details=True)[0]
+    ref = oreg.phase_correlation_registration(fixed.cpu().numpy(), moving.cpu().numpy(), return_details=True)
+    assert np.abs(res["affine_matrix"] - ref["affine_matrix"]).max() <= 0.5 + 1e-6, (res["affine_matrix"][:3, 3], ref["affine_matrix"][:3, 3])
+    for a, b in zip(res["shift_candidates"], ref["shift_candidates"]):
+        assert np.abs(np.asarray(a) - np.asarray(b)).max() <= 0.5 + 1e-6
+    d = (true[1] - stage[1].astype(np.int64)) - (true[0] - stage[0].astype(np.int64))
+    # both implementations land within one upsampling bin (0.5 px) of the true jitter
+    assert np.abs(ref["affine_matrix"][:3, 3] + d).max() <= 0.5 + 1e-6
+    assert np.abs(res["affine_matrix"][:3, 3] + d).max() <= 0.5 + 1e-6
+    if np.array_equal(res["affine_matrix"], ref["affine_matrix"]):
+        assert abs(res["quality"] - ref["quality"]) < 1e-9
