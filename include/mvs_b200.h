@@ -114,6 +114,11 @@ int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunks, int n_ch
                          int fusion_mode, void* stream);
 /* Enqueues the fused kernel for every chunk of the plan. */
 int mvs_fuse_plan_run(mvs_fuse_plan* plan, void* stream);
+/* Same for chunks [first_chunk, first_chunk + n_chunks) only (order of
+ * mvs_fuse_plan_create) -- lets a host pipeline fuse a band of chunks as soon
+ * as its tiles have arrived and download it while the next band is fused.
+ * A plan must not be run concurrently on two streams. */
+int mvs_fuse_plan_run_chunks(mvs_fuse_plan* plan, int first_chunk, int n_chunks, void* stream);
 /* Number of kernel launches one mvs_fuse_plan_run issues / blocks scheduled. */
 int mvs_fuse_plan_info(const mvs_fuse_plan* plan, int* launches, int64_t* blocks,
                        int64_t* out_voxels);

@@ -73,6 +73,7 @@ def mvs_dtype(np_dtype) -> int:
 
 _lock = threading.Lock()
 _lib = None
+_device_ok = False
 
 _P = ctypes.c_void_p
 _SIGNATURES = {
@@ -88,6 +89,7 @@ _SIGNATURES = {
         [ctypes.POINTER(_P), _P, ctypes.c_int, _P, ctypes.c_int, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P],
     ),
     "mvs_fuse_plan_run": (ctypes.c_int, [_P, _P]),
+    "mvs_fuse_plan_run_chunks": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "mvs_fuse_plan_info": (
         ctypes.c_int,
         [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)],
@@ -149,7 +151,7 @@ def load(require_device=False):
                     f"({VIEW_XFORM_DTYPE.itemsize}, {CHUNK_DTYPE.itemsize})"
                 )
             _lib = lib
-    if require_device:
+    if require_device and not _device_ok:
         device_info()
     return _lib
 
@@ -170,6 +172,8 @@ def device_info():
     st = lib.mvs_device_info(name, 256, ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr))
     if st != 0:
         raise EngineUnavailable(f"no usable CUDA device: {last_error()}")
+    global _device_ok
+    _device_ok = True
     return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value)}
 
 

@@ -191,13 +191,13 @@ template <int NDIM, int ORDER, int MODE, bool PARTIAL>
 __global__ void __launch_bounds__(kThreads)
 fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
             int n_chunks, const mvs_view_xform* __restrict__ xforms,
-            const float* __restrict__ tables) {
+            const float* __restrict__ tables, int64_t block_begin, int64_t block_end) {
   __shared__ unsigned char s_flag[kMaxXforms];
   __shared__ int s_nact;
   __shared__ int s_single;
 
-  const int64_t bid = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
-  if (bid >= block_start[n_chunks]) return;
+  const int64_t bid = block_begin + (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+  if (bid >= block_end) return;
   int lo = 0, hi = n_chunks - 1;
   while (lo < hi) {
     int mid = (lo + hi + 1) >> 1;
@@ -403,6 +403,11 @@ struct mvs_fuse_plan {
   CUtensorMap* d_tmaps = nullptr;
   mvs::BlockRec* d_recs = nullptr;  // per-block schedule of the stencil path
   unsigned long long* d_counter = nullptr;  // dynamic block scheduler
+  // original chunk order -> position in the two schedules
+  std::vector<int> prefix_st;          // stencil chunks among chunks[0..c)
+  std::vector<int64_t> h_bs_st, h_bs_gen;  // host copies of the block schedules
+  int n_chunks_total = 0;
+  int64_t run_st[2] = {0, 0}, run_gen[2] = {0, 0};  // block ranges of the current run
   int stencil_dtype = MVS_F32;
   int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
@@ -502,7 +507,7 @@ static bool make_stencil(const mvs_view_xform& X, int ndim, int order, int dtype
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
 static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
-  const int64_t nb = p->total_blocks_st;
+  const int64_t nb = p->run_st[1] - p->run_st[0];
   auto kern = fuse_stencil_kernel<NDIM, T, MODE, PARTIAL>;
   const size_t smem = stencil_smem_bytes<NDIM, T>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -511,7 +516,8 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   // persistent: 2-3 CTAs per SM, each walks blocks bid, bid + grid, ...
   const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * (NDIM == 2 ? 4 : 2));
   kern<<<grid, SBlock<NDIM>::THREADS, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
-                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs, p->d_counter);
+                                            p->d_xforms, p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs, p->d_counter,
+                                            p->run_st[0], p->run_st[1]);
   return cudaGetLastError();
 }
 
@@ -539,12 +545,13 @@ static cudaError_t dispatch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
 
 template <int NDIM, int ORDER, int MODE, bool PARTIAL>
 static cudaError_t launch_fuse(const mvs_fuse_plan* p, cudaStream_t st) {
-  const int64_t nb = p->total_blocks;
+  const int64_t nb = p->run_gen[1] - p->run_gen[0];
   const int64_t gx = std::min<int64_t>(nb, 1 << 30);
   const int64_t gy = (nb + gx - 1) / gx;
   dim3 grid((unsigned)gx, (unsigned)gy);
   fuse_kernel<NDIM, ORDER, MODE, PARTIAL><<<grid, kThreads, 0, st>>>(
-      p->d_chunks, p->d_block_start, p->n_chunks, p->d_xforms, p->d_tables);
+      p->d_chunks, p->d_block_start, p->n_chunks, p->d_xforms, p->d_tables, p->run_gen[0],
+      p->run_gen[1]);
   return cudaGetLastError();
 }
 
@@ -652,6 +659,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   }
   std::vector<mvs_chunk> ch_st, ch_gen;
   std::vector<int64_t> bs_st(1, 0), bs_gen(1, 0);
+  std::vector<int> prefix_st(n_chunks + 1, 0);
   for (int c = 0; c < n_chunks; ++c) {
     const mvs_chunk& ck = chunks[c];
     bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
@@ -662,7 +670,9 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
                          ((ck.shape[0] + BZ - 1) / BZ);
       ch_st.push_back(ck);
       bs_st.push_back(bs_st.back() + nb);
+      prefix_st[c + 1] = prefix_st[c] + 1;
     } else {
+      prefix_st[c + 1] = prefix_st[c];
       const int64_t nbx = (ck.shape[2] + kBX - 1) / kBX, nby = (ck.shape[1] + kBY - 1) / kBY;
       ch_gen.push_back(ck);
       bs_gen.push_back(bs_gen.back() + nbx * nby * (int64_t)ck.shape[0]);
@@ -676,6 +686,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   p->ndim = ndim; p->order = order; p->mode = fusion_mode; p->partial = partial;
   p->total_blocks = bs_gen.back(); p->total_blocks_st = bs_st.back();
   p->stencil_dtype = stencil_dtype;
+  p->prefix_st = prefix_st; p->h_bs_st = bs_st; p->h_bs_gen = bs_gen; p->n_chunks_total = n_chunks;
   {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -740,13 +751,22 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   return MVS_OK;
 }
 
-extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
+extern "C" int mvs_fuse_plan_run_chunks(mvs_fuse_plan* p, int first_chunk, int n_chunks,
+                                        void* stream) {
   MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
+  MVS_REQUIRE(first_chunk >= 0 && n_chunks >= 0 && first_chunk + n_chunks <= p->n_chunks_total,
+              MVS_ERR_INVALID, "chunk range [%d, %d) outside the plan's %d chunks", first_chunk,
+              first_chunk + n_chunks, p->n_chunks_total);
+  const int c0 = first_chunk, c1 = first_chunk + n_chunks;
+  const int s0 = p->prefix_st[c0], s1 = p->prefix_st[c1];
+  const int g0 = c0 - s0, g1 = c1 - s1;
+  p->run_st[0] = p->h_bs_st[s0]; p->run_st[1] = p->h_bs_st[s1];
+  p->run_gen[0] = p->h_bs_gen[g0]; p->run_gen[1] = p->h_bs_gen[g1];
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  if (p->total_blocks_st > 0)
+  if (p->run_st[1] > p->run_st[0])
     e = p->ndim == 2 ? dispatch_stencil<2>(p, st) : dispatch_stencil<3>(p, st);
-  if (e == cudaSuccess && p->total_blocks > 0) {
+  if (e == cudaSuccess && p->run_gen[1] > p->run_gen[0]) {
     if (p->ndim == 2)
       e = p->order == 0 ? dispatch_mode<2, 0>(p, st) : dispatch_mode<2, 1>(p, st);
     else
@@ -757,6 +777,11 @@ extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
     return MVS_ERR_CUDA;
   }
   return MVS_OK;
+}
+
+extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
+  MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
+  return mvs_fuse_plan_run_chunks(p, 0, p->n_chunks_total, stream);
 }
 
 extern "C" int mvs_fuse_plan_info(const mvs_fuse_plan* p, int* launches, int64_t* blocks,

@@ -357,7 +357,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
                     int n_chunks, const mvs_view_xform* __restrict__ xforms,
                     const StencilXform* __restrict__ sxf, const float* __restrict__ tables,
                     const CUtensorMap* __restrict__ tmaps, const BlockRec* __restrict__ recs,
-                    unsigned long long* __restrict__ next_block) {
+                    unsigned long long* __restrict__ next_block, int64_t block_begin,
+                    int64_t block_end) {
   using B = SBlock<NDIM>;
   using Slot = StencilSlot<NDIM, T>;
   constexpr int NS = StencilStages<NDIM, T>::value;
@@ -374,7 +375,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int64_t nblocks = block_start[n_chunks];
+  const int64_t nblocks = min(block_end, (int64_t)block_start[n_chunks]);
 
   if (warp == B::CWARPS) {
     // =========================== producer warp ===========================
@@ -391,7 +392,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     for (;;) {
       unsigned long long nb = 0;
       if (lane == 0) nb = atomicAdd(next_block, 1ull);
-      const int64_t bid = (int64_t)__shfl_sync(0xffffffffu, nb, 0);
+      const int64_t bid = block_begin + (int64_t)__shfl_sync(0xffffffffu, nb, 0);
       if (bid >= nblocks) break;
       const int4 ra = __ldg(recs4 + 2 * bid), rb = __ldg(recs4 + 2 * bid + 1);
       const int ci = ra.x, first = ra.y, x0 = ra.z, y0 = ra.w, z0 = rb.x;

@@ -31,6 +31,7 @@ __all__ = [
     "fuse",
     "fuse_np",
     "FusionPlan",
+    "HostFuser",
     "DeviceView",
     "weighted_average_fusion",
     "max_fusion",
@@ -353,6 +354,7 @@ class FusionPlan:
             self.views, self.params, osp, self.chunksize, halo, sample_origin, full_view_bbs,
             spacings, blending_widths, shrink_distance, chunk_subset,
         )
+        self.work = work
         tables, xarr = work["tables"], work["xforms"]
         n_chunks = len(work["chunks"])
         carr = np.zeros(n_chunks, dtype=_lib.CHUNK_DTYPE)
@@ -402,6 +404,31 @@ class FusionPlan:
         """Enqueue the fused kernel on torch's current stream."""
         _lib.check(self._lib.mvs_fuse_plan_run(self._handle, _lib.current_stream_ptr()), "mvs_fuse_plan_run")
         return self.out
+
+    def run_chunks(self, first_chunk, n_chunks):
+        """Enqueue the fused kernel for chunks [first_chunk, first_chunk + n_chunks)."""
+        _lib.check(
+            self._lib.mvs_fuse_plan_run_chunks(self._handle, int(first_chunk), int(n_chunks), _lib.current_stream_ptr()),
+            "mvs_fuse_plan_run_chunks",
+        )
+        return self.out
+
+    def bands(self):
+        """Chunk ranges sharing their start along the slowest axis, with the views
+        each band reads: [(first_chunk, n_chunks, row0, nrows, [view indices])]."""
+        out = []
+        chunks, vidx = self.work["chunks"], self.work["view_index"]
+        i = 0
+        while i < len(chunks):
+            j = i
+            views = set()
+            while j < len(chunks) and chunks[j][0][0] == chunks[i][0][0]:
+                first, count = chunks[j][2], chunks[j][3]
+                views.update(vidx[first : first + count])
+                j += 1
+            out.append((i, j - i, int(chunks[i][0][0]), int(chunks[i][1][0]), sorted(views)))
+            i = j
+        return out
 
     def algorithmic_bytes(self):
         """B_fuse = sum of view bytes + output bytes."""
@@ -488,6 +515,103 @@ def fuse_np(
     return out.cpu().numpy()
 
 
+def _is_host_view(view):
+    import torch
+
+    if isinstance(view, DeviceView):
+        return False
+    data = _view_fields(view)[0]
+    return isinstance(data, np.ndarray) or (isinstance(data, torch.Tensor) and not data.is_cuda)
+
+
+class HostFuser:
+    """Reusable host-to-host fusion of one tile geometry (many time points /
+    channels share it; the reference likewise plans the spatial fusion once per
+    non-spatial coordinate set, fusion/_core.py:1289-1303).
+
+    Construction does the host geometry, allocates the device tiles and builds
+    the plan.  Every call streams the tiles to the GPU on a copy stream, fuses
+    each band of output chunks as soon as the tiles it reads have landed and
+    streams finished bands back to ``out_host`` while the next band is fused.
+    """
+
+    def __init__(self, views, params, output_stack_properties=None, output_spacing=None,
+                 output_stack_mode="union", output_chunksize=None, fusion_func=None,
+                 interpolation_order=1, blending_widths=None):
+        import torch
+
+        self.dviews = []
+        for v in views:
+            data, origin, spacing = _view_fields(v)
+            tdt = data.dtype if isinstance(data, torch.Tensor) else _np_to_torch(np.asarray(data).dtype)
+            _lib.mvs_dtype(_torch_to_np(tdt))
+            self.dviews.append(DeviceView(torch.empty(tuple(data.shape), dtype=tdt, device="cuda"), origin, spacing))
+        bbs = [v.bb() for v in self.dviews]
+        if output_spacing is None:
+            output_spacing = bbs[0]["spacing"]
+        if output_stack_properties is None:
+            output_stack_properties = geometry.union_stack_props(bbs, params, output_spacing, mode=output_stack_mode)
+        self.osp = output_stack_properties
+        self.plan = FusionPlan(self.dviews, params, self.osp, output_chunksize=output_chunksize,
+                               fusion_func=fusion_func, interpolation_order=interpolation_order,
+                               blending_widths=blending_widths)
+        self._bands = self.plan.bands()
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.out_shape = tuple(self.plan.out.shape)
+        self.out_dtype = self.plan.out.dtype
+
+    def __call__(self, views, out_host):
+        """views: host arrays / CPU tensors (ideally pinned) in the constructor's
+        order; out_host: preallocated host array / CPU tensor (ideally pinned)."""
+        import torch
+
+        cur = torch.cuda.current_stream()
+        out_t = out_host if isinstance(out_host, torch.Tensor) else torch.from_numpy(out_host)
+        if tuple(out_t.shape) != self.out_shape or out_t.dtype != self.out_dtype:
+            raise EngineError("out_host must match the fused stack in shape and dtype")
+        if len(views) != len(self.dviews):
+            raise EngineError("number of views differs from the planned geometry")
+        self.h2d.wait_stream(cur)
+        self.h2d.wait_stream(self.d2h)
+        events = []
+        with torch.cuda.stream(self.h2d):
+            for dv, v in zip(self.dviews, views):
+                data = v["data"] if isinstance(v, dict) else (v if isinstance(v, (np.ndarray, torch.Tensor)) else _view_fields(v)[0])
+                src = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data))
+                dv.tensor.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.h2d)
+                events.append(ev)
+        waited = set()
+        for first, n, row0, nrows, vidx in self._bands:
+            for vi in vidx:
+                if vi not in waited:
+                    cur.wait_event(events[vi])
+                    waited.add(vi)
+            self.plan.run_chunks(first, n)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.d2h.wait_event(done)
+            with torch.cuda.stream(self.d2h):
+                out_t[row0 : row0 + nrows].copy_(self.plan.out[row0 : row0 + nrows], non_blocking=True)
+        self.d2h.synchronize()
+        return out_host
+
+    def close(self):
+        self.plan.close()
+
+
+def _fuse_host_pipelined(views, params, osp, output_chunksize, fusion_func, interpolation_order,
+                         blending_widths, out_host):
+    """One-shot host-to-host fusion through a HostFuser."""
+    fuser = HostFuser(views, params, osp, output_chunksize=output_chunksize, fusion_func=fusion_func,
+                      interpolation_order=interpolation_order, blending_widths=blending_widths)
+    try:
+        return fuser(views, out_host)
+    finally:
+        fuser.close()
+
+
 def fuse(
     views,
     params,
@@ -501,6 +625,7 @@ def fuse(
     interpolation_order=1,
     blending_widths=None,
     output_on_backend=False,
+    out_host=None,
 ):
     """Fuse whole in-memory views (host or device) into one stack.
 
@@ -508,7 +633,26 @@ def fuse(
     output spacing defaults to the first view's (:316-325), the stack is the
     union of the transformed views (:1821-1992), chunks default to 2048^2 /
     256^3 (spatial_image_utils.py:21-22).  Returns ``(fused, stack_props)``.
+
+    With host views and a preallocated ``out_host`` (pinned array / CPU tensor of
+    the fused shape and dtype) uploads, fusion and download are pipelined band
+    by band and ``out_host`` is returned.
     """
+    builtin = getattr(fusion_func, "__name__", None) in _MODE_BY_NAME
+    if out_host is not None and weights_func is None and builtin and all(_is_host_view(v) for v in views):
+        host_bbs = []
+        for v in views:
+            data, origin, spacing = _view_fields(v)
+            dims = geometry.spatial_dims(data.ndim)
+            host_bbs.append({"origin": {d: float(origin[d]) for d in dims}, "spacing": {d: float(spacing[d]) for d in dims},
+                             "shape": dict(zip(dims, map(int, data.shape)))})
+        if output_spacing is None:
+            output_spacing = host_bbs[0]["spacing"]
+        if output_stack_properties is None:
+            output_stack_properties = geometry.union_stack_props(host_bbs, params, output_spacing, mode=output_stack_mode)
+        out = _fuse_host_pipelined(views, params, output_stack_properties, output_chunksize, fusion_func,
+                                   interpolation_order, blending_widths, out_host)
+        return out, output_stack_properties
     dviews = [to_device_view(v) for v in views]
     bbs = [v.bb() for v in dviews]
     if output_spacing is None:
