@@ -325,54 +325,75 @@ ssim_kernel(const Cand* __restrict__ cands, int n_cand, int n0, int n1, int n2,
 }
 
 // ---- stage E: Spearman ---------------------------------------------------------
+// Ranks of several pairs are computed with ONE radix sort per image: the key is
+// (pair slot << 32) | order-preserving bits of the float, so every pair occupies
+// its own N-element segment of the sorted array.
+
+__device__ __forceinline__ unsigned sortable_bits(float v) {
+  const unsigned u = __float_as_uint(v + 0.0f);  // -0 -> +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 template <int NDIM>
 __global__ void __launch_bounds__(256)
-spearman_keys_kernel(Cand c, int n0, int n1, int n2, float* __restrict__ ka,
-                     float* __restrict__ kb, unsigned* __restrict__ idx) {
+spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
+                     unsigned long long* __restrict__ ka, unsigned long long* __restrict__ kb,
+                     unsigned* __restrict__ idx) {
+  const int slot = blockIdx.y;
+  const Cand c = cands[slot];
   const long long N = (long long)n0 * n1 * n2;
+  const unsigned long long hi = (unsigned long long)slot << 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
        i += (long long)gridDim.x * blockDim.x) {
     int x = (int)(i % n2), y = (int)((i / n2) % n1), z = (int)(i / ((long long)n1 * n2));
     float b = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, z, y, x);
     float a = __ldg(c.r0 + i);
     const bool m = (a == a) && (b == b);
-    ka[i] = m ? a : INFINITY;
     // the reference ranks `im1t[mask] - 1` in float32 (registration.py:551-553):
     // the subtraction merges values below ~3e-8 into ties, which changes ranks
-    kb[i] = m ? __fsub_rn(b, 1.0f) : INFINITY;
-    idx[i] = (unsigned)i;
+    const long long e = (long long)slot * N + i;
+    ka[e] = hi | (m ? sortable_bits(a) : 0xffffffffu);
+    kb[e] = hi | (m ? sortable_bits(__fsub_rn(b, 1.0f)) : 0xffffffffu);
+    idx[e] = (unsigned)e;
   }
 }
 
-// average ranks (ties share the mean rank, scipy.stats.rankdata "average")
+// average ranks (ties share the mean rank, scipy.stats.rankdata "average") of the
+// first nmask[slot] sorted entries of every segment
 __global__ void __launch_bounds__(256)
-rank_kernel(const float* __restrict__ sorted, const unsigned* __restrict__ sidx, long long n,
-            double* __restrict__ rank_out) {
+rank_kernel(const unsigned long long* __restrict__ sorted, const unsigned* __restrict__ sidx,
+            long long N, const long long* __restrict__ nmask, double* __restrict__ rank_out) {
+  const int slot = blockIdx.y;
+  const long long n = nmask[slot];
+  const unsigned long long* seg = sorted + (long long)slot * N;
+  const unsigned* sid = sidx + (long long)slot * N;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
-    const float v = sorted[j];
-    long long lo = 0, hi = j;  // first index with sorted[idx] == v (>= v)
-    while (lo < hi) { long long mid = (lo + hi) >> 1; if (sorted[mid] < v) lo = mid + 1; else hi = mid; }
+    const unsigned long long v = seg[j];
+    long long lo = 0, hi = j;  // first index with key == v
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] < v) lo = mid + 1; else hi = mid; }
     const long long first = lo;
-    lo = j; hi = n;            // first index with sorted[idx] > v
-    while (lo < hi) { long long mid = (lo + hi) >> 1; if (sorted[mid] <= v) lo = mid + 1; else hi = mid; }
+    lo = j; hi = n;            // first index with key > v
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] <= v) lo = mid + 1; else hi = mid; }
     const long long last = lo;  // exclusive
-    rank_out[sidx[j]] = 0.5 * (double)(first + last - 1) + 1.0;
+    rank_out[sid[j]] = 0.5 * (double)(first + last - 1) + 1.0;
   }
 }
 
-constexpr int kPearsonBlocks = 128;
+constexpr int kPearsonBlocks = 64;
 
 __global__ void __launch_bounds__(256)
-pearson_kernel(const float* __restrict__ ka, const double* __restrict__ ra,
-               const double* __restrict__ rb, long long N, double mean,
-               double* __restrict__ partial /* [block][3] */) {
+pearson_kernel(const unsigned long long* __restrict__ ka, const double* __restrict__ ra,
+               const double* __restrict__ rb, long long N, const long long* __restrict__ nmask,
+               double* __restrict__ partial /* [slot][block][3] */) {
+  const int slot = blockIdx.y;
+  const double mean = 0.5 * (double)(nmask[slot] + 1);
+  const long long base = (long long)slot * N;
   double sab = 0.0, saa = 0.0, sbb = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
        i += (long long)gridDim.x * blockDim.x) {
-    if (ka[i] != INFINITY) {
-      const double a = ra[i] - mean, b = rb[i] - mean;
+    if ((unsigned)(ka[base + i] & 0xffffffffull) != 0xffffffffu) {
+      const double a = ra[base + i] - mean, b = rb[base + i] - mean;
       sab += a * b; saa += a * a; sbb += b * b;
     }
   }
@@ -384,7 +405,10 @@ pearson_kernel(const float* __restrict__ ka, const double* __restrict__ ra,
     if (t < k) { s[0][t] += s[0][t + k]; s[1][t] += s[1][t + k]; s[2][t] += s[2][t + k]; }
     __syncthreads();
   }
-  if (t == 0) { partial[blockIdx.x * 3] = s[0][0]; partial[blockIdx.x * 3 + 1] = s[1][0]; partial[blockIdx.x * 3 + 2] = s[2][0]; }
+  if (t == 0) {
+    double* p = partial + ((long long)slot * gridDim.x + blockIdx.x) * 3;
+    p[0] = s[0][0]; p[1] = s[1][0]; p[2] = s[2][0];
+  }
 }
 
 }  // namespace mvs
@@ -549,54 +573,63 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
   const int ndim = pc_ndim(p);
   const int* sh = pc_shape(p);
   const long long N = (long long)sh[0] * sh[1] * sh[2];
-  MVS_REQUIRE(N < (1LL << 31), MVS_ERR_UNSUPPORTED, "pair volume too large for the rank sort");
+  // sub-batches of B pairs sorted together (<= 2^26 elements)
+  int B = (int)std::max<long long>(1, std::min<long long>(n, (1LL << 26) / N));
+  MVS_REQUIRE((long long)B * N < (1LL << 31), MVS_ERR_UNSUPPORTED, "pair volume too large for the rank sort");
+  const long long E = (long long)B * N;
+  int seg_bits = 1;
+  while ((1 << seg_bits) < B) ++seg_bits;
   size_t temp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const float*)nullptr, (float*)nullptr,
-                                  (const unsigned*)nullptr, (unsigned*)nullptr, (int)N, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned long long*)nullptr,
+                                  (unsigned long long*)nullptr, (const unsigned*)nullptr,
+                                  (unsigned*)nullptr, (int)E, 0, 32 + seg_bits, st);
   auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
-  const size_t fb = al(sizeof(float) * N), ub = al(sizeof(unsigned) * N),
-               db = al(sizeof(double) * N), pb = al(sizeof(double) * 3 * kPearsonBlocks * n);
+  const size_t kbytes = al(sizeof(unsigned long long) * E), ub = al(sizeof(unsigned) * E),
+               db = al(sizeof(double) * E), pb = al(sizeof(double) * 3 * kPearsonBlocks * B),
+               cb = al(sizeof(Cand) * B), nb = al(sizeof(long long) * B);
   void* scratch;
-  if ((rc = pc_scratch(p, 3 * fb + 2 * ub + 2 * db + pb + al(temp_bytes), &scratch))) return rc;
+  if ((rc = pc_scratch(p, 3 * kbytes + 2 * ub + 2 * db + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
   char* w = (char*)scratch;
-  float* ka = (float*)w; w += fb;
-  float* kb = (float*)w; w += fb;
-  float* ks = (float*)w; w += fb;
+  unsigned long long* ka = (unsigned long long*)w; w += kbytes;
+  unsigned long long* kb = (unsigned long long*)w; w += kbytes;
+  unsigned long long* ks = (unsigned long long*)w; w += kbytes;
   unsigned* idx = (unsigned*)w; w += ub;
   unsigned* sidx = (unsigned*)w; w += ub;
   double* ra = (double*)w; w += db;
   double* rb = (double*)w; w += db;
   double* part = (double*)w; w += pb;
+  Cand* d_c = (Cand*)w; w += cb;
+  long long* d_n = (long long*)w; w += nb;
   void* temp = w;
-  const int grid = (int)std::min<long long>((N + 255) / 256, 148 * 8);
-  // pairs run back to back on the stream (shared scratch), one sync at the end
-  for (int i = 0; i < n; ++i) {
-    const long long nm = n_mask[i];
-    if (nm < 2) continue;
-    if (ndim == 3)
-      spearman_keys_kernel<3><<<grid, 256, 0, st>>>(cands[i], sh[0], sh[1], sh[2], ka, kb, idx);
-    else
-      spearman_keys_kernel<2><<<grid, 256, 0, st>>>(cands[i], sh[0], sh[1], sh[2], ka, kb, idx);
+  const int gx = (int)std::min<long long>((N + 255) / 256, 148 * 4);
+  std::vector<double> hp((size_t)3 * kPearsonBlocks * B);
+  std::vector<long long> hn(B);
+  for (int b0 = 0; b0 < n; b0 += B) {
+    const int nb_ = std::min(B, n - b0);
+    for (int i = 0; i < nb_; ++i) hn[i] = n_mask[b0 + i];
+    MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data() + b0, sizeof(Cand) * nb_, cudaMemcpyHostToDevice, st));
+    MVS_CHECK_CUDA(cudaMemcpyAsync(d_n, hn.data(), sizeof(long long) * nb_, cudaMemcpyHostToDevice, st));
+    dim3 grid(gx, nb_);
+    if (ndim == 3) spearman_keys_kernel<3><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], ka, kb, idx);
+    else spearman_keys_kernel<2><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], ka, kb, idx);
     MVS_CHECK_CUDA(cudaGetLastError());
-    // masked-out voxels carry +inf keys and sort to the end: ranks of the first
-    // nm sorted entries are the ranks within the mask
-    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ka, ks, idx, sidx, (int)N, 0, 32, st));
-    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, nm, ra);
-    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, ks, idx, sidx, (int)N, 0, 32, st));
-    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, nm, rb);
-    pearson_kernel<<<kPearsonBlocks, 256, 0, st>>>(ka, ra, rb, N, 0.5 * (double)(nm + 1),
-                                                   part + (size_t)3 * kPearsonBlocks * i);
+    const int items = (int)((long long)nb_ * N);
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ka, ks, idx, sidx, items, 0, 32 + seg_bits, st));
+    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, N, d_n, ra);
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, ks, idx, sidx, items, 0, 32 + seg_bits, st));
+    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, N, d_n, rb);
+    dim3 pg(kPearsonBlocks, nb_);
+    pearson_kernel<<<pg, 256, 0, st>>>(ka, ra, rb, N, d_n, part);
     MVS_CHECK_CUDA(cudaGetLastError());
-  }
-  std::vector<double> hp((size_t)3 * kPearsonBlocks * n);
-  MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, st));
-  MVS_CHECK_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < n; ++i) {
-    if (n_mask[i] < 2) { rho_host[i] = NAN; continue; }
-    double sab = 0, saa = 0, sbb = 0;
-    const double* q = hp.data() + (size_t)3 * kPearsonBlocks * i;
-    for (int b = 0; b < kPearsonBlocks; ++b) { sab += q[3 * b]; saa += q[3 * b + 1]; sbb += q[3 * b + 2]; }
-    rho_host[i] = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
+    MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * 3 * kPearsonBlocks * nb_, cudaMemcpyDeviceToHost, st));
+    MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < nb_; ++i) {
+      if (hn[i] < 2) { rho_host[b0 + i] = NAN; continue; }
+      double sab = 0, saa = 0, sbb = 0;
+      const double* q = hp.data() + (size_t)3 * kPearsonBlocks * i;
+      for (int k = 0; k < kPearsonBlocks; ++k) { sab += q[3 * k]; saa += q[3 * k + 1]; sbb += q[3 * k + 2]; }
+      rho_host[b0 + i] = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
+    }
   }
   return MVS_OK;
 }
