@@ -1,0 +1,230 @@
+// One pass of the separable n-D transform of phase correlation: L lines of one
+// axis per CTA, each line transformed in registers (fft_reg.cuh), with the
+// element-wise neighbours of the reference's pipeline fused into the passes:
+//   * LOAD_REAL  first forward pass packs the two rescaled real crops of a pair
+//                into one complex line (Z = r0 + i r1, NaN -> 0);
+//   * PAIRED     last forward pass: a CTA owns lines q and mirror(q) together, so
+//                the cross-power spectrum  Q_k = s P_k + i P_k / max(|P_k|, 100 eps),
+//                P = F conj(M), F = (Z_k + conj Z_-k)/2, M = (Z_k - conj Z_-k)/(2i)
+//                (skimage phase_cross_correlation, both normalisations packed,
+//                registration.py:416-431) is formed in the epilogue from shared
+//                memory -- Z itself never goes back to HBM;
+//   * ARGMAX     last inverse pass: the correlation surfaces are only needed for
+//                their first maxima, so the pass reduces (|value|, ~index) keys
+//                and stores nothing.
+// The per-thread pieces are __host__ __device__ (tests/csrc/fft_emul.cu runs the
+// same code thread by thread on the CPU).
+#pragma once
+
+#include <cmath>
+
+#include "fft_reg.cuh"
+
+namespace mvs {
+
+struct FftPassArgs {
+  const float2* src;       // complex input (unused with load_real)
+  float2* dst;             // complex output, may equal src; nullptr: nothing stored
+  const float* re;         // load_real: real sources (NaN -> 0)
+  const float* im;
+  long long outer, inner;  // lines = outer * inner; element k of line (o, in) at (o n + k) inner + in
+  long long batch_stride;  // elements between pairs (blockIdx.y)
+  int n;                   // logical transform length
+  int L;                   // lines per CTA
+  int line_stride;         // float2 elements between two line buffers in shared memory
+  int contig;              // thread mapping: 1 = line-major (contiguous axis), 0 = lines fastest
+  int sign;                // -1 forward, +1 inverse (unnormalised)
+  int load_real;
+  int paired;              // cross-power epilogue (forward only, outer == 1, L even)
+  int argmax;              // reduce keys (contiguous axis only)
+  int n2, n1p, items_x, xblocks;  // paired: innermost length, inner / n2, n2/2 + 1, CTAs along x
+  float cp_scale;          // s: keeps |s P| <= 1 next to the unit-modulus normalised spectrum
+  unsigned long long* keys;  // [pair][2]: slot 0 = |Re| (normalization None), 1 = |Im| ("phase")
+  const float2* tw;
+  const float2* chirp;
+  const float2* bhat;
+};
+
+// order-preserving key: larger |v| wins, then the LOWER flat index (numpy argmax)
+MVS_HD unsigned long long fft_key(float v, unsigned idx) {
+  union { float f; unsigned u; } c;
+  c.f = v < 0.f ? -v : v;
+  if (v != v) c.u = 0x7fc00000u;
+  return ((unsigned long long)c.u << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+template <int M, bool BLUE>
+struct PassThread {
+  using Sc = FftSched<M>;
+  static constexpr int E = Sc::E, T = Sc::T;
+  int t, l;
+  bool valid;
+  long long base;   // element k of this thread's line lives at base + k * inner
+  long long flat0;  // argmax: flat index of element 0 of the line within the pair
+  float2 v[E];
+
+  MVS_HD void init(const FftPassArgs& P, int tid, long long bx, long long by) {
+    if (P.contig) { l = tid / T; t = tid - l * T; }
+    else { t = tid / P.L; l = tid - t * P.L; }
+    const long long boff = by * P.batch_stride;
+    if (P.paired) {
+      const int H = P.L >> 1;
+      const long long yb = bx / P.xblocks;
+      const int xb = (int)(bx - yb * P.xblocks);
+      const int half = l / H, i = l - half * H;
+      const int xi = xb * H + i;
+      valid = xi < P.items_x;
+      int x = xi, y = (int)yb;
+      if (half) { x = xi ? P.n2 - xi : 0; y = y ? P.n1p - y : 0; }
+      base = boff + (long long)y * P.n2 + x;
+      flat0 = 0;
+    } else {
+      const long long q = bx * P.L + l;
+      valid = q < P.outer * P.inner;
+      const long long o = q / P.inner, in = q - o * P.inner;
+      base = boff + o * (long long)P.n * P.inner + in;
+      flat0 = o * (long long)P.n * P.inner + in;
+    }
+  }
+
+  MVS_HD void load(const FftPassArgs& P) {
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = t + q * T;
+      float2 x = make_float2(0.f, 0.f);
+      if (valid && k < P.n) {
+        const long long g = base + (long long)k * P.inner;
+        if (P.load_real) {
+          const float a = MVS_LDG(P.re + g), b = MVS_LDG(P.im + g);
+          x = make_float2(a != a ? 0.f : a, b != b ? 0.f : b);
+        } else {
+          x = P.src[g];
+        }
+        if (P.sign > 0) x.y = -x.y;  // inverse = conj(forward(conj(x)))
+        if (BLUE) x = cmul(x, MVS_LDG(P.chirp + k));
+      }
+      v[q] = x;
+    }
+  }
+
+  // Bluestein: between the two power-of-two transforms (registers only)
+  MVS_HD void mid(const FftPassArgs& P) {
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = t + q * T;
+      const float2 y = cmul(v[q], MVS_LDG(P.bhat + k));
+      v[q] = make_float2(y.x, -y.y);  // conj: the second transform runs forward
+    }
+  }
+
+  MVS_HD void post(const FftPassArgs& P) {
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = t + q * T;
+      float2 y = v[q];
+      if (BLUE) {
+        y.y = -y.y;
+        y = (k < P.n) ? cmul(y, MVS_LDG(P.chirp + k)) : make_float2(0.f, 0.f);
+      }
+      if (P.sign > 0) y.y = -y.y;
+      v[q] = y;
+    }
+  }
+
+  // paired epilogue, step 1: publish the line's spectrum
+  MVS_HD void publish(float2* sline) const {
+#pragma unroll
+    for (int q = 0; q < E; ++q) sline[fft_pad(t + q * T)] = v[q];
+  }
+  // step 2: Q_k from Z_k (registers) and Z_-k (the partner line, reversed)
+  MVS_HD void cross_power(const FftPassArgs& P, const float2* partner) {
+    const float tiny = 100.0f * 1.1920929e-07f;  // 100 * eps(float32)
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = t + q * T;
+      if (k < P.n) {
+        const float2 a = v[q];
+        const float2 bm = partner[fft_pad(k ? P.n - k : 0)];
+        const float2 bc = make_float2(bm.x, -bm.y);                   // conj Z_-k
+        const float2 F = make_float2(0.5f * (a.x + bc.x), 0.5f * (a.y + bc.y));
+        const float2 d = make_float2(a.x - bc.x, a.y - bc.y);
+        const float2 Mm = make_float2(0.5f * d.y, -0.5f * d.x);       // d / (2i)
+        const float2 Pw = make_float2(F.x * Mm.x + F.y * Mm.y, F.y * Mm.x - F.x * Mm.y);
+        // |P| = |F| |M| (the squares of P itself could overflow for N ~ 2^31)
+        const float mag = fmaxf(sqrtf(F.x * F.x + F.y * F.y) * sqrtf(Mm.x * Mm.x + Mm.y * Mm.y), tiny);
+        const float2 Pn = make_float2(Pw.x / mag, Pw.y / mag);
+        v[q] = make_float2(P.cp_scale * Pw.x - Pn.y, P.cp_scale * Pw.y + Pn.x);
+      }
+    }
+  }
+
+  MVS_HD void store(const FftPassArgs& P) const {
+    if (!valid || !P.dst) return;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = t + q * T;
+      if (k < P.n) P.dst[base + (long long)k * P.inner] = v[q];
+    }
+  }
+
+  MVS_HD void keys(const FftPassArgs& P, unsigned long long& k0, unsigned long long& k1) const {
+    k0 = 0; k1 = 0;
+    if (!valid) return;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = t + q * T;
+      if (k < P.n) {
+        const unsigned idx = (unsigned)(flat0 + (long long)k * P.inner);
+        const unsigned long long a = fft_key(v[q].x, idx), b = fft_key(v[q].y, idx);
+        k0 = a > k0 ? a : k0;
+        k1 = b > k1 ? b : k1;
+      }
+    }
+  }
+};
+
+#ifdef __CUDACC__
+template <int M, bool BLUE>
+__global__ void __launch_bounds__(512) fft_reg_pass_kernel(const FftPassArgs P) {
+  extern __shared__ float2 fft_smem[];
+  __shared__ unsigned long long s_keys[2][16];
+  PassThread<M, BLUE> th;
+  th.init(P, threadIdx.x, blockIdx.x, blockIdx.y);
+  float2* sline = fft_smem + th.l * P.line_stride;
+  th.load(P);
+  fft_line_reg<M>(th.v, th.t, sline, P.tw);
+  if (BLUE) {
+    th.mid(P);
+    fft_line_reg<M>(th.v, th.t, sline, P.tw);
+  }
+  th.post(P);
+  if (P.paired) {
+    __syncthreads();
+    th.publish(sline);
+    __syncthreads();
+    const int lp = th.l + (th.l < (P.L >> 1) ? (P.L >> 1) : -(P.L >> 1));
+    th.cross_power(P, fft_smem + lp * P.line_stride);
+  }
+  th.store(P);
+  if (P.argmax) {
+    unsigned long long k0, k1;
+    th.keys(P, k0, k1);
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, k0, o);
+      const unsigned long long b = __shfl_xor_sync(0xffffffffu, k1, o);
+      k0 = a > k0 ? a : k0;
+      k1 = b > k1 ? b : k1;
+    }
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) { s_keys[0][w] = k0; s_keys[1][w] = k1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      unsigned long long m = 0;
+      for (int i = 0; i < nw; ++i) m = s_keys[threadIdx.x][i] > m ? s_keys[threadIdx.x][i] : m;
+      if (m) atomicMax(P.keys + 2 * blockIdx.y + threadIdx.x, m);
+    }
+  }
+}
+#endif
+
+}  // namespace mvs

@@ -8,14 +8,23 @@
 //   Z        = FFT_nd(nan_to_num(r0) + i * nan_to_num(r1))             packed:
 //              F = (Z_k + conj Z_-k)/2,  M = (Z_k - conj Z_-k)/(2i)
 //   P        = F * conj(M);  Pn = P / max(|P|, 100 eps)                 cross power
-//   Q        = P + i * Pn;   cc = IFFT_nd(Q):  Re = cc(None), Im = cc("phase")
+//   Q        = s P + i * Pn;  cc = IFFT_nd(Q):  Re = cc(None), Im = cc("phase")
 //              (P, Pn are Hermitian, so both correlation surfaces are real and
-//               ONE complex inverse transform yields both)
+//               ONE complex inverse transform yields both; s = 1/N^2 keeps
+//               |s P| <= 1 so that neither half drowns in the other's rounding)
 //   peaks    = first argmax of |Re cc|, |Im cc|
 //   C        = conj(upsampled_dft(conj(P or Pn))) on ceil(1.5 u)^ndim samples
-//              around each peak (float64 accumulation)
-// HBM traffic: ndim forward + ndim inverse passes of 8N+8N bytes plus the
-// cross-power pass -- the (32 ndim + 8) N "pass model" of SURVEY.md 8d.
+//              around each peak (float64 accumulation), P / Pn recovered from Q:
+//              s P_k = (Q_k + conj Q_-k)/2,  Pn_k = (Q_k - conj Q_-k)/(2i)
+// Passes over HBM (fft_pass.cuh), N complex voxels of 8 bytes per pair:
+//   forward x   reads r0, r1 (8N)  writes Z (8N)
+//   forward y   [3-D] in place (16N)
+//   forward y/z + cross power: reads Z (8N) writes Q (8N)   -- Z's last axis and the
+//               cross-power spectrum in one kernel (mirror lines paired per CTA)
+//   inverse     first axis Q -> W (16N), [3-D] middle axis in place (16N)
+//   inverse x + argmax: reads W (8N), stores nothing
+// i.e. (32 ndim - 8) N bytes against the (32 ndim + 8) N "pass model" of
+// SURVEY.md 8d that the roofline figure is quoted on.
 
 #include <climits>
 #include <cmath>
@@ -24,7 +33,8 @@
 #include <mutex>
 #include <vector>
 
-#include "fft.cuh"
+#include "common.cuh"
+#include "fft_pass.cuh"
 
 namespace mvs {
 
@@ -68,8 +78,8 @@ const AxisFft* get_axis_fft(int n) {
   ax.n = n;
   if (is_pow2(n)) { ax.m = n; ax.bluestein = 0; }
   else { int m = 1; while (m < 2 * n - 1) m <<= 1; ax.m = m; ax.bluestein = 1; }
-  if (ax.m > 16384) {
-    set_error("axis length %d needs a %d-point shared-memory FFT (max 16384)", n, ax.m);
+  if (ax.m > 8192) {
+    set_error("axis length %d needs a %d-point FFT (max 8192)", n, ax.m);
     return nullptr;
   }
   const int m = ax.m;
@@ -114,78 +124,32 @@ const AxisFft* get_axis_fft(int n) {
   return p;
 }
 
-int fft_lines_per_cta(const AxisFft& ax, bool contiguous) {
-  int L = 2048 / ax.m;           // 32 KB for the two buffers -> several CTAs per SM
-  if (L < 1) L = 1;
-  if (L > 16) L = 16;
-  if (!contiguous && L < 4 && ax.m <= 1024) L = 4;  // 32-byte runs on strided axes
-  if (!contiguous && L < 2 && ax.m <= 4096) L = 2;
-  return L;
-}
+// lines per CTA / shared-memory geometry of one pass (fft_pass.cuh)
+struct PassGeom { int L, line_stride, threads; size_t smem; };
 
-size_t fft_smem_bytes(const AxisFft& ax, int L, int* mp_out) {
-  int pad = L > 1 ? (16 / L > 0 ? 16 / L : 1) : 0;
-  int mp = ax.m + pad;
-  if (mp_out) *mp_out = mp;
-  return sizeof(float2) * 2 * (size_t)L * mp;
-}
-
-// ---------------------------------------------------------------------------
-// FFT pass kernel
-// ---------------------------------------------------------------------------
-
-struct FftPass {
-  float2* data;        // complex volume(s), in place
-  const float* re;     // LOAD_REAL: real sources (NaN -> 0)
-  const float* im;
-  long long outer, inner;  // lines = outer * inner; element k at o*n*inner + in + k*inner
-  long long batch_stride;  // elements between pairs
-  int n, L, mp;
-  AxisFft ax;
-};
-
-template <bool LOAD_REAL, int SIGN>
-__global__ void __launch_bounds__(256) fft_pass_kernel(FftPass P) {
-  extern __shared__ float2 smem[];
-  const int L = P.L, n = P.n, m = P.ax.m, mp = P.mp;
-  float2* a = smem;
-  float2* b = smem + (size_t)L * mp;
-  const long long nlines = P.outer * P.inner;
-  const long long line0 = (long long)blockIdx.x * L;
-  const long long boff = (long long)blockIdx.y * P.batch_stride;
-  const bool contiguous = (P.inner == 1);
-
-  for (int idx = threadIdx.x; idx < L * m; idx += blockDim.x) {
-    int line, k;
-    if (contiguous) { line = idx / m; k = idx - line * m; }
-    else { k = idx / L; line = idx - k * L; }
-    float2 v = make_float2(0.f, 0.f);
-    const long long q = line0 + line;
-    if (k < n && q < nlines) {
-      const long long o = q / P.inner, in = q - o * P.inner;
-      const long long g = boff + o * (long long)n * P.inner + in + (long long)k * P.inner;
-      if (LOAD_REAL) {
-        float x = __ldg(P.re + g), y = __ldg(P.im + g);
-        v = make_float2(x != x ? 0.f : x, y != y ? 0.f : y);
-      } else {
-        v = P.data[g];
-      }
-    }
-    a[line * mp + k] = v;
+static PassGeom pass_geom(int m, bool contiguous, bool paired, long long nlines) {
+  const int E = m < 16 ? m : 16, T = m / E;
+  int L;
+  if (contiguous) {
+    L = T >= 256 ? 1 : 256 / T;  // ~256 threads per CTA
+  } else {
+    // runs of >= 32 bytes along the fastest axis
+    L = T <= 32 ? 256 / T : (T <= 64 ? 8 : (T <= 128 ? 4 : (T <= 256 ? 2 : 1)));
   }
-  __syncthreads();
-  float2* res = fft_lines(a, b, P.ax, mp, L, SIGN);
-  for (int idx = threadIdx.x; idx < L * n; idx += blockDim.x) {
-    int line, k;
-    if (contiguous) { line = idx / n; k = idx - line * n; }
-    else { k = idx / L; line = idx - k * L; }
-    const long long q = line0 + line;
-    if (q < nlines) {
-      const long long o = q / P.inner, in = q - o * P.inner;
-      const long long g = boff + o * (long long)n * P.inner + in + (long long)k * P.inner;
-      P.data[g] = res[line * mp + k];
-    }
-  }
+  if (L > 32) L = 32;
+  while (L > 1 && (long long)(L / 2) >= nlines) L >>= 1;  // few lines: smaller CTAs
+  if (paired && L < 2) L = 2;
+  while (L * T < 32) L <<= 1;  // whole warps
+  PassGeom g;
+  g.L = L;
+  const int padm = m + (m >> 4);
+  // skew successive line buffers so that the "lines fastest" thread mapping spreads
+  // a half-warp over all banks
+  const int skew = contiguous ? (T < 16 ? T : 0) : (L <= 16 ? 16 / L : 1);
+  g.line_stride = padm + skew;
+  g.threads = L * T;
+  g.smem = sizeof(float2) * (size_t)L * g.line_stride;
+  return g;
 }
 
 // ---------------------------------------------------------------------------
@@ -256,68 +220,23 @@ rescale_kernel(const float* const* __restrict__ imgs, const float* __restrict__ 
   }
 }
 
-// Q_k = P_k + i Pn_k from the packed spectrum Z (see file header).
-__global__ void __launch_bounds__(256)
-cross_power_kernel(const float2* __restrict__ Z, float2* __restrict__ Q, int n0, int n1, int n2,
-                   long long N) {
-  const float2* z = Z + (long long)blockIdx.y * N;
-  float2* q = Q + (long long)blockIdx.y * N;
-  const float tiny = 100.0f * 1.1920929e-07f;  // 100 * eps(float32)
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(i % n2), y = (int)((i / n2) % n1), zz = (int)(i / ((long long)n1 * n2));
-    int mx = x ? n2 - x : 0, my = y ? n1 - y : 0, mz = zz ? n0 - zz : 0;
-    float2 a = z[i];
-    float2 bm = z[((long long)mz * n1 + my) * n2 + mx];
-    float2 bc = make_float2(bm.x, -bm.y);                     // conj Z_-k
-    float2 F = make_float2(0.5f * (a.x + bc.x), 0.5f * (a.y + bc.y));
-    float2 d = make_float2(a.x - bc.x, a.y - bc.y);
-    float2 M = make_float2(0.5f * d.y, -0.5f * d.x);          // d / (2i)
-    float2 P = make_float2(F.x * M.x + F.y * M.y, F.y * M.x - F.x * M.y);  // F conj(M)
-    float mag = fmaxf(hypotf(P.x, P.y), tiny);
-    float2 Pn = make_float2(__fdiv_rn(P.x, mag), __fdiv_rn(P.y, mag));
-    q[i] = make_float2(P.x - Pn.y, P.y + Pn.x);
-  }
-}
-
-// first argmax of |Re| (slot 0: normalization None) and |Im| (slot 1: "phase")
-__global__ void __launch_bounds__(256)
-argmax_kernel(const float2* __restrict__ Q, long long N, unsigned long long* __restrict__ keys) {
-  const float2* q = Q + (long long)blockIdx.y * N;
-  unsigned long long k0 = 0, k1 = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (long long)gridDim.x * blockDim.x) {
-    float2 v = q[i];
-    unsigned long long lowbits = 0xffffffffull - (unsigned long long)i;
-    unsigned long long a = ((unsigned long long)__float_as_uint(fabsf(v.x)) << 32) | lowbits;
-    unsigned long long b = ((unsigned long long)__float_as_uint(fabsf(v.y)) << 32) | lowbits;
-    k0 = a > k0 ? a : k0;
-    k1 = b > k1 ? b : k1;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long a = __shfl_xor_sync(0xffffffffu, k0, o);
-    unsigned long long b = __shfl_xor_sync(0xffffffffu, k1, o);
-    k0 = a > k0 ? a : k0;
-    k1 = b > k1 ? b : k1;
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMax(keys + 2 * blockIdx.y + 0, k0);
-    atomicMax(keys + 2 * blockIdx.y + 1, k1);
-  }
-}
-
 // ---------------------------------------------------------------------------
 // upsampled DFT around the integer peaks
 // ---------------------------------------------------------------------------
+// cc'[a..] = sum_k P_k prod_d exp(+2 pi i (a_d - off_d) ks_d(k_d) / (n_d u)),
+// off_d = fix(R/2) - shift_d u, ks = numpy.fft.fftfreq ordering, a_d < R.
+// Along x the kernel factor splits into a peak-dependent ramp H[k] (folded into
+// the spectrum) and the peak-independent geometric sequence g[k]^a, so the x
+// contraction needs no table lookups: acc[a] += w; w *= g.
 
 // Decodes the peaks, applies skimage's wrap (shift > fix(n/2) -> shift - n) and
-// fills E[pair][norm][d][a][k] = exp(+2 pi i (a - off_d) ks(k) / (n_d u)),
-// off_d = fix(R/2) - shift_d * u,  ks = numpy.fft.fftfreq ordering.
+// fills, per (pair, norm): H_x[n2], E_y[R][n1], E_z[R][n0]; block 0 also fills
+// g[n2] = exp(+2 pi i ks / (n2 u)).
 __global__ void __launch_bounds__(256)
 updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, int n2,
                    int ndim, int R, int u, int* __restrict__ peaks /* [pair][2][3] */,
                    float2* __restrict__ E, long long e_stride /* per (pair,norm) */,
-                   int e_off1, int e_off2) {
+                   int e_off1, int e_off0, float2* __restrict__ G) {
   const int pn = blockIdx.x;  // pair*2 + norm
   const unsigned long long key = keys[pn];
   const long long idx = (long long)(0xffffffffull - (key & 0xffffffffull));
@@ -327,94 +246,120 @@ updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, 
   int sh[3];
   for (int d = 0; d < 3; ++d) sh[d] = p[d] > nn[d] / 2 ? p[d] - nn[d] : p[d];
   if (threadIdx.x < 3) peaks[pn * 3 + threadIdx.x] = sh[threadIdx.x];
-  const int eoff[3] = {0, e_off1, e_off2};
-  for (int d = 3 - ndim; d < 3; ++d) {
+  float2* e = E + (long long)pn * e_stride;
+  {
+    const double off = (double)(R / 2) - (double)sh[2] * u;
+    for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+      const int ks = (k <= (n2 - 1) / 2) ? k : k - n2;
+      double s, c;
+      sincospi(-2.0 * off * (double)ks / ((double)n2 * (double)u), &s, &c);
+      e[k] = make_float2((float)c, (float)s);
+      if (pn == 0) {
+        sincospi(2.0 * (double)ks / ((double)n2 * (double)u), &s, &c);
+        G[k] = make_float2((float)c, (float)s);
+      }
+    }
+  }
+  const int eoff[2] = {e_off0, e_off1};
+  for (int d = 3 - ndim; d < 2; ++d) {
     const int n = nn[d];
     const double off = (double)(R / 2) - (double)sh[d] * u;
-    float2* e = E + (long long)pn * e_stride + eoff[d];
+    float2* ed = e + eoff[d];
     for (int i = threadIdx.x; i < R * n; i += blockDim.x) {
       const int a = i / n, k = i - a * n;
       const int ks = (k <= (n - 1) / 2) ? k : k - n;
       double s, c;
       sincospi(2.0 * ((double)a - off) * (double)ks / ((double)n * (double)u), &s, &c);
-      e[i] = make_float2((float)c, (float)s);
+      ed[i] = make_float2((float)c, (float)s);
     }
   }
 }
 
-// Contract the x axis: T[pn][line][b] = sum_x Pnorm[line, x] * Ex[b][x],
-// one warp per line, float partials per lane, float64 across lanes.
+// Contract the x axis for both normalisations: T[pn][line][a] = sum_x P_pn[line, x] H_pn[x] g[x]^a.
+// One warp per line; float partials per lane, combined in float64 in lane order.
+constexpr int kUpWarps = 4;
+
 template <int R>
-__global__ void __launch_bounds__(256)
-updft_x_kernel(const float2* __restrict__ Z, int n0, int n1, int n2, long long N,
-               const float2* __restrict__ E, long long e_stride, int e_off2,
+__global__ void __launch_bounds__(kUpWarps * 32)
+updft_x_kernel(const float2* __restrict__ Q, int n0, int n1, int n2, long long N,
+               const float2* __restrict__ E, long long e_stride, const float2* __restrict__ G,
                double2* __restrict__ T) {
-  const int pair = blockIdx.y, norm = blockIdx.z;
-  const int pn = pair * 2 + norm;
+  __shared__ float2 s_part[kUpWarps][2 * R][33];
+  const int pair = blockIdx.y;
   const long long nlines = (long long)n0 * n1;
-  const long long line = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (line >= nlines) return;
-  const int lane = threadIdx.x & 31;
-  const int y = (int)(line % n1), zz = (int)(line / n1);
-  const int my = y ? n1 - y : 0, mz = zz ? n0 - zz : 0;
-  const float2* z = Z + (long long)pair * N;
-  const float2* row = z + line * n2;
-  const float2* mrow = z + ((long long)mz * n1 + my) * n2;
-  const float2* ex = E + (long long)pn * e_stride + e_off2;
-  const float tiny = 100.0f * 1.1920929e-07f;
-  float2 acc[R];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long line = (long long)blockIdx.x * kUpWarps + warp;
+  if (line < nlines) {
+    const int y = (int)(line % n1), zz = (int)(line / n1);
+    const int my = y ? n1 - y : 0, mz = zz ? n0 - zz : 0;
+    const float2* q = Q + (long long)pair * N;
+    const float2* row = q + line * n2;
+    const float2* mrow = q + ((long long)mz * n1 + my) * n2;
+    const float2* h0 = E + (long long)(2 * pair) * e_stride;
+    const float2* h1 = h0 + e_stride;
+    float2 acc0[R], acc1[R];
 #pragma unroll
-  for (int b = 0; b < R; ++b) acc[b] = make_float2(0.f, 0.f);
-  for (int x = lane; x < n2; x += 32) {
-    const int mx = x ? n2 - x : 0;
-    float2 a = row[x], bm = mrow[mx];
-    float2 bc = make_float2(bm.x, -bm.y);
-    float2 F = make_float2(0.5f * (a.x + bc.x), 0.5f * (a.y + bc.y));
-    float2 d = make_float2(a.x - bc.x, a.y - bc.y);
-    float2 M = make_float2(0.5f * d.y, -0.5f * d.x);
-    float2 P = make_float2(F.x * M.x + F.y * M.y, F.y * M.x - F.x * M.y);
-    if (norm == 1) {
-      float mag = fmaxf(hypotf(P.x, P.y), tiny);
-      P = make_float2(__fdiv_rn(P.x, mag), __fdiv_rn(P.y, mag));
+    for (int a = 0; a < R; ++a) { acc0[a] = make_float2(0.f, 0.f); acc1[a] = make_float2(0.f, 0.f); }
+    for (int x = lane; x < n2; x += 32) {
+      const int mx = x ? n2 - x : 0;
+      const float2 a = row[x], bm = mrow[mx];
+      // s P = (Q_k + conj Q_-k)/2, Pn = (Q_k - conj Q_-k)/(2i)
+      const float2 Ps = make_float2(0.5f * (a.x + bm.x), 0.5f * (a.y - bm.y));
+      const float2 Pn = make_float2(0.5f * (a.y + bm.y), -0.5f * (a.x - bm.x));
+      const float2 g = __ldg(G + x);
+      float2 w0 = cmul(Ps, __ldg(h0 + x));
+      float2 w1 = cmul(Pn, __ldg(h1 + x));
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        acc0[b] = cadd(acc0[b], w0);
+        acc1[b] = cadd(acc1[b], w1);
+        w0 = cmul(w0, g);
+        w1 = cmul(w1, g);
+      }
     }
 #pragma unroll
-    for (int b = 0; b < R; ++b) {
-      float2 e = __ldg(ex + b * n2 + x);
-      acc[b].x += P.x * e.x - P.y * e.y;
-      acc[b].y += P.x * e.y + P.y * e.x;
-    }
+    for (int b = 0; b < R; ++b) { s_part[warp][b][lane] = acc0[b]; s_part[warp][R + b][lane] = acc1[b]; }
   }
-#pragma unroll
-  for (int b = 0; b < R; ++b) {
-    double re = acc[b].x, im = acc[b].y;
-    for (int o = 16; o > 0; o >>= 1) {
-      re += __shfl_xor_sync(0xffffffffu, re, o);
-      im += __shfl_xor_sync(0xffffffffu, im, o);
+  __syncwarp();
+  if (line < nlines) {
+    for (int o = lane; o < 2 * R; o += 32) {
+      double re = 0.0, im = 0.0;
+      for (int i = 0; i < 32; ++i) { const float2 v = s_part[warp][o][i]; re += v.x; im += v.y; }
+      const int norm = o / R, b = o - norm * R;
+      T[((long long)(2 * pair + norm) * nlines + line) * R + b] = make_double2(re, im);
     }
-    if (lane == 0) T[((long long)pn * nlines + line) * R + b] = make_double2(re, im);
   }
 }
 
-// Contract one more axis: out[pn][o][a][r] = sum_k E[a][k] * in[pn][o][k][r]
-// (one thread per output, serial float64 sum -> deterministic).
-__global__ void __launch_bounds__(128)
+// Contract one more axis: out[pn][o][a][r] = sum_k E[a][k] * in[pn][o][k][r].
+// One CTA per (o, a, pn): threads = (k-slice, r), float64 partials combined in
+// slice order (deterministic).
+__global__ void __launch_bounds__(256)
 updft_axis_kernel(const double2* __restrict__ in, double2* __restrict__ out, int outer, int n,
                   int inner, int R, const float2* __restrict__ E, long long e_stride, int e_off) {
+  __shared__ double2 s_part[256];
   const int pn = blockIdx.y;
-  const int total = outer * R * inner;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int r = i % inner, a = (i / inner) % R, o = i / (inner * R);
-  const float2* e = E + (long long)pn * e_stride + e_off + (long long)a * n;
-  const double2* src = in + ((long long)pn * outer + o) * n * inner + r;
+  const int o = blockIdx.x / R, a = blockIdx.x - o * R;
+  const int slices = 256 / inner;  // inner = R^(axes done) <= 225
+  const int sl = threadIdx.x / inner, r = threadIdx.x - sl * inner;
   double re = 0.0, im = 0.0;
-  for (int k = 0; k < n; ++k) {
-    double2 v = src[(long long)k * inner];
-    float2 w = __ldg(e + k);
-    re += v.x * w.x - v.y * w.y;
-    im += v.x * w.y + v.y * w.x;
+  if (sl < slices) {
+    const float2* e = E + (long long)pn * e_stride + e_off + (long long)a * n;
+    const double2* src = in + ((long long)pn * outer + o) * n * inner + r;
+    for (int k = sl; k < n; k += slices) {
+      const double2 v = src[(long long)k * inner];
+      const float2 w = __ldg(e + k);
+      re += v.x * w.x - v.y * w.y;
+      im += v.x * w.y + v.y * w.x;
+    }
   }
-  out[((long long)pn * outer + o) * R * inner + (long long)a * inner + r] = make_double2(re, im);
+  s_part[threadIdx.x] = make_double2(re, im);
+  __syncthreads();
+  if (threadIdx.x < inner) {
+    double sr = 0.0, si = 0.0;
+    for (int i = 0; i < slices; ++i) { const double2 v = s_part[i * inner + threadIdx.x]; sr += v.x; si += v.y; }
+    out[((long long)pn * outer + o) * R * inner + (long long)a * inner + threadIdx.x] = make_double2(sr, si);
+  }
 }
 
 }  // namespace mvs
@@ -441,6 +386,7 @@ struct mvs_pc_plan {
   unsigned long long* d_keys = nullptr;
   int* d_peaks = nullptr;
   float2* d_E = nullptr;
+  float2* d_G = nullptr;  // [n2] geometric-sequence base of the x contraction
   long long e_stride = 0;
   int e_off[3] = {0, 0, 0};
   double2 *d_T0 = nullptr, *d_T1 = nullptr;
@@ -474,7 +420,7 @@ extern "C" int mvs_pc_plan_destroy(mvs_pc_plan* p) {
   if (!p) return MVS_OK;
   cudaFree(p->r0); cudaFree(p->r1); cudaFree(p->Z); cudaFree(p->Q);
   cudaFree((void*)p->d_imgs); cudaFree(p->d_partial); cudaFree(p->d_mn); cudaFree(p->d_scale);
-  cudaFree(p->d_keys); cudaFree(p->d_peaks); cudaFree(p->d_E); cudaFree(p->d_T0);
+  cudaFree(p->d_keys); cudaFree(p->d_peaks); cudaFree(p->d_E); cudaFree(p->d_G); cudaFree(p->d_T0);
   cudaFree(p->d_T1); cudaFree(p->scratch);
   delete p;
   return MVS_OK;
@@ -509,8 +455,11 @@ extern "C" int mvs_pc_plan_create(mvs_pc_plan** plan, int ndim, const int32_t sh
     p->ax[d] = *ax;
   }
   const long long NP = p->N * max_pairs;
-  int off = 0;
-  for (int d = 3 - ndim; d < 3; ++d) { p->e_off[d] = off; off += p->R * shape[d]; }
+  // per (pair, norm): H_x[n2], E_y[R][n1], E_z[R][n0] (updft_setup_kernel)
+  int off = shape[2];
+  p->e_off[2] = 0;
+  p->e_off[1] = off; off += p->R * shape[1];
+  p->e_off[0] = off; if (ndim == 3) off += p->R * shape[0];
   p->e_stride = off;
   const long long lines = p->N / shape[2];
   cudaError_t e = cudaSuccess;
@@ -528,6 +477,7 @@ extern "C" int mvs_pc_plan_create(mvs_pc_plan** plan, int ndim, const int32_t sh
   alloc((void**)&p->d_keys, sizeof(unsigned long long) * 2 * max_pairs);
   alloc((void**)&p->d_peaks, sizeof(int) * 6 * max_pairs);
   alloc((void**)&p->d_E, sizeof(float2) * p->e_stride * 2 * max_pairs);
+  alloc((void**)&p->d_G, sizeof(float2) * shape[2]);
   {
     const long long R = p->R;
     long long t = lines * R;
@@ -601,38 +551,89 @@ extern "C" int mvs_pc_load_pairs(mvs_pc_plan* p, int n, const float* const* fixe
   return MVS_OK;
 }
 
-template <bool LOAD_REAL, int SIGN>
-static int launch_pass(mvs_pc_plan* p, int n, int axis, float2* data, cudaStream_t st) {
-  FftPass a{};
-  a.data = data;
+enum PassKind { PASS_LOAD_REAL, PASS_PLAIN, PASS_PAIRED, PASS_ARGMAX };
+
+template <int M>
+static int launch_pass_m(const FftPassArgs& a, bool blue, dim3 grid, int threads, size_t smem,
+                         cudaStream_t st) {
+  if (blue) {
+    auto kern = fft_reg_pass_kernel<M, true>;
+    MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a);
+  } else {
+    auto kern = fft_reg_pass_kernel<M, false>;
+    MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a);
+  }
+  MVS_CHECK_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+// One pass along `axis` over the n loaded pairs.  sign -1 forward / +1 inverse.
+static int launch_pass(mvs_pc_plan* p, int n, int axis, int sign, PassKind kind, const float2* src,
+                       float2* dst, cudaStream_t st) {
+  FftPassArgs a{};
+  const AxisFft& ax = p->ax[axis];
+  a.src = src; a.dst = dst;
   a.re = p->r0; a.im = p->r1;
   a.n = p->shape[axis];
-  a.ax = p->ax[axis];
   long long inner = 1, outer = 1;
   for (int d = axis + 1; d < 3; ++d) inner *= p->shape[d];
   for (int d = 0; d < axis; ++d) outer *= p->shape[d];
   a.inner = inner; a.outer = outer;
   a.batch_stride = p->N;
-  a.L = fft_lines_per_cta(a.ax, inner == 1);
-  size_t smem = fft_smem_bytes(a.ax, a.L, &a.mp);
-  MVS_REQUIRE(smem <= 227 * 1024, MVS_ERR_UNSUPPORTED,
-              "axis length %d needs %zu bytes of shared memory", a.n, smem);
-  auto kern = fft_pass_kernel<LOAD_REAL, SIGN>;
-  MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+  a.sign = sign;
+  a.load_real = kind == PASS_LOAD_REAL;
+  a.paired = kind == PASS_PAIRED;
+  a.argmax = kind == PASS_ARGMAX;
+  a.contig = (axis == 2);
+  a.keys = p->d_keys;
+  a.tw = ax.tw; a.chirp = ax.chirp; a.bhat = ax.bhat;
   const long long nlines = outer * inner;
-  dim3 grid((unsigned)((nlines + a.L - 1) / a.L), n);
-  kern<<<grid, 256, smem, st>>>(a);
-  MVS_CHECK_CUDA(cudaGetLastError());
-  return MVS_OK;
+  const PassGeom g = pass_geom(ax.m, a.contig != 0, a.paired != 0, nlines);
+  a.L = g.L; a.line_stride = g.line_stride;
+  MVS_REQUIRE(g.smem <= 227 * 1024 && g.threads <= 512, MVS_ERR_UNSUPPORTED,
+              "axis length %d: pass geometry out of range", a.n);
+  dim3 grid((unsigned)((nlines + g.L - 1) / g.L), n);
+  if (a.paired) {
+    // lines along the first data axis, indexed (y', x); a CTA owns L/2 lines
+    // x0.. and their mirrors (-y', -x)
+    MVS_REQUIRE(outer == 1 && sign < 0 && axis < 2, MVS_ERR_INVALID, "paired pass on a wrong axis");
+    a.n2 = p->shape[2];
+    a.n1p = (int)(inner / p->shape[2]);
+    a.items_x = p->shape[2] / 2 + 1;
+    a.xblocks = (a.items_x + g.L / 2 - 1) / (g.L / 2);
+    const double NN = (double)p->N;
+    a.cp_scale = (float)(1.0 / (NN * NN));
+    grid.x = (unsigned)((long long)a.xblocks * a.n1p);
+  }
+  const bool blue = ax.bluestein != 0;
+  switch (ax.m) {
+    case 1: return launch_pass_m<1>(a, blue, grid, g.threads, g.smem, st);
+    case 2: return launch_pass_m<2>(a, blue, grid, g.threads, g.smem, st);
+    case 4: return launch_pass_m<4>(a, blue, grid, g.threads, g.smem, st);
+    case 8: return launch_pass_m<8>(a, blue, grid, g.threads, g.smem, st);
+    case 16: return launch_pass_m<16>(a, blue, grid, g.threads, g.smem, st);
+    case 32: return launch_pass_m<32>(a, blue, grid, g.threads, g.smem, st);
+    case 64: return launch_pass_m<64>(a, blue, grid, g.threads, g.smem, st);
+    case 128: return launch_pass_m<128>(a, blue, grid, g.threads, g.smem, st);
+    case 256: return launch_pass_m<256>(a, blue, grid, g.threads, g.smem, st);
+    case 512: return launch_pass_m<512>(a, blue, grid, g.threads, g.smem, st);
+    case 1024: return launch_pass_m<1024>(a, blue, grid, g.threads, g.smem, st);
+    case 2048: return launch_pass_m<2048>(a, blue, grid, g.threads, g.smem, st);
+    case 4096: return launch_pass_m<4096>(a, blue, grid, g.threads, g.smem, st);
+    case 8192: return launch_pass_m<8192>(a, blue, grid, g.threads, g.smem, st);
+  }
+  set_error("no FFT kernel for length %d", ax.m);
+  return MVS_ERR_UNSUPPORTED;
 }
 
 template <int R>
 static int launch_updft_x(mvs_pc_plan* p, int n, cudaStream_t st) {
   const long long lines = p->N / p->shape[2];
-  dim3 grid((unsigned)((lines + 7) / 8), n, 2);
-  updft_x_kernel<R><<<grid, 256, 0, st>>>(p->Z, p->shape[0], p->shape[1], p->shape[2], p->N,
-                                          p->d_E, p->e_stride, p->e_off[2], p->d_T0);
+  dim3 grid((unsigned)((lines + kUpWarps - 1) / kUpWarps), n);
+  updft_x_kernel<R><<<grid, kUpWarps * 32, 0, st>>>(p->Q, p->shape[0], p->shape[1], p->shape[2],
+                                                    p->N, p->d_E, p->e_stride, p->d_G, p->d_T0);
   MVS_CHECK_CUDA(cudaGetLastError());
   return MVS_OK;
 }
@@ -644,24 +645,21 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
               p->loaded);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  // forward: x (from the real pair), then y, then z
-  if ((rc = launch_pass<true, -1>(p, n, 2, p->Z, st))) return rc;
-  if ((rc = launch_pass<false, -1>(p, n, 1, p->Z, st))) return rc;
-  if (p->ndim == 3 && (rc = launch_pass<false, -1>(p, n, 0, p->Z, st))) return rc;
-  dim3 g(grid_for(p->N), n);
-  cross_power_kernel<<<g, 256, 0, st>>>(p->Z, p->Q, p->shape[0], p->shape[1], p->shape[2], p->N);
-  MVS_CHECK_CUDA(cudaGetLastError());
-  // inverse: z, y, x
-  if (p->ndim == 3 && (rc = launch_pass<false, +1>(p, n, 0, p->Q, st))) return rc;
-  if ((rc = launch_pass<false, +1>(p, n, 1, p->Q, st))) return rc;
-  if ((rc = launch_pass<false, +1>(p, n, 2, p->Q, st))) return rc;
   MVS_CHECK_CUDA(cudaMemsetAsync(p->d_keys, 0, sizeof(unsigned long long) * 2 * n, st));
-  argmax_kernel<<<g, 256, 0, st>>>(p->Q, p->N, p->d_keys);
-  MVS_CHECK_CUDA(cudaGetLastError());
+  // forward: x (packing the real pair), [y], then the first data axis fused with
+  // the cross-power spectrum: Z -> Q
+  if ((rc = launch_pass(p, n, 2, -1, PASS_LOAD_REAL, nullptr, p->Z, st))) return rc;
+  if (p->ndim == 3 && (rc = launch_pass(p, n, 1, -1, PASS_PLAIN, p->Z, p->Z, st))) return rc;
+  const int first = 3 - p->ndim;
+  if ((rc = launch_pass(p, n, first, -1, PASS_PAIRED, p->Z, p->Q, st))) return rc;
+  // inverse: first data axis Q -> Z (Q is kept for the upsampled DFT), [y], x + argmax
+  if ((rc = launch_pass(p, n, first, +1, PASS_PLAIN, p->Q, p->Z, st))) return rc;
+  if (p->ndim == 3 && (rc = launch_pass(p, n, 1, +1, PASS_PLAIN, p->Z, p->Z, st))) return rc;
+  if ((rc = launch_pass(p, n, 2, +1, PASS_ARGMAX, p->Z, nullptr, st))) return rc;
   // slot 0 = |Re| = normalization None, slot 1 = |Im| = "phase"
   updft_setup_kernel<<<2 * n, 256, 0, st>>>(p->d_keys, p->shape[0], p->shape[1], p->shape[2],
                                             p->ndim, p->R, p->upsample, p->d_peaks, p->d_E,
-                                            p->e_stride, p->e_off[1], p->e_off[2]);
+                                            p->e_stride, p->e_off[1], p->e_off[0], p->d_G);
   MVS_CHECK_CUDA(cudaGetLastError());
   const int R = p->R;
   double2* result = nullptr;
@@ -686,8 +684,8 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
     // contract y: in [z][y][R] -> out [z][R_y][R_x]
     {
       const int outer = p->shape[0], nn = p->shape[1], inner = R;
-      dim3 grid((outer * R * inner + 127) / 128, 2 * n);
-      updft_axis_kernel<<<grid, 128, 0, st>>>(p->d_T0, p->d_T1, outer, nn, inner, R, p->d_E,
+      dim3 grid(outer * R, 2 * n);
+      updft_axis_kernel<<<grid, 256, 0, st>>>(p->d_T0, p->d_T1, outer, nn, inner, R, p->d_E,
                                               p->e_stride, p->e_off[1]);
       MVS_CHECK_CUDA(cudaGetLastError());
       result = p->d_T1;
@@ -695,8 +693,8 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
     }
     if (p->ndim == 3) {
       const int outer = 1, nn = p->shape[0], inner = R * R;
-      dim3 grid((outer * R * inner + 127) / 128, 2 * n);
-      updft_axis_kernel<<<grid, 128, 0, st>>>(p->d_T1, p->d_T0, outer, nn, inner, R, p->d_E,
+      dim3 grid(outer * R, 2 * n);
+      updft_axis_kernel<<<grid, 256, 0, st>>>(p->d_T1, p->d_T0, outer, nn, inner, R, p->d_E,
                                               p->e_stride, p->e_off[0]);
       MVS_CHECK_CUDA(cudaGetLastError());
       result = p->d_T0;
@@ -722,6 +720,6 @@ extern "C" int mvs_pc_plan_info(const mvs_pc_plan* p, int* region, int64_t* voxe
   if (region) *region = p->R;
   if (voxels) *voxels = p->N;
   if (launches_per_correlate)
-    *launches_per_correlate = 2 * p->ndim + 3 + (p->upsample > 1 ? p->ndim : 0);
+    *launches_per_correlate = 2 * p->ndim + 1 + (p->upsample > 1 ? p->ndim : 0);
   return MVS_OK;
 }

@@ -1,0 +1,247 @@
+// CPU execution of the phase-correlation passes (fft_pass.cuh) thread by thread:
+// forward x (packed reals) -> [forward y] -> forward first axis + cross power ->
+// inverse passes -> argmax keys, against a float64 reference.
+// Build: nvcc -std=c++17 -I multiview_stitcher_b200/csrc tests/csrc/pass_emul.cu -o /tmp/pass_emul
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fft_pass.cuh"
+
+using namespace mvs;
+typedef std::complex<double> cd;
+
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+struct Axis {
+  int n, m, blue;
+  std::vector<float2> tw, chirp, bhat;
+};
+
+static void dft(std::vector<cd>& x, int sign) {
+  const int n = (int)x.size();
+  std::vector<cd> y(n);
+  for (int k = 0; k < n; ++k) {
+    cd s = 0;
+    for (int j = 0; j < n; ++j) s += x[j] * std::polar(1.0, sign * 2.0 * M_PI * (double)((long long)j * k % n) / n);
+    y[k] = s;
+  }
+  x = y;
+}
+
+static Axis make_axis(int n) {
+  Axis a;
+  a.n = n;
+  if (is_pow2(n)) { a.m = n; a.blue = 0; }
+  else { int m = 1; while (m < 2 * n - 1) m <<= 1; a.m = m; a.blue = 1; }
+  a.tw.resize(a.m);
+  for (int k = 0; k < a.m; ++k) a.tw[k] = make_float2((float)cos(-2 * M_PI * k / a.m), (float)sin(-2 * M_PI * k / a.m));
+  if (a.blue) {
+    a.chirp.resize(n); a.bhat.resize(a.m);
+    std::vector<cd> b(a.m, 0.0);
+    for (int k = 0; k < n; ++k) {
+      long long k2 = ((long long)k * k) % (2LL * n);
+      cd c = std::polar(1.0, -M_PI * (double)k2 / n);
+      a.chirp[k] = make_float2((float)c.real(), (float)c.imag());
+      b[k] = std::conj(c);
+      if (k) b[a.m - k] = std::conj(c);
+    }
+    dft(b, -1);
+    for (int k = 0; k < a.m; ++k) a.bhat[k] = make_float2((float)(b[k].real() / a.m), (float)(b[k].imag() / a.m));
+  }
+  return a;
+}
+
+template <int M, int S, bool BLUE>
+static void run_stages(std::vector<PassThread<M, BLUE>>& th, std::vector<float2>& smem, const FftPassArgs& P) {
+  using Sc = FftSched<M>;
+  if constexpr (S < Sc::NST) {
+    for (auto& t : th) FftStage<M, S>::compute(t.v, t.t, P.tw);
+    if constexpr (S + 1 < Sc::NST) {
+      for (auto& s : smem) s = make_float2(NAN, NAN);
+      for (auto& t : th) FftStage<M, S>::scatter(t.v, t.t, smem.data() + t.l * P.line_stride);
+      for (auto& t : th) fft_gather<M>(t.v, t.t, smem.data() + t.l * P.line_stride);
+      run_stages<M, S + 1, BLUE>(th, smem, P);
+    }
+  }
+}
+
+template <int M, bool BLUE>
+static void emulate_pass(const FftPassArgs& P, int threads, long long gx, int gy) {
+  std::vector<float2> smem((size_t)P.L * P.line_stride);
+  for (int by = 0; by < gy; ++by)
+    for (long long bx = 0; bx < gx; ++bx) {
+      std::vector<PassThread<M, BLUE>> th(threads);
+      for (int tid = 0; tid < threads; ++tid) { th[tid].init(P, tid, bx, by); th[tid].load(P); }
+      run_stages<M, 0, BLUE>(th, smem, P);
+      if (BLUE) {
+        for (auto& t : th) t.mid(P);
+        run_stages<M, 0, BLUE>(th, smem, P);
+      }
+      for (auto& t : th) t.post(P);
+      if (P.paired) {
+        for (auto& s : smem) s = make_float2(NAN, NAN);
+        for (auto& t : th) t.publish(smem.data() + t.l * P.line_stride);
+        for (auto& t : th) {
+          const int lp = t.l + (t.l < (P.L >> 1) ? (P.L >> 1) : -(P.L >> 1));
+          t.cross_power(P, smem.data() + lp * P.line_stride);
+        }
+      }
+      for (auto& t : th) t.store(P);
+      if (P.argmax)
+        for (auto& t : th) {
+          unsigned long long k0, k1;
+          t.keys(P, k0, k1);
+          if (k0 > P.keys[2 * by]) P.keys[2 * by] = k0;
+          if (k1 > P.keys[2 * by + 1]) P.keys[2 * by + 1] = k1;
+        }
+    }
+}
+
+template <int M>
+static void emulate_m(const FftPassArgs& P, bool blue, int threads, long long gx, int gy) {
+  if (blue) emulate_pass<M, true>(P, threads, gx, gy); else emulate_pass<M, false>(P, threads, gx, gy);
+}
+
+enum Kind { LOAD_REAL, PLAIN, PAIRED, ARGMAX };
+
+struct Vol { int sh[3]; long long N; int npairs; std::vector<float> r0, r1; std::vector<float2> Z, Q; std::vector<unsigned long long> keys; Axis ax[3]; };
+
+static void pass(Vol& V, int axis, int sign, Kind kind, const float2* src, float2* dst, int Lreq) {
+  FftPassArgs a{};
+  const Axis& ax = V.ax[axis];
+  a.src = src; a.dst = dst; a.re = V.r0.data(); a.im = V.r1.data();
+  a.n = V.sh[axis];
+  long long inner = 1, outer = 1;
+  for (int d = axis + 1; d < 3; ++d) inner *= V.sh[d];
+  for (int d = 0; d < axis; ++d) outer *= V.sh[d];
+  a.inner = inner; a.outer = outer; a.batch_stride = V.N; a.sign = sign;
+  a.load_real = kind == LOAD_REAL; a.paired = kind == PAIRED; a.argmax = kind == ARGMAX;
+  a.contig = axis == 2;
+  a.keys = V.keys.data();
+  a.tw = ax.tw.data(); a.chirp = ax.chirp.data(); a.bhat = ax.bhat.data();
+  const int m = ax.m, E = m < 16 ? m : 16, T = m / E;
+  int L = Lreq;
+  if (a.paired && L < 2) L = 2;
+  a.L = L; a.line_stride = m + (m >> 4) + (a.contig ? 0 : (L <= 16 ? 16 / L : 1));
+  const long long nlines = outer * inner;
+  long long gx = (nlines + L - 1) / L;
+  if (a.paired) {
+    a.n2 = V.sh[2]; a.n1p = (int)(inner / V.sh[2]); a.items_x = V.sh[2] / 2 + 1;
+    a.xblocks = (a.items_x + L / 2 - 1) / (L / 2);
+    a.cp_scale = (float)(1.0 / ((double)V.N * (double)V.N));
+    gx = (long long)a.xblocks * a.n1p;
+  }
+  const bool blue = ax.blue;
+  const int threads = L * T;
+  switch (m) {
+    case 1: emulate_m<1>(a, blue, threads, gx, V.npairs); break;
+    case 2: emulate_m<2>(a, blue, threads, gx, V.npairs); break;
+    case 4: emulate_m<4>(a, blue, threads, gx, V.npairs); break;
+    case 8: emulate_m<8>(a, blue, threads, gx, V.npairs); break;
+    case 16: emulate_m<16>(a, blue, threads, gx, V.npairs); break;
+    case 32: emulate_m<32>(a, blue, threads, gx, V.npairs); break;
+    case 64: emulate_m<64>(a, blue, threads, gx, V.npairs); break;
+    case 128: emulate_m<128>(a, blue, threads, gx, V.npairs); break;
+    case 256: emulate_m<256>(a, blue, threads, gx, V.npairs); break;
+    case 512: emulate_m<512>(a, blue, threads, gx, V.npairs); break;
+    default: printf("unsupported m %d\n", m); exit(2);
+  }
+}
+
+// float64 reference of the whole chain
+static void fftn(std::vector<cd>& v, const int sh[3], int sign) {
+  const long long N = (long long)sh[0] * sh[1] * sh[2];
+  long long stride = 1;
+  for (int ax = 2; ax >= 0; --ax) {
+    const int n = sh[ax];
+    for (long long i = 0; i < N; ++i) {
+      if ((i / stride) % n) continue;
+      std::vector<cd> line(n);
+      for (int k = 0; k < n; ++k) line[k] = v[i + k * stride];
+      dft(line, sign);
+      for (int k = 0; k < n; ++k) v[i + k * stride] = line[k];
+    }
+    stride *= n;
+  }
+}
+
+static int run_case(int n0, int n1, int n2, int L1, int L2) {
+  Vol V;
+  V.sh[0] = n0; V.sh[1] = n1; V.sh[2] = n2; V.N = (long long)n0 * n1 * n2; V.npairs = 2;
+  const int ndim = n0 > 1 ? 3 : 2;
+  const long long NP = V.N * V.npairs;
+  V.r0.resize(NP); V.r1.resize(NP); V.Z.assign(NP, make_float2(NAN, NAN)); V.Q.assign(NP, make_float2(NAN, NAN));
+  V.keys.assign(2 * V.npairs, 0);
+  for (int d = 0; d < 3; ++d) V.ax[d] = make_axis(V.sh[d]);
+  for (long long i = 0; i < NP; ++i) { V.r0[i] = (float)rand() / RAND_MAX; V.r1[i] = (float)rand() / RAND_MAX; }
+  // make pair 0's moving image a circular shift of the fixed one (+ noise) so that a clear peak exists
+  for (int z = 0; z < n0; ++z) for (int y = 0; y < n1; ++y) for (int x = 0; x < n2; ++x) {
+    int zs = (z + (n0 > 1 ? 1 : 0)) % n0, ys = (y + 3) % n1, xs = (x + n2 - 2) % n2;
+    V.r1[((long long)z * n1 + y) * n2 + x] = V.r0[((long long)zs * n1 + ys) * n2 + xs] * 0.9f + 0.05f * V.r1[((long long)z * n1 + y) * n2 + x];
+  }
+  V.r0[5] = NAN;  // NaN -> 0 on load
+  const int first = 3 - ndim;
+  pass(V, 2, -1, LOAD_REAL, nullptr, V.Z.data(), L1);
+  if (ndim == 3) pass(V, 1, -1, PLAIN, V.Z.data(), V.Z.data(), L2);
+  pass(V, first, -1, PAIRED, V.Z.data(), V.Q.data(), L2);
+  std::vector<float2> Qkeep = V.Q;
+  pass(V, first, +1, PLAIN, V.Q.data(), V.Z.data(), L2);
+  if (ndim == 3) pass(V, 1, +1, PLAIN, V.Z.data(), V.Z.data(), L2);
+  std::vector<float2> W(NP, make_float2(NAN, NAN));
+  pass(V, 2, +1, ARGMAX, V.Z.data(), W.data(), L1);  // store as well, for the check
+
+  int bad = 0;
+  for (int p = 0; p < V.npairs; ++p) {
+    std::vector<cd> z(V.N);
+    for (long long i = 0; i < V.N; ++i) {
+      float a = V.r0[p * V.N + i], b = V.r1[p * V.N + i];
+      z[i] = cd(a != a ? 0 : a, b != b ? 0 : b);
+    }
+    fftn(z, V.sh, -1);
+    std::vector<cd> q(V.N);
+    const double s = 1.0 / ((double)V.N * (double)V.N);
+    double qerr = 0;
+    for (int zz = 0; zz < n0; ++zz) for (int y = 0; y < n1; ++y) for (int x = 0; x < n2; ++x) {
+      long long i = ((long long)zz * n1 + y) * n2 + x;
+      long long mi = ((long long)((n0 - zz) % n0) * n1 + (n1 - y) % n1) * n2 + (n2 - x) % n2;
+      cd F = 0.5 * (z[i] + std::conj(z[mi])), Mm = (z[i] - std::conj(z[mi])) / cd(0, 2);
+      cd P = F * std::conj(Mm);
+      cd Pn = P / std::max(std::abs(P), 100.0 * 1.1920929e-07);
+      q[i] = s * P + cd(0, 1) * Pn;
+      float2 g = Qkeep[p * V.N + i];
+      qerr = std::max(qerr, std::abs(cd(g.x, g.y) - q[i]));
+    }
+    fftn(q, V.sh, +1);
+    double werr = 0, wmax = 0;
+    long long am0 = 0, am1 = 0;
+    for (long long i = 0; i < V.N; ++i) {
+      float2 g = W[p * V.N + i];
+      werr = std::max(werr, std::abs(cd(g.x, g.y) - q[i]));
+      wmax = std::max(wmax, std::abs(q[i]));
+      if (fabsf(W[p * V.N + i].x) > fabsf(W[p * V.N + am0].x)) am0 = i;
+      if (fabsf(W[p * V.N + i].y) > fabsf(W[p * V.N + am1].y)) am1 = i;
+    }
+    long long k0 = 0xffffffffull - (V.keys[2 * p] & 0xffffffffull), k1 = 0xffffffffull - (V.keys[2 * p + 1] & 0xffffffffull);
+    bool ok = qerr < 2e-5 && werr / wmax < 2e-5 && k0 == am0 && k1 == am1;
+    printf("  shape %dx%dx%d L=%d/%d pair %d: |dQ| %.2e  |dW|/max %.2e  argmax %lld/%lld (exp %lld/%lld) %s\n", n0, n1, n2, L1, L2, p,
+           qerr, werr / wmax, k0, k1, am0, am1, ok ? "ok" : "BAD");
+    bad += !ok;
+  }
+  return bad;
+}
+
+int main() {
+  int bad = 0;
+  bad += run_case(1, 16, 32, 2, 4);    // powers of two
+  bad += run_case(1, 20, 13, 4, 4);    // Bluestein on both axes (odd x)
+  bad += run_case(1, 12, 10, 8, 2);    // even n2 (self-mirror column n2/2), L/2 = 1
+  bad += run_case(1, 64, 7, 16, 8);
+  bad += run_case(4, 6, 8, 4, 4);      // 3-D
+  bad += run_case(3, 5, 9, 2, 8);      // 3-D all Bluestein
+  bad += run_case(2, 33, 4, 8, 16);
+  printf(bad ? "FAIL\n" : "OK\n");
+  return bad != 0;
+}
