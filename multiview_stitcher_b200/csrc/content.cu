@@ -12,6 +12,8 @@
 // (post-resample level) and the multi-pass half of content-weighted
 // fusion.  A stack is V contiguous volumes of N = nz*ny*nx voxels, NaN = outside.
 
+#include <climits>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -84,6 +86,259 @@ gauss1d_kernel(const float* __restrict__ in, float* __restrict__ out, int nz, in
     for (int j = radius; j >= 1; --j)
       tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(c - j), at(c + j)), fw[j]));
     out[i] = (float)tmp;
+  }
+}
+
+// ---- fast path of the same pass -------------------------------------------------
+// A warp owns a strip: 32 lanes across a non-filter axis x kGTA outputs along the
+// filter axis, staged (with its 2 r' halo rows, reflect-resolved) in shared memory
+// as [k][lane] so every read is conflict-free.  Each lane produces 4 consecutive
+// outputs at a time from two 4-deep rotating register windows (left / right taps):
+// 2 shared-memory reads feed 4 x (DADD, DMUL, DADD) -- scipy's exact float64
+// operation order -- so the pass runs at the FP64 pipe's rate instead of being
+// load-bound.  r' = radius rounded up to a multiple of 4 with zero weights
+// (x + 0.0 * finite == x).  Strips whose inputs are all one value (the 0/1 validity
+// mask of nan_gaussian_filter away from edges, empty space) collapse to one chain.
+// `boxes` (optional) restricts a volume to the bounding box of its valid voxels:
+// inputs outside read as 0, outputs outside are not produced (they are exact
+// zeros that nobody reads, weights.py:314-320 divides only where the view exists).
+
+constexpr int kGTA = 32;
+constexpr int kGPitch = 33;
+
+struct GaussArgs {
+  const float* in;
+  float* out;
+  int nz, ny, nx, batch;
+  const double* fw;  // [rp + 1], zero beyond the true radius
+  int rp;            // radius rounded up to a multiple of 4, >= 4
+  const int* boxes;  // [box_mod][6]: lo z,y,x then hi z,y,x (inclusive); nullptr = whole volume
+  int box_mod;
+};
+
+__device__ __forceinline__ int reflect_idx(int k, int n) {
+  // half-sample symmetric reflection: d c b a | a b c d | d c b a
+  if (k < 0 || k >= n) {
+    const int period = 2 * n;
+    k %= period;
+    if (k < 0) k += period;
+    if (k >= n) k = period - 1 - k;
+  }
+  return k;
+}
+
+#define MVS_GSTEP(JJ, A4)                                                                      \
+  {                                                                                            \
+    const double w = wts[(JJ)];                                                                \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i)                                              \
+      acc[i] = __dadd_rn(acc[i], __dmul_rn(__dadd_rn(Lw[(i - (A4)) & 3], Rw[((A4) + i) & 3]), w)); \
+    Lw[(4 - (A4)) & 3] = (double)sp[(4 - (JJ)) * kGPitch];                                     \
+    Rw[((A4) + 3) & 3] = (double)sp[((JJ)-1) * kGPitch];                                       \
+  }
+
+template <int AXIS>
+__global__ void __launch_bounds__(256) gauss_strip_kernel(const GaussArgs A) {
+  extern __shared__ double gs_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int rp = A.rp, span = kGTA + 2 * rp;
+  double* wts = gs_smem;
+  const int per_warp = span * kGPitch + (AXIS == 2 ? kGTA * kGPitch : 0);
+  float* strip = reinterpret_cast<float*>(wts + rp + 1) + (size_t)warp * per_warp;
+  float* otile = strip + span * kGPitch;
+  for (int i = threadIdx.x; i <= rp; i += blockDim.x) wts[i] = A.fw[i];
+  __syncthreads();
+  const int nA = AXIS == 0 ? A.nz : (AXIS == 1 ? A.ny : A.nx);
+  const int nL = AXIS == 2 ? A.ny : A.nx;
+  const int nT = AXIS == 0 ? A.ny : A.nz;
+  const int tilesA = (nA + kGTA - 1) / kGTA, tilesL = (nL + 31) / 32;
+  const long long per_vol = (long long)nT * tilesA * tilesL;
+  const long long strips = per_vol * A.batch;
+  const long long sy = A.nx, sz = (long long)A.ny * A.nx;
+  const long long strideA = AXIS == 0 ? sz : (AXIS == 1 ? sy : 1);
+  const long long strideT = AXIS == 0 ? sy : sz;
+  const unsigned full = 0xffffffffu;
+  for (long long sidx = (long long)blockIdx.x * W + warp; sidx < strips;
+       sidx += (long long)gridDim.x * W) {
+    const int b = (int)(sidx / per_vol);
+    long long rem = sidx - (long long)b * per_vol;
+    const int tl = (int)(rem % tilesL);
+    rem /= tilesL;
+    const int ta = (int)(rem % tilesA);
+    const int th = (int)(rem / tilesA);
+    const int a0 = ta * kGTA, l0 = tl * 32;
+    int loA = 0, hiA = nA - 1, loL = 0, hiL = nL - 1, loT = 0, hiT = nT - 1;
+    if (A.boxes) {
+      const int* bx = A.boxes + 6 * (b % A.box_mod);
+      const int iA = AXIS, iL = AXIS == 2 ? 1 : 2, iT = AXIS == 0 ? 1 : 0;
+      loA = max(loA, bx[iA]); hiA = min(hiA, bx[3 + iA]);
+      loL = max(loL, bx[iL]); hiL = min(hiL, bx[3 + iL]);
+      loT = max(loT, bx[iT]); hiT = min(hiT, bx[3 + iT]);
+    }
+    if (th < loT || th > hiT || a0 > hiA || a0 + kGTA - 1 < loA || l0 > hiL || l0 + 31 < loL)
+      continue;  // nothing of this strip is wanted (warp-uniform)
+    const long long voff = (long long)b * A.nz * sz + (long long)th * strideT;
+    const float* vin = A.in + voff;
+    float* vout = A.out + voff;
+    __syncwarp();  // the previous strip's readers are done
+    // ---- stage the strip: loads issued eight at a time (clamped addresses) ----
+    bool same = true;
+    float first = 0.f;
+    if (AXIS != 2) {
+      const int xl = l0 + lane;
+      const bool lane_ok = xl >= loL && xl <= hiL;
+      for (int kk0 = 0; kk0 < span; kk0 += 8) {  // span is a multiple of 8
+        float tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int a = reflect_idx(a0 - rp + kk0 + u, nA);
+          const bool ok = lane_ok && a >= loA && a <= hiA;
+          const float x = __ldg(ok ? vin + (long long)a * strideA + xl : A.in);
+          tv[u] = ok ? x : 0.f;
+        }
+        if (kk0 == 0) first = tv[0];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          strip[(kk0 + u) * kGPitch + lane] = tv[u];
+          same = same && (tv[u] == first);
+        }
+      }
+    } else {
+      const int nk = (span + 31) >> 5;  // 32-wide chunks per row
+      for (int e0 = 0; e0 < 32 * nk; e0 += 8) {
+        float tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u, row = e / nk, kk = (e - row * nk) * 32 + lane;
+          const int y = l0 + row;
+          const int a = reflect_idx(a0 - rp + kk, nA);
+          const bool ok = kk < span && y >= loL && y <= hiL && a >= loA && a <= hiA;
+          const float x = __ldg(ok ? vin + (long long)y * sy + a : A.in);
+          tv[u] = ok ? x : 0.f;
+        }
+        if (e0 == 0) first = tv[0];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u, row = e / nk, kk = (e - row * nk) * 32 + lane;
+          if (kk < span) {
+            strip[kk * kGPitch + row] = tv[u];
+            same = same && (tv[u] == first);
+          }
+        }
+      }
+    }
+    const float f0 = __shfl_sync(full, first, 0);
+    const bool uniform = __all_sync(full, same && first == f0);
+    __syncwarp();
+    const int lpos = l0 + lane;  // this lane's coordinate on the lane axis
+    const bool lane_out = lpos >= loL && lpos <= hiL;
+    if (uniform) {
+      double tmp = __dmul_rn((double)f0, wts[0]);
+      const double two = __dadd_rn((double)f0, (double)f0);
+      for (int j = rp; j >= 1; --j) tmp = __dadd_rn(tmp, __dmul_rn(two, wts[j]));
+      const float o = (float)tmp;
+      if (AXIS != 2) {
+        if (lane_out)
+          for (int k = max(a0, loA); k <= min(a0 + kGTA - 1, hiA); ++k)
+            vout[(long long)k * strideA + lpos] = o;
+      } else {
+        for (int row = max(l0, loL); row <= min(l0 + 31, hiL); ++row) {
+          const int a = a0 + lane;
+          if (a >= loA && a <= hiA) vout[(long long)row * sy + a] = o;
+        }
+      }
+      continue;
+    }
+    for (int g = 0; g < kGTA / 4; ++g) {
+      const int c0 = a0 + 4 * g;
+      if (c0 > hiA || c0 + 3 < loA) continue;  // warp-uniform
+      const float* sp = strip + (rp + 4 * g) * kGPitch + lane;
+      double acc[4], Lw[4], Rw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i] = __dmul_rn((double)sp[i * kGPitch], wts[0]);
+        Lw[i] = (double)sp[(i - rp) * kGPitch];
+        Rw[i] = (double)sp[(i + rp) * kGPitch];
+      }
+      for (int j = rp; j >= 4; j -= 4) {
+        MVS_GSTEP(j, 0)
+        MVS_GSTEP(j - 1, 3)
+        MVS_GSTEP(j - 2, 2)
+        MVS_GSTEP(j - 3, 1)
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = c0 + i;
+        if (AXIS != 2) {
+          if (lane_out && a >= loA && a <= hiA) vout[(long long)a * strideA + lpos] = (float)acc[i];
+        } else {
+          otile[(4 * g + i) * kGPitch + lane] = (float)acc[i];
+        }
+      }
+    }
+    if (AXIS == 2) {
+      __syncwarp();
+      const int a = a0 + lane;
+      if (a >= loA && a <= hiA)
+        for (int row = max(l0, loL); row <= min(l0 + 31, hiL); ++row)
+          vout[(long long)row * sy + a] = otile[lane * kGPitch + (row - l0)];
+    }
+  }
+}
+#undef MVS_GSTEP
+
+// bounding boxes (lo z,y,x / hi z,y,x) of the non-NaN voxels of every volume
+__global__ void box_init_kernel(int* __restrict__ boxes, int V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * V) boxes[i] = (i % 6) < 3 ? INT_MAX : -1;
+}
+
+__global__ void __launch_bounds__(256)
+box_kernel(const float* __restrict__ vols, int nz, int ny, int nx, int* __restrict__ boxes) {
+  const long long N = (long long)nz * ny * nx;
+  const float* v = vols + (long long)blockIdx.y * N;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float x = v[i];
+    if (x == x) {
+      const int c[3] = {(int)(i / ((long long)ny * nx)), (int)((i / nx) % ny), (int)(i % nx)};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { lo[d] = min(lo[d], c[d]); hi[d] = max(hi[d], c[d]); }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+    int* bx = boxes + 6 * blockIdx.y;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (lo[d] != INT_MAX) atomicMin(bx + d, lo[d]);
+      if (hi[d] >= 0) atomicMax(bx + 3 + d, hi[d]);
+    }
+  }
+}
+
+// T = (M - VV/WW)^2 with the NaN pattern of M (weights.py:57-65) split straight
+// into the zero-filled values / validity mask of the next nan_gaussian_filter
+__global__ void __launch_bounds__(256)
+sqdiff_split_kernel(const float* __restrict__ vv, const float* __restrict__ ww,
+                    const float* __restrict__ ref, float* __restrict__ v0, float* __restrict__ w0,
+                    long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float r = ref[i];
+    float t = NAN;
+    if (r == r) {
+      const float d = __fsub_rn(r, __fdiv_rn(vv[i], ww[i]));
+      t = __fmul_rn(d, d);
+    }
+    const bool nan = t != t;
+    v0[i] = nan ? 0.f : t;
+    w0[i] = nan ? 0.f : 1.f;
   }
 }
 
@@ -173,9 +428,39 @@ static int check_stack(const void* a, int V, const int32_t shape[3]) {
   return MVS_OK;
 }
 
-// gaussian_filter of `batch` volumes: src -> dst, using tmp as the ping-pong buffer
+static int round_up4(int r) { return r < 4 ? 4 : ((r + 3) / 4) * 4; }
+
+// warps per CTA that fit the strip kernel's shared memory (0: use the plain kernel)
+static int strip_warps(int rp, int axis, size_t* smem_out) {
+  const size_t per_warp = sizeof(float) * ((size_t)(kGTA + 2 * rp) * kGPitch + (axis == 2 ? kGTA * kGPitch : 0));
+  const size_t fixed = sizeof(double) * (rp + 1);
+  int W = 8;
+  while (W > 0 && fixed + W * per_warp > 200 * 1024) --W;
+  if (smem_out) *smem_out = fixed + W * per_warp;
+  return W;
+}
+
+template <int AXIS>
+static int launch_strip(const GaussArgs& a, int W, size_t smem, cudaStream_t st) {
+  auto kern = gauss_strip_kernel<AXIS>;
+  MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nA = AXIS == 0 ? a.nz : (AXIS == 1 ? a.ny : a.nx);
+  const int nL = AXIS == 2 ? a.ny : a.nx;
+  const int nT = AXIS == 0 ? a.ny : a.nz;
+  const long long strips = (long long)a.batch * nT * ((nA + kGTA - 1) / kGTA) * ((nL + 31) / 32);
+  long long blocks = (strips + W - 1) / W;
+  const long long cap = 148LL * 4;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, W * 32, smem, st>>>(a);
+  MVS_CHECK_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+// gaussian_filter of `batch` volumes: src -> dst, using tmp as the ping-pong buffer.
+// d_fw holds rp + 1 weights (zero beyond `radius`).  boxes: see gauss_strip_kernel.
 static int gaussian_batch(const float* src, float* dst, float* tmp, int batch, const int32_t shape[3],
-                          int ndim, const double* d_fw, int radius, cudaStream_t st) {
+                          int ndim, const double* d_fw, int radius, int rp, const int* boxes,
+                          int box_mod, cudaStream_t st) {
   const long long total = (long long)batch * shape[0] * shape[1] * shape[2];
   const int grid = ew_grid(total);
   // axes in scipy's order (z, y, x); an odd number of passes must end in dst
@@ -184,13 +469,49 @@ static int gaussian_batch(const float* src, float* dst, float* tmp, int batch, c
   for (int axis = first_axis; axis < 3; ++axis) {
     const int remaining = 3 - axis;  // passes left including this one
     float* o = (remaining % 2 == 1) ? dst : tmp;
-    gauss1d_kernel<<<grid, 256, 0, st>>>(cur, o, shape[0], shape[1], shape[2], axis, d_fw, radius,
-                                         total);
-    MVS_CHECK_CUDA(cudaGetLastError());
+    size_t smem = 0;
+    const int W = strip_warps(rp, axis, &smem);
+    if (W >= 1) {
+      GaussArgs a{cur, o, shape[0], shape[1], shape[2], batch, d_fw, rp, boxes, box_mod};
+      int rc = axis == 0 ? launch_strip<0>(a, W, smem, st)
+                         : (axis == 1 ? launch_strip<1>(a, W, smem, st) : launch_strip<2>(a, W, smem, st));
+      if (rc) return rc;
+    } else {
+      // very wide kernels: one thread per output, taps from global memory (computes
+      // the whole volume, which is a superset of any box)
+      gauss1d_kernel<<<grid, 256, 0, st>>>(cur, o, shape[0], shape[1], shape[2], axis, d_fw, radius,
+                                           total);
+      MVS_CHECK_CUDA(cudaGetLastError());
+    }
     cur = o;
   }
   return MVS_OK;
 }
+
+// grow-only device workspace shared by the multi-pass entry points (one call at a
+// time: callers are serialised by g_ws_mutex and synchronise their stream before
+// returning, so the buffer is never in use by two calls)
+static std::mutex g_ws_mutex;
+static void* g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+
+static int workspace(size_t bytes, void** out) {
+  if (g_ws_bytes < bytes) {
+    if (g_ws) cudaFree(g_ws);
+    g_ws = nullptr;
+    g_ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&g_ws, bytes);
+    if (e != cudaSuccess) {
+      set_error("workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+      return MVS_ERR_CUDA;
+    }
+    g_ws_bytes = bytes;
+  }
+  *out = g_ws;
+  return MVS_OK;
+}
+
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
 }  // namespace mvs
 
@@ -213,16 +534,18 @@ extern "C" int mvs_gaussian_filter(const float* d_in, float* d_out, int batch,
   MVS_REQUIRE(ndim == 2 || ndim == 3, MVS_ERR_INVALID, "ndim must be 2 or 3");
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)batch * shape[0] * shape[1] * shape[2];
-  double* d_fw = nullptr;
-  float* tmp = nullptr;
-  MVS_CHECK_CUDA(cudaMalloc(&d_fw, sizeof(double) * (radius + 1)));
-  cudaError_t e = cudaMalloc(&tmp, sizeof(float) * total);
-  if (e != cudaSuccess) { cudaFree(d_fw); set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
-  cudaMemcpyAsync(d_fw, weights, sizeof(double) * (radius + 1), cudaMemcpyHostToDevice, st);
-  rc = gaussian_batch(d_in, d_out, tmp, batch, shape, ndim, d_fw, radius, st);
+  const int rp = round_up4(radius);
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  void* ws = nullptr;
+  const size_t wbytes = align256(sizeof(double) * (rp + 1));
+  if ((rc = workspace(wbytes + sizeof(float) * total, &ws))) return rc;
+  double* d_fw = (double*)ws;
+  float* tmp = (float*)((char*)ws + wbytes);
+  std::vector<double> hw(rp + 1, 0.0);
+  for (int i = 0; i <= radius; ++i) hw[i] = weights[i];
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_fw, hw.data(), sizeof(double) * (rp + 1), cudaMemcpyHostToDevice, st));
+  rc = gaussian_batch(d_in, d_out, tmp, batch, shape, ndim, d_fw, radius, rp, nullptr, 1, st);
   cudaStreamSynchronize(st);
-  cudaFree(d_fw);
-  cudaFree(tmp);
   return rc;
 }
 
@@ -239,40 +562,45 @@ extern "C" int mvs_content_based(const float* d_views, const float* d_blending, 
   const long long N = (long long)shape[0] * shape[1] * shape[2];
   const long long total = N * V;
   const int grid = ew_grid(total);
-  // workspace: masked views M, and a batch of 2V volumes [V0 | W0] plus two
-  // filter buffers of the same size
-  float* ws = nullptr;
-  double* d_fw = nullptr;
-  MVS_CHECK_CUDA(cudaMalloc(&d_fw, sizeof(double) * (r1 + r2 + 2)));
-  cudaError_t e = cudaMalloc(&ws, sizeof(float) * total * 7);
-  if (e != cudaSuccess) {
-    cudaFree(d_fw);
-    set_error("content_based workspace (%lld bytes): %s", (long long)sizeof(float) * total * 7,
-              cudaGetErrorString(e));
-    return MVS_ERR_CUDA;
-  }
+  const int rp1 = round_up4(r1), rp2 = round_up4(r2);
+  // workspace: filter weights, per-view boxes, masked views M, a batch of 2V
+  // volumes [V0 | W0] and two filter buffers of the same size
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  const size_t wbytes = align256(sizeof(double) * (rp1 + rp2 + 2));
+  const size_t bbytes = align256(sizeof(int) * 6 * V);
+  void* wsp = nullptr;
+  if ((rc = workspace(wbytes + bbytes + sizeof(float) * total * 7, &wsp))) return rc;
+  double* d_w1 = (double*)wsp;
+  double* d_w2 = d_w1 + rp1 + 1;
+  int* d_boxes = (int*)((char*)wsp + wbytes);
+  float* ws = (float*)((char*)wsp + wbytes + bbytes);
   float* M = ws;                // masked views
   float* VW = ws + total;       // [V0 | W0]  (2*total)
   float* F = ws + 3 * total;    // filtered   (2*total)
   float* T = ws + 5 * total;    // ping-pong  (2*total)
-  double* d_w1 = d_fw;
-  double* d_w2 = d_fw + r1 + 1;
-  cudaMemcpyAsync(d_w1, w1, sizeof(double) * (r1 + 1), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(d_w2, w2, sizeof(double) * (r2 + 1), cudaMemcpyHostToDevice, st);
-  auto fail = [&](int code) { cudaStreamSynchronize(st); cudaFree(ws); cudaFree(d_fw); return code; };
+  std::vector<double> hw(rp1 + rp2 + 2, 0.0);
+  for (int i = 0; i <= r1; ++i) hw[i] = w1[i];
+  for (int i = 0; i <= r2; ++i) hw[rp1 + 1 + i] = w2[i];
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_w1, hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice, st));
+  auto fail = [&](int code) { cudaStreamSynchronize(st); return code; };
 
   // transformed_views[blending_weights < 1e-7] = NaN; split into V0 / W0
   mask_split_kernel<<<grid, 256, 0, st>>>(d_views, d_blending, 1e-7f, M, VW, VW + total, total);
-  // inner nan-gaussian (sigma_1) and squared difference
-  if ((rc = gaussian_batch(VW, F, T, 2 * V, shape, ndim, d_w1, r1, st))) return fail(rc);
-  nan_divide_kernel<true><<<grid, 256, 0, st>>>(F, F + total, M, T, total);  // T = (M - Z)^2
-  // outer nan-gaussian (sigma_2)
-  mask_split_kernel<<<grid, 256, 0, st>>>(T, nullptr, 0.f, nullptr, VW, VW + total, total);
-  // keep the NaN pattern of the squared difference (== pattern of M)
-  if ((rc = gaussian_batch(VW, F, T, 2 * V, shape, ndim, d_w2, r2, st))) return fail(rc);
+  // per-view bounding box of what is left: all filtering is confined to it
+  box_init_kernel<<<(6 * V + 255) / 256, 256, 0, st>>>(d_boxes, V);
+  {
+    const long long bb = (N + 255) / 256;
+    dim3 bg((unsigned)(bb < 296 ? (bb < 1 ? 1 : bb) : 296), V);
+    box_kernel<<<bg, 256, 0, st>>>(M, shape[0], shape[1], shape[2], d_boxes);
+  }
+  // inner nan-gaussian (sigma_1), squared difference, split again
+  if ((rc = gaussian_batch(VW, F, T, 2 * V, shape, ndim, d_w1, r1, rp1, d_boxes, V, st))) return fail(rc);
+  sqdiff_split_kernel<<<grid, 256, 0, st>>>(F, F + total, M, VW, VW + total, total);
+  // outer nan-gaussian (sigma_2); the NaN pattern is still that of M
+  if ((rc = gaussian_batch(VW, F, T, 2 * V, shape, ndim, d_w2, r2, rp2, d_boxes, V, st))) return fail(rc);
   nan_divide_kernel<false><<<grid, 256, 0, st>>>(F, F + total, M, d_out_weights, total);
   normalize_weights_kernel<<<ew_grid(N), 256, 0, st>>>(d_out_weights, V, N);
-  e = cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("content_based launch: %s", cudaGetErrorString(e)); return fail(MVS_ERR_CUDA); }
   return fail(MVS_OK);
 }

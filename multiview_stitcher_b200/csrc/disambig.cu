@@ -370,6 +370,11 @@ rank_kernel(const unsigned long long* __restrict__ sorted, const unsigned* __res
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     const unsigned long long v = seg[j];
+    // untied values (the common case for float data) need no search
+    if ((j == 0 || seg[j - 1] != v) && (j + 1 >= n || seg[j + 1] != v)) {
+      rank_out[sid[j]] = (double)(j + 1);
+      continue;
+    }
     long long lo = 0, hi = j;  // first index with key == v
     while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] < v) lo = mid + 1; else hi = mid; }
     const long long first = lo;

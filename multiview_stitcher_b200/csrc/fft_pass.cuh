@@ -76,35 +76,55 @@ struct PassThread {
       valid = xi < P.items_x;
       int x = xi, y = (int)yb;
       if (half) { x = xi ? P.n2 - xi : 0; y = y ? P.n1p - y : 0; }
-      base = boff + (long long)y * P.n2 + x;
+      base = valid ? boff + (long long)y * P.n2 + x : boff;
       flat0 = 0;
     } else {
       const long long q = bx * P.L + l;
       valid = q < P.outer * P.inner;
       const long long o = q / P.inner, in = q - o * P.inner;
-      base = boff + o * (long long)P.n * P.inner + in;
+      base = valid ? boff + o * (long long)P.n * P.inner + in : boff;
       flat0 = o * (long long)P.n * P.inner + in;
     }
   }
 
+  // All global loads of the thread are issued back to back (clamped addresses, no
+  // branches) before any of them is consumed: E independent requests in flight.
   MVS_HD void load(const FftPassArgs& P) {
+    const float sgn = P.sign > 0 ? -1.f : 1.f;  // inverse = conj(forward(conj(x)))
+    if (P.load_real) {
+      float a[E], b[E];
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-      const int k = t + q * T;
-      float2 x = make_float2(0.f, 0.f);
-      if (valid && k < P.n) {
-        const long long g = base + (long long)k * P.inner;
-        if (P.load_real) {
-          const float a = MVS_LDG(P.re + g), b = MVS_LDG(P.im + g);
-          x = make_float2(a != a ? 0.f : a, b != b ? 0.f : b);
-        } else {
-          x = P.src[g];
-        }
-        if (P.sign > 0) x.y = -x.y;  // inverse = conj(forward(conj(x)))
-        if (BLUE) x = cmul(x, MVS_LDG(P.chirp + k));
+      for (int q = 0; q < E; ++q) {
+        const int k = t + q * T;
+        const long long g = base + (long long)(k < P.n ? k : 0) * P.inner;
+        a[q] = MVS_LDG(P.re + g);
+        b[q] = MVS_LDG(P.im + g);
       }
-      v[q] = x;
+#pragma unroll
+      for (int q = 0; q < E; ++q) v[q] = make_float2(a[q] != a[q] ? 0.f : a[q], b[q] != b[q] ? 0.f : b[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int k = t + q * T;
+        v[q] = P.src[base + (long long)(k < P.n ? k : 0) * P.inner];
+      }
     }
+    if (BLUE) {
+      float2 c[E];
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const int k = t + q * T;
+        c[q] = MVS_LDG(P.chirp + (k < P.n ? k : 0));
+      }
+#pragma unroll
+      for (int q = 0; q < E; ++q) v[q] = cmul(make_float2(v[q].x, sgn * v[q].y), c[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < E; ++q) v[q].y *= sgn;
+    }
+#pragma unroll
+    for (int q = 0; q < E; ++q)
+      if (!valid || t + q * T >= P.n) v[q] = make_float2(0.f, 0.f);
   }
 
   // Bluestein: between the two power-of-two transforms (registers only)
@@ -118,16 +138,22 @@ struct PassThread {
   }
 
   MVS_HD void post(const FftPassArgs& P) {
+    const float sgn = P.sign > 0 ? -1.f : 1.f;
+    if (BLUE) {
+      float2 c[E];
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-      const int k = t + q * T;
-      float2 y = v[q];
-      if (BLUE) {
-        y.y = -y.y;
-        y = (k < P.n) ? cmul(y, MVS_LDG(P.chirp + k)) : make_float2(0.f, 0.f);
+      for (int q = 0; q < E; ++q) {
+        const int k = t + q * T;
+        c[q] = MVS_LDG(P.chirp + (k < P.n ? k : 0));
       }
-      if (P.sign > 0) y.y = -y.y;
-      v[q] = y;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        const float2 y = cmul(make_float2(v[q].x, -v[q].y), c[q]);
+        v[q] = (t + q * T < P.n) ? make_float2(y.x, sgn * y.y) : make_float2(0.f, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < E; ++q) v[q].y *= sgn;
     }
   }
 

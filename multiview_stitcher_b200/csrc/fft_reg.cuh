@@ -175,15 +175,27 @@ struct FftStage {
       for (int r = 0; r < R; ++r) v[b + r * B] = x[r];
     }
   }
-  // autosort permutation: results to their Stockham positions in the line buffer
+  // autosort permutation: results to their Stockham positions in the line buffer.
+  // The padded index of (base + r NS) is pad(base) + r * const whenever the stride
+  // keeps the low four bits, so the stores use immediate offsets.
   static MVS_HD void scatter(const float2* v, int t, float2* sline) {
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       const int j = t + b * T;
       const int k = j & (NS - 1);
       const int base = (j - k) * R + k;
+      if constexpr (NS % 16 == 0) {
+        float2* p = sline + fft_pad(base);
 #pragma unroll
-      for (int r = 0; r < R; ++r) sline[fft_pad(base + r * NS)] = v[b + r * B];
+        for (int r = 0; r < R; ++r) p[r * (NS + NS / 16)] = v[b + r * B];
+      } else if constexpr (NS == 1 && R == 16) {
+        float2* p = sline + 17 * j;  // pad(16 j + r) = 17 j + r
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r] = v[b + r * B];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sline[fft_pad(base + r * NS)] = v[b + r * B];
+      }
     }
   }
 };
@@ -192,8 +204,14 @@ struct FftStage {
 template <int M>
 MVS_HD void fft_gather(float2* v, int t, const float2* sline) {
   using Sc = FftSched<M>;
+  if constexpr (Sc::T % 16 == 0) {
+    const float2* p = sline + fft_pad(t);
 #pragma unroll
-  for (int q = 0; q < Sc::E; ++q) v[q] = sline[fft_pad(t + q * Sc::T)];
+    for (int q = 0; q < Sc::E; ++q) v[q] = p[q * (Sc::T + Sc::T / 16)];
+  } else {
+#pragma unroll
+    for (int q = 0; q < Sc::E; ++q) v[q] = sline[fft_pad(t + q * Sc::T)];
+  }
 }
 
 #ifdef __CUDACC__

@@ -230,6 +230,42 @@ def _expand_candidates(shift_cands, shape, max_shift_per_dim):
     return t_candidates
 
 
+def _valid_range(n, t):
+    """Integer x in [0, n) with 0 <= x + t <= n - 1 in float64 -- the outside
+    predicate of scipy's affine_transform (and of the engine's shifted_value)."""
+    t = float(t)
+    lo = max(0, int(np.ceil(-t)))
+    while lo > 0 and float(lo - 1) + t >= 0.0:
+        lo -= 1
+    while lo < n and float(lo) + t < 0.0:
+        lo += 1
+    hi = min(n - 1, int(np.floor(float(n - 1) - t)))
+    while hi < n - 1 and float(hi + 1) + t <= float(n - 1):
+        hi += 1
+    while hi >= 0 and float(hi) + t > float(n - 1):
+        hi -= 1
+    return lo, hi
+
+
+def _box_candidate_stats(shape, t):
+    """mvs_pc_candidate_stats for a pair without NaNs: [n_mask, n_valid, lo zyx, hi zyx]."""
+    ndim = len(shape)
+    out = np.zeros(8, dtype=np.int64)
+    out[2:5] = 0
+    out[5:8] = 0
+    count = 1
+    for d in range(ndim):
+        lo, hi = _valid_range(int(shape[d]), t[d])
+        count *= max(0, hi - lo + 1)
+        out[2 + 3 - ndim + d] = lo
+        out[5 + 3 - ndim + d] = hi
+    if count == 0:
+        out[2:5] = np.iinfo(np.int32).max
+        out[5:8] = -1
+    out[0] = out[1] = count
+    return out
+
+
 def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=False):
     """Stages B-E for the pairs loaded into ``plan``; one result dict per pair."""
     n, ndim, shape = plan.n, plan.ndim, plan.shape
@@ -261,7 +297,20 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
         key = (cp_,) + tuple(float(x) for x in ct_)
         umap.append(uniq.setdefault(key, len(uniq)))
     ukeys = list(uniq.keys())
-    cstats_u = plan.candidate_stats([k[0] for k in ukeys], np.array([k[1:] for k in ukeys], dtype=np.float64))
+    # NaN-free pairs: the valid region of the shifted image is the box the
+    # coordinate predicate cuts out, so its statistics have a closed form; only
+    # pairs with NaNs need the counting kernel
+    cstats_u = np.zeros((len(ukeys), 8), dtype=np.int64)
+    need_kernel = []
+    for j, k in enumerate(ukeys):
+        if per_pair[k[0]]["has_nan"]:
+            need_kernel.append(j)
+        else:
+            cstats_u[j] = _box_candidate_stats(shape, k[1:])
+    if need_kernel:
+        cstats_u[need_kernel] = plan.candidate_stats(
+            [ukeys[j][0] for j in need_kernel], np.array([ukeys[j][1:] for j in need_kernel], dtype=np.float64)
+        )
     cstats = cstats_u[np.array(umap)]
 
     # decide which candidates need SSIM (:501-536)
