@@ -149,21 +149,17 @@ cand_stats_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
 // im1t is materialised once per candidate (slice region only) by
 // materialize_kernel; the tiles then read plain float32 windows.
 
-constexpr int kTX = 32, kTY = 16, kTZ3 = 4, kTY3 = 8;
+// Tiles march along the first filter axis (z in 3-D, y in 2-D) with float64
+// running sums per column, so the halo of that axis is paid once per tile and
+// the per-voxel work does not grow with the window:
+//   2-D: a CTA owns up to 128 output columns x 64 output rows; thread = column.
+//   3-D: a CTA owns 32 x 8 output columns x 32 output planes; thread = up to 3
+//        of the (32+6) x (8+6) input columns; each plane then gets its y and x
+//        passes through shared memory.
 constexpr int kMaxWin = 7;
-
-template <int NDIM>
-struct SsimTile {
-  static constexpr int TZ = NDIM == 3 ? kTZ3 : 1;
-  static constexpr int TY = NDIM == 3 ? kTY3 : kTY;
-  static constexpr int TX = kTX;
-  static constexpr int WZ = NDIM == 3 ? TZ + kMaxWin - 1 : 1;
-  static constexpr int WY = TY + kMaxWin - 1;
-  static constexpr int WX = TX + kMaxWin - 1;
-  static constexpr int WVOL = WZ * WY * WX;
-  static constexpr int OUT = TZ * TY * TX;
-  static constexpr int PER_THREAD = OUT / 256;
-};
+constexpr int kS2TX = 128, kS2TY = 64, kS2Threads = 160, kS2Cols = kS2TX + kMaxWin - 1;
+constexpr int kS3TX = 32, kS3TY = 8, kS3TZ = 32, kS3Threads = 256;
+constexpr int kS3WX = kS3TX + kMaxWin - 1, kS3WY = kS3TY + kMaxWin - 1, kS3P = kS3WX + 1;
 
 // im1t[slices] of every candidate, packed one after the other (offset mat_off)
 template <int NDIM>
@@ -181,147 +177,259 @@ materialize_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
   }
 }
 
-template <int NDIM>
-__global__ void __launch_bounds__(256)
-ssim_kernel(const Cand* __restrict__ cands, int n_cand, int n0, int n1, int n2,
-            const float* __restrict__ mat, double* __restrict__ tile_sum,
-            float* __restrict__ tile_max) {
-  using T = SsimTile<NDIM>;
-  extern __shared__ float ssim_smem[];
-  float* Q = ssim_smem;                 // 5 quantity windows: a, b, aa, bb, ab
-  float* R = ssim_smem + 5 * T::WVOL;   // 5 filtered windows (ping-pong partner)
-  __shared__ double s_red[256];
-  __shared__ float s_max[256];
+// float32 SSIM of one window from its five float32 means (skimage
+// structural_similarity, gaussian_weights=False, use_sample_covariance=True)
+__device__ __forceinline__ float ssim_value(float ux, float uy, float uxx, float uyy, float uxy,
+                                            float cov_norm) {
+  const float C1 = __fmul_rn(0.01f, 0.01f);  // (K1 * R)^2 with R = 1 in float32
+  const float C2 = __fmul_rn(0.03f, 0.03f);
+  const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
+  const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
+  const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
+  const float A1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, ux), uy), C1);
+  const float A2 = __fadd_rn(__fmul_rn(2.f, vxy), C2);
+  const float B1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), C1);
+  const float B2 = __fadd_rn(__fadd_rn(vx, vy), C2);
+  return __fdiv_rn(__fmul_rn(A1, A2), __fmul_rn(B1, B2));
+}
 
-  // locate the candidate this tile belongs to
-  const long long tile = blockIdx.x;
+__device__ __forceinline__ int find_cand(const Cand* __restrict__ cands, int n_cand, long long tile) {
   int ci = 0, chi = n_cand - 1;
   while (ci < chi) {
     const int mid = (ci + chi + 1) >> 1;
     if (cands[mid].tile_base <= tile) ci = mid; else chi = mid - 1;
   }
-  const Cand c = cands[ci];
+  return ci;
+}
+
+// the five filtered quantities a, b, aa, bb, ab (products in float32 like skimage)
+__device__ __forceinline__ void five(float a, float b, double* q) {
+  q[0] = (double)a; q[1] = (double)b;
+  q[2] = (double)__fmul_rn(a, a); q[3] = (double)__fmul_rn(b, b); q[4] = (double)__fmul_rn(a, b);
+}
+
+template <int THREADS>
+__device__ __forceinline__ void ssim_block_reduce(double sum, float vmax, long long tile,
+                                                  double* __restrict__ tile_sum,
+                                                  float* __restrict__ tile_max) {
+  __shared__ double s_red[THREADS / 32];
+  __shared__ float s_max[THREADS / 32];
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = vmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    float m = -INFINITY;
+    for (int i = 0; i < THREADS / 32; ++i) { s += s_red[i]; m = fmaxf(m, s_max[i]); }
+    tile_sum[tile] = s;
+    tile_max[tile] = m;
+  }
+}
+
+__global__ void __launch_bounds__(kS2Threads)
+ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
+              const float* __restrict__ mat, double* __restrict__ tile_sum,
+              float* __restrict__ tile_max) {
+  __shared__ double rowbuf[2][5][kS2Cols + 2];
+  const long long tile = blockIdx.x;
+  const Cand c = cands[find_cand(cands, n_cand, tile)];
+  const long long local = tile - c.tile_base;
+  const int tx_i = (int)(local % c.tiles[2]), ty_i = (int)(local / c.tiles[2]);
+  const int ox = tx_i * kS2TX, oy = ty_i * kS2TY;  // output origin in the slice
+  const int win = c.win;
+  const int leny = c.len[1], lenx = c.len[2];
+  const int nxo = min(kS2TX, lenx - win + 1 - ox), nyo = min(kS2TY, leny - win + 1 - oy);
+  const int ncols = nxo + win - 1;
+  const int t = threadIdx.x;
+  const bool col_ok = t < ncols;
+  const float* pa = c.r0 + (long long)(c.lo[1] + oy) * n2 + c.lo[2] + ox + (col_ok ? t : 0);
+  const float* pb = mat + c.mat_off + (long long)oy * lenx + ox + (col_ok ? t : 0);
+  const double inv = 1.0 / (double)win;
+  const int np = win * win;
+  const float cov_norm = (float)((double)np / (double)(np - 1));
+  double S[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double sum = 0.0;
+  float vmax = -INFINITY;
+  const int nrows = nyo + win - 1;
+  // software pipeline: the loads of row r + 1 are in flight while row r is processed
+  float na = 0.f, nb = 0.f, oa = 0.f, ob = 0.f;
+  if (col_ok) { na = __ldg(pa); nb = __ldg(pb); }
+  for (int r = 0; r < nrows; ++r) {
+    float a = na, b = nb, a0 = oa, b0 = ob;
+    if (col_ok && r + 1 < nrows) {
+      na = __ldg(pa + (long long)(r + 1) * n2);
+      nb = __ldg(pb + (long long)(r + 1) * lenx);
+      if (r + 1 >= win) {
+        oa = __ldg(pa + (long long)(r + 1 - win) * n2);
+        ob = __ldg(pb + (long long)(r + 1 - win) * lenx);
+      }
+    }
+    if (col_ok) {
+      if (b == b) vmax = fmaxf(vmax, b); else b = 0.f;
+      if (a != a) a = 0.f;
+      double qn[5];
+      five(a, b, qn);
+      if (r >= win) {
+        if (b0 != b0) b0 = 0.f;
+        if (a0 != a0) a0 = 0.f;
+        double qo[5];
+        five(a0, b0, qo);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) S[q] += qn[q] - qo[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) S[q] += qn[q];
+      }
+    }
+    if (r >= win - 1) {
+      double (*buf)[kS2Cols + 2] = rowbuf[r & 1];
+      if (col_ok) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) buf[q][t] = (double)(float)(S[q] * inv);  // float32 between passes
+      }
+      __syncthreads();
+      if (t < nxo) {
+        float U[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          double s = 0.0;
+          for (int k = 0; k < win; ++k) s += buf[q][t + k];
+          U[q] = (float)(s * inv);
+        }
+        sum += (double)ssim_value(U[0], U[1], U[2], U[3], U[4], cov_norm);
+      }
+    }
+  }
+  ssim_block_reduce<kS2Threads>(sum, vmax, tile, tile_sum, tile_max);
+}
+
+__global__ void __launch_bounds__(kS3Threads)
+ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
+              const float* __restrict__ mat, double* __restrict__ tile_sum,
+              float* __restrict__ tile_max) {
+  __shared__ float zf[5][kS3WY][kS3P];  // z-filtered plane
+  __shared__ float yf[5][kS3TY][kS3P];  // then y-filtered
+  const long long tile = blockIdx.x;
+  const Cand c = cands[find_cand(cands, n_cand, tile)];
   long long local = tile - c.tile_base;
   const int tx_i = (int)(local % c.tiles[2]);
   const int ty_i = (int)((local / c.tiles[2]) % c.tiles[1]);
   const int tz_i = (int)(local / ((long long)c.tiles[2] * c.tiles[1]));
-  const int ox = tx_i * T::TX, oy = ty_i * T::TY, oz = tz_i * T::TZ;  // output origin in slice
+  const int ox = tx_i * kS3TX, oy = ty_i * kS3TY, oz = tz_i * kS3TZ;
   const int win = c.win;
-  const int wz = NDIM == 3 ? T::TZ + win - 1 : 1, wy = T::TY + win - 1, wx = T::TX + win - 1;
-  const float* m1 = mat + c.mat_off;
-
-  // ---- load windows (nan_to_num), build the five products, track nanmax(im1t) ----
+  const int lenz = c.len[0], leny = c.len[1], lenx = c.len[2];
+  const int nxo = min(kS3TX, lenx - win + 1 - ox), nyo = min(kS3TY, leny - win + 1 - oy);
+  const int nzo = min(kS3TZ, lenz - win + 1 - oz);
+  const int t = threadIdx.x;
+  const double inv = 1.0 / (double)win;
+  const int np = win * win * win;
+  const float cov_norm = (float)((double)np / (double)(np - 1));
+  constexpr int NCOL = kS3WX * kS3WY;                       // input columns of the tile
+  constexpr int CPT = (NCOL + kS3Threads - 1) / kS3Threads;  // columns per thread
+  int cy[CPT], cx[CPT];
+  bool ok[CPT];
+  long long offa[CPT], offb[CPT];
+  double S[CPT][5];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int col = t + i * kS3Threads;
+    cy[i] = col / kS3WX; cx[i] = col - cy[i] * kS3WX;
+    ok[i] = col < NCOL && oy + cy[i] < leny && ox + cx[i] < lenx;
+    if (col >= NCOL) { cy[i] = 0; cx[i] = 0; }
+    offa[i] = ok[i] ? ((long long)(c.lo[0] + oz) * n1 + c.lo[1] + oy + cy[i]) * n2 + c.lo[2] + ox + cx[i] : 0;
+    offb[i] = ok[i] ? ((long long)oz * leny + oy + cy[i]) * lenx + ox + cx[i] : 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) S[i][q] = 0.0;
+  }
+  const long long pla = (long long)n1 * n2, plb = (long long)leny * lenx;
+  const float* ra = c.r0;
+  const float* rb = mat + c.mat_off;
+  double sum = 0.0;
   float vmax = -INFINITY;
-  for (int i = threadIdx.x; i < wz * wy * wx; i += 256) {
-    const int lx = i % wx, ly = (i / wx) % wy, lz = i / (wx * wy);
-    const int sx = ox + lx, sy = oy + ly, sz = oz + lz;  // slice-local
-    float a = 0.f, b = 0.f;
-    if (sx < c.len[2] && sy < c.len[1] && sz < c.len[0]) {
-      const int gx = c.lo[2] + sx, gy = c.lo[1] + sy, gz = c.lo[0] + sz;
-      a = __ldg(c.r0 + ((long long)gz * n1 + gy) * n2 + gx);
-      b = __ldg(m1 + ((long long)sz * c.len[1] + sy) * c.len[2] + sx);
+  const int nplanes = nzo + win - 1;
+  const int yo = t / kS3TX, xo = t - yo * kS3TX;  // this thread's output in the x pass
+  // software pipeline: the loads of plane r + 1 are in flight while plane r is processed
+  float na[CPT], nb[CPT], oa[CPT], ob[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    na[i] = ok[i] ? __ldg(ra + offa[i]) : 0.f;
+    nb[i] = ok[i] ? __ldg(rb + offb[i]) : 0.f;
+    oa[i] = 0.f; ob[i] = 0.f;
+  }
+  for (int r = 0; r < nplanes; ++r) {
+    float ca[CPT], cb[CPT], c0a[CPT], c0b[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { ca[i] = na[i]; cb[i] = nb[i]; c0a[i] = oa[i]; c0b[i] = ob[i]; }
+    if (r + 1 < nplanes) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        if (!ok[i]) continue;
+        na[i] = __ldg(ra + offa[i] + (r + 1) * pla);
+        nb[i] = __ldg(rb + offb[i] + (r + 1) * plb);
+        if (r + 1 >= win) {
+          oa[i] = __ldg(ra + offa[i] + (r + 1 - win) * pla);
+          ob[i] = __ldg(rb + offb[i] + (r + 1 - win) * plb);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      if (!ok[i]) continue;
+      float a = ca[i], b = cb[i];
       if (b == b) vmax = fmaxf(vmax, b); else b = 0.f;
       if (a != a) a = 0.f;
-    }
-    const int w = (lz * T::WY + ly) * T::WX + lx;
-    Q[w] = a;
-    Q[T::WVOL + w] = b;
-    Q[2 * T::WVOL + w] = __fmul_rn(a, a);
-    Q[3 * T::WVOL + w] = __fmul_rn(b, b);
-    Q[4 * T::WVOL + w] = __fmul_rn(a, b);
-  }
-  __syncthreads();
-
-  const double dwin = (double)win;
-  float* src = Q;
-  float* dst = R;
-  if (NDIM == 3) {
-    // z pass: running sums down each (y, x) column of the 5 windows
-    for (int i = threadIdx.x; i < 5 * wy * wx; i += 256) {
-      const int q = i / (wy * wx), r = i - q * (wy * wx);
-      const int ly = r / wx, lx = r - ly * wx;
-      const float* p = src + q * T::WVOL + ly * T::WX + lx;
-      float* o = dst + q * T::WVOL + ly * T::WX + lx;
-      double sum = 0.0;
-      for (int k = 0; k < win; ++k) sum += (double)p[k * T::WY * T::WX];
-      for (int lz = 0; lz < T::TZ; ++lz) {
-        o[lz * T::WY * T::WX] = (float)(sum / dwin);
-        if (lz + 1 < T::TZ)
-          sum += (double)p[(lz + win) * T::WY * T::WX] - (double)p[lz * T::WY * T::WX];
-      }
-    }
-    __syncthreads();
-    float* tmp = src; src = dst; dst = tmp;
-  }
-  {
-    // y pass: running sums down each column (per plane, per quantity)
-    const int nzp = NDIM == 3 ? T::TZ : 1;
-    for (int i = threadIdx.x; i < 5 * nzp * wx; i += 256) {
-      const int q = i / (nzp * wx), r = i - q * (nzp * wx);
-      const int lz = r / wx, lx = r - lz * wx;
-      const float* p = src + q * T::WVOL + lz * T::WY * T::WX + lx;
-      float* o = dst + q * T::WVOL + lz * T::WY * T::WX + lx;
-      double sum = 0.0;
-      for (int k = 0; k < win; ++k) sum += (double)p[k * T::WX];
-      for (int ly = 0; ly < T::TY; ++ly) {
-        o[ly * T::WX] = (float)(sum / dwin);
-        if (ly + 1 < T::TY) sum += (double)p[(ly + win) * T::WX] - (double)p[ly * T::WX];
-      }
-    }
-    __syncthreads();
-    float* tmp = src; src = dst; dst = tmp;
-  }
-  // x pass into registers: every thread owns PER_THREAD outputs
-  float U[5][T::PER_THREAD];
+      double qn[5];
+      five(a, b, qn);
+      if (r >= win) {
+        float a0 = c0a[i], b0 = c0b[i];
+        if (b0 != b0) b0 = 0.f;
+        if (a0 != a0) a0 = 0.f;
+        double qo[5];
+        five(a0, b0, qo);
 #pragma unroll
-  for (int r = 0; r < T::PER_THREAD; ++r) {
-    const int i = threadIdx.x + r * 256;
-    const int lx = i % T::TX, ly = (i / T::TX) % T::TY, lz = i / (T::TX * T::TY);
-    const float* p = src + (lz * T::WY + ly) * T::WX + lx;
+        for (int q = 0; q < 5; ++q) S[i][q] += qn[q] - qo[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) S[i][q] += qn[q];
+      }
+    }
+    if (r < win - 1) continue;
+    // z-filtered plane (float32 between passes); columns outside the slice hold 0
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      if (t + i * kS3Threads < NCOL) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) zf[q][cy[i]][cx[i]] = ok[i] ? (float)(S[i][q] * inv) : 0.f;
+      }
+    }
+    __syncthreads();
+    // y pass: 5 x kS3TY x kS3WX values
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
-      double sum = 0.0;
-      for (int k = 0; k < win; ++k) sum += (double)p[q * T::WVOL + k];
-      U[q][r] = (float)(sum / dwin);
-    }
-  }
-
-  // ---- SSIM map on this tile's interior outputs ----
-  int np = win * win * (NDIM == 3 ? win : 1);
-  const float cov_norm = (float)((double)np / (double)(np - 1));
-  const float C1 = __fmul_rn(0.01f, 0.01f);  // (K1 * R)^2 with R = 1 in float32
-  const float C2 = __fmul_rn(0.03f, 0.03f);
-  const int nout_x = c.len[2] - win + 1, nout_y = c.len[1] - win + 1,
-            nout_z = NDIM == 3 ? c.len[0] - win + 1 : 1;
-  double sum = 0.0;
-#pragma unroll
-  for (int r = 0; r < T::PER_THREAD; ++r) {
-    const int i = threadIdx.x + r * 256;
-    const int lx = i % T::TX, ly = (i / T::TX) % T::TY, lz = i / (T::TX * T::TY);
-    if (ox + lx < nout_x && oy + ly < nout_y && oz + lz < nout_z) {
-      const float ux = U[0][r], uy = U[1][r], uxx = U[2][r], uyy = U[3][r], uxy = U[4][r];
-      const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
-      const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
-      const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
-      const float A1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, ux), uy), C1);
-      const float A2 = __fadd_rn(__fmul_rn(2.f, vxy), C2);
-      const float B1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), C1);
-      const float B2 = __fadd_rn(__fadd_rn(vx, vy), C2);
-      const float S = __fdiv_rn(__fmul_rn(A1, A2), __fmul_rn(B1, B2));
-      sum += (double)S;
-    }
-  }
-  s_red[threadIdx.x] = sum;
-  s_max[threadIdx.x] = vmax;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      s_red[threadIdx.x] += s_red[threadIdx.x + s];
-      s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + s]);
+      for (int idx = t; idx < kS3TY * kS3WX; idx += kS3Threads) {
+        const int y = idx / kS3WX, x = idx - y * kS3WX;
+        double s = 0.0;
+        for (int k = 0; k < win; ++k) s += (double)zf[q][y + k][x];
+        yf[q][y][x] = (float)(s * inv);
+      }
     }
     __syncthreads();
+    // x pass + SSIM for this thread's output voxel
+    if (yo < nyo && xo < nxo) {
+      float U[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        double s = 0.0;
+        for (int k = 0; k < win; ++k) s += (double)yf[q][yo][xo + k];
+        U[q] = (float)(s * inv);
+      }
+      sum += (double)ssim_value(U[0], U[1], U[2], U[3], U[4], cov_norm);
+    }
   }
-  if (threadIdx.x == 0) { tile_sum[tile] = s_red[0]; tile_max[tile] = s_max[0]; }
+  ssim_block_reduce<kS3Threads>(sum, vmax, tile, tile_sum, tile_max);
 }
 
 // ---- stage E: Spearman ---------------------------------------------------------
@@ -486,7 +594,7 @@ extern "C" int mvs_pc_candidate_ssim(mvs_pc_plan* p, int n_cand, const int32_t* 
   if (rc) return rc;
   const int ndim = pc_ndim(p);
   const int* sh = pc_shape(p);
-  const int TZ = ndim == 3 ? kTZ3 : 1, TY = ndim == 3 ? kTY3 : kTY, TX = kTX;
+  const int TZ = ndim == 3 ? kS3TZ : 1, TY = ndim == 3 ? kS3TY : kS2TY, TX = ndim == 3 ? kS3TX : kS2TX;
   long long total_tiles = 0;
   for (int i = 0; i < n_cand; ++i) {
     Cand& c = cands[i];
@@ -534,14 +642,10 @@ extern "C" int mvs_pc_candidate_ssim(mvs_pc_plan* p, int n_cand, const int32_t* 
     else materialize_kernel<2><<<g, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], d_mat);
     MVS_CHECK_CUDA(cudaGetLastError());
   }
-  if (ndim == 3) {
-    const int smem = (int)(sizeof(float) * 10 * SsimTile<3>::WVOL);
-    MVS_CHECK_CUDA(cudaFuncSetAttribute(ssim_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ssim_kernel<3><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_mat, d_sum, d_max);
-  } else {
-    const int smem = (int)(sizeof(float) * 10 * SsimTile<2>::WVOL);
-    ssim_kernel<2><<<(unsigned)total_tiles, 256, smem, st>>>(d_c, n_cand, sh[0], sh[1], sh[2], d_mat, d_sum, d_max);
-  }
+  if (ndim == 3)
+    ssim3d_kernel<<<(unsigned)total_tiles, kS3Threads, 0, st>>>(d_c, n_cand, sh[1], sh[2], d_mat, d_sum, d_max);
+  else
+    ssim2d_kernel<<<(unsigned)total_tiles, kS2Threads, 0, st>>>(d_c, n_cand, sh[1], sh[2], d_mat, d_sum, d_max);
   MVS_CHECK_CUDA(cudaGetLastError());
   std::vector<double> hs(total_tiles);
   std::vector<float> hm(total_tiles);

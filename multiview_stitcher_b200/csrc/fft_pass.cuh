@@ -8,7 +8,8 @@
 //                P = F conj(M), F = (Z_k + conj Z_-k)/2, M = (Z_k - conj Z_-k)/(2i)
 //                (skimage phase_cross_correlation, both normalisations packed,
 //                registration.py:416-431) is formed in the epilogue from shared
-//                memory -- Z itself never goes back to HBM;
+//                memory (for the inverse transform), next to the plain P that the
+//                upsampled DFT refines on (overwriting Z in place);
 //   * ARGMAX     last inverse pass: the correlation surfaces are only needed for
 //                their first maxima, so the pass reduces (|value|, ~index) keys
 //                and stores nothing.
@@ -25,6 +26,7 @@ namespace mvs {
 struct FftPassArgs {
   const float2* src;       // complex input (unused with load_real)
   float2* dst;             // complex output, may equal src; nullptr: nothing stored
+  float2* dst2;            // paired: the plain cross-power spectrum P (may equal src)
   const float* re;         // load_real: real sources (NaN -> 0)
   const float* im;
   long long outer, inner;  // lines = outer * inner; element k of line (o, in) at (o n + k) inner + in
@@ -73,8 +75,12 @@ struct PassThread {
       const int xb = (int)(bx - yb * P.xblocks);
       const int half = l / H, i = l - half * H;
       const int xi = xb * H + i;
-      valid = xi < P.items_x;
       int x = xi, y = (int)yb;
+      // columns that mirror onto themselves (x = 0, x = n2/2) pair the rows y' and
+      // -y': only the smaller row index owns the pair, so every line is read and
+      // written by exactly one CTA (P may then overwrite Z in place)
+      const bool self_col = xi == 0 || 2 * xi == P.n2;
+      valid = xi < P.items_x && !(self_col && y != 0 && P.n1p - y < y);
       if (half) { x = xi ? P.n2 - xi : 0; y = y ? P.n1p - y : 0; }
       base = valid ? boff + (long long)y * P.n2 + x : boff;
       flat0 = 0;
@@ -180,6 +186,7 @@ struct PassThread {
         const float mag = fmaxf(sqrtf(F.x * F.x + F.y * F.y) * sqrtf(Mm.x * Mm.x + Mm.y * Mm.y), tiny);
         const float2 Pn = make_float2(Pw.x / mag, Pw.y / mag);
         v[q] = make_float2(P.cp_scale * Pw.x - Pn.y, P.cp_scale * Pw.y + Pn.x);
+        if (valid && P.dst2) P.dst2[base + (long long)k * P.inner] = Pw;
       }
     }
   }

@@ -11,20 +11,21 @@
 //   Q        = s P + i * Pn;  cc = IFFT_nd(Q):  Re = cc(None), Im = cc("phase")
 //              (P, Pn are Hermitian, so both correlation surfaces are real and
 //               ONE complex inverse transform yields both; s = 1/N^2 keeps
-//               |s P| <= 1 so that neither half drowns in the other's rounding)
+//               |s P| <= 1 next to the unit-modulus Pn; only the integer peaks
+//               are read off this packed transform)
 //   peaks    = first argmax of |Re cc|, |Im cc|
 //   C        = conj(upsampled_dft(conj(P or Pn))) on ceil(1.5 u)^ndim samples
-//              around each peak (float64 accumulation), P / Pn recovered from Q:
-//              s P_k = (Q_k + conj Q_-k)/2,  Pn_k = (Q_k - conj Q_-k)/(2i)
+//              around each peak (float64 accumulation) from the plain P
 // Passes over HBM (fft_pass.cuh), N complex voxels of 8 bytes per pair:
 //   forward x   reads r0, r1 (8N)  writes Z (8N)
 //   forward y   [3-D] in place (16N)
-//   forward y/z + cross power: reads Z (8N) writes Q (8N)   -- Z's last axis and the
-//               cross-power spectrum in one kernel (mirror lines paired per CTA)
-//   inverse     first axis Q -> W (16N), [3-D] middle axis in place (16N)
-//   inverse x + argmax: reads W (8N), stores nothing
-// i.e. (32 ndim - 8) N bytes against the (32 ndim + 8) N "pass model" of
-// SURVEY.md 8d that the roofline figure is quoted on.
+//   forward y/z + cross power: reads Z (8N) writes Q and P (16N) -- Z's last axis
+//               and the cross-power spectrum in one kernel (mirror lines paired per CTA)
+//   inverse     first axis in place (16N), [3-D] middle axis in place (16N)
+//   inverse x + argmax: reads Q (8N), stores nothing
+//   upsampled DFT: reads P (8N)
+// i.e. (32 ndim + 8) N bytes, the "pass model" of SURVEY.md 8d that the roofline
+// figure is quoted on.
 
 #include <climits>
 #include <cmath>
@@ -281,7 +282,7 @@ constexpr int kUpWarps = 4;
 
 template <int R>
 __global__ void __launch_bounds__(kUpWarps * 32)
-updft_x_kernel(const float2* __restrict__ Q, int n0, int n1, int n2, long long N,
+updft_x_kernel(const float2* __restrict__ Pg, int n0, int n1, int n2, long long N,
                const float2* __restrict__ E, long long e_stride, const float2* __restrict__ G,
                double2* __restrict__ T) {
   __shared__ float2 s_part[kUpWarps][2 * R][33];
@@ -290,22 +291,17 @@ updft_x_kernel(const float2* __restrict__ Q, int n0, int n1, int n2, long long N
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long line = (long long)blockIdx.x * kUpWarps + warp;
   if (line < nlines) {
-    const int y = (int)(line % n1), zz = (int)(line / n1);
-    const int my = y ? n1 - y : 0, mz = zz ? n0 - zz : 0;
-    const float2* q = Q + (long long)pair * N;
-    const float2* row = q + line * n2;
-    const float2* mrow = q + ((long long)mz * n1 + my) * n2;
+    const float2* row = Pg + (long long)pair * N + line * n2;
     const float2* h0 = E + (long long)(2 * pair) * e_stride;
     const float2* h1 = h0 + e_stride;
+    const float tiny = 100.0f * 1.1920929e-07f;  // 100 * eps(float32)
     float2 acc0[R], acc1[R];
 #pragma unroll
     for (int a = 0; a < R; ++a) { acc0[a] = make_float2(0.f, 0.f); acc1[a] = make_float2(0.f, 0.f); }
     for (int x = lane; x < n2; x += 32) {
-      const int mx = x ? n2 - x : 0;
-      const float2 a = row[x], bm = mrow[mx];
-      // s P = (Q_k + conj Q_-k)/2, Pn = (Q_k - conj Q_-k)/(2i)
-      const float2 Ps = make_float2(0.5f * (a.x + bm.x), 0.5f * (a.y - bm.y));
-      const float2 Pn = make_float2(0.5f * (a.y + bm.y), -0.5f * (a.x - bm.x));
+      const float2 Ps = row[x];
+      const float mag = fmaxf(hypotf(Ps.x, Ps.y), tiny);
+      const float2 Pn = make_float2(__fdiv_rn(Ps.x, mag), __fdiv_rn(Ps.y, mag));
       const float2 g = __ldg(G + x);
       float2 w0 = cmul(Ps, __ldg(h0 + x));
       float2 w1 = cmul(Pn, __ldg(h1 + x));
@@ -571,10 +567,10 @@ static int launch_pass_m(const FftPassArgs& a, bool blue, dim3 grid, int threads
 
 // One pass along `axis` over the n loaded pairs.  sign -1 forward / +1 inverse.
 static int launch_pass(mvs_pc_plan* p, int n, int axis, int sign, PassKind kind, const float2* src,
-                       float2* dst, cudaStream_t st) {
+                       float2* dst, cudaStream_t st, float2* dst2 = nullptr) {
   FftPassArgs a{};
   const AxisFft& ax = p->ax[axis];
-  a.src = src; a.dst = dst;
+  a.src = src; a.dst = dst; a.dst2 = dst2;
   a.re = p->r0; a.im = p->r1;
   a.n = p->shape[axis];
   long long inner = 1, outer = 1;
@@ -632,7 +628,7 @@ template <int R>
 static int launch_updft_x(mvs_pc_plan* p, int n, cudaStream_t st) {
   const long long lines = p->N / p->shape[2];
   dim3 grid((unsigned)((lines + kUpWarps - 1) / kUpWarps), n);
-  updft_x_kernel<R><<<grid, kUpWarps * 32, 0, st>>>(p->Q, p->shape[0], p->shape[1], p->shape[2],
+  updft_x_kernel<R><<<grid, kUpWarps * 32, 0, st>>>(p->Z, p->shape[0], p->shape[1], p->shape[2],
                                                     p->N, p->d_E, p->e_stride, p->d_G, p->d_T0);
   MVS_CHECK_CUDA(cudaGetLastError());
   return MVS_OK;
@@ -651,11 +647,12 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
   if ((rc = launch_pass(p, n, 2, -1, PASS_LOAD_REAL, nullptr, p->Z, st))) return rc;
   if (p->ndim == 3 && (rc = launch_pass(p, n, 1, -1, PASS_PLAIN, p->Z, p->Z, st))) return rc;
   const int first = 3 - p->ndim;
-  if ((rc = launch_pass(p, n, first, -1, PASS_PAIRED, p->Z, p->Q, st))) return rc;
-  // inverse: first data axis Q -> Z (Q is kept for the upsampled DFT), [y], x + argmax
-  if ((rc = launch_pass(p, n, first, +1, PASS_PLAIN, p->Q, p->Z, st))) return rc;
-  if (p->ndim == 3 && (rc = launch_pass(p, n, 1, +1, PASS_PLAIN, p->Z, p->Z, st))) return rc;
-  if ((rc = launch_pass(p, n, 2, +1, PASS_ARGMAX, p->Z, nullptr, st))) return rc;
+  // (Z is overwritten in place by the plain cross-power spectrum P)
+  if ((rc = launch_pass(p, n, first, -1, PASS_PAIRED, p->Z, p->Q, st, p->Z))) return rc;
+  // inverse of Q in place: first data axis, [y], x + argmax
+  if ((rc = launch_pass(p, n, first, +1, PASS_PLAIN, p->Q, p->Q, st))) return rc;
+  if (p->ndim == 3 && (rc = launch_pass(p, n, 1, +1, PASS_PLAIN, p->Q, p->Q, st))) return rc;
+  if ((rc = launch_pass(p, n, 2, +1, PASS_ARGMAX, p->Q, nullptr, st))) return rc;
   // slot 0 = |Re| = normalization None, slot 1 = |Im| = "phase"
   updft_setup_kernel<<<2 * n, 256, 0, st>>>(p->d_keys, p->shape[0], p->shape[1], p->shape[2],
                                             p->ndim, p->R, p->upsample, p->d_peaks, p->d_E,
