@@ -20,6 +20,7 @@ mirrors the reference line by line.  No CPU fallback exists for the array work.
 from __future__ import annotations
 
 import ctypes
+import itertools
 import warnings
 
 import numpy as np
@@ -186,83 +187,75 @@ class PhaseCorrPlan:
 
 def _subpixel_shifts(plan, peaks, updft):
     """skimage.phase_cross_correlation's float32 shift arithmetic on the
-    engine's integer peaks and upsampled-DFT samples.  Returns
-    shifts[pair][norm] (norm 0 = None, 1 = "phase")."""
+    engine's integer peaks and upsampled-DFT samples (vectorised over pairs).
+    Returns shifts[pair][norm] (norm 0 = None, 1 = "phase")."""
     n, ndim, u = peaks.shape[0], plan.ndim, plan.upsample
-    out = np.zeros((n, 2, ndim), dtype=np.float32)
     uf = np.float32(u)
     region = plan.region
-    dftshift = np.fix(np.float32(region) / np.float32(2.0))
-    for i in range(n):
-        for k in range(2):
-            shift = peaks[i, k, 3 - ndim :].astype(np.float32)
-            if u > 1:
-                shift = np.round(shift * uf) / uf
-                cc = updft[i, k].reshape((region,) * ndim).astype(np.complex64)
-                maxima = np.unravel_index(np.argmax(np.abs(cc)), cc.shape)
-                maxima = np.stack(maxima).astype(np.float32) - dftshift
-                shift = shift + maxima / uf
-            for d in range(ndim):
-                if plan.shape[d] == 1:
-                    shift[d] = 0
-            out[i, k] = shift
-    return out
+    shift = peaks[:, :, 3 - ndim :].astype(np.float32)
+    if u > 1:
+        dftshift = np.fix(np.float32(region) / np.float32(2.0))
+        shift = np.round(shift * uf) / uf
+        cc = np.abs(updft.reshape(n, 2, -1).astype(np.complex64))
+        flat = np.argmax(cc, axis=-1)
+        maxima = np.stack(np.unravel_index(flat, (region,) * ndim), axis=-1).astype(np.float32) - dftshift
+        shift = shift + maxima / uf
+    for d in range(ndim):
+        if plan.shape[d] == 1:
+            shift[:, :, d] = 0
+    return shift.astype(np.float32)
 
 
 def _expand_candidates(shift_cands, shape, max_shift_per_dim):
-    """registration.py:461-477."""
+    """registration.py:461-477: per shift and dim {s, -s, -(s - N), -s - N} (one
+    option when s == 0), in np.ndindex order; float32 arithmetic like the
+    reference's (skimage returns float32 shifts)."""
     ndim = len(shape)
     t_candidates = []
     for sc in shift_cands:
-        for s in np.ndindex(tuple(1 if sc[d] == 0 else 4 for d in range(ndim))):
-            t = []
-            for d in range(ndim):
-                if s[d] == 0:
-                    t.append(sc[d])
-                elif s[d] == 1:
-                    t.append(-sc[d])
-                elif s[d] == 2:
-                    t.append(-(sc[d] - shape[d]))
-                else:
-                    t.append(-sc[d] - shape[d])
-            if np.max(np.abs(t)) < max_shift_per_dim:
-                t_candidates.append(t)
+        opts = []
+        for d in range(ndim):
+            s_ = np.float32(sc[d])
+            if s_ == 0:
+                opts.append((float(s_),))
+            else:
+                opts.append((float(s_), float(-s_), float(-(s_ - shape[d])), float(-s_ - shape[d])))
+        for t in itertools.product(*opts):
+            if max(abs(x) for x in t) < max_shift_per_dim:
+                t_candidates.append(list(t))
     return t_candidates
 
 
 def _valid_range(n, t):
-    """Integer x in [0, n) with 0 <= x + t <= n - 1 in float64 -- the outside
-    predicate of scipy's affine_transform (and of the engine's shifted_value)."""
-    t = float(t)
-    lo = max(0, int(np.ceil(-t)))
-    while lo > 0 and float(lo - 1) + t >= 0.0:
-        lo -= 1
-    while lo < n and float(lo) + t < 0.0:
-        lo += 1
-    hi = min(n - 1, int(np.floor(float(n - 1) - t)))
-    while hi < n - 1 and float(hi + 1) + t <= float(n - 1):
-        hi += 1
-    while hi >= 0 and float(hi) + t > float(n - 1):
-        hi -= 1
+    """Integers x in [0, n) with 0 <= x + t <= n - 1 in float64 -- the outside
+    predicate of scipy's affine_transform (and of the engine's shifted_value).
+    ``t``: float64 array; returns (lo, hi) int64 arrays (hi < lo: empty)."""
+    t = np.asarray(t, dtype=np.float64)
+    lo = np.maximum(0, np.ceil(-t)).astype(np.int64)
+    lo = np.where((lo > 0) & ((lo - 1).astype(np.float64) + t >= 0.0), lo - 1, lo)
+    lo = np.where((lo < n) & (lo.astype(np.float64) + t < 0.0), lo + 1, lo)
+    hi = np.minimum(n - 1, np.floor(float(n - 1) - t)).astype(np.int64)
+    hi = np.where((hi < n - 1) & ((hi + 1).astype(np.float64) + t <= float(n - 1)), hi + 1, hi)
+    hi = np.where((hi >= 0) & (hi.astype(np.float64) + t > float(n - 1)), hi - 1, hi)
     return lo, hi
 
 
-def _box_candidate_stats(shape, t):
-    """mvs_pc_candidate_stats for a pair without NaNs: [n_mask, n_valid, lo zyx, hi zyx]."""
+def _box_candidate_stats(shape, ts):
+    """mvs_pc_candidate_stats for pairs without NaNs, ``ts``: (n, ndim) float64.
+    Rows of [n_mask, n_valid, lo zyx, hi zyx]."""
+    ts = np.asarray(ts, dtype=np.float64).reshape(-1, len(shape))
     ndim = len(shape)
-    out = np.zeros(8, dtype=np.int64)
-    out[2:5] = 0
-    out[5:8] = 0
-    count = 1
+    out = np.zeros((len(ts), 8), dtype=np.int64)
+    count = np.ones(len(ts), dtype=np.int64)
     for d in range(ndim):
-        lo, hi = _valid_range(int(shape[d]), t[d])
-        count *= max(0, hi - lo + 1)
-        out[2 + 3 - ndim + d] = lo
-        out[5 + 3 - ndim + d] = hi
-    if count == 0:
-        out[2:5] = np.iinfo(np.int32).max
-        out[5:8] = -1
-    out[0] = out[1] = count
+        lo, hi = _valid_range(int(shape[d]), ts[:, d])
+        count *= np.maximum(0, hi - lo + 1)
+        out[:, 2 + 3 - ndim + d] = lo
+        out[:, 5 + 3 - ndim + d] = hi
+    empty = count == 0
+    out[empty, 2:5] = np.iinfo(np.int32).max
+    out[empty, 5:8] = -1
+    out[:, 0] = out[:, 1] = count
     return out
 
 
@@ -294,53 +287,54 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
     # once; the reference evaluates them twice with identical results
     uniq, umap = {}, []
     for cp_, ct_ in zip(cand_pair, cand_t):
-        key = (cp_,) + tuple(float(x) for x in ct_)
+        key = (cp_,) + tuple(ct_)
         umap.append(uniq.setdefault(key, len(uniq)))
     ukeys = list(uniq.keys())
     # NaN-free pairs: the valid region of the shifted image is the box the
     # coordinate predicate cuts out, so its statistics have a closed form; only
     # pairs with NaNs need the counting kernel
     cstats_u = np.zeros((len(ukeys), 8), dtype=np.int64)
-    need_kernel = []
-    for j, k in enumerate(ukeys):
-        if per_pair[k[0]]["has_nan"]:
-            need_kernel.append(j)
-        else:
-            cstats_u[j] = _box_candidate_stats(shape, k[1:])
+    need_kernel = [j for j, k in enumerate(ukeys) if per_pair[k[0]]["has_nan"]]
+    closed = [j for j, k in enumerate(ukeys) if not per_pair[k[0]]["has_nan"]]
+    if closed:
+        cstats_u[closed] = _box_candidate_stats(shape, [ukeys[j][1:] for j in closed])
     if need_kernel:
         cstats_u[need_kernel] = plan.candidate_stats(
             [ukeys[j][0] for j in need_kernel], np.array([ukeys[j][1:] for j in need_kernel], dtype=np.float64)
         )
     cstats = cstats_u[np.array(umap)]
 
-    # decide which candidates need SSIM (:501-536)
+    # decide which candidates need SSIM (:501-536), vectorised over all candidates
+    n_c = len(cand_pair)
+    cp_arr = np.asarray(cand_pair)
+    nmask_all = cstats[:, 0]
+    valid1 = np.array([int(plan.voxels - stats[i, 1, 2]) for i in range(n)], dtype=np.float64)[cp_arr]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        low = (nmask_all == 0) | (nmask_all.astype(np.float64) / valid1 < 0.1)
+    im0_lo = stats[:, 0, 3 + 3 - ndim : 6].astype(np.int64)[cp_arr]
+    im0_hi = stats[:, 0, 6 + 3 - ndim : 9].astype(np.int64)[cp_arr]
+    lo1 = cstats[:, 2 + 3 - ndim : 5]
+    hi1 = cstats[:, 5 + 3 - ndim : 8]
+    union = np.array([pp["mode"] == "union" for pp in per_pair])[cp_arr][:, None]
+    lo_all = np.where(union, np.minimum(im0_lo, lo1), np.maximum(im0_lo, lo1))
+    hi_all = np.where(union, np.maximum(im0_hi, hi1), np.minimum(im0_hi, hi1)) + 1
+    min_shape = (hi_all - lo_all).min(axis=1)
+    win_all = np.minimum(7, min_shape - ((min_shape - 1) % 2))
     ssim_req = []  # (flat cand index, slices lo, hi, win)
     pos = 0
     for i, pp in enumerate(per_pair):
-        valid_pixels1 = int(plan.voxels - stats[i, 1, 2])
-        im0_lo = stats[i, 0, 3 + 3 - ndim : 6].astype(int)
-        im0_hi = stats[i, 0, 6 + 3 - ndim : 9].astype(int)
-        pp["kind"] = []
+        kinds = []
         for _ in pp["t"]:
-            st = cstats[pos]
-            nmask = int(st[0])
-            if nmask == 0 or float(nmask) / valid_pixels1 < 0.1:
-                pp["kind"].append(("low", None))
+            if low[pos]:
+                kinds.append(("low", None))
             else:
-                lo1 = st[2 + 3 - ndim : 5].astype(int)
-                hi1 = st[5 + 3 - ndim : 8].astype(int)
-                if pp["mode"] == "union":
-                    lo = np.minimum(im0_lo, lo1)
-                    hi = np.maximum(im0_hi, hi1) + 1
-                else:
-                    lo = np.maximum(im0_lo, lo1)
-                    hi = np.minimum(im0_hi, hi1) + 1
-                min_shape = int(np.min(hi - lo))
-                win = int(min(7, min_shape - ((min_shape - 1) % 2)))
-                pp["kind"].append(("eval", (pos, lo, hi, win)))
-                if win >= 3:
-                    ssim_req.append((pos, lo, hi, win))
+                info = (pos, lo_all[pos], hi_all[pos], int(win_all[pos]))
+                kinds.append(("eval", info))
+                if info[3] >= 3:
+                    ssim_req.append(info)
             pos += 1
+        pp["kind"] = kinds
+    assert pos == n_c
 
     ssim_out = {}
     if ssim_req:
