@@ -199,6 +199,10 @@ int mvs_pc_plan_destroy(mvs_pc_plan* plan);
 /* region = ceil(1.5 * upsample) samples per axis of the upsampled DFT. */
 int mvs_pc_plan_info(const mvs_pc_plan* plan, int* region, int64_t* voxels,
                      int* launches_per_correlate);
+/* Test hook: copies the complex work buffer `which` (0: plain cross-power spectrum
+ * P left by mvs_pc_correlate, 1: packed spectrum after the inverse passes that
+ * store) of one pair to host[2 * voxels]. */
+int mvs_pc_debug_copy(const mvs_pc_plan* plan, int which, int pair, float* host);
 
 /* Stage A: per-image statistics and rescale_intensity to [0,1] (NaN kept).
  * fixed/moving: n device pointers to contiguous float32 crops of the plan's

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "mvs_pc_plan_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int]),
     "mvs_pc_plan_destroy": (ctypes.c_int, [_P]),
     "mvs_pc_plan_info": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]),
+    "mvs_pc_debug_copy": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "mvs_pc_load_pairs": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, _P]),
     "mvs_pc_correlate": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P]),
     "mvs_pc_candidate_stats": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, _P]),

@@ -18,6 +18,7 @@
 #pragma once
 
 #include <cmath>
+#include <cstring>
 
 #include "fft_reg.cuh"
 
@@ -47,12 +48,20 @@ struct FftPassArgs {
   const float2* bhat;
 };
 
-// order-preserving key: larger |v| wins, then the LOWER flat index (numpy argmax)
-MVS_HD unsigned long long fft_key(float v, unsigned idx) {
-  union { float f; unsigned u; } c;
-  c.f = v < 0.f ? -v : v;
-  if (v != v) c.u = 0x7fc00000u;
-  return ((unsigned long long)c.u << 32) | (unsigned long long)(0xffffffffu - idx);
+// order-preserving 32-bit image of |v| (NaN ranks above every number, like numpy's argmax)
+MVS_HD unsigned fft_abs_bits(float v) {
+#ifdef __CUDA_ARCH__
+  const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+#else
+  unsigned u;
+  memcpy(&u, &v, 4);
+  u &= 0x7fffffffu;
+#endif
+  return u;
+}
+// larger |v| wins, then the LOWER flat index (first maximum in C order)
+MVS_HD unsigned long long fft_key(unsigned abs_bits, unsigned idx) {
+  return ((unsigned long long)abs_bits << 32) | (unsigned long long)(0xffffffffu - idx);
 }
 
 template <int M, bool BLUE>
@@ -200,19 +209,27 @@ struct PassThread {
     }
   }
 
-  MVS_HD void keys(const FftPassArgs& P, unsigned long long& k0, unsigned long long& k1) const {
-    k0 = 0; k1 = 0;
+  // this thread's best (|value| bits, flat index) per surface: x = Re, y = Im
+  MVS_HD void best(const FftPassArgs& P, unsigned* bits, unsigned* idx) const {
+    bits[0] = bits[1] = 0u;
+    idx[0] = idx[1] = 0xffffffffu;
     if (!valid) return;
 #pragma unroll
     for (int q = 0; q < E; ++q) {
       const int k = t + q * T;
       if (k < P.n) {
-        const unsigned idx = (unsigned)(flat0 + (long long)k * P.inner);
-        const unsigned long long a = fft_key(v[q].x, idx), b = fft_key(v[q].y, idx);
-        k0 = a > k0 ? a : k0;
-        k1 = b > k1 ? b : k1;
+        const unsigned i = (unsigned)(flat0 + (long long)k * P.inner);
+        const unsigned bx = fft_abs_bits(v[q].x), by = fft_abs_bits(v[q].y);
+        if (bx > bits[0] || (bx == bits[0] && i < idx[0])) { bits[0] = bx; idx[0] = i; }
+        if (by > bits[1] || (by == bits[1] && i < idx[1])) { bits[1] = by; idx[1] = i; }
       }
     }
+  }
+  MVS_HD void keys(const FftPassArgs& P, unsigned long long& k0, unsigned long long& k1) const {
+    unsigned bits[2], idx[2];
+    best(P, bits, idx);
+    k0 = idx[0] == 0xffffffffu ? 0ull : fft_key(bits[0], idx[0]);
+    k1 = idx[1] == 0xffffffffu ? 0ull : fft_key(bits[1], idx[1]);
   }
 };
 
@@ -240,20 +257,25 @@ __global__ void __launch_bounds__(512) fft_reg_pass_kernel(const FftPassArgs P) 
   }
   th.store(P);
   if (P.argmax) {
-    unsigned long long k0, k1;
-    th.keys(P, k0, k1);
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long a = __shfl_xor_sync(0xffffffffu, k0, o);
-      const unsigned long long b = __shfl_xor_sync(0xffffffffu, k1, o);
-      k0 = a > k0 ? a : k0;
-      k1 = b > k1 ? b : k1;
+    unsigned bits[2], idx[2];
+    th.best(P, bits, idx);
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      // warp: largest |value|, then the lowest index among the lanes holding it
+      const unsigned m = __reduce_max_sync(0xffffffffu, bits[s]);
+      const unsigned i = __reduce_min_sync(0xffffffffu, bits[s] == m ? idx[s] : 0xffffffffu);
+      if ((threadIdx.x & 31) == 0)
+        s_keys[s][threadIdx.x >> 5] = i == 0xffffffffu ? 0ull : fft_key(m, i);
     }
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) { s_keys[0][w] = k0; s_keys[1][w] = k1; }
     __syncthreads();
     if (threadIdx.x < 2) {
+      const int nw = (blockDim.x + 31) >> 5;
       unsigned long long m = 0;
-      for (int i = 0; i < nw; ++i) m = s_keys[threadIdx.x][i] > m ? s_keys[threadIdx.x][i] : m;
+      for (int i = 0; i < nw; ++i) {
+        const unsigned long long c = s_keys[threadIdx.x][i];
+        m = c > m ? c : m;
+      }
       if (m) atomicMax(P.keys + 2 * blockIdx.y + threadIdx.x, m);
     }
   }

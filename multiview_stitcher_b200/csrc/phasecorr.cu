@@ -28,6 +28,7 @@
 // figure is quoted on.
 
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -599,8 +600,12 @@ static int launch_pass(mvs_pc_plan* p, int n, int axis, int sign, PassKind kind,
     a.n1p = (int)(inner / p->shape[2]);
     a.items_x = p->shape[2] / 2 + 1;
     a.xblocks = (a.items_x + g.L / 2 - 1) / (g.L / 2);
+    // Scale of P next to the unit-modulus Pn in the packed spectrum.  1: P keeps its
+    // full float32 precision (the broad normalization=None peak needs it) and Pn
+    // loses precision only at the few strongest frequencies (|P| > 2^24), which the
+    // sharp phase-correlation peak does not depend on.
     const double NN = (double)p->N;
-    a.cp_scale = (float)(1.0 / (NN * NN));
+    a.cp_scale = getenv("MVS_PC_SCALE_N2") ? (float)(1.0 / (NN * NN)) : 1.0f;
     grid.x = (unsigned)((long long)a.xblocks * a.n1p);
   }
   const bool blue = ax.bluestein != 0;
@@ -652,7 +657,9 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
   // inverse of Q in place: first data axis, [y], x + argmax
   if ((rc = launch_pass(p, n, first, +1, PASS_PLAIN, p->Q, p->Q, st))) return rc;
   if (p->ndim == 3 && (rc = launch_pass(p, n, 1, +1, PASS_PLAIN, p->Q, p->Q, st))) return rc;
-  if ((rc = launch_pass(p, n, 2, +1, PASS_ARGMAX, p->Q, nullptr, st))) return rc;
+  // (test hook: MVS_PC_DEBUG_STORE keeps the correlation surfaces in Q)
+  float2* surf = getenv("MVS_PC_DEBUG_STORE") ? p->Q : nullptr;
+  if ((rc = launch_pass(p, n, 2, +1, PASS_ARGMAX, p->Q, surf, st))) return rc;
   // slot 0 = |Re| = normalization None, slot 1 = |Im| = "phase"
   updft_setup_kernel<<<2 * n, 256, 0, st>>>(p->d_keys, p->shape[0], p->shape[1], p->shape[2],
                                             p->ndim, p->R, p->upsample, p->d_peaks, p->d_E,
@@ -708,6 +715,16 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
                                      cudaMemcpyDeviceToHost, st));
   }
   MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+  return MVS_OK;
+}
+
+// test hook: copies pair `pair` of the plan's complex work buffers to the host
+// (which = 0: Z / plain cross power P after mvs_pc_correlate, 1: Q after the
+// inverse passes that store)
+extern "C" int mvs_pc_debug_copy(const mvs_pc_plan* p, int which, int pair, float* host) {
+  MVS_REQUIRE(p && host && pair >= 0 && pair < p->max_pairs, MVS_ERR_INVALID, "bad arguments");
+  const float2* src = (which == 0 ? p->Z : p->Q) + (long long)pair * p->N;
+  MVS_CHECK_CUDA(cudaMemcpy(host, src, sizeof(float2) * p->N, cudaMemcpyDeviceToHost));
   return MVS_OK;
 }
 

@@ -147,6 +147,8 @@ static void pass(Vol& V, int axis, int sign, Kind kind, const float2* src, float
     case 128: emulate_m<128>(a, blue, threads, gx, V.npairs); break;
     case 256: emulate_m<256>(a, blue, threads, gx, V.npairs); break;
     case 512: emulate_m<512>(a, blue, threads, gx, V.npairs); break;
+    case 1024: emulate_m<1024>(a, blue, threads, gx, V.npairs); break;
+    case 2048: emulate_m<2048>(a, blue, threads, gx, V.npairs); break;
     default: printf("unsupported m %d\n", m); exit(2);
   }
 }
@@ -236,8 +238,13 @@ static int run_case(int n0, int n1, int n2, int L1, int L2) {
   return bad;
 }
 
-int main() {
+int main(int argc, char** argv) {
   int bad = 0;
+  if (argc == 6) {  // pass_emul n0 n1 n2 L1 L2: one (large) case
+    bad = run_case(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
+    printf(bad ? "FAIL\n" : "OK\n");
+    return bad != 0;
+  }
   bad += run_case(1, 16, 32, 2, 4);    // powers of two
   bad += run_case(1, 20, 13, 4, 4);    // Bluestein on both axes (odd x)
   bad += run_case(1, 12, 10, 8, 2);    // even n2 (self-mirror column n2/2), L/2 = 1

@@ -153,3 +153,65 @@ def test_candidate_expansion_matches_oracle():
             a = reg._expand_candidates(sc, shape, max(shape))
             b = oreg.expand_candidates(sc, shape, max(shape))
             assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ---- registration host glue (closed-form candidate statistics, candidate expansion) ----
+
+
+def test_valid_range_matches_scipy_outside_predicate():
+    """0 <= x + t <= n - 1 evaluated in float64, the predicate of
+    scipy.ndimage.affine_transform(mode="constant") that decides where the shifted
+    moving image is NaN (registration.py:494-505)."""
+    from multiview_stitcher_b200.registration import _valid_range
+
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        n = int(rng.integers(1, 60))
+        t = np.array([rng.uniform(-70, 70), float(rng.integers(-70, 70)), float(np.float32(rng.uniform(-3, 3))), 0.0])
+        lo, hi = _valid_range(n, t)
+        for tt, l, h in zip(t, lo, hi):
+            x = np.arange(n, dtype=np.float64) + tt
+            v = ~((x < 0) | (x > n - 1))
+            if v.any():
+                assert l == np.argmax(v) and h == n - 1 - np.argmax(v[::-1]) and v.sum() == h - l + 1
+            else:
+                assert h < l
+
+
+def test_box_candidate_stats_matches_affine_transform():
+    """For NaN-free pairs the candidate statistics (mask count, bbox of the valid
+    region of im1t) follow from the shift alone; check against scipy on a real image."""
+    from scipy import ndimage
+
+    from multiview_stitcher_b200.registration import _box_candidate_stats
+    from oracle import registration as oreg
+
+    rng = np.random.default_rng(1)
+    im = rng.random((23, 31)).astype(np.float32)
+    ts = [[0.0, 0.0], [1.5, -2.25], [-22.0, 3.0], [40.0, 0.0], [-0.1, 30.0], [22.0, -30.0]]
+    got = _box_candidate_stats(im.shape, ts)
+    for t, g in zip(ts, got):
+        im1t = ndimage.affine_transform(im, oreg.affine_from_translation(list(t)), order=1, mode="constant", cval=np.nan)
+        valid = ~np.isnan(im1t)
+        assert g[0] == valid.sum() and g[1] == valid.sum()
+        if valid.any():
+            bb = oreg.get_bb_from_nanmask(valid)
+            assert list(g[3:5]) == [b[0] for b in bb] and list(g[6:8]) == [b[1] for b in bb]
+
+
+def test_expand_candidates_matches_oracle():
+    """registration.py:461-477 in float32 arithmetic, np.ndindex order."""
+    from multiview_stitcher_b200.registration import _expand_candidates
+    from oracle import registration as oreg
+
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        ndim = int(rng.integers(2, 4))
+        shape = tuple(int(x) for x in rng.integers(5, 400, ndim))
+        scs = [np.round(rng.uniform(-6, 6, ndim) * 10).astype(np.float32) / np.float32(10) for _ in range(2)]
+        scs[1][0] = 0
+        a = oreg.expand_candidates(scs, shape, max(shape))
+        b = _expand_candidates(scs, shape, max(shape))
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert all(float(p) == q for p, q in zip(x, y))
