@@ -67,13 +67,6 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t
                "r"(bytes)
                : "memory");
 }
-// transaction bytes only (no arrival): the producer arrives separately once the
-// slot's metadata is written, so the copy can be issued first
-__device__ __forceinline__ void mbar_expect_tx_only(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -355,7 +348,7 @@ constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 
 template <int NDIM, typename T>
 struct StencilStages {
-  static constexpr int value = 4;
+  static constexpr int value = NDIM == 3 ? 3 : 4;
 };
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
@@ -395,38 +388,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     // dynamic schedule: every producer pulls the next block from a global counter,
     // so CTAs stay busy whatever the mix of single- and multi-view blocks, and
     // concurrently processed blocks are neighbours (halo rows hit in L2)
-    // Blocks are grabbed G at a time and two grabs ahead: the counter's round trip
-    // and the fetch of the schedule records overlap the batch being issued.
     const int4* recs4 = reinterpret_cast<const int4*>(recs);
-    constexpr int G = 2;
-    auto grab = [&]() -> int64_t {
+    for (;;) {
       unsigned long long nb = 0;
-      if (lane == 0) nb = atomicAdd(next_block, (unsigned long long)G);
-      return block_begin + (int64_t)__shfl_sync(0xffffffffu, nb, 0);
-    };
-    auto load_recs = [&](int64_t bid0) -> int4 {
-      const int64_t bq = bid0 + (lane >> 1);  // lane l holds int4 #(l & 1) of block bid0 + (l >> 1)
-      return (lane < 2 * G && bq < nblocks) ? __ldg(recs4 + 2 * bq + (lane & 1)) : make_int4(0, 0, 0, 0);
-    };
-    int64_t bidA = grab();
-    int4 recA = load_recs(bidA);
-    int64_t bidB = grab();
-    int4 recB = load_recs(bidB);
-    int64_t bidC = grab();
-    for (int g = 0;; ++g) {
-      if (g == G) {
-        g = 0;
-        bidA = bidB; recA = recB;
-        bidB = bidC; recB = load_recs(bidB);  // in flight while batch A is issued
-        bidC = grab();
-      }
-      const int64_t bid = bidA + g;
+      if (lane == 0) nb = atomicAdd(next_block, 1ull);
+      const int64_t bid = block_begin + (int64_t)__shfl_sync(0xffffffffu, nb, 0);
       if (bid >= nblocks) break;
-      int4 ra, rb;
-      ra.x = __shfl_sync(0xffffffffu, recA.x, 2 * g); ra.y = __shfl_sync(0xffffffffu, recA.y, 2 * g);
-      ra.z = __shfl_sync(0xffffffffu, recA.z, 2 * g); ra.w = __shfl_sync(0xffffffffu, recA.w, 2 * g);
-      rb.x = __shfl_sync(0xffffffffu, recA.x, 2 * g + 1); rb.y = __shfl_sync(0xffffffffu, recA.y, 2 * g + 1);
-      rb.z = __shfl_sync(0xffffffffu, recA.z, 2 * g + 1); rb.w = __shfl_sync(0xffffffffu, recA.w, 2 * g + 1);
+      const int4 ra = __ldg(recs4 + 2 * bid), rb = __ldg(recs4 + 2 * bid + 1);
       const int ci = ra.x, first = ra.y, x0 = ra.z, y0 = ra.w, z0 = rb.x;
       const unsigned active = (unsigned)rb.y;
       const unsigned long long codes = (unsigned long long)(unsigned)rb.z | ((unsigned long long)(unsigned)rb.w << 32);
@@ -462,34 +430,17 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           if (nact == 1 && !PARTIAL && code >= VIEW_POSITIVE) wmode = 0;
           else wmode = code == VIEW_UNIT ? 1 : 2;
         }
-        // the view's stencil record travels through registers (one word per lane),
-        // requested before the wait for a free slot
-        constexpr int kSxWords = (int)(sizeof(StencilXform) / 4);
-        int sreg = 0;
-        if (lane < kSxWords) sreg = __ldg(reinterpret_cast<const int*>(&S) + lane);
         Slot& sl = acquire();
-        const int shz = __shfl_sync(0xffffffffu, sreg, 0), shy = __shfl_sync(0xffffffffu, sreg, 1);
-        const int shx = __shfl_sync(0xffffffffu, sreg, 2), tmi = __shfl_sync(0xffffffffu, sreg, 15);
-        // TMA needs a 16-byte aligned innermost start coordinate
-        const int x0g = x0s + shx;
-        const int xa = floor_div(x0g, A) * A;
-        unsigned long long* fb = &full_bar[it % NS];
-        if (lane == 0) {
-          // copy first: it is in flight while the slot's metadata is written
-          mbar_expect_tx_only(fb, kBoxBytes);
-          const CUtensorMap* map = tmaps + tmi;
-          if (NDIM == 3)
-            tma_load_3d(sl.stage, map, xa, y0s + shy, z0s + shz, fb);
-          else
-            tma_load_2d(sl.stage, map, xa, y0s + shy, fb);
-        }
-        if (lane < kSxWords) reinterpret_cast<int*>(&sl.sx)[lane] = sreg;
-        if (lane == 0) {
-          sl.chunk = ci; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
-          sl.flags = (seen == 0 ? ITEM_FIRST : 0) | (seen == nact - 1 ? ITEM_LAST : 0) |
-                     (simple ? ITEM_SIMPLE : 0);
-          sl.wmode = wmode;
-          sl.xoff = x0g - xa;
+        {
+          const int* src = reinterpret_cast<const int*>(&S);
+          int* dst = reinterpret_cast<int*>(&sl.sx);
+          for (int q = lane; q < (int)(sizeof(StencilXform) / 4); q += 32) dst[q] = src[q];
+          if (lane == 0) {
+            sl.chunk = ci; sl.x0 = x0; sl.y0 = y0; sl.z0 = z0;
+            sl.flags = (seen == 0 ? ITEM_FIRST : 0) | (seen == nact - 1 ? ITEM_LAST : 0) |
+                       (simple ? ITEM_SIMPLE : 0);
+            sl.wmode = wmode;
+          }
         }
         if (wmode == 2) {
           for (int q = lane; q < B::NW; q += 32) {
@@ -508,8 +459,20 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           const float* tab = tables + (int64_t)xforms[first + vi].table * 125;
           for (int q = lane; q < (NDIM == 3 ? 125 : 25); q += 32) sl.tab[q] = __ldg(tab + q);
         }
+        // TMA needs a 16-byte aligned innermost start coordinate
+        const int x0g = x0s + S.shift[2];
+        const int xa = floor_div(x0g, A) * A;
+        if (lane == 0) sl.xoff = x0g - xa;
         __syncwarp();
-        if (lane == 0) mbar_arrive(fb);  // releases the metadata; the copy completes the phase
+        if (lane == 0) {
+          unsigned long long* fb = &full_bar[it % NS];
+          mbar_expect_tx(fb, kBoxBytes);
+          const CUtensorMap* map = tmaps + S.tmap;
+          if (NDIM == 3)
+            tma_load_3d(sl.stage, map, xa, y0s + S.shift[1], z0s + S.shift[0], fb);
+          else
+            tma_load_2d(sl.stage, map, xa, y0s + S.shift[1], fb);
+        }
         ++it;
         ++seen;
       }
