@@ -229,6 +229,7 @@ __device__ __forceinline__ void ssim_block_reduce(double sum, float vmax, long l
   }
 }
 
+template <int WIN>
 __global__ void __launch_bounds__(kS2Threads)
 ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
               const float* __restrict__ mat, double* __restrict__ tile_sum,
@@ -239,7 +240,7 @@ ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
   const long long local = tile - c.tile_base;
   const int tx_i = (int)(local % c.tiles[2]), ty_i = (int)(local / c.tiles[2]);
   const int ox = tx_i * kS2TX, oy = ty_i * kS2TY;  // output origin in the slice
-  const int win = c.win;
+  constexpr int win = WIN;  // all candidates of a launch share the window
   const int leny = c.len[1], lenx = c.len[2];
   const int nxo = min(kS2TX, lenx - win + 1 - ox), nyo = min(kS2TY, leny - win + 1 - oy);
   const int ncols = nxo + win - 1;
@@ -296,6 +297,7 @@ ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
           double s = 0.0;
+#pragma unroll
           for (int k = 0; k < win; ++k) s += buf[q][t + k];
           U[q] = (float)(s * inv);
         }
@@ -306,6 +308,7 @@ ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
   ssim_block_reduce<kS2Threads>(sum, vmax, tile, tile_sum, tile_max);
 }
 
+template <int WIN>
 __global__ void __launch_bounds__(kS3Threads)
 ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
               const float* __restrict__ mat, double* __restrict__ tile_sum,
@@ -319,7 +322,7 @@ ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
   const int ty_i = (int)((local / c.tiles[2]) % c.tiles[1]);
   const int tz_i = (int)(local / ((long long)c.tiles[2] * c.tiles[1]));
   const int ox = tx_i * kS3TX, oy = ty_i * kS3TY, oz = tz_i * kS3TZ;
-  const int win = c.win;
+  constexpr int win = WIN;  // all candidates of a launch share the window
   const int lenz = c.len[0], leny = c.len[1], lenx = c.len[2];
   const int nxo = min(kS3TX, lenx - win + 1 - ox), nyo = min(kS3TY, leny - win + 1 - oy);
   const int nzo = min(kS3TZ, lenz - win + 1 - oz);
@@ -412,6 +415,7 @@ ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
       for (int idx = t; idx < kS3TY * kS3WX; idx += kS3Threads) {
         const int y = idx / kS3WX, x = idx - y * kS3WX;
         double s = 0.0;
+#pragma unroll
         for (int k = 0; k < win; ++k) s += (double)zf[q][y + k][x];
         yf[q][y][x] = (float)(s * inv);
       }
@@ -423,6 +427,7 @@ ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
         double s = 0.0;
+#pragma unroll
         for (int k = 0; k < win; ++k) s += (double)yf[q][yo][xo + k];
         U[q] = (float)(s * inv);
       }
@@ -442,11 +447,14 @@ __device__ __forceinline__ unsigned sortable_bits(float v) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Stage E without scatters: sort (a-key, b-bits) by a; the position in the sorted
+// segment is a's rank, written (doubled, so tie averages stay integers) as the
+// payload of a second sort by b; in b-sorted order both ranks are at hand and the
+// Pearson sums stream out.
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
-                     unsigned long long* __restrict__ ka, unsigned long long* __restrict__ kb,
-                     unsigned* __restrict__ idx) {
+                     unsigned long long* __restrict__ ka, unsigned* __restrict__ vb) {
   const int slot = blockIdx.y;
   const Cand c = cands[slot];
   const long long N = (long long)n0 * n1 * n2;
@@ -461,54 +469,69 @@ spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
     // the subtraction merges values below ~3e-8 into ties, which changes ranks
     const long long e = (long long)slot * N + i;
     ka[e] = hi | (m ? sortable_bits(a) : 0xffffffffu);
-    kb[e] = hi | (m ? sortable_bits(__fsub_rn(b, 1.0f)) : 0xffffffffu);
-    idx[e] = (unsigned)e;
+    vb[e] = m ? sortable_bits(__fsub_rn(b, 1.0f)) : 0xffffffffu;
   }
 }
 
-// average ranks (ties share the mean rank, scipy.stats.rankdata "average") of the
-// first nmask[slot] sorted entries of every segment
+// [first, last) of the run of keys equal to seg[j] within the first n entries
+__device__ __forceinline__ void tie_bounds(const unsigned long long* __restrict__ seg, long long n,
+                                           long long j, long long& first, long long& last) {
+  const unsigned long long v = seg[j];
+  // untied values (the common case for float data) need no search
+  if ((j == 0 || seg[j - 1] != v) && (j + 1 >= n || seg[j + 1] != v)) { first = j; last = j + 1; return; }
+  long long lo = 0, hi = j;
+  while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] < v) lo = mid + 1; else hi = mid; }
+  first = lo;
+  lo = j; hi = n;
+  while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] <= v) lo = mid + 1; else hi = mid; }
+  last = lo;
+}
+
+// a-sorted order -> keys / payload of the sort by b.  Payload = 2 * average rank of a
+// (scipy.stats.rankdata "average": ties share the mean rank).
 __global__ void __launch_bounds__(256)
-rank_kernel(const unsigned long long* __restrict__ sorted, const unsigned* __restrict__ sidx,
-            long long N, const long long* __restrict__ nmask, double* __restrict__ rank_out) {
+rank_a_kernel(const unsigned long long* __restrict__ sorted_a, const unsigned* __restrict__ vb_sorted,
+              long long N, const long long* __restrict__ nmask, unsigned long long* __restrict__ kb,
+              unsigned* __restrict__ ra2) {
   const int slot = blockIdx.y;
   const long long n = nmask[slot];
-  const unsigned long long* seg = sorted + (long long)slot * N;
-  const unsigned* sid = sidx + (long long)slot * N;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+  const unsigned long long* seg = sorted_a + (long long)slot * N;
+  const unsigned long long hi = (unsigned long long)slot << 32;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N;
        j += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long v = seg[j];
-    // untied values (the common case for float data) need no search
-    if ((j == 0 || seg[j - 1] != v) && (j + 1 >= n || seg[j + 1] != v)) {
-      rank_out[sid[j]] = (double)(j + 1);
-      continue;
+    const long long e = (long long)slot * N + j;
+    if (j < n) {
+      long long first, last;
+      tie_bounds(seg, n, j, first, last);
+      kb[e] = hi | vb_sorted[e];
+      ra2[e] = (unsigned)(first + last + 1);  // 2 * ((first + last - 1) / 2 + 1)
+    } else {
+      kb[e] = hi | 0xffffffffu;
+      ra2[e] = 0u;
     }
-    long long lo = 0, hi = j;  // first index with key == v
-    while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] < v) lo = mid + 1; else hi = mid; }
-    const long long first = lo;
-    lo = j; hi = n;            // first index with key > v
-    while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] <= v) lo = mid + 1; else hi = mid; }
-    const long long last = lo;  // exclusive
-    rank_out[sid[j]] = 0.5 * (double)(first + last - 1) + 1.0;
   }
 }
 
 constexpr int kPearsonBlocks = 64;
 
+// b-sorted order: rank of b from the position, rank of a from the payload
 __global__ void __launch_bounds__(256)
-pearson_kernel(const unsigned long long* __restrict__ ka, const double* __restrict__ ra,
-               const double* __restrict__ rb, long long N, const long long* __restrict__ nmask,
-               double* __restrict__ partial /* [slot][block][3] */) {
+pearson_sorted_kernel(const unsigned long long* __restrict__ sorted_b, const unsigned* __restrict__ ra2,
+                      long long N, const long long* __restrict__ nmask,
+                      double* __restrict__ partial /* [slot][block][3] */) {
   const int slot = blockIdx.y;
-  const double mean = 0.5 * (double)(nmask[slot] + 1);
-  const long long base = (long long)slot * N;
+  const long long n = nmask[slot];
+  const double mean = 0.5 * (double)(n + 1);
+  const unsigned long long* seg = sorted_b + (long long)slot * N;
+  const unsigned* pa = ra2 + (long long)slot * N;
   double sab = 0.0, saa = 0.0, sbb = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (long long)gridDim.x * blockDim.x) {
-    if ((unsigned)(ka[base + i] & 0xffffffffull) != 0xffffffffu) {
-      const double a = ra[base + i] - mean, b = rb[base + i] - mean;
-      sab += a * b; saa += a * a; sbb += b * b;
-    }
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    long long first, last;
+    tie_bounds(seg, n, j, first, last);
+    const double a = 0.5 * (double)pa[j] - mean;
+    const double b = 0.5 * (double)(first + last + 1) - mean;
+    sab += a * b; saa += a * a; sbb += b * b;
   }
   __shared__ double s[3][256];
   const int t = threadIdx.x;
@@ -642,10 +665,21 @@ extern "C" int mvs_pc_candidate_ssim(mvs_pc_plan* p, int n_cand, const int32_t* 
     else materialize_kernel<2><<<g, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], d_mat);
     MVS_CHECK_CUDA(cudaGetLastError());
   }
-  if (ndim == 3)
-    ssim3d_kernel<<<(unsigned)total_tiles, kS3Threads, 0, st>>>(d_c, n_cand, sh[1], sh[2], d_mat, d_sum, d_max);
-  else
-    ssim2d_kernel<<<(unsigned)total_tiles, kS2Threads, 0, st>>>(d_c, n_cand, sh[1], sh[2], d_mat, d_sum, d_max);
+  // one launch per window size present (3 / 5 / 7): the kernels are specialised on it
+  {
+    int w0 = cands[0].win;
+    bool same = true;
+    for (int i = 1; i < n_cand; ++i) same = same && cands[i].win == w0;
+    MVS_REQUIRE(same, MVS_ERR_UNSUPPORTED, "SSIM candidates of one call must share the window size");
+    const unsigned g = (unsigned)total_tiles;
+#define MVS_SSIM_LAUNCH(W)                                                                         \
+  if (ndim == 3) ssim3d_kernel<W><<<g, kS3Threads, 0, st>>>(d_c, n_cand, sh[1], sh[2], d_mat, d_sum, d_max); \
+  else ssim2d_kernel<W><<<g, kS2Threads, 0, st>>>(d_c, n_cand, sh[1], sh[2], d_mat, d_sum, d_max);
+    if (w0 == 7) { MVS_SSIM_LAUNCH(7) }
+    else if (w0 == 5) { MVS_SSIM_LAUNCH(5) }
+    else { MVS_SSIM_LAUNCH(3) }
+#undef MVS_SSIM_LAUNCH
+  }
   MVS_CHECK_CUDA(cudaGetLastError());
   std::vector<double> hs(total_tiles);
   std::vector<float> hm(total_tiles);
@@ -694,18 +728,15 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
                                   (unsigned*)nullptr, (int)E, 0, 32 + seg_bits, st);
   auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
   const size_t kbytes = al(sizeof(unsigned long long) * E), ub = al(sizeof(unsigned) * E),
-               db = al(sizeof(double) * E), pb = al(sizeof(double) * 3 * kPearsonBlocks * B),
+               pb = al(sizeof(double) * 3 * kPearsonBlocks * B),
                cb = al(sizeof(Cand) * B), nb = al(sizeof(long long) * B);
   void* scratch;
-  if ((rc = pc_scratch(p, 3 * kbytes + 2 * ub + 2 * db + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
+  if ((rc = pc_scratch(p, 2 * kbytes + 2 * ub + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
   char* w = (char*)scratch;
-  unsigned long long* ka = (unsigned long long*)w; w += kbytes;
-  unsigned long long* kb = (unsigned long long*)w; w += kbytes;
-  unsigned long long* ks = (unsigned long long*)w; w += kbytes;
-  unsigned* idx = (unsigned*)w; w += ub;
-  unsigned* sidx = (unsigned*)w; w += ub;
-  double* ra = (double*)w; w += db;
-  double* rb = (double*)w; w += db;
+  unsigned long long* k1 = (unsigned long long*)w; w += kbytes;   // keys in
+  unsigned long long* k2 = (unsigned long long*)w; w += kbytes;   // keys sorted
+  unsigned* v1 = (unsigned*)w; w += ub;                           // payload in
+  unsigned* v2 = (unsigned*)w; w += ub;                           // payload sorted
   double* part = (double*)w; w += pb;
   Cand* d_c = (Cand*)w; w += cb;
   long long* d_n = (long long*)w; w += nb;
@@ -719,16 +750,17 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
     MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data() + b0, sizeof(Cand) * nb_, cudaMemcpyHostToDevice, st));
     MVS_CHECK_CUDA(cudaMemcpyAsync(d_n, hn.data(), sizeof(long long) * nb_, cudaMemcpyHostToDevice, st));
     dim3 grid(gx, nb_);
-    if (ndim == 3) spearman_keys_kernel<3><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], ka, kb, idx);
-    else spearman_keys_kernel<2><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], ka, kb, idx);
+    if (ndim == 3) spearman_keys_kernel<3><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], k1, v1);
+    else spearman_keys_kernel<2><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], k1, v1);
     MVS_CHECK_CUDA(cudaGetLastError());
     const int items = (int)((long long)nb_ * N);
-    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ka, ks, idx, sidx, items, 0, 32 + seg_bits, st));
-    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, N, d_n, ra);
-    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kb, ks, idx, sidx, items, 0, 32 + seg_bits, st));
-    rank_kernel<<<grid, 256, 0, st>>>(ks, sidx, N, d_n, rb);
+    // by a: (a key, b bits) -> k2, v2
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, 32 + seg_bits, st));
+    rank_a_kernel<<<grid, 256, 0, st>>>(k2, v2, N, d_n, k1, v1);  // -> (b key, 2 rank_a) in k1, v1
+    // by b: -> k2, v2
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, 32 + seg_bits, st));
     dim3 pg(kPearsonBlocks, nb_);
-    pearson_kernel<<<pg, 256, 0, st>>>(ka, ra, rb, N, d_n, part);
+    pearson_sorted_kernel<<<pg, 256, 0, st>>>(k2, v2, N, d_n, part);
     MVS_CHECK_CUDA(cudaGetLastError());
     MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * 3 * kPearsonBlocks * nb_, cudaMemcpyDeviceToHost, st));
     MVS_CHECK_CUDA(cudaStreamSynchronize(st));

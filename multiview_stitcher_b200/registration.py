@@ -341,15 +341,18 @@ def _register_loaded(plan, stats, disambiguate_region_mode=None, return_details=
         first_req = {}
         for r in ssim_req:
             first_req.setdefault(umap[r[0]], r)
-        reqs = list(first_req.values())
-        idx = [r[0] for r in reqs]
-        res = plan.candidate_ssim(
-            [cand_pair[j] for j in idx],
-            np.array([cand_t[j] for j in idx], dtype=np.float64),
-            np.array([[r[1], r[2]] for r in reqs]),
-            [r[3] for r in reqs],
-        )
-        by_u = {umap[j]: r for j, r in zip(idx, res)}
+        by_u = {}
+        for w in sorted({r[3] for r in first_req.values()}):
+            # one batch per window size (the kernels are specialised on it)
+            reqs = [r for r in first_req.values() if r[3] == w]
+            idx = [r[0] for r in reqs]
+            res = plan.candidate_ssim(
+                [cand_pair[j] for j in idx],
+                np.array([cand_t[j] for j in idx], dtype=np.float64),
+                np.array([[r[1], r[2]] for r in reqs]),
+                [r[3] for r in reqs],
+            )
+            by_u.update({umap[j]: r for j, r in zip(idx, res)})
         for r in ssim_req:
             ssim_out[r[0]] = by_u[umap[r[0]]]
 
