@@ -10,6 +10,7 @@
 // scipy's float64 tap arithmetic so masks and values are bit-identical.
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <vector>
 
@@ -473,38 +474,43 @@ spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
   }
 }
 
-// [first, last) of the run of keys equal to seg[j] within the first n entries
-__device__ __forceinline__ void tie_bounds(const unsigned long long* __restrict__ seg, long long n,
-                                           long long j, long long& first, long long& last) {
-  const unsigned long long v = seg[j];
-  // untied values (the common case for float data) need no search
-  if ((j == 0 || seg[j - 1] != v) && (j + 1 >= n || seg[j + 1] != v)) { first = j; last = j + 1; return; }
-  long long lo = 0, hi = j;
-  while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] < v) lo = mid + 1; else hi = mid; }
-  first = lo;
-  lo = j; hi = n;
-  while (lo < hi) { long long mid = (lo + hi) >> 1; if (seg[mid] <= v) lo = mid + 1; else hi = mid; }
-  last = lo;
+// Runs of equal keys (ties) without per-element searches: run heads / tails are
+// flagged with their own index, an inclusive max-scan carries the head index
+// forward, a min-scan over the reversed tail flags carries the tail index back.
+// (Integer-valued microscopy data is tie-heavy; a binary search per element
+// costs ~40 dependent L2 reads.)
+__global__ void __launch_bounds__(256)
+run_flags_kernel(const unsigned long long* __restrict__ sorted, long long E,
+                 unsigned* __restrict__ head, unsigned* __restrict__ tail_rev) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < E;
+       j += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long v = sorted[j];
+    head[j] = (j == 0 || sorted[j - 1] != v) ? (unsigned)j : 0u;
+    tail_rev[E - 1 - j] = (j == E - 1 || sorted[j + 1] != v) ? (unsigned)j : 0xffffffffu;
+  }
 }
+
+struct MaxOp { __device__ __forceinline__ unsigned operator()(unsigned a, unsigned b) const { return a > b ? a : b; } };
+struct MinOp { __device__ __forceinline__ unsigned operator()(unsigned a, unsigned b) const { return a < b ? a : b; } };
 
 // a-sorted order -> keys / payload of the sort by b.  Payload = 2 * average rank of a
 // (scipy.stats.rankdata "average": ties share the mean rank).
 __global__ void __launch_bounds__(256)
-rank_a_kernel(const unsigned long long* __restrict__ sorted_a, const unsigned* __restrict__ vb_sorted,
-              long long N, const long long* __restrict__ nmask, unsigned long long* __restrict__ kb,
+rank_a_kernel(const unsigned* __restrict__ first, const unsigned* __restrict__ last_rev,
+              const unsigned* __restrict__ vb_sorted, long long N, long long E,
+              const long long* __restrict__ nmask, unsigned long long* __restrict__ kb,
               unsigned* __restrict__ ra2) {
   const int slot = blockIdx.y;
   const long long n = nmask[slot];
-  const unsigned long long* seg = sorted_a + (long long)slot * N;
+  const long long base = (long long)slot * N;
   const unsigned long long hi = (unsigned long long)slot << 32;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N;
        j += (long long)gridDim.x * blockDim.x) {
-    const long long e = (long long)slot * N + j;
+    const long long e = base + j;
     if (j < n) {
-      long long first, last;
-      tie_bounds(seg, n, j, first, last);
+      const long long f = (long long)first[e] - base, l = (long long)last_rev[E - 1 - e] - base;  // inclusive
       kb[e] = hi | vb_sorted[e];
-      ra2[e] = (unsigned)(first + last + 1);  // 2 * ((first + last - 1) / 2 + 1)
+      ra2[e] = (unsigned)(f + l + 2);  // 2 * ((f + l) / 2 + 1)
     } else {
       kb[e] = hi | 0xffffffffu;
       ra2[e] = 0u;
@@ -516,21 +522,21 @@ constexpr int kPearsonBlocks = 64;
 
 // b-sorted order: rank of b from the position, rank of a from the payload
 __global__ void __launch_bounds__(256)
-pearson_sorted_kernel(const unsigned long long* __restrict__ sorted_b, const unsigned* __restrict__ ra2,
-                      long long N, const long long* __restrict__ nmask,
+pearson_sorted_kernel(const unsigned* __restrict__ first, const unsigned* __restrict__ last_rev,
+                      const unsigned* __restrict__ ra2, long long N, long long E,
+                      const long long* __restrict__ nmask,
                       double* __restrict__ partial /* [slot][block][3] */) {
   const int slot = blockIdx.y;
   const long long n = nmask[slot];
   const double mean = 0.5 * (double)(n + 1);
-  const unsigned long long* seg = sorted_b + (long long)slot * N;
-  const unsigned* pa = ra2 + (long long)slot * N;
+  const long long base = (long long)slot * N;
   double sab = 0.0, saa = 0.0, sbb = 0.0;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
-    long long first, last;
-    tie_bounds(seg, n, j, first, last);
-    const double a = 0.5 * (double)pa[j] - mean;
-    const double b = 0.5 * (double)(first + last + 1) - mean;
+    const long long e = base + j;
+    const long long f = (long long)first[e] - base, l = (long long)last_rev[E - 1 - e] - base;
+    const double a = 0.5 * (double)ra2[e] - mean;
+    const double b = 0.5 * (double)(f + l + 2) - mean;
     sab += a * b; saa += a * a; sbb += b * b;
   }
   __shared__ double s[3][256];
@@ -726,17 +732,27 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
   cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned long long*)nullptr,
                                   (unsigned long long*)nullptr, (const unsigned*)nullptr,
                                   (unsigned*)nullptr, (int)E, 0, 32 + seg_bits, st);
+  {
+    size_t scan_bytes = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                   MaxOp(), (int)E, st);
+    temp_bytes = std::max(temp_bytes, scan_bytes);
+  }
   auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
   const size_t kbytes = al(sizeof(unsigned long long) * E), ub = al(sizeof(unsigned) * E),
                pb = al(sizeof(double) * 3 * kPearsonBlocks * B),
                cb = al(sizeof(Cand) * B), nb = al(sizeof(long long) * B);
   void* scratch;
-  if ((rc = pc_scratch(p, 2 * kbytes + 2 * ub + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
+  if ((rc = pc_scratch(p, 2 * kbytes + 6 * ub + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
   char* w = (char*)scratch;
   unsigned long long* k1 = (unsigned long long*)w; w += kbytes;   // keys in
   unsigned long long* k2 = (unsigned long long*)w; w += kbytes;   // keys sorted
   unsigned* v1 = (unsigned*)w; w += ub;                           // payload in
   unsigned* v2 = (unsigned*)w; w += ub;                           // payload sorted
+  unsigned* f_in = (unsigned*)w; w += ub;                         // run-head flags / scanned
+  unsigned* f_out = (unsigned*)w; w += ub;
+  unsigned* l_in = (unsigned*)w; w += ub;                         // run-tail flags (reversed) / scanned
+  unsigned* l_out = (unsigned*)w; w += ub;
   double* part = (double*)w; w += pb;
   Cand* d_c = (Cand*)w; w += cb;
   long long* d_n = (long long*)w; w += nb;
@@ -756,11 +772,19 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
     const int items = (int)((long long)nb_ * N);
     // by a: (a key, b bits) -> k2, v2
     MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, 32 + seg_bits, st));
-    rank_a_kernel<<<grid, 256, 0, st>>>(k2, v2, N, d_n, k1, v1);  // -> (b key, 2 rank_a) in k1, v1
+    auto run_bounds = [&]() -> int {  // ties of k2 -> f_out (first), l_out (last, reversed order)
+      run_flags_kernel<<<148 * 8, 256, 0, st>>>(k2, items, f_in, l_in);
+      MVS_CHECK_CUDA(cub::DeviceScan::InclusiveScan(temp, temp_bytes, f_in, f_out, MaxOp(), items, st));
+      MVS_CHECK_CUDA(cub::DeviceScan::InclusiveScan(temp, temp_bytes, l_in, l_out, MinOp(), items, st));
+      return MVS_OK;
+    };
+    if ((rc = run_bounds())) return rc;
+    rank_a_kernel<<<grid, 256, 0, st>>>(f_out, l_out, v2, N, items, d_n, k1, v1);  // -> (b key, 2 rank_a)
     // by b: -> k2, v2
     MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, 32 + seg_bits, st));
     dim3 pg(kPearsonBlocks, nb_);
-    pearson_sorted_kernel<<<pg, 256, 0, st>>>(k2, v2, N, d_n, part);
+    if ((rc = run_bounds())) return rc;
+    pearson_sorted_kernel<<<pg, 256, 0, st>>>(f_out, l_out, v2, N, items, d_n, part);
     MVS_CHECK_CUDA(cudaGetLastError());
     MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * 3 * kPearsonBlocks * nb_, cudaMemcpyDeviceToHost, st));
     MVS_CHECK_CUDA(cudaStreamSynchronize(st));

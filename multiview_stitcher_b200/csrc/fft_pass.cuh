@@ -41,7 +41,7 @@ struct FftPassArgs {
   int paired;              // cross-power epilogue (forward only, outer == 1, L even)
   int argmax;              // reduce keys (contiguous axis only)
   int n2, n1p, items_x, xblocks;  // paired: innermost length, inner / n2, n2/2 + 1, CTAs along x
-  float cp_scale;          // s: keeps |s P| <= 1 next to the unit-modulus normalised spectrum
+  const float* cp_scales;  // [pair] s: puts max |s P| at 2^12 next to the unit-modulus normalised spectrum
   unsigned long long* keys;  // [pair][2]: slot 0 = |Re| (normalization None), 1 = |Im| ("phase")
   const float2* tw;
   const float2* chirp;
@@ -178,7 +178,7 @@ struct PassThread {
     for (int q = 0; q < E; ++q) sline[fft_pad(t + q * T)] = v[q];
   }
   // step 2: Q_k from Z_k (registers) and Z_-k (the partner line, reversed)
-  MVS_HD void cross_power(const FftPassArgs& P, const float2* partner) {
+  MVS_HD void cross_power(const FftPassArgs& P, const float2* partner, float cps) {
     const float tiny = 100.0f * 1.1920929e-07f;  // 100 * eps(float32)
 #pragma unroll
     for (int q = 0; q < E; ++q) {
@@ -194,7 +194,7 @@ struct PassThread {
         // |P| = |F| |M| (the squares of P itself could overflow for N ~ 2^31)
         const float mag = fmaxf(sqrtf(F.x * F.x + F.y * F.y) * sqrtf(Mm.x * Mm.x + Mm.y * Mm.y), tiny);
         const float2 Pn = make_float2(Pw.x / mag, Pw.y / mag);
-        v[q] = make_float2(P.cp_scale * Pw.x - Pn.y, P.cp_scale * Pw.y + Pn.x);
+        v[q] = make_float2(cps * Pw.x - Pn.y, cps * Pw.y + Pn.x);
         if (valid && P.dst2) P.dst2[base + (long long)k * P.inner] = Pw;
       }
     }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(512) fft_reg_pass_kernel(const FftPassArgs P) 
     th.publish(sline);
     __syncthreads();
     const int lp = th.l + (th.l < (P.L >> 1) ? (P.L >> 1) : -(P.L >> 1));
-    th.cross_power(P, fft_smem + lp * P.line_stride);
+    th.cross_power(P, fft_smem + lp * P.line_stride, P.cp_scales[blockIdx.y]);
   }
   th.store(P);
   if (P.argmax) {

@@ -160,34 +160,38 @@ static PassGeom pass_geom(int m, bool contiguous, bool paired, long long nlines)
 
 constexpr int kRedBlocks = 64;  // partial-reduction blocks per image
 
-// per-image partial min / max / NaN count / bbox of non-NaN voxels
+// per-image partial min / max / NaN count / bbox of non-NaN voxels / sum of the values
 __global__ void __launch_bounds__(256)
 stats_kernel(const float* const* __restrict__ imgs, long long N, int n1, int n2,
-             double* __restrict__ partial /* [img][block][9] */) {
+             double* __restrict__ partial /* [img][block][10] */) {
   const float* im = imgs[blockIdx.y];
   float mn = INFINITY, mx = -INFINITY;
   long long nan = 0;
+  double vsum = 0.0;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
        i += (long long)gridDim.x * blockDim.x) {
     float v = __ldg(im + i);
     if (v != v) { ++nan; continue; }
     mn = fminf(mn, v); mx = fmaxf(mx, v);
+    vsum += (double)v;
     int x = (int)(i % n2), y = (int)((i / n2) % n1), z = (int)(i / ((long long)n1 * n2));
     lo[0] = min(lo[0], z); lo[1] = min(lo[1], y); lo[2] = min(lo[2], x);
     hi[0] = max(hi[0], z); hi[1] = max(hi[1], y); hi[2] = max(hi[2], x);
   }
   __shared__ float s_mn[256], s_mx[256];
   __shared__ long long s_nan[256];
+  __shared__ double s_sum[256];
   __shared__ int s_lo[3][256], s_hi[3][256];
   const int t = threadIdx.x;
-  s_mn[t] = mn; s_mx[t] = mx; s_nan[t] = nan;
+  s_mn[t] = mn; s_mx[t] = mx; s_nan[t] = nan; s_sum[t] = vsum;
   for (int d = 0; d < 3; ++d) { s_lo[d][t] = lo[d]; s_hi[d][t] = hi[d]; }
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if (t < s) {
       s_mn[t] = fminf(s_mn[t], s_mn[t + s]); s_mx[t] = fmaxf(s_mx[t], s_mx[t + s]);
       s_nan[t] += s_nan[t + s];
+      s_sum[t] += s_sum[t + s];
       for (int d = 0; d < 3; ++d) {
         s_lo[d][t] = min(s_lo[d][t], s_lo[d][t + s]);
         s_hi[d][t] = max(s_hi[d][t], s_hi[d][t + s]);
@@ -196,9 +200,10 @@ stats_kernel(const float* const* __restrict__ imgs, long long N, int n1, int n2,
     __syncthreads();
   }
   if (t == 0) {
-    double* p = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 9;
+    double* p = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 10;
     p[0] = s_mn[0]; p[1] = s_mx[0]; p[2] = (double)s_nan[0];
     for (int d = 0; d < 3; ++d) { p[3 + d] = s_lo[d][0]; p[6 + d] = s_hi[d][0]; }
+    p[9] = s_sum[0];
   }
 }
 
@@ -380,6 +385,7 @@ struct mvs_pc_plan {
   const float** d_imgs = nullptr;  // [2*max_pairs]
   double* d_partial = nullptr;     // stats partials
   float *d_mn = nullptr, *d_scale = nullptr;
+  float* d_cp = nullptr;  // per pair: scale of P in the packed spectrum
   unsigned long long* d_keys = nullptr;
   int* d_peaks = nullptr;
   float2* d_E = nullptr;
@@ -416,7 +422,7 @@ int pc_scratch(mvs_pc_plan* p, size_t bytes, void** out) {
 extern "C" int mvs_pc_plan_destroy(mvs_pc_plan* p) {
   if (!p) return MVS_OK;
   cudaFree(p->r0); cudaFree(p->r1); cudaFree(p->Z); cudaFree(p->Q);
-  cudaFree((void*)p->d_imgs); cudaFree(p->d_partial); cudaFree(p->d_mn); cudaFree(p->d_scale);
+  cudaFree((void*)p->d_imgs); cudaFree(p->d_partial); cudaFree(p->d_mn); cudaFree(p->d_scale); cudaFree(p->d_cp);
   cudaFree(p->d_keys); cudaFree(p->d_peaks); cudaFree(p->d_E); cudaFree(p->d_G); cudaFree(p->d_T0);
   cudaFree(p->d_T1); cudaFree(p->scratch);
   delete p;
@@ -468,7 +474,8 @@ extern "C" int mvs_pc_plan_create(mvs_pc_plan** plan, int ndim, const int32_t sh
   alloc((void**)&p->Z, sizeof(float2) * NP);
   alloc((void**)&p->Q, sizeof(float2) * NP);
   alloc((void**)&p->d_imgs, sizeof(float*) * 2 * max_pairs);
-  alloc((void**)&p->d_partial, sizeof(double) * 9 * kRedBlocks * 2 * max_pairs);
+  alloc((void**)&p->d_partial, sizeof(double) * 10 * kRedBlocks * 2 * max_pairs);
+  alloc((void**)&p->d_cp, sizeof(float) * max_pairs);
   alloc((void**)&p->d_mn, sizeof(float) * 2 * max_pairs);
   alloc((void**)&p->d_scale, sizeof(float) * 2 * max_pairs);
   alloc((void**)&p->d_keys, sizeof(unsigned long long) * 2 * max_pairs);
@@ -515,18 +522,21 @@ extern "C" int mvs_pc_load_pairs(mvs_pc_plan* p, int n, const float* const* fixe
   dim3 g(kRedBlocks, 2 * n);
   stats_kernel<<<g, 256, 0, st>>>(p->d_imgs, p->N, p->shape[1], p->shape[2], p->d_partial);
   MVS_CHECK_CUDA(cudaGetLastError());
-  std::vector<double> part((size_t)9 * kRedBlocks * 2 * n);
+  std::vector<double> part((size_t)10 * kRedBlocks * 2 * n);
   MVS_CHECK_CUDA(cudaMemcpyAsync(part.data(), p->d_partial, sizeof(double) * part.size(),
                                  cudaMemcpyDeviceToHost, st));
   MVS_CHECK_CUDA(cudaStreamSynchronize(st));
-  std::vector<float> mn(2 * n), sc(2 * n);
+  std::vector<float> mn(2 * n), sc(2 * n), cp(n);
+  std::vector<double> rsum(2 * n);
   for (int img = 0; img < 2 * n; ++img) {
     double* s = stats_host + (size_t)img * 9;
+    double vsum = 0.0;
     s[0] = INFINITY; s[1] = -INFINITY; s[2] = 0;
     for (int d = 0; d < 3; ++d) { s[3 + d] = 2147483647.0; s[6 + d] = -1; }
     for (int b = 0; b < kRedBlocks; ++b) {
-      const double* q = part.data() + ((size_t)img * kRedBlocks + b) * 9;
+      const double* q = part.data() + ((size_t)img * kRedBlocks + b) * 10;
       s[0] = std::min(s[0], q[0]); s[1] = std::max(s[1], q[1]); s[2] += q[2];
+      vsum += q[9];
       for (int d = 0; d < 3; ++d) {
         s[3 + d] = std::min(s[3 + d], q[3 + d]);
         s[6 + d] = std::max(s[6 + d], q[6 + d]);
@@ -535,7 +545,19 @@ extern "C" int mvs_pc_load_pairs(mvs_pc_plan* p, int n, const float* const* fixe
     mn[img] = (float)s[0];
     // (imax - imin) evaluated in float64, used as a float32 divisor (skimage)
     sc[img] = (s[1] > s[0]) ? (float)(s[1] - s[0]) : 0.0f;
+    // sum of the rescaled image = DC term of its spectrum
+    const double nvalid = (double)p->N - s[2];
+    rsum[img] = (s[1] > s[0]) ? (vsum - nvalid * s[0]) / (s[1] - s[0]) : nvalid;
   }
+  // Packed spectrum Q = s P + i Pn: s puts the largest |P| (the DC product) at 2^12,
+  // so the unit-modulus Pn keeps >= 12 bits next to it everywhere while P keeps a
+  // 2^36 dynamic range above the float32 rounding of Pn -- both correlation
+  // surfaces come out of ONE inverse transform at full working precision.
+  for (int i = 0; i < n; ++i) {
+    const double dc = rsum[2 * i] * rsum[2 * i + 1];
+    cp[i] = (float)(dc > 1e-30 ? 4096.0 / dc : 1.0);
+  }
+  MVS_CHECK_CUDA(cudaMemcpyAsync(p->d_cp, cp.data(), sizeof(float) * n, cudaMemcpyHostToDevice, st));
   MVS_CHECK_CUDA(cudaMemcpyAsync(p->d_mn, mn.data(), sizeof(float) * 2 * n,
                                  cudaMemcpyHostToDevice, st));
   MVS_CHECK_CUDA(cudaMemcpyAsync(p->d_scale, sc.data(), sizeof(float) * 2 * n,
@@ -600,12 +622,7 @@ static int launch_pass(mvs_pc_plan* p, int n, int axis, int sign, PassKind kind,
     a.n1p = (int)(inner / p->shape[2]);
     a.items_x = p->shape[2] / 2 + 1;
     a.xblocks = (a.items_x + g.L / 2 - 1) / (g.L / 2);
-    // Scale of P next to the unit-modulus Pn in the packed spectrum.  1: P keeps its
-    // full float32 precision (the broad normalization=None peak needs it) and Pn
-    // loses precision only at the few strongest frequencies (|P| > 2^24), which the
-    // sharp phase-correlation peak does not depend on.
-    const double NN = (double)p->N;
-    a.cp_scale = getenv("MVS_PC_SCALE_N2") ? (float)(1.0 / (NN * NN)) : 1.0f;
+    a.cp_scales = p->d_cp;  // per pair, set by mvs_pc_load_pairs
     grid.x = (unsigned)((long long)a.xblocks * a.n1p);
   }
   const bool blue = ax.bluestein != 0;

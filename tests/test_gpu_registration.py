@@ -41,7 +41,7 @@ def _plan_for(reg, f, m, u=None):
     return plan, stats_
 
 
-SHAPES = [(64, 128), (128, 77), (100, 100), (37, 307), (307, 2048), (2048, 307), (16, 32, 64), (24, 64, 51), (9, 20, 33), (40, 307, 64)]
+SHAPES = [(64, 128), (128, 77), (100, 100), (37, 307), (307, 2048), (2048, 307), (16, 32, 64), (24, 64, 51), (9, 20, 33), (40, 307, 64), (128, 256, 51)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
