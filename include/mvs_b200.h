@@ -229,7 +229,9 @@ int mvs_pc_candidate_stats(mvs_pc_plan* plan, int n_cand, const int32_t* cand_pa
                            const double* cand_t, int64_t* stats_host, void* stream);
 
 /* Stage D: SSIM of nan_to_num(im0) vs nan_to_num(im1t) on slices[i] =
- * lo z,y,x, hi z,y,x (exclusive) with an odd window win[i] in 3..7.
+ * lo z,y,x, hi z,y,x (exclusive) with an odd window win[i] in 3..7; all
+ * candidates of one call share the window size (the kernels are specialised
+ * on it; the host batches by window).
  * out_host[i][2] = mean SSIM, nanmax(im1t[slices]) (NaN if all-NaN). */
 int mvs_pc_candidate_ssim(mvs_pc_plan* plan, int n_cand, const int32_t* cand_pair,
                           const double* cand_t, const int32_t* slices, const int32_t* win,

@@ -105,6 +105,7 @@ gauss1d_kernel(const float* __restrict__ in, float* __restrict__ out, int nz, in
 
 constexpr int kGTA = 32;
 constexpr int kGPitch = 33;
+constexpr int kGB = 24;  // strip rows requested per batch of loads
 
 struct GaussArgs {
   const float* in;
@@ -137,7 +138,7 @@ __device__ __forceinline__ int reflect_idx(int k, int n) {
   }
 
 template <int AXIS>
-__global__ void __launch_bounds__(256) gauss_strip_kernel(const GaussArgs A) {
+__global__ void __launch_bounds__(512) gauss_strip_kernel(const GaussArgs A) {
   extern __shared__ double gs_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   const int rp = A.rp, span = kGTA + 2 * rp;
@@ -180,26 +181,29 @@ __global__ void __launch_bounds__(256) gauss_strip_kernel(const GaussArgs A) {
     const float* vin = A.in + voff;
     float* vout = A.out + voff;
     __syncwarp();  // the previous strip's readers are done
-    // ---- stage the strip: loads issued eight at a time (clamped addresses) ----
+    // ---- stage the strip: loads issued kGB at a time (clamped addresses) ----
     bool same = true;
     float first = 0.f;
     if (AXIS != 2) {
       const int xl = l0 + lane;
       const bool lane_ok = xl >= loL && xl <= hiL;
-      for (int kk0 = 0; kk0 < span; kk0 += 8) {  // span is a multiple of 8
-        float tv[8];
+      for (int kk0 = 0; kk0 < span; kk0 += kGB) {  // span is a multiple of 8; the tail is clamped
+        float tv[kGB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int a = reflect_idx(a0 - rp + kk0 + u, nA);
+        for (int u = 0; u < kGB; ++u) {
+          const int kk = min(kk0 + u, span - 1);
+          const int a = reflect_idx(a0 - rp + kk, nA);
           const bool ok = lane_ok && a >= loA && a <= hiA;
           const float x = __ldg(ok ? vin + (long long)a * strideA + xl : A.in);
           tv[u] = ok ? x : 0.f;
         }
         if (kk0 == 0) first = tv[0];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          strip[(kk0 + u) * kGPitch + lane] = tv[u];
-          same = same && (tv[u] == first);
+        for (int u = 0; u < kGB; ++u) {
+          if (kk0 + u < span) {
+            strip[(kk0 + u) * kGPitch + lane] = tv[u];
+            same = same && (tv[u] == first);
+          }
         }
       }
     } else {
@@ -434,7 +438,7 @@ static int round_up4(int r) { return r < 4 ? 4 : ((r + 3) / 4) * 4; }
 static int strip_warps(int rp, int axis, size_t* smem_out) {
   const size_t per_warp = sizeof(float) * ((size_t)(kGTA + 2 * rp) * kGPitch + (axis == 2 ? kGTA * kGPitch : 0));
   const size_t fixed = sizeof(double) * (rp + 1);
-  int W = 8;
+  int W = 16;
   while (W > 0 && fixed + W * per_warp > 200 * 1024) --W;
   if (smem_out) *smem_out = fixed + W * per_warp;
   return W;

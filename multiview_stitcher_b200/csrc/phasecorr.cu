@@ -133,7 +133,7 @@ static PassGeom pass_geom(int m, bool contiguous, bool paired, long long nlines)
   const int E = m < 16 ? m : 16, T = m / E;
   int L;
   if (contiguous) {
-    L = T >= 256 ? 1 : 256 / T;  // ~256 threads per CTA
+    L = T >= 128 ? 1 : 128 / T;  // ~128 threads per CTA: several CTAs per SM in different phases
   } else {
     // runs of >= 32 bytes along the fastest axis
     L = T <= 32 ? 256 / T : (T <= 64 ? 8 : (T <= 128 ? 4 : (T <= 256 ? 2 : 1)));
@@ -304,19 +304,24 @@ updft_x_kernel(const float2* __restrict__ Pg, int n0, int n1, int n2, long long 
     float2 acc0[R], acc1[R];
 #pragma unroll
     for (int a = 0; a < R; ++a) { acc0[a] = make_float2(0.f, 0.f); acc1[a] = make_float2(0.f, 0.f); }
-    for (int x = lane; x < n2; x += 32) {
-      const float2 Ps = row[x];
-      const float mag = fmaxf(hypotf(Ps.x, Ps.y), tiny);
-      const float2 Pn = make_float2(__fdiv_rn(Ps.x, mag), __fdiv_rn(Ps.y, mag));
-      const float2 g = __ldg(G + x);
-      float2 w0 = cmul(Ps, __ldg(h0 + x));
-      float2 w1 = cmul(Pn, __ldg(h1 + x));
+    // two x per iteration: the g-power chains of the two elements are independent
+    for (int x = lane; x < n2; x += 64) {
+      const int x2 = x + 32;
+      const bool has2 = x2 < n2;
+      const float2 PsA = row[x];
+      const float2 PsB = has2 ? row[x2] : make_float2(0.f, 0.f);
+      const float magA = fmaxf(hypotf(PsA.x, PsA.y), tiny), magB = fmaxf(hypotf(PsB.x, PsB.y), tiny);
+      const float2 PnA = make_float2(__fdiv_rn(PsA.x, magA), __fdiv_rn(PsA.y, magA));
+      const float2 PnB = make_float2(__fdiv_rn(PsB.x, magB), __fdiv_rn(PsB.y, magB));
+      const float2 gA = __ldg(G + x), gB = __ldg(G + (has2 ? x2 : x));
+      float2 w0A = cmul(PsA, __ldg(h0 + x)), w1A = cmul(PnA, __ldg(h1 + x));
+      float2 w0B = cmul(PsB, __ldg(h0 + (has2 ? x2 : x))), w1B = cmul(PnB, __ldg(h1 + (has2 ? x2 : x)));
 #pragma unroll
       for (int b = 0; b < R; ++b) {
-        acc0[b] = cadd(acc0[b], w0);
-        acc1[b] = cadd(acc1[b], w1);
-        w0 = cmul(w0, g);
-        w1 = cmul(w1, g);
+        acc0[b] = cadd(acc0[b], cadd(w0A, w0B));
+        acc1[b] = cadd(acc1[b], cadd(w1A, w1B));
+        w0A = cmul(w0A, gA); w1A = cmul(w1A, gA);
+        w0B = cmul(w0B, gB); w1B = cmul(w1B, gB);
       }
     }
 #pragma unroll

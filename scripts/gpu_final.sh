@@ -1,0 +1,12 @@
+#!/bin/bash
+# End-of-session validation: parity tests, smoke, bench (both arms), launch list.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"
+cat gpurun_out/bench_ref.json | cut -c1-700; tail -5 gpurun_out/bench_ref.err
+timeout 600 python scripts/bench_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err; echo "configs rc=$?"
+cat gpurun_out/configs.json | tr -d '\n '; tail -5 gpurun_out/configs.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/b_ncu.log 2>&1; echo "ncu list rc=$?"
