@@ -73,8 +73,11 @@ def resample_stack(dviews, params, chunk_props, interpolation_order=1, full_view
     # view it is given (all-NaN rows), so re-expand to the full list
     xarr, tables, vidx = work["xforms"], work["tables"], work["view_index"]
     V = len(dviews)
-    tv = torch.full((V,) + shape, float("nan"), dtype=torch.float32, device="cuda")
-    bw = torch.zeros((V,) + shape, dtype=torch.float32, device="cuda") if want_weights else None
+    all_kept = len(xarr) == V and list(vidx) == list(range(V))
+    tv = bw = None
+    if not all_kept:
+        tv = torch.full((V,) + shape, float("nan"), dtype=torch.float32, device="cuda")
+        bw = torch.zeros((V,) + shape, dtype=torch.float32, device="cuda") if want_weights else None
     if len(xarr):
         n = len(xarr)
         tv_c = torch.empty((n,) + shape, dtype=torch.float32, device="cuda")
@@ -89,6 +92,8 @@ def resample_stack(dviews, params, chunk_props, interpolation_order=1, full_view
             ),
             "mvs_resample_views",
         )
+        if all_kept:
+            return tv_c, bw_c  # every view touches the chunk: the stacks are already in view order
         idx = torch.tensor(vidx, device="cuda")
         tv[idx] = tv_c
         if want_weights:

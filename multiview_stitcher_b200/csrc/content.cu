@@ -492,14 +492,21 @@ static int gaussian_batch(const float* src, float* dst, float* tmp, int batch, c
   return MVS_OK;
 }
 
-// grow-only device workspace shared by the multi-pass entry points (one call at a
-// time: callers are serialised by g_ws_mutex and synchronise their stream before
-// returning, so the buffer is never in use by two calls)
+// Grow-only device workspace shared by the multi-pass entry points.  Calls are
+// serialised by g_ws_mutex while they ENQUEUE; on one stream the work of two
+// calls is ordered by the stream itself, so nothing waits for the GPU.  A call on
+// another stream first waits for the previous user's stream; growing the buffer
+// frees it (cudaFree synchronises the device).
 static std::mutex g_ws_mutex;
 static void* g_ws = nullptr;
 static size_t g_ws_bytes = 0;
+static cudaStream_t g_ws_stream = nullptr;
+static bool g_ws_used = false;
 
-static int workspace(size_t bytes, void** out) {
+static int workspace(size_t bytes, void** out, cudaStream_t st) {
+  if (g_ws_used && g_ws_stream != st) cudaStreamSynchronize(g_ws_stream);
+  g_ws_stream = st;
+  g_ws_used = true;
   if (g_ws_bytes < bytes) {
     if (g_ws) cudaFree(g_ws);
     g_ws = nullptr;
@@ -542,15 +549,13 @@ extern "C" int mvs_gaussian_filter(const float* d_in, float* d_out, int batch,
   std::lock_guard<std::mutex> lock(g_ws_mutex);
   void* ws = nullptr;
   const size_t wbytes = align256(sizeof(double) * (rp + 1));
-  if ((rc = workspace(wbytes + sizeof(float) * total, &ws))) return rc;
+  if ((rc = workspace(wbytes + sizeof(float) * total, &ws, st))) return rc;
   double* d_fw = (double*)ws;
   float* tmp = (float*)((char*)ws + wbytes);
   std::vector<double> hw(rp + 1, 0.0);
   for (int i = 0; i <= radius; ++i) hw[i] = weights[i];
   MVS_CHECK_CUDA(cudaMemcpyAsync(d_fw, hw.data(), sizeof(double) * (rp + 1), cudaMemcpyHostToDevice, st));
-  rc = gaussian_batch(d_in, d_out, tmp, batch, shape, ndim, d_fw, radius, rp, nullptr, 1, st);
-  cudaStreamSynchronize(st);
-  return rc;
+  return gaussian_batch(d_in, d_out, tmp, batch, shape, ndim, d_fw, radius, rp, nullptr, 1, st);
 }
 
 extern "C" int mvs_content_based(const float* d_views, const float* d_blending, int V,
@@ -573,7 +578,7 @@ extern "C" int mvs_content_based(const float* d_views, const float* d_blending, 
   const size_t wbytes = align256(sizeof(double) * (rp1 + rp2 + 2));
   const size_t bbytes = align256(sizeof(int) * 6 * V);
   void* wsp = nullptr;
-  if ((rc = workspace(wbytes + bbytes + sizeof(float) * total * 7, &wsp))) return rc;
+  if ((rc = workspace(wbytes + bbytes + sizeof(float) * total * 7, &wsp, st))) return rc;
   double* d_w1 = (double*)wsp;
   double* d_w2 = d_w1 + rp1 + 1;
   int* d_boxes = (int*)((char*)wsp + wbytes);
@@ -586,7 +591,7 @@ extern "C" int mvs_content_based(const float* d_views, const float* d_blending, 
   for (int i = 0; i <= r1; ++i) hw[i] = w1[i];
   for (int i = 0; i <= r2; ++i) hw[rp1 + 1 + i] = w2[i];
   MVS_CHECK_CUDA(cudaMemcpyAsync(d_w1, hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice, st));
-  auto fail = [&](int code) { cudaStreamSynchronize(st); return code; };
+  auto fail = [&](int code) { return code; };  // stream-ordered: nothing to wait for
 
   // transformed_views[blending_weights < 1e-7] = NaN; split into V0 / W0
   mask_split_kernel<<<grid, 256, 0, st>>>(d_views, d_blending, 1e-7f, M, VW, VW + total, total);

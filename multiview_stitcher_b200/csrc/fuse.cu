@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -840,15 +841,32 @@ extern "C" int mvs_resample_views(const mvs_view_xform* xforms, int n_views, con
   const long long N = (long long)shape[0] * shape[1] * shape[2];
   if (N <= 0) return MVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  mvs_view_xform* d_x = nullptr;
-  float* d_t = nullptr;
-  MVS_CHECK_CUDA(cudaMalloc(&d_x, sizeof(mvs_view_xform) * n_views));
-  if (d_weights) {
-    cudaError_t e = cudaMalloc(&d_t, sizeof(float) * 125 * n_tables);
-    if (e != cudaSuccess) { cudaFree(d_x); set_error("cudaMalloc: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
-    cudaMemcpyAsync(d_t, tables, sizeof(float) * 125 * n_tables, cudaMemcpyHostToDevice, st);
+  // Parameter buffers are cached (grow-only) and reused stream-ordered: calls are
+  // serialised while they enqueue; a call on another stream first waits for the
+  // previous user's stream.  The host arrays are pageable, so the async copies
+  // have staged them when they return.
+  static std::mutex mtx;
+  static void* d_buf = nullptr;
+  static size_t d_bytes = 0;
+  static cudaStream_t last_stream = nullptr;
+  static bool used = false;
+  std::lock_guard<std::mutex> lock(mtx);
+  if (used && last_stream != st) cudaStreamSynchronize(last_stream);
+  last_stream = st;
+  used = true;
+  const size_t xbytes = ((sizeof(mvs_view_xform) * n_views + 255) / 256) * 256;
+  const size_t tbytes = d_weights ? sizeof(float) * 125 * n_tables : 0;
+  if (d_bytes < xbytes + tbytes) {
+    if (d_buf) cudaFree(d_buf);
+    d_buf = nullptr; d_bytes = 0;
+    MVS_CHECK_CUDA(cudaMalloc(&d_buf, 2 * (xbytes + tbytes)));
+    d_bytes = 2 * (xbytes + tbytes);
   }
-  cudaMemcpyAsync(d_x, xforms, sizeof(mvs_view_xform) * n_views, cudaMemcpyHostToDevice, st);
+  mvs_view_xform* d_x = (mvs_view_xform*)d_buf;
+  float* d_t = d_weights ? (float*)((char*)d_buf + xbytes) : nullptr;
+  if (d_weights)
+    MVS_CHECK_CUDA(cudaMemcpyAsync(d_t, tables, tbytes, cudaMemcpyHostToDevice, st));
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_x, xforms, sizeof(mvs_view_xform) * n_views, cudaMemcpyHostToDevice, st));
   dim3 grid((unsigned)std::min<long long>((N + 255) / 256, 148 * 16), n_views);
   if (ndim == 2) {
     if (order == 0) resample_views_kernel<2, 0><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
@@ -858,9 +876,6 @@ extern "C" int mvs_resample_views(const mvs_view_xform* xforms, int n_views, con
     else resample_views_kernel<3, 1><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
   }
   cudaError_t e = cudaGetLastError();
-  cudaStreamSynchronize(st);
-  cudaFree(d_x);
-  cudaFree(d_t);
   if (e != cudaSuccess) { set_error("resample launch: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
   return MVS_OK;
 }

@@ -41,7 +41,7 @@ def main():
         (res, _), dt = wall(lambda: fusion.fuse(views, true, output_stack_properties=osp, weights_func=fusion.content_based,
                                                  output_on_backend=True))
         out["c3_content_full"] = {"out_shape": [osp["shape"][d] for d in "zyx"], "s": dt, "Mvoxel_per_s": vox / dt / 1e6,
-                                  "min": int(res.min()), "nonzero_frac": float((res > 0).float().mean())}
+                                  "nonzero_frac": float((res[::4, ::4, ::4].to(torch.int32) > 0).float().mean())}
         del views, res
         torch.cuda.empty_cache()
     if "c4" in which:
@@ -72,7 +72,7 @@ def main():
         (res, _), dt = wall(lambda: fusion.fuse(views, params, output_stack_properties=osp, weights_func=fusion.content_based,
                                                  output_on_backend=True))
         out["c4_content_full"] = {"out_shape": [osp["shape"][d] for d in "zyx"], "s": dt, "Mvoxel_per_s": vox / dt / 1e6,
-                                  "nonzero_frac": float((res > 0).float().mean())}
+                                  "nonzero_frac": float((res[::4, ::4, ::4].to(torch.int32) > 0).float().mean())}
         (res2, _), dt2 = wall(lambda: fusion.fuse(views, params, output_stack_properties=osp, output_on_backend=True))
         (res2, _), dt2 = wall(lambda: fusion.fuse(views, params, output_stack_properties=osp, output_on_backend=True))
         out["c4_blend_full"] = {"s": dt2, "Mvoxel_per_s": vox / dt2 / 1e6}

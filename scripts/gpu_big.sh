@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for c in c5 c3 c4; do
-  timeout 400 python scripts/bench_configs_big.py $c > gpurun_out/big_$c.json 2> gpurun_out/big_$c.err; echo "$c rc=$?"
+for c in c3 c4; do
+  timeout 500 python scripts/bench_configs_big.py $c > gpurun_out/big_$c.json 2> gpurun_out/big_$c.err; echo "$c rc=$?"
   cat gpurun_out/big_$c.json | tr -d '\n '; echo; tail -3 gpurun_out/big_$c.err
 done
-nvidia-smi --query-gpu=memory.used,memory.total --format=csv
