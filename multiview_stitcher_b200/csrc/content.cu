@@ -90,22 +90,24 @@ gauss1d_kernel(const float* __restrict__ in, float* __restrict__ out, int nz, in
 }
 
 // ---- fast path of the same pass -------------------------------------------------
-// A warp owns a strip: 32 lanes across a non-filter axis x kGTA outputs along the
-// filter axis, staged (with its 2 r' halo rows, reflect-resolved) in shared memory
-// as [k][lane] so every read is conflict-free.  Each lane produces 4 consecutive
-// outputs at a time from two 4-deep rotating register windows (left / right taps):
-// 2 shared-memory reads feed 4 x (DADD, DMUL, DADD) -- scipy's exact float64
-// operation order -- so the pass runs at the FP64 pipe's rate instead of being
-// load-bound.  r' = radius rounded up to a multiple of 4 with zero weights
-// (x + 0.0 * finite == x).  Strips whose inputs are all one value (the 0/1 validity
-// mask of nan_gaussian_filter away from edges, empty space) collapse to one chain.
-// `boxes` (optional) restricts a volume to the bounding box of its valid voxels:
-// inputs outside read as 0, outputs outside are not produced (they are exact
-// zeros that nobody reads, weights.py:314-320 divides only where the view exists).
+// A CTA of 4 warps owns a tile: 32 lanes across a non-filter axis x 128 outputs
+// along the filter axis, staged once (with its 2 r' halo rows, reflect-resolved) in
+// shared memory as [k][lane] so every read is conflict-free; each warp then produces
+// a 32-output sub-range.  A lane computes 4 consecutive outputs at a time from two
+// 4-deep rotating register windows (left / right taps): 2 shared-memory reads feed
+// 4 x (DADD, DMUL, DADD) -- scipy's exact float64 operation order.  r' = radius
+// rounded up to a multiple of 4 with zero weights (x + 0.0 * finite == x).  Tiles
+// whose inputs are all one value (the 0/1 validity mask of nan_gaussian_filter away
+// from edges, empty space) collapse to one chain.  `boxes` (optional) restricts a
+// volume to the bounding box of its valid voxels: inputs outside read as 0, outputs
+// outside are not produced (they are exact zeros that nobody reads,
+// weights.py:314-320 divides only where the view exists).
 
-constexpr int kGTA = 32;
+constexpr int kGTA = 128;     // outputs per tile along the filter axis
+constexpr int kGSub = 32;     // ... per warp
+constexpr int kGWarps = kGTA / kGSub;
 constexpr int kGPitch = 33;
-constexpr int kGB = 24;  // strip rows requested per batch of loads
+constexpr int kGB = 8;        // loads requested per batch
 
 struct GaussArgs {
   const float* in;
@@ -138,34 +140,32 @@ __device__ __forceinline__ int reflect_idx(int k, int n) {
   }
 
 template <int AXIS>
-__global__ void __launch_bounds__(512) gauss_strip_kernel(const GaussArgs A) {
+__global__ void __launch_bounds__(kGWarps * 32) gauss_tile_kernel(const GaussArgs A) {
   extern __shared__ double gs_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rp = A.rp, span = kGTA + 2 * rp;
   double* wts = gs_smem;
-  const int per_warp = span * kGPitch + (AXIS == 2 ? kGTA * kGPitch : 0);
-  float* strip = reinterpret_cast<float*>(wts + rp + 1) + (size_t)warp * per_warp;
-  float* otile = strip + span * kGPitch;
-  for (int i = threadIdx.x; i <= rp; i += blockDim.x) wts[i] = A.fw[i];
-  __syncthreads();
+  float* strip = reinterpret_cast<float*>(wts + rp + 1);
+  float* otile = strip + span * kGPitch;  // AXIS == 2 only
+  for (int i = tid; i <= rp; i += blockDim.x) wts[i] = A.fw[i];
   const int nA = AXIS == 0 ? A.nz : (AXIS == 1 ? A.ny : A.nx);
   const int nL = AXIS == 2 ? A.ny : A.nx;
   const int nT = AXIS == 0 ? A.ny : A.nz;
   const int tilesA = (nA + kGTA - 1) / kGTA, tilesL = (nL + 31) / 32;
-  const long long per_vol = (long long)nT * tilesA * tilesL;
-  const long long strips = per_vol * A.batch;
+  // tile index decode in 32-bit arithmetic (64-bit divisions cost ~100 instructions each)
+  const unsigned per_row = (unsigned)tilesA * (unsigned)tilesL;
+  const unsigned per_vol = (unsigned)nT * per_row;
+  const unsigned tiles = per_vol * (unsigned)A.batch;  // < 2^31 (checked by the launcher)
   const long long sy = A.nx, sz = (long long)A.ny * A.nx;
   const long long strideA = AXIS == 0 ? sz : (AXIS == 1 ? sy : 1);
   const long long strideT = AXIS == 0 ? sy : sz;
-  const unsigned full = 0xffffffffu;
-  for (long long sidx = (long long)blockIdx.x * W + warp; sidx < strips;
-       sidx += (long long)gridDim.x * W) {
-    const int b = (int)(sidx / per_vol);
-    long long rem = sidx - (long long)b * per_vol;
-    const int tl = (int)(rem % tilesL);
-    rem /= tilesL;
-    const int ta = (int)(rem % tilesA);
-    const int th = (int)(rem / tilesA);
+  for (unsigned su = blockIdx.x; su < tiles; su += gridDim.x) {
+    const int b = (int)(su / per_vol);
+    unsigned rem = su - (unsigned)b * per_vol;
+    const int th = (int)(rem / per_row);
+    rem -= (unsigned)th * per_row;
+    const int ta = (int)(rem / (unsigned)tilesL);
+    const int tl = (int)(rem - (unsigned)ta * (unsigned)tilesL);
     const int a0 = ta * kGTA, l0 = tl * 32;
     int loA = 0, hiA = nA - 1, loL = 0, hiL = nL - 1, loT = 0, hiT = nT - 1;
     if (A.boxes) {
@@ -176,65 +176,72 @@ __global__ void __launch_bounds__(512) gauss_strip_kernel(const GaussArgs A) {
       loT = max(loT, bx[iT]); hiT = min(hiT, bx[3 + iT]);
     }
     if (th < loT || th > hiT || a0 > hiA || a0 + kGTA - 1 < loA || l0 > hiL || l0 + 31 < loL)
-      continue;  // nothing of this strip is wanted (warp-uniform)
+      continue;  // nothing of this tile is wanted (CTA-uniform)
     const long long voff = (long long)b * A.nz * sz + (long long)th * strideT;
     const float* vin = A.in + voff;
     float* vout = A.out + voff;
-    __syncwarp();  // the previous strip's readers are done
-    // ---- stage the strip: loads issued kGB at a time (clamped addresses) ----
+    __syncthreads();  // the previous tile's readers are done (also publishes wts)
+    // ---- stage the tile: loads issued kGB at a time (clamped addresses) ----
     bool same = true;
     float first = 0.f;
     if (AXIS != 2) {
+      // warp w stages rows w, w + 4, ...; lanes along x
       const int xl = l0 + lane;
       const bool lane_ok = xl >= loL && xl <= hiL;
-      for (int kk0 = 0; kk0 < span; kk0 += kGB) {  // span is a multiple of 8; the tail is clamped
+      const int myrows = (span - warp + kGWarps - 1) / kGWarps;
+      for (int i0 = 0; i0 < myrows; i0 += kGB) {
         float tv[kGB];
 #pragma unroll
         for (int u = 0; u < kGB; ++u) {
-          const int kk = min(kk0 + u, span - 1);
+          const int kk = warp + kGWarps * min(i0 + u, myrows - 1);
           const int a = reflect_idx(a0 - rp + kk, nA);
           const bool ok = lane_ok && a >= loA && a <= hiA;
           const float x = __ldg(ok ? vin + (long long)a * strideA + xl : A.in);
           tv[u] = ok ? x : 0.f;
         }
-        if (kk0 == 0) first = tv[0];
+        if (i0 == 0) first = tv[0];
 #pragma unroll
         for (int u = 0; u < kGB; ++u) {
-          if (kk0 + u < span) {
-            strip[(kk0 + u) * kGPitch + lane] = tv[u];
+          if (i0 + u < myrows) {
+            strip[(warp + kGWarps * (i0 + u)) * kGPitch + lane] = tv[u];
             same = same && (tv[u] == first);
           }
         }
       }
     } else {
-      const int nk = (span + 31) >> 5;  // 32-wide chunks per row
-      for (int e0 = 0; e0 < 32 * nk; e0 += 8) {
-        float tv[8];
+      // consecutive threads read consecutive x of one row: coalesced; transposed into [k][row]
+      const int spad = (span + 31) & ~31;
+      const int total = 32 * spad;
+      for (int e0 = 0; e0 < total; e0 += kGB * 128) {
+        float tv[kGB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u, row = e / nk, kk = (e - row * nk) * 32 + lane;
+        for (int u = 0; u < kGB; ++u) {
+          const int e = e0 + u * 128 + tid;
+          const int row = e / spad, kk = e - row * spad;
           const int y = l0 + row;
           const int a = reflect_idx(a0 - rp + kk, nA);
-          const bool ok = kk < span && y >= loL && y <= hiL && a >= loA && a <= hiA;
+          const bool ok = e < total && kk < span && y >= loL && y <= hiL && a >= loA && a <= hiA;
           const float x = __ldg(ok ? vin + (long long)y * sy + a : A.in);
           tv[u] = ok ? x : 0.f;
         }
         if (e0 == 0) first = tv[0];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u, row = e / nk, kk = (e - row * nk) * 32 + lane;
-          if (kk < span) {
+        for (int u = 0; u < kGB; ++u) {
+          const int e = e0 + u * 128 + tid;
+          const int row = e / spad, kk = e - row * spad;
+          if (e < total && kk < span) {
             strip[kk * kGPitch + row] = tv[u];
             same = same && (tv[u] == first);
           }
         }
       }
     }
-    const float f0 = __shfl_sync(full, first, 0);
-    const bool uniform = __all_sync(full, same && first == f0);
-    __syncwarp();
+    __syncthreads();
+    const float f0 = strip[0];
+    const bool uniform = __syncthreads_and(same && first == f0) != 0;
     const int lpos = l0 + lane;  // this lane's coordinate on the lane axis
     const bool lane_out = lpos >= loL && lpos <= hiL;
+    const int s0 = a0 + warp * kGSub;  // this warp's first output
     if (uniform) {
       double tmp = __dmul_rn((double)f0, wts[0]);
       const double two = __dadd_rn((double)f0, (double)f0);
@@ -242,20 +249,19 @@ __global__ void __launch_bounds__(512) gauss_strip_kernel(const GaussArgs A) {
       const float o = (float)tmp;
       if (AXIS != 2) {
         if (lane_out)
-          for (int k = max(a0, loA); k <= min(a0 + kGTA - 1, hiA); ++k)
+          for (int k = max(s0, loA); k <= min(s0 + kGSub - 1, hiA); ++k)
             vout[(long long)k * strideA + lpos] = o;
       } else {
-        for (int row = max(l0, loL); row <= min(l0 + 31, hiL); ++row) {
-          const int a = a0 + lane;
-          if (a >= loA && a <= hiA) vout[(long long)row * sy + a] = o;
-        }
+        const int a = a0 + tid;
+        if (a >= loA && a <= hiA)
+          for (int row = max(l0, loL); row <= min(l0 + 31, hiL); ++row) vout[(long long)row * sy + a] = o;
       }
       continue;
     }
-    for (int g = 0; g < kGTA / 4; ++g) {
-      const int c0 = a0 + 4 * g;
+    for (int g = 0; g < kGSub / 4; ++g) {
+      const int c0 = s0 + 4 * g;
       if (c0 > hiA || c0 + 3 < loA) continue;  // warp-uniform
-      const float* sp = strip + (rp + 4 * g) * kGPitch + lane;
+      const float* sp = strip + (rp + warp * kGSub + 4 * g) * kGPitch + lane;
       double acc[4], Lw[4], Rw[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -275,16 +281,16 @@ __global__ void __launch_bounds__(512) gauss_strip_kernel(const GaussArgs A) {
         if (AXIS != 2) {
           if (lane_out && a >= loA && a <= hiA) vout[(long long)a * strideA + lpos] = (float)acc[i];
         } else {
-          otile[(4 * g + i) * kGPitch + lane] = (float)acc[i];
+          otile[(warp * kGSub + 4 * g + i) * kGPitch + lane] = (float)acc[i];
         }
       }
     }
     if (AXIS == 2) {
-      __syncwarp();
-      const int a = a0 + lane;
+      __syncthreads();
+      const int a = a0 + tid;  // 128 consecutive x per row: coalesced
       if (a >= loA && a <= hiA)
         for (int row = max(l0, loL); row <= min(l0 + 31, hiL); ++row)
-          vout[(long long)row * sy + a] = otile[lane * kGPitch + (row - l0)];
+          vout[(long long)row * sy + a] = otile[tid * kGPitch + (row - l0)];
     }
   }
 }
@@ -434,34 +440,33 @@ static int check_stack(const void* a, int V, const int32_t shape[3]) {
 
 static int round_up4(int r) { return r < 4 ? 4 : ((r + 3) / 4) * 4; }
 
-// warps per CTA that fit the strip kernel's shared memory (0: use the plain kernel)
-static int strip_warps(int rp, int axis, size_t* smem_out) {
-  const size_t per_warp = sizeof(float) * ((size_t)(kGTA + 2 * rp) * kGPitch + (axis == 2 ? kGTA * kGPitch : 0));
-  const size_t fixed = sizeof(double) * (rp + 1);
-  int W = 16;
-  while (W > 0 && fixed + W * per_warp > 200 * 1024) --W;
-  if (smem_out) *smem_out = fixed + W * per_warp;
-  return W;
+// shared memory of one tile (0 in *fits: use the plain kernel)
+static size_t tile_smem(int rp, int axis, bool* fits) {
+  const size_t bytes = sizeof(double) * (rp + 1) +
+                       sizeof(float) * ((size_t)(kGTA + 2 * rp) * kGPitch + (axis == 2 ? kGTA * kGPitch : 0));
+  *fits = bytes <= 200 * 1024;
+  return bytes;
 }
 
 template <int AXIS>
-static int launch_strip(const GaussArgs& a, int W, size_t smem, cudaStream_t st) {
-  auto kern = gauss_strip_kernel<AXIS>;
+static int launch_tile(const GaussArgs& a, size_t smem, cudaStream_t st) {
+  auto kern = gauss_tile_kernel<AXIS>;
   MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nA = AXIS == 0 ? a.nz : (AXIS == 1 ? a.ny : a.nx);
   const int nL = AXIS == 2 ? a.ny : a.nx;
   const int nT = AXIS == 0 ? a.ny : a.nz;
-  const long long strips = (long long)a.batch * nT * ((nA + kGTA - 1) / kGTA) * ((nL + 31) / 32);
-  long long blocks = (strips + W - 1) / W;
-  const long long cap = 148LL * 4;
+  const long long tiles = (long long)a.batch * nT * ((nA + kGTA - 1) / kGTA) * ((nL + 31) / 32);
+  MVS_REQUIRE(tiles < (1LL << 31), MVS_ERR_UNSUPPORTED, "stack too large for one Gaussian pass");
+  long long blocks = tiles;
+  const long long cap = 148LL * 16;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, W * 32, smem, st>>>(a);
+  kern<<<(unsigned)blocks, kGWarps * 32, smem, st>>>(a);
   MVS_CHECK_CUDA(cudaGetLastError());
   return MVS_OK;
 }
 
 // gaussian_filter of `batch` volumes: src -> dst, using tmp as the ping-pong buffer.
-// d_fw holds rp + 1 weights (zero beyond `radius`).  boxes: see gauss_strip_kernel.
+// d_fw holds rp + 1 weights (zero beyond `radius`).  boxes: see gauss_tile_kernel.
 static int gaussian_batch(const float* src, float* dst, float* tmp, int batch, const int32_t shape[3],
                           int ndim, const double* d_fw, int radius, int rp, const int* boxes,
                           int box_mod, cudaStream_t st) {
@@ -473,12 +478,12 @@ static int gaussian_batch(const float* src, float* dst, float* tmp, int batch, c
   for (int axis = first_axis; axis < 3; ++axis) {
     const int remaining = 3 - axis;  // passes left including this one
     float* o = (remaining % 2 == 1) ? dst : tmp;
-    size_t smem = 0;
-    const int W = strip_warps(rp, axis, &smem);
-    if (W >= 1) {
+    bool fits = false;
+    const size_t smem = tile_smem(rp, axis, &fits);
+    if (fits) {
       GaussArgs a{cur, o, shape[0], shape[1], shape[2], batch, d_fw, rp, boxes, box_mod};
-      int rc = axis == 0 ? launch_strip<0>(a, W, smem, st)
-                         : (axis == 1 ? launch_strip<1>(a, W, smem, st) : launch_strip<2>(a, W, smem, st));
+      int rc = axis == 0 ? launch_tile<0>(a, smem, st)
+                         : (axis == 1 ? launch_tile<1>(a, smem, st) : launch_tile<2>(a, smem, st));
       if (rc) return rc;
     } else {
       // very wide kernels: one thread per output, taps from global memory (computes

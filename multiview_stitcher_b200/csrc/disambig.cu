@@ -314,8 +314,10 @@ __global__ void __launch_bounds__(kS3Threads)
 ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
               const float* __restrict__ mat, double* __restrict__ tile_sum,
               float* __restrict__ tile_max) {
-  __shared__ float zf[5][kS3WY][kS3P];  // z-filtered plane
-  __shared__ float yf[5][kS3TY][kS3P];  // then y-filtered
+  // float32-rounded values kept as doubles (no conversions in the running sums)
+  __shared__ double zf[5][kS3WY][kS3P];  // z-filtered plane
+  __shared__ double yf[5][kS3TY][kS3P];  // then y-filtered
+  __shared__ float xf[5][kS3TY][kS3TX + 1];  // then x-filtered: the five means per output
   const long long tile = blockIdx.x;
   const Cand c = cands[find_cand(cands, n_cand, tile)];
   long long local = tile - c.tile_base;
@@ -406,34 +408,41 @@ ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
     for (int i = 0; i < CPT; ++i) {
       if (t + i * kS3Threads < NCOL) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) zf[q][cy[i]][cx[i]] = ok[i] ? (float)(S[i][q] * inv) : 0.f;
+        for (int q = 0; q < 5; ++q) zf[q][cy[i]][cx[i]] = ok[i] ? (double)(float)(S[i][q] * inv) : 0.0;
       }
     }
     __syncthreads();
-    // y pass: 5 x kS3TY x kS3WX values
+    // y pass: thread = (quantity, x column), a running window sum down the kS3TY outputs
+    if (t < 5 * kS3WX) {
+      const int q = t / kS3WX, x = t - q * kS3WX;
+      double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      for (int idx = t; idx < kS3TY * kS3WX; idx += kS3Threads) {
-        const int y = idx / kS3WX, x = idx - y * kS3WX;
-        double s = 0.0;
+      for (int k = 0; k < win; ++k) s += zf[q][k][x];
 #pragma unroll
-        for (int k = 0; k < win; ++k) s += (double)zf[q][y + k][x];
-        yf[q][y][x] = (float)(s * inv);
+      for (int y = 0; y < kS3TY; ++y) {
+        yf[q][y][x] = (double)(float)(s * inv);
+        if (y + 1 < kS3TY) s += zf[q][y + win][x] - zf[q][y][x];
       }
     }
     __syncthreads();
-    // x pass + SSIM for this thread's output voxel
-    if (yo < nyo && xo < nxo) {
-      float U[5];
+    // x pass: thread = (quantity, row, 8-output segment), a running window sum along x
+    if (t < 5 * kS3TY * (kS3TX / 8)) {
+      const int q = t / (kS3TY * (kS3TX / 8));
+      const int r2 = t - q * (kS3TY * (kS3TX / 8));
+      const int y = r2 / (kS3TX / 8), x0 = (r2 - y * (kS3TX / 8)) * 8;
+      double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        double s = 0.0;
+      for (int k = 0; k < win; ++k) s += yf[q][y][x0 + k];
 #pragma unroll
-        for (int k = 0; k < win; ++k) s += (double)yf[q][yo][xo + k];
-        U[q] = (float)(s * inv);
+      for (int j = 0; j < 8; ++j) {
+        xf[q][y][x0 + j] = (float)(s * inv);
+        if (j + 1 < 8) s += yf[q][y][x0 + j + win] - yf[q][y][x0 + j];
       }
-      sum += (double)ssim_value(U[0], U[1], U[2], U[3], U[4], cov_norm);
     }
+    __syncthreads();
+    // SSIM of this thread's output voxel
+    if (yo < nyo && xo < nxo)
+      sum += (double)ssim_value(xf[0][yo][xo], xf[1][yo][xo], xf[2][yo][xo], xf[3][yo][xo], xf[4][yo][xo], cov_norm);
   }
   ssim_block_reduce<kS3Threads>(sum, vmax, tile, tile_sum, tile_max);
 }
