@@ -100,6 +100,47 @@ __device__ __forceinline__ float blend_weight(const float* __restrict__ tab, dou
   return fminf(fmaxf(w, 0.0f), 1.0f);
 }
 
+// Order-0 / order-1 sample of view X at the (valid) window position (xz, xy, xx):
+// scipy's tap indices (edge tap clamped), float32 interpolation.
+template <int NDIM, int ORDER, typename T>
+__device__ __forceinline__ float sample_view(const mvs_view_xform& X, double xz, double xy, double xx) {
+  const T* base = reinterpret_cast<const T*>(X.data);
+  const int nz = X.shape[0], ny = X.shape[1], nx = X.shape[2];
+  const int64_t sz = X.stride[0], sy = X.stride[1], sx = X.stride[2];
+  if (ORDER == 0) {
+    const int64_t ix = (int64_t)floor(__dadd_rn(xx, 0.5));
+    const int64_t iy = (int64_t)floor(__dadd_rn(xy, 0.5));
+    const int64_t iz = NDIM == 3 ? (int64_t)floor(__dadd_rn(xz, 0.5)) : 0;
+    return (float)__ldg(base + iz * sz + iy * sy + ix * sx);
+  }
+  const double fx = floor(xx), fy = floor(xy);
+  const int ix = (int)fx, iy = (int)fy;
+  const float tx = (float)(xx - fx), ty = (float)(xy - fy);
+  const int64_t ox0 = ix * sx, ox1 = (ix + 1 > nx - 1 ? ix : ix + 1) * sx;
+  const int64_t oy0 = iy * sy, oy1 = (iy + 1 > ny - 1 ? iy : iy + 1) * sy;
+  if (NDIM == 3) {
+    const double fz = floor(xz);
+    const int iz = (int)fz;
+    const float tz = (float)(xz - fz);
+    const T* p00 = base + iz * sz + oy0;
+    const T* p01 = base + iz * sz + oy1;
+    const T* p10 = base + (iz + 1 > nz - 1 ? iz : iz + 1) * sz + oy0;
+    const T* p11 = p10 - oy0 + oy1;
+    const float v000 = (float)__ldg(p00 + ox0), v001 = (float)__ldg(p00 + ox1);
+    const float v010 = (float)__ldg(p01 + ox0), v011 = (float)__ldg(p01 + ox1);
+    const float v100 = (float)__ldg(p10 + ox0), v101 = (float)__ldg(p10 + ox1);
+    const float v110 = (float)__ldg(p11 + ox0), v111 = (float)__ldg(p11 + ox1);
+    const float a0 = lerp(lerp(v000, v001, tx), lerp(v010, v011, tx), ty);
+    const float a1 = lerp(lerp(v100, v101, tx), lerp(v110, v111, tx), ty);
+    return lerp(a0, a1, tz);
+  }
+  const T* p0 = base + oy0;
+  const T* p1 = base + oy1;
+  const float v00 = (float)__ldg(p0 + ox0), v01 = (float)__ldg(p0 + ox1);
+  const float v10 = (float)__ldg(p1 + ox0), v11 = (float)__ldg(p1 + ox1);
+  return lerp(lerp(v00, v01, tx), lerp(v10, v11, tx), ty);
+}
+
 // Evaluates view X at output sample index (cz, cy, cx) (already halo-shifted).
 template <int NDIM, int ORDER, bool WANT_V, bool WANT_B>
 __device__ __forceinline__ ViewEval eval_view(const mvs_view_xform& X,
@@ -120,44 +161,11 @@ __device__ __forceinline__ ViewEval eval_view(const mvs_view_xform& X,
   if (!valid) return r;
 
   if (WANT_V) {
-    const void* base = X.data;
+    // one (warp-uniform) dtype switch per view instead of one per tap
     const int dt = X.dtype;
-    const int64_t sz = X.stride[0], sy = X.stride[1], sx = X.stride[2];
-    if (ORDER == 0) {
-      int64_t ix = (int64_t)floor(__dadd_rn(xx, 0.5));
-      int64_t iy = (int64_t)floor(__dadd_rn(xy, 0.5));
-      int64_t iz = NDIM == 3 ? (int64_t)floor(__dadd_rn(xz, 0.5)) : 0;
-      r.v = load_as_float(base, dt, iz * sz + iy * sy + ix * sx);
-    } else {
-      double fx = floor(xx), fy = floor(xy);
-      int64_t ix = (int64_t)fx, iy = (int64_t)fy;
-      float tx = (float)(xx - fx), ty = (float)(xy - fy);
-      int64_t ox0 = ix * sx, ox1 = (ix + 1 > nx - 1 ? ix : ix + 1) * sx;
-      int64_t oy0 = iy * sy, oy1 = (iy + 1 > ny - 1 ? iy : iy + 1) * sy;
-      if (NDIM == 3) {
-        double fz = floor(xz);
-        int64_t iz = (int64_t)fz;
-        float tz = (float)(xz - fz);
-        int64_t oz0 = iz * sz, oz1 = (iz + 1 > nz - 1 ? iz : iz + 1) * sz;
-        float v000 = load_as_float(base, dt, oz0 + oy0 + ox0);
-        float v001 = load_as_float(base, dt, oz0 + oy0 + ox1);
-        float v010 = load_as_float(base, dt, oz0 + oy1 + ox0);
-        float v011 = load_as_float(base, dt, oz0 + oy1 + ox1);
-        float v100 = load_as_float(base, dt, oz1 + oy0 + ox0);
-        float v101 = load_as_float(base, dt, oz1 + oy0 + ox1);
-        float v110 = load_as_float(base, dt, oz1 + oy1 + ox0);
-        float v111 = load_as_float(base, dt, oz1 + oy1 + ox1);
-        float a0 = lerp(lerp(v000, v001, tx), lerp(v010, v011, tx), ty);
-        float a1 = lerp(lerp(v100, v101, tx), lerp(v110, v111, tx), ty);
-        r.v = lerp(a0, a1, tz);
-      } else {
-        float v00 = load_as_float(base, dt, oy0 + ox0);
-        float v01 = load_as_float(base, dt, oy0 + ox1);
-        float v10 = load_as_float(base, dt, oy1 + ox0);
-        float v11 = load_as_float(base, dt, oy1 + ox1);
-        r.v = lerp(lerp(v00, v01, tx), lerp(v10, v11, tx), ty);
-      }
-    }
+    if (dt == MVS_U16) r.v = sample_view<NDIM, ORDER, unsigned short>(X, xz, xy, xx);
+    else if (dt == MVS_F32) r.v = sample_view<NDIM, ORDER, float>(X, xz, xy, xx);
+    else r.v = sample_view<NDIM, ORDER, unsigned char>(X, xz, xy, xx);
   }
   if (WANT_B) {
     const double* w = X.wmatrix;
@@ -259,31 +267,15 @@ fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ bl
         }
       }
     } else if (nact >= 1) {
-      // pass 1: s = sum_i b_i * valid_i  (sequential float32, view order)
-      float s[kVPT];
+      // One pass over the views: acc = sum_i v_i b_i, s = sum_i b_i (sequential
+      // float32, view order), out = acc / s.  A voxel that exactly one view weights
+      // keeps that view's value untouched (the reference's b/b == 1), so single-view
+      // voxels stay bit-exact; blended voxels differ from the reference's
+      // sum_i v_i (b_i / s) by float32 rounding only.
+      float s[kVPT], vone[kVPT];
+      int npos[kVPT];
 #pragma unroll
-      for (int k = 0; k < kVPT; ++k) s[k] = 0.0f;
-      for (int i = 0; i < nxf; ++i) {
-        if (!s_flag[i]) continue;
-        const mvs_view_xform& X = xforms[first + i];
-#pragma unroll
-        for (int k = 0; k < kVPT; ++k) {
-          int x = x0 + lane + 32 * k;
-          if (x < sh_x) {
-            ViewEval e = eval_view<NDIM, ORDER, false, true>(X, tables, cz, cy,
-                                                             (double)(x + ck.halo[2]));
-            s[k] = __fadd_rn(s[k], e.b);
-          }
-        }
-      }
-      if (PARTIAL) {
-#pragma unroll
-        for (int k = 0; k < kVPT; ++k) den[k] = s[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < kVPT; ++k) if (s[k] == 0.0f) s[k] = 1.0f;
-      }
-      // pass 2: sum_i v_i * (b_i / s)
+      for (int k = 0; k < kVPT; ++k) { s[k] = 0.0f; vone[k] = 0.0f; npos[k] = 0; }
       for (int i = 0; i < nxf; ++i) {
         if (!s_flag[i]) continue;
         const mvs_view_xform& X = xforms[first + i];
@@ -294,11 +286,17 @@ fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ bl
             ViewEval e = eval_view<NDIM, ORDER, true, true>(X, tables, cz, cy,
                                                             (double)(x + ck.halo[2]));
             if (e.valid) {
-              float w = PARTIAL ? e.b : __fdiv_rn(e.b, s[k]);
-              res[k] = __fadd_rn(res[k], __fmul_rn(e.v, w));
+              s[k] = __fadd_rn(s[k], e.b);
+              res[k] = __fadd_rn(res[k], __fmul_rn(e.v, e.b));
+              if (e.b > 0.0f) { vone[k] = e.v; ++npos[k]; }
             }
           }
         }
+      }
+#pragma unroll
+      for (int k = 0; k < kVPT; ++k) {
+        if (PARTIAL) den[k] = s[k];
+        else res[k] = npos[k] == 0 ? 0.0f : (npos[k] == 1 ? vone[k] : __fdiv_rn(res[k], s[k]));
       }
     }
   } else {
