@@ -71,15 +71,13 @@ __device__ __forceinline__ float blend_weight(const float* __restrict__ tab, dou
                                               double uy, double ux) {
   if (ux < 0.0 || ux > 4.0 || uy < 0.0 || uy > 4.0) return 0.0f;
   if (NDIM == 3 && (uz < 0.0 || uz > 4.0)) return 0.0f;
-  double fx = floor(ux), fy = floor(uy);
-  int ix = (int)fx, iy = (int)fy;
-  float tx = (float)(ux - fx), ty = (float)(uy - fy);
+  int ix = __double2int_rd(ux), iy = __double2int_rd(uy);  // in [0, 4]: round-down == floor
+  float tx = (float)(ux - (double)ix), ty = (float)(uy - (double)iy);
   int ix1 = min(ix + 1, 4), iy1 = min(iy + 1, 4);
   float w;
   if (NDIM == 3) {
-    double fz = floor(uz);
-    int iz = (int)fz;
-    float tz = (float)(uz - fz);
+    int iz = __double2int_rd(uz);
+    float tz = (float)(uz - (double)iz);
     int iz1 = min(iz + 1, 4);
     const float* p0 = tab + iz * 25;
     const float* p1 = tab + iz1 * 25;
@@ -113,15 +111,14 @@ __device__ __forceinline__ float sample_view(const mvs_view_xform& X, double xz,
     const int64_t iz = NDIM == 3 ? (int64_t)floor(__dadd_rn(xz, 0.5)) : 0;
     return (float)__ldg(base + iz * sz + iy * sy + ix * sx);
   }
-  const double fx = floor(xx), fy = floor(xy);
-  const int ix = (int)fx, iy = (int)fy;
-  const float tx = (float)(xx - fx), ty = (float)(xy - fy);
+  // positions are valid (>= 0): round-down conversion == floor
+  const int ix = __double2int_rd(xx), iy = __double2int_rd(xy);
+  const float tx = (float)(xx - (double)ix), ty = (float)(xy - (double)iy);
   const int64_t ox0 = ix * sx, ox1 = (ix + 1 > nx - 1 ? ix : ix + 1) * sx;
   const int64_t oy0 = iy * sy, oy1 = (iy + 1 > ny - 1 ? iy : iy + 1) * sy;
   if (NDIM == 3) {
-    const double fz = floor(xz);
-    const int iz = (int)fz;
-    const float tz = (float)(xz - fz);
+    const int iz = __double2int_rd(xz);
+    const float tz = (float)(xz - (double)iz);
     const T* p00 = base + iz * sz + oy0;
     const T* p01 = base + iz * sz + oy1;
     const T* p10 = base + (iz + 1 > nz - 1 ? iz : iz + 1) * sz + oy0;
