@@ -433,7 +433,8 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
             raise EngineError(f"pair {i}: shapes differ {tuple(f.shape)} vs {tuple(m.shape)}")
         groups.setdefault(tuple(f.shape), []).append(i)
     results = [None] * n
-    for shape, idx in groups.items():
+
+    def run_group(shape, idx):
         ndim = len(shape)
         u = upsample_factor if upsample_factor is not None else (10 if ndim == 2 else 2)
         key = (shape, u)
@@ -465,6 +466,34 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
                 results[idx[k]] = r
         if plans is None:
             plan.close()
+
+    items = list(groups.items())
+    if len(items) == 1:
+        run_group(*items[0])
+        return results
+    # Several crop shapes (e.g. the x- and the y-neighbours of a tile grid): each group
+    # runs on its own stream from its own thread, so the host glue of one group (the
+    # stages return to the host between launches) overlaps the kernels of another.
+    # ctypes and the synchronising CUDA calls release the GIL.
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    cur = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    device = torch.cuda.current_device()
+
+    def worker(item):
+        torch.cuda.set_device(device)
+        st = torch.cuda.Stream()
+        st.wait_event(ready)  # the crops were produced on the caller's stream
+        with torch.cuda.stream(st):
+            run_group(*item)
+        st.synchronize()
+
+    with ThreadPoolExecutor(max_workers=min(len(items), 4)) as pool:
+        for f in [pool.submit(worker, it) for it in items]:
+            f.result()
     return results
 
 
