@@ -244,7 +244,10 @@ updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, 
                    int ndim, int R, int u, int* __restrict__ peaks /* [pair][2][3] */,
                    float2* __restrict__ E, long long e_stride /* per (pair,norm) */,
                    int e_off1, int e_off0, float2* __restrict__ G) {
-  const int pn = blockIdx.x;  // pair*2 + norm
+  // grid (pair*2 + norm, slices): the table entries of one (pair, norm) are spread
+  // over gridDim.y blocks
+  const int pn = blockIdx.x;
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
   const unsigned long long key = keys[pn];
   const long long idx = (long long)(0xffffffffull - (key & 0xffffffffull));
   int p[3];
@@ -252,11 +255,11 @@ updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, 
   const int nn[3] = {n0, n1, n2};
   int sh[3];
   for (int d = 0; d < 3; ++d) sh[d] = p[d] > nn[d] / 2 ? p[d] - nn[d] : p[d];
-  if (threadIdx.x < 3) peaks[pn * 3 + threadIdx.x] = sh[threadIdx.x];
+  if (blockIdx.y == 0 && threadIdx.x < 3) peaks[pn * 3 + threadIdx.x] = sh[threadIdx.x];
   float2* e = E + (long long)pn * e_stride;
   {
     const double off = (double)(R / 2) - (double)sh[2] * u;
-    for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+    for (int k = tid; k < n2; k += nth) {
       const int ks = (k <= (n2 - 1) / 2) ? k : k - n2;
       double s, c;
       sincospi(-2.0 * off * (double)ks / ((double)n2 * (double)u), &s, &c);
@@ -272,7 +275,7 @@ updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, 
     const int n = nn[d];
     const double off = (double)(R / 2) - (double)sh[d] * u;
     float2* ed = e + eoff[d];
-    for (int i = threadIdx.x; i < R * n; i += blockDim.x) {
+    for (int i = tid; i < R * n; i += nth) {
       const int a = i / n, k = i - a * n;
       const int ks = (k <= (n - 1) / 2) ? k : k - n;
       double s, c;
@@ -353,11 +356,24 @@ updft_axis_kernel(const double2* __restrict__ in, double2* __restrict__ out, int
   if (sl < slices) {
     const float2* e = E + (long long)pn * e_stride + e_off + (long long)a * n;
     const double2* src = in + ((long long)pn * outer + o) * n * inner + r;
-    for (int k = sl; k < n; k += slices) {
-      const double2 v = src[(long long)k * inner];
-      const float2 w = __ldg(e + k);
-      re += v.x * w.x - v.y * w.y;
-      im += v.x * w.y + v.y * w.x;
+    // eight independent loads in flight per thread (the loop is latency-bound otherwise)
+    for (int k0 = sl; k0 < n; k0 += 8 * slices) {
+      double2 v[8];
+      float2 w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j * slices;
+        const int kc = k < n ? k : sl;
+        v[j] = src[(long long)kc * inner];
+        w[j] = __ldg(e + kc);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (k0 + j * slices < n) {
+          re += v[j].x * w[j].x - v[j].y * w[j].y;
+          im += v[j].x * w[j].y + v[j].y * w[j].x;
+        }
+      }
     }
   }
   s_part[threadIdx.x] = make_double2(re, im);
@@ -683,7 +699,7 @@ extern "C" int mvs_pc_correlate(mvs_pc_plan* p, int n, int32_t* peaks_host, doub
   float2* surf = getenv("MVS_PC_DEBUG_STORE") ? p->Q : nullptr;
   if ((rc = launch_pass(p, n, 2, +1, PASS_ARGMAX, p->Q, surf, st))) return rc;
   // slot 0 = |Re| = normalization None, slot 1 = |Im| = "phase"
-  updft_setup_kernel<<<2 * n, 256, 0, st>>>(p->d_keys, p->shape[0], p->shape[1], p->shape[2],
+  updft_setup_kernel<<<dim3(2 * n, 16), 256, 0, st>>>(p->d_keys, p->shape[0], p->shape[1], p->shape[2],
                                             p->ndim, p->R, p->upsample, p->d_peaks, p->d_E,
                                             p->e_stride, p->e_off[1], p->e_off[0], p->d_G);
   MVS_CHECK_CUDA(cudaGetLastError());
