@@ -593,17 +593,32 @@ extern "C" int mvs_pc_load_pairs(mvs_pc_plan* p, int n, const float* const* fixe
 
 enum PassKind { PASS_LOAD_REAL, PASS_PLAIN, PASS_PAIRED, PASS_ARGMAX };
 
+// The dynamic shared-memory cap of a kernel is per-function state shared by every
+// thread of the process (crop-shape groups are registered from concurrent threads
+// with different line counts): raise it once to the largest size any launch uses.
+constexpr int kFftSmemCap = 200 * 1024;
+
+template <int M, bool BLUE>
+static cudaError_t fft_kernel_ready() {
+  static std::once_flag once;
+  static cudaError_t status = cudaSuccess;
+  std::call_once(once, [] {
+    status = cudaFuncSetAttribute(fft_reg_pass_kernel<M, BLUE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemCap);
+  });
+  return status;
+}
+
 template <int M>
 static int launch_pass_m(const FftPassArgs& a, bool blue, dim3 grid, int threads, size_t smem,
                          cudaStream_t st) {
+  MVS_REQUIRE(smem <= (size_t)kFftSmemCap, MVS_ERR_UNSUPPORTED, "FFT pass needs %zu bytes of shared memory", smem);
   if (blue) {
-    auto kern = fft_reg_pass_kernel<M, true>;
-    MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(a);
+    MVS_CHECK_CUDA((fft_kernel_ready<M, true>()));
+    fft_reg_pass_kernel<M, true><<<grid, threads, smem, st>>>(a);
   } else {
-    auto kern = fft_reg_pass_kernel<M, false>;
-    MVS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(a);
+    MVS_CHECK_CUDA((fft_kernel_ready<M, false>()));
+    fft_reg_pass_kernel<M, false><<<grid, threads, smem, st>>>(a);
   }
   MVS_CHECK_CUDA(cudaGetLastError());
   return MVS_OK;
@@ -632,7 +647,7 @@ static int launch_pass(mvs_pc_plan* p, int n, int axis, int sign, PassKind kind,
   const long long nlines = outer * inner;
   const PassGeom g = pass_geom(ax.m, a.contig != 0, a.paired != 0, nlines);
   a.L = g.L; a.line_stride = g.line_stride;
-  MVS_REQUIRE(g.smem <= 227 * 1024 && g.threads <= 512, MVS_ERR_UNSUPPORTED,
+  MVS_REQUIRE(g.smem <= (size_t)kFftSmemCap && g.threads <= 512, MVS_ERR_UNSUPPORTED,
               "axis length %d: pass geometry out of range", a.n);
   dim3 grid((unsigned)((nlines + g.L - 1) / g.L), n);
   if (a.paired) {
