@@ -444,10 +444,11 @@ static bool make_tensor_map(const mvs_view_xform& X, int ndim, CUtensorMap* out)
   const CUtensorMapDataType dt = X.dtype == MVS_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : X.dtype == MVS_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
                                                       : CU_TENSOR_MAP_DATA_TYPE_UINT8;
-  const cuuint32_t bw = (cuuint32_t)(128 + 16 / es);
+  const cuuint32_t bw = (cuuint32_t)((ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX) + 16 / es);
   cuuint64_t gdim[3] = {(cuuint64_t)X.shape[2], (cuuint64_t)X.shape[1], (cuuint64_t)X.shape[0]};
   cuuint64_t gstr[2] = {(cuuint64_t)X.stride[1] * es, (cuuint64_t)X.stride[0] * es};
-  cuuint32_t box[3] = {bw, (cuuint32_t)(ndim == 3 ? 9 : 17), (cuuint32_t)(ndim == 3 ? 5 : 1)};
+  cuuint32_t box[3] = {bw, (cuuint32_t)(ndim == 3 ? SBlock<3>::ROWS_Y : SBlock<2>::ROWS_Y),
+                       (cuuint32_t)(ndim == 3 ? SBlock<3>::ROWS_Z : 1)};
   cuuint32_t estr[3] = {1, 1, 1};
   // a rank-2 map needs a sane stride even for single-row windows
   if (X.shape[1] == 1) gstr[0] = ((gdim[0] * es + 15) / 16) * 16;
@@ -661,7 +662,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
     bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
     if (ok) {
-      const int BX = 128, BY = ndim == 3 ? 8 : 16, BZ = ndim == 3 ? 4 : 1;
+      const int BX = ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX, BY = SBlock<2>::BY, BZ = ndim == 3 ? SBlock<3>::BZ : 1;
       const int64_t nb = (int64_t)((ck.shape[2] + BX - 1) / BX) * ((ck.shape[1] + BY - 1) / BY) *
                          ((ck.shape[0] + BZ - 1) / BZ);
       ch_st.push_back(ck);

@@ -39,22 +39,24 @@ struct StencilXform {
 
 template <int NDIM>
 struct SBlock {
-  static constexpr int BX = 128;
-  static constexpr int BY = NDIM == 3 ? 8 : 16;
+  // 3-D blocks are 64 wide: a tile overlap (tens of pixels) then makes fewer
+  // block columns two-view blocks than with 128-wide blocks
+  static constexpr int BX = NDIM == 3 ? 64 : 128;
+  static constexpr int BY = 16;
   static constexpr int BZ = NDIM == 3 ? 4 : 1;
   static constexpr int ROWS_Y = BY + 1;
   static constexpr int ROWS_Z = NDIM == 3 ? BZ + 1 : 1;
   static constexpr int NROWS = ROWS_Y * ROWS_Z;
   static constexpr int OUTS = 8;  // outputs per thread: one column x 8 rows
-  // consumer warps: 4 column groups x (2 row groups in 2-D | 4 planes in 3-D)
+  // consumer warps: 2-D 4 column groups x 2 row groups; 3-D 2 column groups x 2 row groups x 4 planes
   static constexpr int CWARPS = NDIM == 3 ? 16 : 8;
   static constexpr int THREADS = (CWARPS + 1) * 32;
   static constexpr int NW = BX + BY + BZ;
 };
 
 // staged row pitch in elements: >= BX + 1 and a multiple of 16 bytes
-template <typename T>
-struct BoxW { static constexpr int value = 128 + 16 / (int)sizeof(T); };
+template <int NDIM, typename T>
+struct BoxW { static constexpr int value = SBlock<NDIM>::BX + 16 / (int)sizeof(T); };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -335,7 +337,7 @@ __device__ __forceinline__ void store_column(OT* __restrict__ p, int64_t sy, int
 template <int NDIM, typename T>
 struct alignas(128) StencilSlot {
   using B = SBlock<NDIM>;
-  T stage[B::NROWS * BoxW<T>::value];
+  T stage[B::NROWS * BoxW<NDIM, T>::value];
   float tab[128];
   int wi[B::NW];
   float wt[B::NW];
@@ -362,7 +364,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   using B = SBlock<NDIM>;
   using Slot = StencilSlot<NDIM, T>;
   constexpr int NS = StencilStages<NDIM, T>::value;
-  constexpr int BW = BoxW<T>::value;
+  constexpr int BW = BoxW<NDIM, T>::value;
   constexpr int A = 16 / (int)sizeof(T);  // elements per 16 bytes
   constexpr uint32_t kBoxBytes = (uint32_t)(B::NROWS * BW * sizeof(T));
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -491,7 +493,11 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   // lanes run along x (conflict-free shared-memory reads for any sub-vector
   // misalignment of the staged box): thread = one column x 16 rows.
   // 2-D: column (w&3)*32 + lane, rows (w>>2)*8 + k.   3-D: plane w>>2, rows k.
-  const int cg = warp & 3, half = warp >> 2;
+  // 2-D: column group warp & 3, row group warp >> 2.  3-D: column group warp & 1,
+  // row group (warp >> 1) & 1, plane warp >> 2.
+  const int cg = NDIM == 3 ? (warp & 1) : (warp & 3);
+  const int zpl = NDIM == 3 ? (warp >> 2) : 0;
+  const int yoff = (NDIM == 3 ? ((warp >> 1) & 1) : (warp >> 2)) * B::OUTS;
   const int jx = cg * 32 + lane;
 
   // writes this thread's 16 outputs of the block at (x0, y0, z0)
@@ -499,7 +505,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     const int xo = x0 + jx;
     if (xo >= ck.shape[2]) return;
     const int64_t sy = ck.stride[1], sz = ck.stride[0];
-    const int zrow0 = NDIM == 3 ? half : 0, yrow0 = NDIM == 3 ? 0 : half * B::OUTS;
+    const int zrow0 = zpl, yrow0 = yoff;
     const int64_t o0 = (int64_t)(z0 + zrow0) * sz + (int64_t)(y0 + yrow0) * sy + (int64_t)xo;
     const int ylim = ck.shape[1] - y0 - yrow0;
     const int zlim = NDIM == 3 ? ck.shape[0] - z0 - zrow0 : 1;
@@ -549,13 +555,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         const bool vx = sx >= S.omin[2] && sx <= S.omax[2] && x0 + jx < sh_x;
         const int ya = max(S.omin[1] - y0s, 0), yb = min(S.omax[1] - y0s, sh_y - 1 - y0);
         if (NDIM == 2) {
-          const int ka = max(ya - half * B::OUTS, 0), kb = min(yb - half * B::OUTS, B::OUTS - 1);
+          const int ka = max(ya - yoff, 0), kb = min(yb - yoff, B::OUTS - 1);
           vm = (vx && kb >= ka) ? ((kAll >> (B::OUTS - 1 - kb)) & (kAll << ka) & kAll) : 0u;
         } else {
-          const int ka = max(ya, 0), kb = min(yb, 7);
+          const int ka = max(ya - yoff, 0), kb = min(yb - yoff, 7);
           const unsigned ym = kb >= ka ? ((0xffu >> (7 - kb)) & (0xffu << ka)) : 0u;
           const int za = max(S.omin[0] - z0s, 0), zb = min(S.omax[0] - z0s, sh_z - 1 - z0);
-          vm = (vx && half >= za && half <= zb) ? ym : 0u;
+          vm = (vx && zpl >= za && zpl <= zb) ? ym : 0u;
         }
       }
       const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
@@ -566,7 +572,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       // ---- interpolate this thread's outputs from shared memory ----
       float val[B::OUTS];
       if (NDIM == 2) {
-        const T* p = sl.stage + (half * B::OUTS) * BW;
+        const T* p = sl.stage + yoff * BW;
         float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
         for (int k = 0; k < B::OUTS; ++k) {
@@ -580,7 +586,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         float g0[8];
 #pragma unroll
         for (int pz = 0; pz < 2; ++pz) {
-          const T* p = sl.stage + ((half + pz) * B::ROWS_Y) * BW;
+          const T* p = sl.stage + ((zpl + pz) * B::ROWS_Y + yoff) * BW;
           float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
 #pragma unroll
           for (int y = 0; y < 8; ++y) {
@@ -630,12 +636,12 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
           ix = sl.wi[jx];
           const float wtx = sl.wt[jx];
           const int ixc = max(ix, 0), ix1 = min(ixc + 1, 4);
-          const int ky0 = NDIM == 3 ? 0 : half * B::OUTS;
+          const int ky0 = yoff;
           iyA = max(sl.wi[B::BX + ky0], 0);
           const int n0 = min(iyA, 4), n1 = min(iyA + 1, 4), n2 = min(iyA + 2, 4);
           if (NDIM == 3) {
-            iz = sl.wi[B::BX + B::BY + half];
-            const float wtz = sl.wt[B::BX + B::BY + half];
+            iz = sl.wi[B::BX + B::BY + zpl];
+            const float wtz = sl.wt[B::BX + B::BY + zpl];
             const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
             const float* p0 = sl.tab + izc * 25;
             const float* p1 = sl.tab + iz1 * 25;
@@ -651,7 +657,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         }
 #pragma unroll
         for (int k = 0; k < B::OUTS; ++k) {
-          const int ky = NDIM == 3 ? k : half * B::OUTS + k;
+          const int ky = yoff + k;
           const bool valid = (vm >> k) & 1;
           float b = valid ? 1.f : 0.f;
           if (wmode == 2) {
@@ -666,7 +672,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
               const int ixc = max(ix, 0), ix1 = min(ixc + 1, 4);
               const int iyc = max(iy, 0), iy1 = min(iyc + 1, 4);
               if (NDIM == 3) {
-                const float wtz = sl.wt[B::BX + B::BY + half];
+                const float wtz = sl.wt[B::BX + B::BY + zpl];
                 const int izc = max(iz, 0), iz1 = min(izc + 1, 4);
                 const float* p0 = sl.tab + izc * 25;
                 const float* p1 = sl.tab + iz1 * 25;
