@@ -34,6 +34,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("MVS_EXTRA_NVCC"):  # e.g. "-DMVS_BX3=32" for block-shape experiments
+    NVCC_FLAGS += os.environ["MVS_EXTRA_NVCC"].split()
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

@@ -662,7 +662,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
     bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
     if (ok) {
-      const int BX = ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX, BY = SBlock<2>::BY, BZ = ndim == 3 ? SBlock<3>::BZ : 1;
+      const int BX = ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX, BY = ndim == 3 ? SBlock<3>::BY : SBlock<2>::BY, BZ = ndim == 3 ? SBlock<3>::BZ : 1;
       const int64_t nb = (int64_t)((ck.shape[2] + BX - 1) / BX) * ((ck.shape[1] + BY - 1) / BY) *
                          ((ck.shape[0] + BZ - 1) / BZ);
       ch_st.push_back(ck);
