@@ -5,8 +5,8 @@
 // of a view is a constant-coefficient 2^ndim-tap stencil on a shifted window:
 //   x_in = o + off,  floor(x_in) = o + floor(off),  frac = off - floor(off).
 //
-// Persistent, warp-specialised kernel.  CTAs pull output blocks (BZ x BY x 128
-// voxels) from a global counter:
+// Persistent, warp-specialised kernel.  CTAs pull output blocks (2-D: 32 x 64,
+// 3-D: 4 x 32 x 32 voxels) from a global counter:
 //   * warp 8, the producer, culls the chunk's views against the block,
 //     classifies their blending weights (all ones / all positive / general) from
 //     the weight at the corners of block x valid-box, and pulls each contributing
@@ -48,7 +48,7 @@ struct SBlock {
 #define MVS_BX3 32
 #endif
 #ifndef MVS_BX2
-#define MVS_BX2 128
+#define MVS_BX2 64  // C2: 16x128 -> 0.204 ms, 32x64 -> 0.186 ms, 64x32 -> 0.187 ms
 #endif
   static constexpr int BX = NDIM == 3 ? MVS_BX3 : MVS_BX2;
   static constexpr int BY = NDIM == 3 ? 1024 / MVS_BX3 : 2048 / MVS_BX2;
