@@ -89,11 +89,12 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 class FakeSim:
     """Minimal stand-in for the reference's xarray 'sim'."""
 
-    def __init__(self, data, dims, origin, spacing):
+    def __init__(self, data, dims, origin, spacing, attrs=None):
         self.data = data
         self.dims = tuple(dims)
         self.origin = {d: float(origin[d]) for d in dims}
         self.spacing = {d: float(spacing[d]) for d in dims}
+        self.attrs = attrs if attrs is not None else {}
 
     @property
     def dtype(self):
@@ -224,6 +225,96 @@ def load_reference():
     ns.registration = importlib.import_module("multiview_stitcher.registration")
     ns.FakeSim = FakeSim
     _loaded = ns
+    return ns
+
+
+class FakeAffine(np.ndarray):
+    """ndarray with the three xarray attributes the pair-preparation code touches
+    (``.data``, ``.dims``, ``.squeeze()``)."""
+
+    dims = ("x_in", "x_out")
+
+    @property
+    def data(self):
+        return np.asarray(self)
+
+
+def fake_affine(a):
+    return np.asarray(a, dtype=float).view(FakeAffine)
+
+
+def _coords_of(sim, d):
+    n = sim.data.shape[sim.dims.index(d)]
+    # spatial_image_utils.py:316-317
+    return sim.origin[d] + sim.spacing[d] * np.arange(n, dtype=float)
+
+
+def _extend_si_utils_for_pairs(m):
+    """Adds the coordinate-level helpers ``register_pair_of_msims`` calls.  These
+    restate xarray behaviour (label-based ``sel``, origin/spacing read back from
+    the coordinates); everything that consumes them is the reference's code."""
+
+    def get_affine_from_sim(sim, transform_key):
+        return sim.attrs["transforms"][transform_key]
+
+    def set_sim_affine(sim, xaffine, transform_key, base_transform_key=None):
+        sim.attrs.setdefault("transforms", {})[transform_key] = xaffine
+
+    def get_stack_properties_from_sim(sim, transform_key=None, asarray=False):
+        sp = {
+            "shape": m.get_shape_from_sim(sim, asarray=asarray),
+            "spacing": m.get_spacing_from_sim(sim, asarray=asarray),
+            "origin": m.get_origin_from_sim(sim, asarray=asarray),
+        }
+        if transform_key is not None:
+            sp["transform"] = get_affine_from_sim(sim, transform_key)
+        return sp
+
+    def extend_stack_props(stack_props, extend_by):
+        # spatial_image_utils.py:889-913
+        sdims = [d for d in m.SPATIAL_DIMS if d in stack_props["spacing"]]
+        if not isinstance(extend_by, dict):
+            extend_by = {d: extend_by for d in sdims}
+        for d, val in extend_by.items():
+            stack_props["shape"][d] += int(np.ceil(2 * val / stack_props["spacing"][d]))
+            stack_props["origin"][d] -= val
+        return stack_props
+
+    def sim_sel_coords(sim, sel_dict):
+        sl, origin, spacing = [], {}, {}
+        for d in sim.dims:
+            c = _coords_of(sim, d)
+            s = sel_dict[d]
+            i0 = int(np.searchsorted(c, s.start, side="left"))
+            i1 = int(np.searchsorted(c, s.stop, side="right"))
+            sl.append(slice(i0, i1))
+            cc = c[i0:i1]
+            origin[d] = cc[0]
+            spacing[d] = cc[1] - cc[0] if len(cc) > 1 else 1.0
+        return FakeSim(sim.data[tuple(sl)], sim.dims, origin, spacing, attrs=dict(sim.attrs))
+
+    m.get_affine_from_sim = get_affine_from_sim
+    m.set_sim_affine = set_sim_affine
+    m.get_stack_properties_from_sim = get_stack_properties_from_sim
+    m.extend_stack_props = extend_stack_props
+    m.sim_sel_coords = sim_sel_coords
+
+
+def load_reference_pairs():
+    """``load_reference()`` plus the reference's real ``mv_graph`` (half-space
+    geometry) wired into its ``registration`` module."""
+    ns = load_reference()
+    if getattr(ns, "mv_graph", None) is not None:
+        return ns
+    _extend_si_utils_for_pairs(sys.modules["multiview_stitcher.spatial_image_utils"])
+    sys.modules.pop("multiview_stitcher.mv_graph", None)
+    real = importlib.import_module("multiview_stitcher.mv_graph")
+    sys.modules["multiview_stitcher"].mv_graph = real
+    ns.registration.mv_graph = real
+    ns.mv_graph = real
+    # param_utils.py:124-150 wraps np.eye in an xr.DataArray (placeholder here)
+    ns.param_utils.identity_transform = lambda ndim, t_coords=None: fake_affine(np.eye(ndim + 1))
+    ns.fake_affine = fake_affine
     return ns
 
 

@@ -247,3 +247,74 @@ def registration_cases():
         (-1.0, 2.5, -1.5),
     )
     return cases
+
+
+def pair_cases():
+    """name -> dict(views=[fixed, moving], affines=[A1, A2], kwargs) for pair
+    preparation (``register_pair_of_msims``): two tiles cut from one smooth
+    ground truth with a hidden jitter; ``affines`` are the stage transforms
+    (view physical -> world) the overlap is computed in."""
+    cases = {}
+
+    def cut(gt, start, shape, dtype):
+        sl = tuple(slice(int(s), int(s) + int(n)) for s, n in zip(start, shape))
+        t = gt[sl]
+        if dtype == np.uint16:
+            return np.round(t * 4000).astype(np.uint16)
+        return t.astype(np.float32)
+
+    # 2-D, pixel-aligned stage positions, neighbours along x, uint16
+    rng = np.random.default_rng(21)
+    gt = _smooth(rng, (140, 260), 1.3)
+    a = cut(gt, (10, 8), (96, 128), np.uint16)
+    b = cut(gt, (12, 8 + 102 - 3), (96, 128), np.uint16)  # true offset (2, 99), stage says (0, 102)
+    cases["grid2d_x_u16"] = {
+        "views": [_view(a, (0, 0), (1, 1)), _view(b, (0, 0), (1, 1))],
+        "affines": [_translation((0, 0)), _translation((0, 102))],
+        "kwargs": {"registration_binning": {"y": 1, "x": 1}},
+    }
+
+    # 2-D, neighbours along y, float32, spacing 0.5 and a stage position off the pixel grid
+    rng = np.random.default_rng(22)
+    gt = _smooth(rng, (230, 150), 1.3)
+    a = cut(gt, (6, 10), (110, 120), np.float32)
+    b = cut(gt, (6 + 88 + 2, 9), (110, 120), np.float32)
+    cases["grid2d_y_f32_subpixel"] = {
+        "views": [_view(a, (3.0, -2.0), (0.5, 0.5)), _view(b, (3.0, -2.0), (0.5, 0.5))],
+        "affines": [_translation((0, 0)), _translation((88 * 0.5 + 0.15, 0.2))],
+        "kwargs": {"registration_binning": {"y": 1, "x": 1}},
+    }
+
+    # 2-D, second view rotated by 3 degrees: polytope overlap, general pre-transform
+    rng = np.random.default_rng(23)
+    gt = _smooth(rng, (150, 150), 1.5)
+    a = cut(gt, (5, 5), (100, 100), np.float32)
+    b = cut(gt, (20, 40), (100, 100), np.float32)
+    cases["rot2d_f32"] = {
+        "views": [_view(a, (0, 0), (1, 1)), _view(b, (0, 0), (1, 1))],
+        "affines": [_translation((0, 0)), _rot2d(np.deg2rad(3.0), t=(15.0, 35.0), center=(50, 50))],
+        "kwargs": {"registration_binning": {"y": 1, "x": 1}},
+    }
+
+    # 3-D, anisotropic spacing, neighbours along x, uint16, overlap tolerance
+    rng = np.random.default_rng(24)
+    gt = _smooth(rng, (30, 60, 100), 1.0)
+    a = cut(gt, (2, 4, 3), (24, 48, 56), np.uint16)
+    b = cut(gt, (3, 5, 3 + 40 - 2), (24, 48, 56), np.uint16)
+    cases["grid3d_x_u16_tol"] = {
+        "views": [_view(a, (0, 0, 0), (2, 1, 1)), _view(b, (0, 0, 0), (2, 1, 1))],
+        "affines": [_translation((0, 0, 0)), _translation((0, 0, 40))],
+        "kwargs": {"registration_binning": {"z": 1, "y": 1, "x": 1}, "overlap_tolerance": 2.0},
+    }
+
+    # 2-D, binned 2 x 2 (uint16 means are truncated), odd tile size (trimmed)
+    rng = np.random.default_rng(25)
+    gt = _smooth(rng, (260, 420), 2.5)
+    a = cut(gt, (8, 8), (201, 223), np.uint16)
+    b = cut(gt, (10, 8 + 180 + 4), (201, 223), np.uint16)
+    cases["grid2d_binned_u16"] = {
+        "views": [_view(a, (0, 0), (1, 1)), _view(b, (0, 0), (1, 1))],
+        "affines": [_translation((0, 0)), _translation((0, 180))],
+        "kwargs": {"registration_binning": {"y": 2, "x": 2}},
+    }
+    return cases

@@ -1,0 +1,53 @@
+"""oracle.pairs against fixtures produced by the reference's own pair-preparation
+code (tests/golden/make_golden_pairs.py -> pairs_golden.npz)."""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import cases  # noqa: E402
+from oracle import pairs as opairs  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "pairs_golden.npz"))
+CASES = cases.pair_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_prepare_pair_matches_reference(name):
+    c = CASES[name]
+    prep = opairs.prepare_pair(c["views"][0], c["views"][1], c["affines"][0], c["affines"][1], **c["kwargs"])
+    np.testing.assert_array_equal(np.array(prep["lowers"]), GOLD[name + "/lowers"])
+    np.testing.assert_array_equal(np.array(prep["uppers"]), GOLD[name + "/uppers"])
+    dims = opairs.SPATIAL_DIMS[-c["views"][0]["data"].ndim:]
+    np.testing.assert_array_equal([prep["grid"]["origin"][d] for d in dims], GOLD[name + "/grid_origin"])
+    np.testing.assert_array_equal([prep["grid"]["spacing"][d] for d in dims], GOLD[name + "/grid_spacing"])
+    for k in ("fixed", "moving"):
+        assert prep[k].dtype == np.float32
+        np.testing.assert_array_equal(prep[k], GOLD[name + "/" + k])  # NaNs compare equal
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_register_pair_matches_reference(name):
+    c = CASES[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = opairs.register_pair(c["views"][0], c["views"][1], c["affines"][0], c["affines"][1], **c["kwargs"])
+    np.testing.assert_array_equal(res["affine_matrix"], GOLD[name + "/affine_matrix"])
+    np.testing.assert_array_equal(res["transform"], GOLD[name + "/transform"])
+    np.testing.assert_array_equal(res["bbox"], GOLD[name + "/bbox"])
+    assert float(res["quality"]) == float(GOLD[name + "/quality"])
+
+
+def test_optimal_binning_heuristic():
+    # registration.py:114-191: bins the finest-spaced axes until the tile has < 400^3 voxels
+    v = lambda shape, sp: opairs.with_coords(
+        {"data": np.zeros(shape, np.uint8), "origin": dict(zip("zyx", (0, 0, 0))), "spacing": dict(zip("zyx", sp))})
+    assert opairs.optimal_registration_binning(v((256, 512, 512), (1, 1, 1)), v((256, 512, 512), (1, 1, 1))) == {"z": 2, "y": 1, "x": 1}
+    assert opairs.optimal_registration_binning(v((256, 512, 512), (2, 1, 1)), v((256, 512, 512), (2, 1, 1))) == {"z": 1, "y": 2, "x": 2}
+    assert opairs.optimal_registration_binning(v((100, 100, 100), (1, 1, 1)), v((100, 100, 100), (1, 1, 1))) == {"z": 1, "y": 1, "x": 1}
