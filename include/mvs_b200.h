@@ -245,6 +245,21 @@ int mvs_pc_spearman_batch(mvs_pc_plan* plan, int n, const int32_t* pairs, const 
                           const int64_t* n_mask, double* rho_host, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Pair preparation (register_pair_of_msims, registration.py:1732-1968): the
+ * views are mean-binned (`sim.coarsen(binning, boundary="trim").mean()
+ * .astype(dtype)`, :1732-1743), cropped to the overlap box plus one pixel
+ * (:1765-1779; a strided window, no kernel) and resampled onto the fixed
+ * view's pixel grid (sims_to_intrinsic_coord_system, :280-350 =
+ * mvs_resample_views with cval NaN).
+ * ---------------------------------------------------------------------- */
+
+/* d_out (C-contiguous, shape[d] / bin[d] per axis, same dtype) = window means of
+ * the strided volume d_in; integer means are float64 means truncated, float32
+ * windows skip NaNs.  All triples are (z, y, x); 2-D uses z extent / bin 1. */
+int mvs_bin_mean(const void* d_in, int dtype, const int32_t shape[3],
+                 const int64_t stride[3], const int32_t bin[3], void* d_out, void* stream);
+
+/* ------------------------------------------------------------------------
  * Synthetic tiles (benchmark / test inputs).  Integer-only
  * value-noise ground truth sampled at integer global coordinates
  * origin + index, so overlapping tiles agree exactly.

@@ -1,0 +1,91 @@
+"""Host geometry of pair preparation (multiview_stitcher_b200.pairs) -- no GPU needed.
+
+The engine's plan for every fixture pair must carry exactly the reference's numbers:
+overlap boxes, crop windows, the common grid, and pixel matrices / offsets which, fed
+to scipy on the cropped data, reproduce the reference's crops bit for bit."""
+
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+from scipy import ndimage
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import cases  # noqa: E402
+from multiview_stitcher_b200 import pairs as epairs  # noqa: E402
+from oracle import pairs as opairs  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "pairs_golden.npz"))
+CASES = cases.pair_cases()
+
+
+def _axes(view):
+    dims = opairs.SPATIAL_DIMS[-view["data"].ndim:]
+    dv = types.SimpleNamespace(dims=dims, origin=view["origin"], spacing=view["spacing"], shape=view["data"].shape)
+    return epairs._Axes.of_view(dv)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_plan_pair_reproduces_reference_crops(name):
+    c = CASES[name]
+    dims = opairs.SPATIAL_DIMS[-c["views"][0]["data"].ndim:]
+    b = tuple(c["kwargs"]["registration_binning"][d] for d in dims)
+    views = [opairs.with_coords(v) for v in c["views"]]
+    axes = [_axes(v) for v in c["views"]]
+    if max(b) > 1:
+        views = [opairs.bin_view(v, dict(zip(dims, b))) for v in views]
+        axes = [a.binned(b) for a in axes]
+        for a, v in zip(axes, views):
+            for ca, d in zip(a.coords, dims):
+                np.testing.assert_array_equal(ca, v["coords"][d])
+    tol = epairs._tolerance(c["kwargs"].get("overlap_tolerance"), dims)
+    pl = epairs.plan_pair(axes[0], axes[1], np.asarray(c["affines"][0], float), np.asarray(c["affines"][1], float), tol)
+    np.testing.assert_array_equal(np.array(pl["lowers"]), GOLD[name + "/lowers"])
+    np.testing.assert_array_equal(np.array(pl["uppers"]), GOLD[name + "/uppers"])
+    np.testing.assert_array_equal(pl["origin"], GOLD[name + "/grid_origin"])
+    np.testing.assert_array_equal(pl["spacing"], GOLD[name + "/grid_spacing"])
+    assert pl["shape"] == GOLD[name + "/fixed"].shape
+    for side, key in ((0, "fixed"), (1, "moving")):
+        win = views[side]["data"][tuple(slice(i0, i1) for i0, i1 in pl["ranges"][side])].astype(np.float32)
+        m, off = pl["xforms"][side]
+        got = ndimage.affine_transform(win, matrix=m, offset=off, output_shape=pl["shape"], mode="constant",
+                                       cval=np.nan, order=1)
+        np.testing.assert_array_equal(got.astype(np.float32), GOLD[name + "/" + key])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_physical_transform_and_bbox(name):
+    c = CASES[name]
+    dims = opairs.SPATIAL_DIMS[-c["views"][0]["data"].ndim:]
+    grid = {"origin": GOLD[name + "/grid_origin"], "spacing": GOLD[name + "/grid_spacing"]}
+    t = epairs.physical_transform(GOLD[name + "/affine_matrix"], grid, np.asarray(c["affines"][0], float))
+    np.testing.assert_array_equal(t, GOLD[name + "/transform"])
+    tol = epairs._tolerance(c["kwargs"].get("overlap_tolerance"), dims)
+    lo, hi = epairs.overlap_bboxes(_axes(c["views"][0]), _axes(c["views"][1]), np.asarray(c["affines"][0], float),
+                                   np.asarray(c["affines"][1], float), tol, intrinsic=False)
+    np.testing.assert_array_equal(np.array([lo[0], hi[0]]), GOLD[name + "/bbox"])
+
+
+def test_binning_heuristic_matches_oracle():
+    for shape, sp in (((256, 512, 512), (1, 1, 1)), ((256, 512, 512), (2, 1, 1)), ((100, 100, 100), (1, 1, 1)),
+                      ((2048, 2048), (1, 1)), ((9000, 9000), (0.5, 0.5))):
+        dims = opairs.SPATIAL_DIMS[-len(shape):]
+        v = opairs.with_coords({"data": np.broadcast_to(np.zeros((1,) * len(shape), np.uint8), shape),
+                                "origin": dict(zip(dims, (0,) * len(shape))), "spacing": dict(zip(dims, sp))})
+        want = opairs.optimal_registration_binning(v, v)
+        got = epairs.optimal_registration_binning(shape, shape, sp, sp, dims)
+        assert got == want
+
+
+def test_disjoint_views_raise():
+    from multiview_stitcher_b200._lib import EngineError
+
+    v = {"data": np.zeros((10, 10), np.float32), "origin": {"y": 0.0, "x": 0.0}, "spacing": {"y": 1.0, "x": 1.0}}
+    a1, a2 = np.eye(3), np.eye(3)
+    a2[:2, 2] = (0, 50)
+    with pytest.raises(EngineError):
+        epairs.plan_pair(_axes(v), _axes(v), a1, a2, {"y": 0.0, "x": 0.0})
