@@ -215,3 +215,22 @@ def test_expand_candidates_matches_oracle():
         assert len(a) == len(b)
         for x, y in zip(a, b):
             assert all(float(p) == q for p, q in zip(x, y))
+
+
+def test_batch_block_geometry_is_the_regular_chunk_grid():
+    """Hook C: block ids -> offsets / shapes as dask's ``normalize_chunks`` lays them out
+    for ``_fuse_chunk_to_zarr`` (fusion/_core.py:2065-2090): full chunks, remainder last."""
+    from multiview_stitcher_b200.batch import block_geometry
+
+    osp = {"origin": {"z": 0.0, "y": 1.0, "x": 2.0}, "spacing": {"z": 2.0, "y": 1.0, "x": 1.0},
+           "shape": {"z": 5, "y": 70, "x": 64}}
+    cs = {"z": 4, "y": 32, "x": 32}
+    table = block_geometry(osp, cs)
+    assert sorted(table) == [(a, b, c) for a in range(2) for b in range(3) for c in range(2)]
+    lin, start, shape = table[(1, 2, 1)]
+    assert start == (4, 64, 32) and shape == (1, 6, 32)
+    assert [table[k][0] for k in sorted(table)] == list(range(12))
+    covered = np.zeros((5, 70, 64), int)
+    for _, st, sh in table.values():
+        covered[tuple(slice(a, a + n) for a, n in zip(st, sh))] += 1
+    assert (covered == 1).all()
