@@ -77,6 +77,18 @@ def register_pairs_sharded(fixed_list, moving_list, **kwargs):
     return gather_objects(local, n, owned)
 
 
+def register_views_sharded(views, affines, pairs, **kwargs):
+    """``pairs.register_views`` with the pairs dealt round-robin over the ranks: every rank
+    plans, uploads (only the views its pairs touch), prepares and registers its share and
+    all ranks receive the full result list.  ``views`` must be indexable on every rank."""
+    from . import pairs as pairs_mod
+
+    rank, ws = world()
+    owned = shard_round_robin(len(pairs), rank, ws)
+    local = pairs_mod.register_views(views, affines, [pairs[i] for i in owned], **kwargs) if owned else []
+    return gather_objects(local, len(pairs), owned)
+
+
 def fuse_sharded(views, params, output_stack_properties, output_chunksize=None, gather=False, **plan_kwargs):
     """Fuses this rank's slab of output chunks.  Returns ``(out, owned_chunks)``:
     ``out`` is the full-size output tensor with only the owned chunks written

@@ -265,6 +265,14 @@ class PairPlan:
         for v in views:
             if isinstance(v, DeviceView):
                 meta.append((v.dims, v.origin, v.spacing, tuple(v.shape)))
+            elif isinstance(v, dict):
+                dims = geometry.spatial_dims(len(v["data"].shape))
+                meta.append((dims, v["origin"], v["spacing"], tuple(int(n) for n in v["data"].shape)))
+            elif hasattr(v, "coords") and hasattr(v, "dims"):  # xarray-like: no data access (may be lazy)
+                dims = [d for d in v.dims if d in geometry.SPATIAL_DIMS]
+                cs = {d: np.asarray(getattr(v.coords[d], "values", v.coords[d])) for d in dims}
+                # the coordinate arrays themselves, not origin + spacing * arange
+                meta.append((dims, None, None, tuple(len(cs[d]) for d in dims), [cs[d] for d in dims]))
             else:
                 data, origin, spacing = _view_fields(v)
                 dims = geometry.spatial_dims(len(data.shape))
@@ -279,9 +287,9 @@ class PairPlan:
 
         class _Meta:
             def __init__(self, m):
-                self.dims, self.origin, self.spacing, self.shape = m
+                self.dims, self.origin, self.spacing, self.shape = m[:4]
 
-        base = [_Axes.of_view(_Meta(m)) for m in meta]
+        base = [_Axes(m[0], m[4]) if len(m) > 4 else _Axes.of_view(_Meta(m)) for m in meta]
         axes_at = {}
 
         def axes(i, b):
@@ -307,6 +315,10 @@ class PairPlan:
             self.bbox.append(np.array([lo[0], hi[0]]))
         self._axes_at = axes_at
 
+    @property
+    def used_views(self):
+        return sorted({i for e in self.pairs for i in e})
+
     def grid(self, k):
         pl = self.items[k]
         return {"origin": pl["origin"], "spacing": pl["spacing"], "shape": pl["shape"]}
@@ -319,8 +331,12 @@ class PairPlan:
         from .fusion import DeviceView, to_device_view
 
         lib = _lib.load(require_device=True)
-        dviews = [to_device_view(v) for v in views]
-        if [tuple(v.shape) for v in dviews] != self.shapes:
+        if len(views) != len(self.shapes):
+            raise EngineError("PairPlan.prepare: number of views differs from the planned one")
+        # only the views this plan's pairs touch are uploaded (a rank of a sharded run owns
+        # a subset of the pairs)
+        dviews = {i: to_device_view(views[i]) for i in self.used_views}
+        if any(tuple(v.shape) != self.shapes[i] for i, v in dviews.items()):
             raise EngineError("PairPlan.prepare: view shapes differ from the planned ones")
         ndim, dims = self.ndim, self.dims
         binned = {}
@@ -400,12 +416,10 @@ def register_views(views, affines=None, pairs=None, overlap_tolerance=None, regi
     ``PairPlan`` to reuse (then ``affines`` / ``pairs`` / tolerance / binning are the
     plan's); ``pc_plans``: dict that keeps the phase-correlation buffers across calls."""
     from . import registration
-    from .fusion import to_device_view
 
-    dviews = [to_device_view(v) for v in views]
     if plan is None:
-        plan = PairPlan(dviews, affines, pairs, overlap_tolerance, registration_binning)
-    prep = plan.prepare(dviews)
+        plan = PairPlan(views, affines, pairs, overlap_tolerance, registration_binning)
+    prep = plan.prepare(views)
     kw = dict(pairwise_reg_func_kwargs or {})
     res = registration.register_pairs(
         prep.fixed, prep.moving, kw.pop("disambiguate_region_mode", None), kw.pop("upsample_factor", None),

@@ -55,6 +55,38 @@ def main():
     err = max(float(np.abs(r["affine_matrix"][:3, 3] + (true_t[b_] - true_t[a])).max()) for r, (a, b_) in zip(res, pairs))
     out["c3_registration"] = {"pairs": len(pairs), "crop": list(fixed[0].shape), "pairs_per_s": len(pairs) / dt, "max_shift_err_px": err,
                               "quality_min": min(r["quality"] for r in res)}
+    # ---- C3 registration from the resident tiles: all 64 face pairs through pairs.register_views
+    # (overlap boxes, crop windows, resampling onto the fixed tile's grid, registration, physical
+    # transform); binning 1 and the reference's default heuristic (bins z by 2 here)
+    from multiview_stitcher_b200 import pairs as pairs_mod
+
+    all_pairs = []
+    for i, t in enumerate(idx):
+        for ax in range(3):
+            if t[ax] + 1 < grid[ax]:
+                u = list(t)
+                u[ax] += 1
+                all_pairs.append((i, idx.index(tuple(u))))
+    for label, binning in (("c3_registration_from_tiles", {"z": 1, "y": 1, "x": 1}), ("c3_registration_from_tiles_default_binning", None)):
+        t0 = time.perf_counter()
+        pplan = pairs_mod.PairPlan(views, stage, all_pairs, registration_binning=binning)
+        plan_s = time.perf_counter() - t0
+        pcp = {}
+        res = pairs_mod.register_views(views, plan=pplan, pc_plans=pcp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = pairs_mod.register_views(views, plan=pplan, pc_plans=pcp)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        err = max(float(np.abs(r["transform"][:3, 3] + (true_t[b_] - true_t[a])).max()) for r, (a, b_) in zip(res, all_pairs))
+        out[label] = {"pairs": len(all_pairs), "crops": sorted({tuple(it["shape"]) for it in pplan.items}),
+                      "binning": sorted({it["binning"] for it in pplan.items}), "pairs_per_s": len(all_pairs) / dt,
+                      "ms": dt * 1e3, "host_geometry_plan_s_once": plan_s, "max_shift_err_world": err,
+                      "quality_min": min(float(r["quality"]) for r in res)}
+        for p_ in pcp.values():
+            p_.close()
+        del pcp, res, pplan
+        torch.cuda.empty_cache()
     # ---- C3 content-weighted fusion of one 256^3 chunk (sigma 5 / 11, halo 22) ----
     sub = {"origin": {d: osp["origin"][d] + 300 * osp["spacing"][d] for d in "zyx"}, "spacing": osp["spacing"],
            "shape": {"z": 128 + 44, "y": 256 + 44, "x": 256 + 44}}

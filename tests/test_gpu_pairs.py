@@ -181,3 +181,26 @@ def test_pairwise_executor_hook(epairs):
 
     with pytest.raises(EngineError):
         epairs.pairwise_executor(msims, pairs, dict(kw, pairwise_reg_func=lambda fixed_data, moving_data: None))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32])
+def test_synthetic_kernel_equals_host_mirror(dtype):
+    """csrc/synth.cu and its numpy mirror generate the same tiles (negative origins too), so
+    the oracle can be run on the bench's inputs without a GPU."""
+    from multiview_stitcher_b200 import synthetic
+
+    for shape, origin in (((5, 33, 70), (-7, 1000, -20)), ((64, 96), (123456, -5))):
+        got = synthetic.make_tile(shape, origin, dtype, seed=4).cpu().numpy()
+        np.testing.assert_array_equal(got, synthetic.ground_truth(shape, origin, dtype, seed=4))
+
+
+def test_register_views_sharded_single_rank(epairs):
+    from multiview_stitcher_b200 import distributed
+
+    views, affines, pairs, _ = _grid_dataset(1, 3, 128, 30, seed=6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = distributed.register_views_sharded(views, affines, pairs, registration_binning={"y": 1, "x": 1})
+        b = epairs.register_views(views, affines, pairs, registration_binning={"y": 1, "x": 1})
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x["transform"], y["transform"])

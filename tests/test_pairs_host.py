@@ -89,3 +89,50 @@ def test_disjoint_views_raise():
     a2[:2, 2] = (0, 50)
     with pytest.raises(EngineError):
         epairs.plan_pair(_axes(v), _axes(v), a1, a2, {"y": 0.0, "x": 0.0})
+
+
+def test_pair_plan_from_xarray_likes_and_view_subset():
+    """PairPlan reads only coordinates from xarray-like views (no data access) and a plan
+    over a subset of the pairs names exactly the views it needs (sharded runs)."""
+
+    class Coord:
+        def __init__(self, v):
+            self.values = np.asarray(v)
+
+    class XView:
+        def __init__(self, view):
+            dims = opairs.SPATIAL_DIMS[-view["data"].ndim:]
+            self.dims = tuple(dims)
+            self.coords = {d: Coord(view["origin"][d] + view["spacing"][d] * np.arange(n, dtype=float))
+                           for d, n in zip(dims, view["data"].shape)}
+
+        @property
+        def data(self):
+            raise AssertionError("planning must not touch the voxels")
+
+    c = CASES["grid2d_y_f32_subpixel"]
+    views3 = [c["views"][0], c["views"][1], c["views"][1]]
+    aff3 = [c["affines"][0], c["affines"][1], c["affines"][1]]
+    kw = dict(overlap_tolerance=None, registration_binning=c["kwargs"]["registration_binning"])
+    p_dict = epairs.PairPlan(views3, aff3, [(0, 1), (0, 2)], **kw)
+    p_x = epairs.PairPlan([XView(v) for v in views3], aff3, [(0, 2)], **kw)
+    assert p_x.used_views == [0, 2] and p_dict.used_views == [0, 1, 2]
+    a, b = p_dict.items[1], p_x.items[0]
+    assert a["shape"] == b["shape"] and a["ranges"] == b["ranges"]
+    for s in (0, 1):
+        np.testing.assert_array_equal(a["xforms"][s][0], b["xforms"][s][0])
+        np.testing.assert_array_equal(a["xforms"][s][1], b["xforms"][s][1])
+    np.testing.assert_array_equal(p_dict.bbox[0], GOLD["grid2d_y_f32_subpixel/bbox"])
+
+
+def test_synthetic_host_mirror_overlaps_agree():
+    """Tiles of the synthetic ground truth agree exactly where they overlap (the property
+    the registration ground truth rests on); values stay below the documented bound."""
+    from multiview_stitcher_b200 import synthetic
+
+    a = synthetic.ground_truth((6, 40, 48), (-3, 10, 5), np.uint16, seed=3)
+    b = synthetic.ground_truth((6, 40, 48), (-1, 25, 20), np.uint16, seed=3)
+    np.testing.assert_array_equal(a[2:, 15:, 15:], b[:4, :25, :33])
+    assert a.max() < 5376 and a.std() > 100
+    f = synthetic.ground_truth((40, 48), (10, 5), np.float32, seed=3)
+    np.testing.assert_array_equal(f, synthetic.ground_truth((1, 40, 48), (0, 10, 5), np.uint16, seed=3)[0].astype(np.float32) / np.float32(8192))
