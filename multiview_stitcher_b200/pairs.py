@@ -442,24 +442,26 @@ def register_views(views, affines=None, pairs=None, overlap_tolerance=None, regi
 # --- hook A: pairwise_executor (registration.py:2634-2655) ----------------------------
 
 
-def _view_and_affine(msim, transform_key):
-    """(view, affine) of one element of ``msims``: a MultiscaleSpatialImage-like mapping
-    (``msim["scale0/image"]``, ``msim["scale0"][transform_key]``; msi_utils.py:108-113,
-    351-361) or a plain view dict carrying ``"transforms": {key: affine}``."""
+def _n_timepoints(msim):
+    if isinstance(msim, dict) and "data" in msim:
+        return None
+    sim = msim["scale0/image"]
+    return int(sim.sizes["t"]) if hasattr(sim, "dims") and "t" in sim.dims else None
+
+
+def _view_and_affine(msim, transform_key, it=None):
+    """(view, affine) of one element of ``msims`` at time index ``it``: a
+    MultiscaleSpatialImage-like mapping (``msim["scale0/image"]``,
+    ``msim["scale0"][transform_key]``; msi_utils.py:108-113, 351-361) or a plain view dict
+    carrying ``"transforms": {key: affine}``."""
     if isinstance(msim, dict) and "data" in msim:
         return msim, np.asarray(msim["transforms"][transform_key], dtype=np.float64)
     sim = msim["scale0/image"]
     aff = msim["scale0"][transform_key]
-    for obj_name in ("sim", "aff"):
-        obj = sim if obj_name == "sim" else aff
-        if hasattr(obj, "dims") and "t" in obj.dims:
-            if obj.sizes["t"] != 1:
-                raise EngineError("pairwise_executor: select one time point per call")
-            obj = obj.isel(t=0)
-        if obj_name == "sim":
-            sim = obj
-        else:
-            aff = obj
+    if hasattr(sim, "dims") and "t" in sim.dims:
+        sim = sim.isel(t=0 if it is None else it)
+    if hasattr(aff, "dims") and "t" in aff.dims:
+        aff = aff.isel(t=0 if it is None or aff.sizes["t"] == 1 else it)
     if hasattr(sim, "dims") and "c" in sim.dims:
         raise EngineError("pairwise_executor: select the registration channel first (register(reg_channel=...))")
     return sim, np.asarray(getattr(aff, "data", aff), dtype=np.float64)
@@ -468,10 +470,12 @@ def _view_and_affine(msim, transform_key):
 def pairwise_executor(msims, edges, register_kwargs):
     """Drop-in ``pairwise_executor`` for ``registration.register`` (called as
     ``pairwise_executor(msims, edges, register_kwargs)``, registration.py:2649-2655):
-    all ``edges`` are prepared and registered on the GPU in a handful of launches.
-    Returns one ``{"transform" (t, n+1, n+1), "quality" (t,), "bbox" (t, 2, n)}`` per
-    edge -- ``xr.DataArray``s with the reference's dims when xarray is importable,
-    else numpy arrays of those shapes."""
+    all ``edges`` are prepared and registered on the GPU in a handful of launches per
+    time point (the reference loops ``register_pair_of_msims`` over "t", :2061-2093; the
+    host plan is reused while the transforms do not change).  Returns one
+    ``{"transform" (t, n+1, n+1), "quality" (t,), "bbox" (t, 2, n)}`` per edge --
+    ``xr.DataArray``s with the reference's dims when xarray is importable, else numpy
+    arrays of those shapes."""
     kw = dict(register_kwargs)
     transform_key = kw.pop("transform_key")
     func = kw.pop("pairwise_reg_func", None)
@@ -481,26 +485,37 @@ def pairwise_executor(msims, edges, register_kwargs):
         kw.pop(ignored, None)
     if kw.pop("reg_res_level", None) not in (None, 0):
         raise EngineError("pairwise_executor: reg_res_level other than 0 is not supported")
-    va = [_view_and_affine(m, transform_key) for m in msims]
-    res = register_views(
-        [v for v, _ in va], [a for _, a in va], [tuple(e) for e in edges],
-        overlap_tolerance=kw.pop("overlap_tolerance", None),
-        registration_binning=kw.pop("registration_binning", None),
-        pairwise_reg_func_kwargs=kw.pop("pairwise_reg_func_kwargs", None),
-    )
+    tolerance = kw.pop("overlap_tolerance", None)
+    binning = kw.pop("registration_binning", None)
+    func_kwargs = kw.pop("pairwise_reg_func_kwargs", None)
     if kw:
         raise EngineError(f"pairwise_executor: unsupported register kwargs {sorted(kw)}")
+    edges = [tuple(e) for e in edges]
+    if not edges:
+        return []
+    nt = _n_timepoints(msims[0])
+    per_t, plan, plan_affines, pc_plans = [], None, None, {}
+    for it in range(nt or 1):
+        va = [_view_and_affine(m, transform_key, it if nt else None) for m in msims]
+        affines = [a for _, a in va]
+        if plan is None or any(not np.array_equal(a, b) for a, b in zip(affines, plan_affines)):
+            plan = PairPlan([v for v, _ in va], affines, edges, tolerance, binning)
+            plan_affines = affines
+        per_t.append(register_views([v for v, _ in va], plan=plan, pairwise_reg_func_kwargs=func_kwargs, pc_plans=pc_plans))
+    for p in pc_plans.values():
+        p.close()
     try:
         import xarray as xr
     except ImportError:
         xr = None
-    n = va[0][1].shape[0] - 1
-    sd = geometry.spatial_dims(n)
+    n = plan_affines[0].shape[0] - 1
+    labels = geometry.spatial_dims(n) + ["1"]
     out = []
-    for r in res:
-        tr, q, bb = r["transform"][None], np.array([r["quality"]], dtype=float), r["bbox"][None]
+    for k in range(len(edges)):
+        tr = np.stack([r[k]["transform"] for r in per_t])
+        q = np.array([r[k]["quality"] for r in per_t], dtype=float)
+        bb = np.stack([r[k]["bbox"] for r in per_t])
         if xr is not None:
-            labels = sd + ["1"]
             tr = xr.DataArray(tr, dims=["t", "x_in", "x_out"], coords={"x_in": labels, "x_out": labels})
             q = xr.DataArray(q, dims=["t"])
             bb = xr.DataArray(bb, dims=["t", "point_index", "dim"])

@@ -204,3 +204,54 @@ def test_register_views_sharded_single_rank(epairs):
         b = epairs.register_views(views, affines, pairs, registration_binning={"y": 1, "x": 1})
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x["transform"], y["transform"])
+
+
+class _XA:
+    """xarray.DataArray stand-in: dims / sizes / coords[d].values / data / isel(**kw)."""
+
+    class _C:
+        def __init__(self, v):
+            self.values = np.asarray(v)
+
+    def __init__(self, data, dims, coords=None):
+        self.data, self.dims = data, tuple(dims)
+        self.coords = coords or {}
+        self.sizes = dict(zip(self.dims, data.shape))
+
+    def isel(self, indexers=None, **kw):
+        sel = dict(indexers or {}, **kw)
+        idx = tuple(sel.get(d, slice(None)) for d in self.dims)
+        dims = [d for d in self.dims if d not in sel]
+        return _XA(self.data[idx], dims, {d: c for d, c in self.coords.items() if d in dims})
+
+
+def test_pairwise_executor_on_timelapse_msims(epairs):
+    """msim-like mappings with a "t" axis (two time points, per-time-point transforms):
+    one result per edge with a leading t axis, each time point equal to register_views."""
+    rng = np.random.default_rng(8)
+    per_t = [_grid_dataset(1, 3, 128, 30, seed=10 + t, dtype=np.float32) for t in range(2)]
+    pairs = per_t[0][2]
+    msims = []
+    for v in range(3):
+        data = np.stack([per_t[t][0][v]["data"] for t in range(2)])
+        aff = np.stack([per_t[t][1][v] for t in range(2)])
+        aff[1, 0, 2] += 0.25 * v  # the stage drifts between time points -> a second plan
+        coords = {"y": _XA._C(np.arange(128, dtype=float)), "x": _XA._C(np.arange(128, dtype=float))}
+        msims.append({"scale0/image": _XA(data, ("t", "y", "x"), coords), "scale0": {"stage": _XA(aff, ("t", "x_in", "x_out"))}})
+    kw = {"transform_key": "stage", "registration_binning": {"y": 1, "x": 1}, "overlap_tolerance": None,
+          "pairwise_reg_func_kwargs": None, "points_key": "beads", "prefilter_markers": False, "reg_res_level": None}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = epairs.pairwise_executor(msims, pairs, kw)
+    assert len(out) == len(pairs)
+    for t in range(2):
+        views = [{"data": m["scale0/image"].data[t], "origin": {"y": 0.0, "x": 0.0}, "spacing": {"y": 1.0, "x": 1.0}} for m in msims]
+        affs = [m["scale0"]["stage"].data[t] for m in msims]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = epairs.register_views(views, affs, pairs, registration_binning={"y": 1, "x": 1})
+        for o, w in zip(out, want):
+            assert np.asarray(o["transform"]).shape == (2, 3, 3) and np.asarray(o["bbox"]).shape == (2, 2, 2)
+            np.testing.assert_array_equal(np.asarray(o["transform"])[t], w["transform"])
+            np.testing.assert_array_equal(np.asarray(o["bbox"])[t], w["bbox"])
+            assert float(np.asarray(o["quality"])[t]) == float(w["quality"])
