@@ -166,7 +166,7 @@ def _to_intrinsic(affine, pts):
     return np.array([np.dot(inv, p) for p in h])[:, :-1]  # transformation.py:151-161
 
 
-def overlap_bboxes(axes1, axes2, affine1, affine2, tol, intrinsic=True):
+def overlap_bboxes(axes1, axes2, affine1, affine2, tol, intrinsic=True, return_vertices=False):
     """``_get_overlap_bboxes`` (registration.py:194-277): ``(lowers, uppers)`` of the
     overlap polytope, per view in its intrinsic physical coordinates, or in the
     world system."""
@@ -178,6 +178,8 @@ def overlap_bboxes(axes1, axes2, affine1, affine2, tol, intrinsic=True):
         boxes.append((origin, sp, shape, A))
     verts = overlap_vertices(*boxes)
     per_view = [_to_intrinsic(A, verts) for A in (affine1, affine2)] if intrinsic else [verts, verts]
+    if return_vertices:
+        return [v.min(axis=0) for v in per_view], [v.max(axis=0) for v in per_view], verts
     return [v.min(axis=0) for v in per_view], [v.max(axis=0) for v in per_view]
 
 
@@ -226,7 +228,7 @@ def plan_pair(axes1, axes2, affine1, affine2, tol):
     """Host geometry of one pair (registration.py:1745-1779, :280-316): crop index ranges
     per view, the common grid, and the pixel matrices / offsets ``transform_sim`` would
     hand to scipy for the fixed (identity) and the moving (``inv(A2) @ A1``) crop."""
-    lowers, uppers = overlap_bboxes(axes1, axes2, affine1, affine2, tol)
+    lowers, uppers, verts = overlap_bboxes(axes1, axes2, affine1, affine2, tol, return_vertices=True)
     eps = 1e-6
     rng, crop_axes = [], []
     for k, ax in enumerate((axes1, axes2)):
@@ -245,7 +247,7 @@ def plan_pair(axes1, axes2, affine1, affine2, tol):
     for c, p in ((crop_axes[0], np.eye(ndim + 1)), (crop_axes[1], transf)):
         xf.append(geometry.pixel_affine(p, origin, spacing, c.origin, c.spacing))
     return {"ranges": rng, "origin": origin, "spacing": spacing, "shape": tuple(int(s) for s in shape),
-            "xforms": xf, "lowers": lowers, "uppers": uppers}
+            "xforms": xf, "lowers": lowers, "uppers": uppers, "world_vertices": verts}
 
 
 class PairPlan:
@@ -297,22 +299,36 @@ class PairPlan:
                 axes_at[(i, b)] = base[i].binned(b) if max(b) > 1 else base[i]
             return axes_at[(i, b)]
 
-        self.items, self.groups, self.bbox = [], {}, []
-        for k, (i, j) in enumerate(self.pairs):
+        binnings = []
+        for i, j in self.pairs:
             if registration_binning is None:
                 bd = optimal_registration_binning(self.shapes[i], self.shapes[j], base[i].spacing, base[j].spacing, dims)
             else:
                 bd = registration_binning
             b = tuple(int(bd.get(d, 1)) for d in dims)
-            pl = plan_pair(axes(i, b), axes(j, b), self.affines[i], self.affines[j], self.tol)
+            binnings.append(b)
+            axes(i, b), axes(j, b)
+
+        def plan_one(k):
+            (i, j), b = self.pairs[k], binnings[k]
+            pl = plan_pair(axes_at[(i, b)], axes_at[(j, b)], self.affines[i], self.affines[j], self.tol)
             if any(s < 1 for s in pl["shape"]):
                 raise EngineError(f"pair {(i, j)}: empty overlap grid {pl['shape']}")
             pl["binning"] = b
-            self.items.append(pl)
+            # world-space box of the un-binned views (registration.py:2038-2056): the same
+            # polytope when nothing was binned, else a second intersection
+            if max(b) > 1:
+                lo, hi = overlap_bboxes(base[i], base[j], self.affines[i], self.affines[j], self.tol, intrinsic=False)
+                return pl, np.array([lo[0], hi[0]])
+            v = pl["world_vertices"]
+            return pl, np.array([v.min(axis=0), v.max(axis=0)])
+
+        planned = [plan_one(k) for k in range(len(self.pairs))]
+        self.items = [p for p, _ in planned]
+        self.bbox = [b for _, b in planned]
+        self.groups = {}
+        for k, pl in enumerate(self.items):
             self.groups.setdefault(pl["shape"], []).append(k)
-            # world-space box of the un-binned views (registration.py:2038-2056)
-            lo, hi = overlap_bboxes(base[i], base[j], self.affines[i], self.affines[j], self.tol, intrinsic=False)
-            self.bbox.append(np.array([lo[0], hi[0]]))
         self._axes_at = axes_at
 
     @property
