@@ -254,10 +254,14 @@ int mvs_pc_spearman_batch(mvs_pc_plan* plan, int n, const int32_t* pairs, const 
  * ---------------------------------------------------------------------- */
 
 /* d_out (C-contiguous, shape[d] / bin[d] per axis, same dtype) = window means of
- * the strided volume d_in; integer means are float64 means truncated, float32
- * windows skip NaNs.  All triples are (z, y, x); 2-D uses z extent / bin 1. */
+ * the strided volume d_in; integer means are float64 means truncated.  float32
+ * windows skip NaNs when skip_nan != 0 (xarray's `.mean()`), else propagate them
+ * (`np.mean(...).astype(dtype)`: the level-to-level step of the output pyramid,
+ * ngff_utils.py:1284-1285, msi_utils.py:21-22, 49-60).  All triples are (z, y, x);
+ * 2-D uses z extent / bin 1. */
 int mvs_bin_mean(const void* d_in, int dtype, const int32_t shape[3],
-                 const int64_t stride[3], const int32_t bin[3], void* d_out, void* stream);
+                 const int64_t stride[3], const int32_t bin[3], int skip_nan, void* d_out,
+                 void* stream);
 
 /* ------------------------------------------------------------------------
  * Synthetic tiles (benchmark / test inputs).  Integer-only

@@ -113,7 +113,7 @@ _SIGNATURES = {
     "mvs_pc_spearman_batch": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, _P, _P]),
     "mvs_bin_mean": (
         ctypes.c_int,
-        [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), _P, _P],
+        [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _P, _P],
     ),
     "mvs_synth_tile": (
         ctypes.c_int,

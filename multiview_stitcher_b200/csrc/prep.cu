@@ -1,5 +1,6 @@
-// Pair preparation on the device: the mean-binning that
-// register_pair_of_msims applies before cropping (registration.py:1732-1743).
+// Mean-binning on the device: the coarsening register_pair_of_msims applies before
+// cropping (registration.py:1732-1743) and the level-to-level step of
+// the output pyramid (ngff_utils.py:1284-1285, msi_utils.py:49-60).
 // The crop itself is a strided window (no kernel) and the resampling onto the
 // fixed view's grid is mvs_resample_views (fuse.cu).
 #include "common.cuh"
@@ -10,8 +11,9 @@ namespace mvs {
 
 // One thread per output voxel; the window is walked in C order with a float64
 // accumulator: integer sums are exact, so `mean(dtype=float64).astype(dtype)`
-// is reproduced bit for bit; float32 windows skip NaNs like xarray's skipna mean.
-template <typename T>
+// is reproduced bit for bit; float32 windows skip NaNs like xarray's skipna mean
+// (SKIP) or propagate them like np.mean (pyramid levels).
+template <typename T, bool SKIP>
 __global__ void __launch_bounds__(256)
 bin_mean_kernel(const T* __restrict__ in, int64_t sz, int64_t sy, int64_t sx, int nz, int ny,
                 int nx, int bz, int by, int bx, T* __restrict__ out) {
@@ -30,7 +32,7 @@ bin_mean_kernel(const T* __restrict__ in, int64_t sz, int64_t sy, int64_t sx, in
         const T* row = p + dz * sz + dy * sy;
         for (int dx = 0; dx < bx; ++dx) {
           const T v = __ldg(row + dx * sx);
-          if (v == v) { acc += (double)v; ++cnt; }
+          if (!SKIP || v == v) { acc += (double)v; ++cnt; }
         }
       }
     T res;
@@ -47,8 +49,8 @@ bin_mean_kernel(const T* __restrict__ in, int64_t sz, int64_t sy, int64_t sx, in
 }  // namespace mvs
 
 extern "C" int mvs_bin_mean(const void* d_in, int dtype, const int32_t shape[3],
-                            const int64_t stride[3], const int32_t bin[3], void* d_out,
-                            void* stream) {
+                            const int64_t stride[3], const int32_t bin[3], int skip_nan,
+                            void* d_out, void* stream) {
   using namespace mvs;
   MVS_REQUIRE(d_in && d_out && shape && stride && bin, MVS_ERR_INVALID, "NULL pointer");
   MVS_REQUIRE(dtype == MVS_U8 || dtype == MVS_U16 || dtype == MVS_F32, MVS_ERR_UNSUPPORTED,
@@ -61,17 +63,14 @@ extern "C" int mvs_bin_mean(const void* d_in, int dtype, const int32_t shape[3],
   if (N <= 0) return MVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)std::min<long long>((N + 255) / 256, 148 * 8);
-  if (dtype == MVS_U8)
-    bin_mean_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)d_in, stride[0], stride[1],
-                                                         stride[2], nz, ny, nx, bin[0], bin[1], bin[2],
-                                                         (unsigned char*)d_out);
-  else if (dtype == MVS_U16)
-    bin_mean_kernel<unsigned short><<<grid, 256, 0, st>>>((const unsigned short*)d_in, stride[0], stride[1],
-                                                          stride[2], nz, ny, nx, bin[0], bin[1], bin[2],
-                                                          (unsigned short*)d_out);
-  else
-    bin_mean_kernel<float><<<grid, 256, 0, st>>>((const float*)d_in, stride[0], stride[1], stride[2], nz, ny,
-                                                 nx, bin[0], bin[1], bin[2], (float*)d_out);
+#define MVS_BIN_LAUNCH(T, SKIP)                                                              \
+  bin_mean_kernel<T, SKIP><<<grid, 256, 0, st>>>((const T*)d_in, stride[0], stride[1], stride[2], \
+                                                 nz, ny, nx, bin[0], bin[1], bin[2], (T*)d_out)
+  if (dtype == MVS_U8) MVS_BIN_LAUNCH(unsigned char, false);
+  else if (dtype == MVS_U16) MVS_BIN_LAUNCH(unsigned short, false);
+  else if (skip_nan) MVS_BIN_LAUNCH(float, true);
+  else MVS_BIN_LAUNCH(float, false);
+#undef MVS_BIN_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bin_mean launch: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
   return MVS_OK;

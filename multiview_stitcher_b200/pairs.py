@@ -186,9 +186,10 @@ def overlap_bboxes(axes1, axes2, affine1, affine2, tol, intrinsic=True, return_v
 # --- device steps ---------------------------------------------------------------------
 
 
-def bin_view(dv, binning):
+def bin_view(dv, binning, skip_nan=True):
     """``sim.coarsen(binning, boundary="trim").mean().astype(dtype)`` of a resident view
-    (registration.py:1732-1743) -> CUDA tensor of the same dtype."""
+    (registration.py:1732-1743) -> CUDA tensor of the same dtype.  ``skip_nan=False``:
+    ``np.mean`` semantics (NaNs propagate; the pyramid step)."""
     import torch
 
     lib = _lib.load(require_device=True)
@@ -203,7 +204,7 @@ def bin_view(dv, binning):
             ctypes.c_void_p(t.data_ptr()), dv.mvs_dtype,
             (ctypes.c_int32 * 3)(*([1] * pad + list(t.shape))),
             (ctypes.c_int64 * 3)(*([0] * pad + list(t.stride()))),
-            (ctypes.c_int32 * 3)(*([1] * pad + b)),
+            (ctypes.c_int32 * 3)(*([1] * pad + b)), int(bool(skip_nan)),
             ctypes.c_void_p(out.data_ptr()), _lib.current_stream_ptr(),
         ),
         "mvs_bin_mean",
