@@ -48,6 +48,25 @@ def _worker(rank, ws, port, q):
         both = torch.stack([num, den])
         dist.all_reduce(both, op=dist.ReduceOp.SUM)
         ok = ok and torch.all(both[0] == sum(range(1, ws + 1))).item() and torch.all(both[1] == 0.5 * ws).item()
+        # register_views_sharded: pairs dealt round-robin, each rank registers only its share
+        # (the device call is stubbed: this checks the dealing and the gather, not the kernels)
+        from multiview_stitcher_b200 import pairs as pairs_mod
+
+        seen = []
+
+        def fake_register_views(views, affines, pairs, **kw):
+            seen.extend(pairs)
+            return [{"transform": np.eye(3) * (10 * a + b), "quality": float(a + b), "bbox": np.zeros((2, 2))} for a, b in pairs]
+
+        real = pairs_mod.register_views
+        pairs_mod.register_views = fake_register_views
+        try:
+            all_pairs = [(0, 1), (1, 2), (2, 3), (0, 4), (1, 5), (2, 6), (3, 7)]
+            res = D.register_views_sharded([None] * 8, [np.eye(3)] * 8, all_pairs, registration_binning={"y": 1, "x": 1})
+        finally:
+            pairs_mod.register_views = real
+        ok = ok and seen == all_pairs[rank::ws]
+        ok = ok and all(r["transform"][0, 0] == 10 * a + b and r["quality"] == float(a + b) for r, (a, b) in zip(res, all_pairs))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -97,3 +97,50 @@ def test_c3_fusion_and_pairs():
     t = np.array([p[:3, 3] for p in true])
     for r, (a, b) in zip(res, pairs):
         np.testing.assert_allclose(r["affine_matrix"][:3, 3], -(t[b] - t[a]), atol=0.1)
+
+
+def test_c2_all_pairs_from_tiles_and_register_then_fuse():
+    """The whole path at C2's size without pre-cut crops: ``pairs.register_views`` on the
+    resident tiles at their STAGE positions (overlap boxes, crop windows, resampling, 40
+    registrations, physical transforms) recovers every pair's jitter difference; fusing
+    with transforms chained from those pairwise results reproduces the ground truth."""
+    import torch
+
+    import bench
+
+    from multiview_stitcher_b200 import fusion, geometry, pairs as pairs_mod, synthetic
+
+    views, stage, true = synthetic.make_grid(bench.GRID, bench.TILE, bench.OVERLAP, np.float32, jitter=2, seed=0)
+    edges = [(a, b) for a, b, _ in bench.c2_pairs()]
+    res, prep = pairs_mod.register_views(views, stage, edges, registration_binning={"y": 1, "x": 1}, return_prepared=True)
+    assert prep.launches == 2 and sorted({tuple(f.shape) for f in prep.fixed}) == [(307, 2048), (2048, 307)]
+    t = np.array([p[:2, 2] for p in true])
+    for r, (a, b) in zip(res, edges):
+        np.testing.assert_allclose(r["transform"][:2, 2], -(t[b] - t[a]), atol=0.1)
+        assert r["quality"] > 0.95
+    # chain the pairwise transforms along a spanning tree rooted at tile 0 (first row, then
+    # down each column): view-to-world translation of tile b = that of a minus the pair's
+    # shift (transform maps fixed world -> moving world)
+    nx = bench.GRID[1]
+    shift = {e: r["transform"][:2, 2] for e, r in zip(edges, res)}
+    pos = {0: np.zeros(2)}
+    for k in range(1, len(views)):
+        a = k - 1 if k < nx else k - nx
+        pos[k] = pos[a] - shift[(a, k)]
+    params = []
+    for k in range(len(views)):
+        p = np.eye(3)
+        p[:2, 2] = np.round(pos[k] - pos[0] + t[0])  # anchor on tile 0's true offset
+        params.append(p)
+    for p, q in zip(params, true):
+        np.testing.assert_array_equal(p, q)
+    osp = geometry.union_stack_props([v.bb() for v in views], params, views[0].spacing)
+    plan = fusion.FusionPlan(views, params, osp)
+    plan.run()
+    torch.cuda.synchronize()
+    gt = _ground_truth(osp, "yx", np.float32)
+    covered = plan.out != 0
+    err = (plan.out - gt).abs()
+    tol = 1e-4 * gt.abs() + 1e-6 * float(gt.abs().max())
+    assert bool(((err <= tol) | ~covered).all())
+    plan.close()
