@@ -89,12 +89,13 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 class FakeSim:
     """Minimal stand-in for the reference's xarray 'sim'."""
 
-    def __init__(self, data, dims, origin, spacing, attrs=None):
+    def __init__(self, data, dims, origin, spacing, attrs=None, coords=None):
         self.data = data
         self.dims = tuple(dims)
         self.origin = {d: float(origin[d]) for d in dims}
         self.spacing = {d: float(spacing[d]) for d in dims}
         self.attrs = attrs if attrs is not None else {}
+        self.coord_arrays = coords  # explicit coordinates (after sel / coarsen), else None
 
     @property
     def dtype(self):
@@ -109,7 +110,8 @@ class FakeSim:
         return self.data.ndim
 
     def astype(self, dtype):
-        return FakeSim(self.data.astype(dtype), self.dims, self.origin, self.spacing)
+        return FakeSim(self.data.astype(dtype), self.dims, self.origin, self.spacing, attrs=dict(self.attrs),
+                       coords=self.coord_arrays)
 
     def copy(self, data=None):
         return FakeSim(
@@ -244,6 +246,8 @@ def fake_affine(a):
 
 
 def _coords_of(sim, d):
+    if getattr(sim, "coord_arrays", None) is not None:
+        return sim.coord_arrays[d]
     n = sim.data.shape[sim.dims.index(d)]
     # spatial_image_utils.py:316-317
     return sim.origin[d] + sim.spacing[d] * np.arange(n, dtype=float)
@@ -253,6 +257,23 @@ def _extend_si_utils_for_pairs(m):
     """Adds the coordinate-level helpers ``register_pair_of_msims`` calls.  These
     restate xarray behaviour (label-based ``sel``, origin/spacing read back from
     the coordinates); everything that consumes them is the reference's code."""
+
+    # origin / spacing read back from the coordinate arrays, like the real getters
+    # (spatial_image_utils.py:554-589): spacing = c[1] - c[0] carries the rounding of
+    # origin + spacing * 1.0
+    def get_origin_from_sim(sim, asarray=False):
+        d = {k: float(_coords_of(sim, k)[0]) for k in sim.dims}
+        return np.array([d[k] for k in sim.dims]) if asarray else d
+
+    def get_spacing_from_sim(sim, asarray=False):
+        d = {}
+        for k in sim.dims:
+            c = _coords_of(sim, k)
+            d[k] = float(c[1] - c[0]) if len(c) > 1 else 1.0
+        return np.array([d[k] for k in sim.dims]) if asarray else d
+
+    m.get_origin_from_sim = get_origin_from_sim
+    m.get_spacing_from_sim = get_spacing_from_sim
 
     def get_affine_from_sim(sim, transform_key):
         return sim.attrs["transforms"][transform_key]
@@ -281,7 +302,7 @@ def _extend_si_utils_for_pairs(m):
         return stack_props
 
     def sim_sel_coords(sim, sel_dict):
-        sl, origin, spacing = [], {}, {}
+        sl, origin, spacing, cs = [], {}, {}, {}
         for d in sim.dims:
             c = _coords_of(sim, d)
             s = sel_dict[d]
@@ -289,9 +310,10 @@ def _extend_si_utils_for_pairs(m):
             i1 = int(np.searchsorted(c, s.stop, side="right"))
             sl.append(slice(i0, i1))
             cc = c[i0:i1]
+            cs[d] = cc
             origin[d] = cc[0]
             spacing[d] = cc[1] - cc[0] if len(cc) > 1 else 1.0
-        return FakeSim(sim.data[tuple(sl)], sim.dims, origin, spacing, attrs=dict(sim.attrs))
+        return FakeSim(sim.data[tuple(sl)], sim.dims, origin, spacing, attrs=dict(sim.attrs), coords=cs)
 
     m.get_affine_from_sim = get_affine_from_sim
     m.set_sim_affine = set_sim_affine

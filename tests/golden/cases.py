@@ -249,11 +249,13 @@ def registration_cases():
     return cases
 
 
-def pair_cases():
+def pair_cases(extra=False):
     """name -> dict(views=[fixed, moving], affines=[A1, A2], kwargs) for pair
     preparation (``register_pair_of_msims``): two tiles cut from one smooth
     ground truth with a hidden jitter; ``affines`` are the stage transforms
-    (view physical -> world) the overlap is computed in."""
+    (view physical -> world) the overlap is computed in.  ``extra=True`` adds
+    geometry-heavy cases used by the CPU tests only (mixed spacings, a rotated
+    3-D view, negative origins with a per-axis tolerance)."""
     cases = {}
 
     def cut(gt, start, shape, dtype):
@@ -316,5 +318,44 @@ def pair_cases():
         "views": [_view(a, (0, 0), (1, 1)), _view(b, (0, 0), (1, 1))],
         "affines": [_translation((0, 0)), _translation((0, 180))],
         "kwargs": {"registration_binning": {"y": 2, "x": 2}},
+    }
+    if not extra:
+        return cases
+
+    # moving view sampled twice as finely as the fixed one: common grid at the coarser spacing
+    rng = np.random.default_rng(26)
+    gt = _smooth(rng, (200, 300), 2.0)
+    a = cut(gt, (10, 10), (120, 140), np.float32)
+    fine = ndimage.zoom(gt, 2, order=1)
+    b = fine[2 * 14 : 2 * 14 + 240, 2 * 118 : 2 * 118 + 280].astype(np.float32)
+    cases["mixed_spacing2d_f32"] = {
+        "views": [_view(a, (0, 0), (1, 1)), _view(b, (0.25, -0.25), (0.5, 0.5))],
+        "affines": [_translation((0, 0)), _translation((3.0, 110.0))],
+        "kwargs": {"registration_binning": {"y": 1, "x": 1}},
+    }
+
+    # 3-D, anisotropic, second view rotated about z and slightly tilted
+    rng = np.random.default_rng(27)
+    gt = _smooth(rng, (30, 90, 120), 1.0)
+    a = cut(gt, (2, 5, 5), (24, 64, 72), np.uint16)
+    b = cut(gt, (3, 12, 50), (24, 64, 60), np.uint16)
+    cases["rot3d_u16"] = {
+        "views": [_view(a, (0, 0, 0), (2, 1, 1)), _view(b, (1.0, -3.0, 2.0), (2, 1, 1))],
+        "affines": [
+            _translation((0, 0, 0)),
+            _rot3d(np.deg2rad([4.0, 0.5, -0.3]), t=(1.0, 9.0, 44.0), center=(24, 32, 30)),
+        ],
+        "kwargs": {"registration_binning": {"z": 1, "y": 1, "x": 1}},
+    }
+
+    # negative origins, spacing 0.65, tolerance on one axis only
+    rng = np.random.default_rng(28)
+    gt = _smooth(rng, (160, 260), 1.5)
+    a = cut(gt, (8, 8), (100, 128), np.uint16)
+    b = cut(gt, (20, 8 + 96), (100, 128), np.uint16)
+    cases["neg_origin2d_u16_tol_x"] = {
+        "views": [_view(a, (-40.3, -100.0), (0.65, 0.65)), _view(b, (-40.3, -100.0), (0.65, 0.65))],
+        "affines": [_translation((0.0, 0.0)), _translation((12 * 0.65 + 0.1, 96 * 0.65))],
+        "kwargs": {"registration_binning": {"y": 1, "x": 1}, "overlap_tolerance": {"x": 3.0}},
     }
     return cases

@@ -45,19 +45,19 @@ def coarsen(sim, binning, FakeSim):
         shp += [n[i], b[i]]
     axes = tuple(range(1, 2 * len(dims), 2))
     m = np.mean(t.reshape(shp), axis=axes, dtype=np.float64).astype(sim.data.dtype)
-    origin, spacing = {}, {}
+    origin, spacing, cs = {}, {}, {}
     for i, d in enumerate(dims):
         c = (sim.origin[d] + sim.spacing[d] * np.arange(sim.data.shape[i], dtype=float))[: n[i] * b[i]]
         c = c.reshape(n[i], b[i]).mean(axis=1)
-        origin[d], spacing[d] = c[0], c[1] - c[0]
-    return FakeSim(m, dims, origin, spacing, attrs=dict(sim.attrs))
+        origin[d], spacing[d], cs[d] = c[0], c[1] - c[0], c
+    return FakeSim(m, dims, origin, spacing, attrs=dict(sim.attrs), coords=cs)
 
 
 def main():
     ref = load_reference_pairs()
     reg, FakeSim, fa = ref.registration, ref.FakeSim, ref.fake_affine
     out = {}
-    for name, case in cases.pair_cases().items():
+    for name, case in cases.pair_cases(extra=True).items():
         ndim = case["views"][0]["data"].ndim
         dims = DIMS[-ndim:]
         sims = [
@@ -66,7 +66,10 @@ def main():
         ]
         kw = case["kwargs"]
         tolv = kw.get("overlap_tolerance")
-        tol_d = {d: 0.0 if tolv is None else float(tolv) for d in dims}
+        if isinstance(tolv, dict):  # registration.py:1624-1637
+            tol_d = {d: float(tolv.get(d, 0.0)) for d in dims}
+        else:
+            tol_d = {d: 0.0 if tolv is None else float(tolv) for d in dims}
         binning = kw["registration_binning"]
         b_sims = [coarsen(s, binning, FakeSim) for s in sims] if max(binning.values()) > 1 else sims
 

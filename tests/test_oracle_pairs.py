@@ -15,7 +15,7 @@ import cases  # noqa: E402
 from oracle import pairs as opairs  # noqa: E402
 
 GOLD = np.load(os.path.join(HERE, "golden", "pairs_golden.npz"))
-CASES = cases.pair_cases()
+CASES = cases.pair_cases(extra=True)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

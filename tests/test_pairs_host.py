@@ -20,7 +20,7 @@ from multiview_stitcher_b200 import pairs as epairs  # noqa: E402
 from oracle import pairs as opairs  # noqa: E402
 
 GOLD = np.load(os.path.join(HERE, "golden", "pairs_golden.npz"))
-CASES = cases.pair_cases()
+CASES = cases.pair_cases(extra=True)
 
 
 def _axes(view):
