@@ -254,8 +254,8 @@ def pair_cases(extra=False):
     preparation (``register_pair_of_msims``): two tiles cut from one smooth
     ground truth with a hidden jitter; ``affines`` are the stage transforms
     (view physical -> world) the overlap is computed in.  ``extra=True`` adds
-    geometry-heavy cases used by the CPU tests only (mixed spacings, a rotated
-    3-D view, negative origins with a per-axis tolerance)."""
+    the geometry-heavy cases (mixed spacings, a rotated 3-D view, negative origins
+    with a per-axis tolerance)."""
     cases = {}
 
     def cut(gt, start, shape, dtype):

@@ -19,7 +19,7 @@ from oracle import pairs as opairs
 
 pytestmark = pytest.mark.gpu
 
-CASES = cases.pair_cases()
+CASES = cases.pair_cases(extra=True)
 TOL_PX = 0.1 + 1e-4
 
 
