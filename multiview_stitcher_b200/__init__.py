@@ -5,8 +5,13 @@ Public surface mirrors the reference's names for this path:
 
 * ``fusion.fuse`` / ``fusion.fuse_np`` / ``fusion.weighted_average_fusion`` /
   ``fusion.max_fusion`` / ``fusion.simple_average_fusion``
-* ``registration.phase_correlation_registration`` /
-  ``registration.pairwise_executor``
+* ``registration.phase_correlation_registration`` (``pairwise_reg_func``) /
+  ``registration.pairwise_executor`` = ``pairs.pairwise_executor`` (hook A), with
+  ``pairs.PairPlan`` / ``pairs.register_views`` underneath
+* ``hooks.*`` (``fusion_func`` / ``weights_func`` on resampled stacks),
+  ``batch.BatchFuser`` (``batch_options["batch_func"]``, hook C)
+* ``pyramid.build_pyramid`` (output resolution levels), ``distributed.*`` (one process
+  per GPU)
 
 Everything computes on the GPU through ``libmvs_b200.so`` (C ABI,
 include/mvs_b200.h); there is no CPU fallback.

@@ -11,9 +11,6 @@ Encoding / writing the chunks (zarr, compression) stays with the caller.
 
 from __future__ import annotations
 
-import numpy as np
-
-from . import geometry
 from ._lib import EngineError
 
 

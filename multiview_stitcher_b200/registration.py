@@ -520,3 +520,11 @@ def dispatch_pairwise_reg_func(pairwise_reg_func, fixed_data=None, moving_data=N
         kwargs["fixed_data"] = fixed_data
         kwargs["moving_data"] = moving_data
     return pairwise_reg_func(**kwargs)
+
+
+def pairwise_executor(msims, edges, register_kwargs):
+    """Hook A of ``registration.register`` (registration.py:2649-2655): see
+    ``pairs.pairwise_executor`` (batched pair preparation + registration on the GPU)."""
+    from . import pairs
+
+    return pairs.pairwise_executor(msims, edges, register_kwargs)
