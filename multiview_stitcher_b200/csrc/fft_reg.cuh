@@ -9,6 +9,10 @@
 //   * only the autosort permutation between two stages goes through (padded,
 //     conflict-free) shared memory: ceil(p/4) - 1 round trips per transform
 //     instead of one per radix-4 stage.
+// One smooth non-power-of-two length is built on the same scheme: M = 640 = 20*4*4*2
+// with E = 20 values per thread and T = 32 threads (one warp) per line -- the
+// Bluestein length for 257 <= n <= 320 (C2's 307-px overlap), 0.58x the flops of
+// the 1024-point transform it replaces (enabled with -DMVS_BLUESTEIN_SMOOTH).
 // Any other length n runs Bluestein's chirp-z on the same core with
 // m = 2^k >= 2n-1 (exact length-n DFT -- zero padding would change the circular
 // correlation the reference computes, SURVEY.md 7 hard part 1); the product
@@ -131,6 +135,67 @@ struct DftReg<16> {
   }
 };
 
+// 5-point DFT (forward), natural order in and out
+MVS_HD void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;  // cos(2 pi/5), cos(4 pi/5)
+  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;   // sin(2 pi/5), sin(4 pi/5)
+  const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+  const float2 m1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+  const float2 m2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+  const float2 u1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const float2 u2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  x0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+  const float2 r1 = cmul_mi(u1), r2 = cmul_mi(u2);  // -i u
+  x1 = cadd(m1, r1);
+  x4 = csub(m1, r1);
+  x2 = cadd(m2, r2);
+  x3 = csub(m2, r2);
+}
+
+template <>
+struct DftReg<5> {
+  static MVS_HD void run(float2* x) { dft5(x[0], x[1], x[2], x[3], x[4]); }
+};
+
+// n = 5 n1 + n2, k = k1 + 4 k2:  X[k1 + 4 k2] = DFT5_n2 ( W20^(n2 k1) * DFT4_n1 x[5 n1 + n2] )
+template <>
+struct DftReg<20> {
+  static MVS_HD void run(float2* x) {
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) dft4(x[n2], x[5 + n2], x[10 + n2], x[15 + n2]);  // y[n2][k1] in x[5 k1 + n2]
+    // W20^e = (cos(pi e / 10), -sin(pi e / 10))
+    const float c1 = 0.95105651629515357212f, s1 = 0.30901699437494742410f;  // e = 1
+    const float c2 = 0.80901699437494742410f, s2 = 0.58778525229247312917f;  // e = 2
+    const float c3 = s2, s3 = c2;                                            // e = 3
+    const float c4 = s1, s4 = c1;                                            // e = 4
+    // k1 = 1: e = n2
+    x[6] = cmul(x[6], make_float2(c1, -s1));
+    x[7] = cmul(x[7], make_float2(c2, -s2));
+    x[8] = cmul(x[8], make_float2(c3, -s3));
+    x[9] = cmul(x[9], make_float2(c4, -s4));
+    // k1 = 2: e = 2 n2
+    x[11] = cmul(x[11], make_float2(c2, -s2));
+    x[12] = cmul(x[12], make_float2(c4, -s4));
+    x[13] = cmul(x[13], make_float2(-c4, -s4));   // e = 6
+    x[14] = cmul(x[14], make_float2(-c2, -s2));   // e = 8
+    // k1 = 3: e = 3 n2
+    x[16] = cmul(x[16], make_float2(c3, -s3));
+    x[17] = cmul(x[17], make_float2(-c4, -s4));   // e = 6
+    x[18] = cmul(x[18], make_float2(-c1, -s1));   // e = 9
+    x[19] = cmul(x[19], make_float2(-c2, s2));    // e = 12
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft5(x[5 * k1], x[5 * k1 + 1], x[5 * k1 + 2], x[5 * k1 + 3], x[5 * k1 + 4]);
+    // X[k1 + 4 k2] sits in x[5 k1 + k2]: reorder to natural order
+    float2 y[20];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+      for (int k2 = 0; k2 < 5; ++k2) y[k1 + 4 * k2] = x[5 * k1 + k2];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) x[i] = y[i];
+  }
+};
+
 // ---- stage schedule ------------------------------------------------------------
 
 template <int M>
@@ -144,6 +209,20 @@ struct FftSched {
   static constexpr int ns(int s) { return s == 0 ? 1 : 16 * ns(s - 1); }  // product of earlier radices
   static constexpr int PADM = M + (M >> 4);   // padded line length in shared memory
 };
+
+// 640 = 20 * 4 * 4 * 2: one warp per line, 20 values per thread
+template <>
+struct FftSched<640> {
+  static constexpr int E = 20;
+  static constexpr int T = 32;
+  static constexpr int NST = 4;
+  static constexpr int radix(int s) { return s == 0 ? 20 : (s == 3 ? 2 : 4); }
+  static constexpr int ns(int s) { return s == 0 ? 1 : (s == 1 ? 20 : (s == 2 ? 80 : 320)); }
+  static constexpr int PADM = 640 + (640 >> 4);
+};
+
+// values per thread of the M-point kernel (host-side launch geometry)
+constexpr int fft_values_per_thread(int m) { return m == 640 ? 20 : (m < 16 ? m : 16); }
 
 MVS_HD int fft_pad(int i) { return i + (i >> 4); }
 
@@ -165,7 +244,7 @@ struct FftStage {
       for (int r = 0; r < R; ++r) x[r] = v[b + r * B];
       if (NS > 1) {
         const int j = t + b * T;
-        const int k = j & (NS - 1);
+        const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (j % NS);
         constexpr int tstep = M / (NS * R);
 #pragma unroll
         for (int r = 1; r < R; ++r) x[r] = cmul(x[r], MVS_LDG(tw + k * r * tstep));
@@ -182,7 +261,7 @@ struct FftStage {
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       const int j = t + b * T;
-      const int k = j & (NS - 1);
+      const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (j % NS);
       const int base = (j - k) * R + k;
       if constexpr (NS % 16 == 0) {
         float2* p = sline + fft_pad(base);

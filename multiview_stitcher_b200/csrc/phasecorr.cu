@@ -71,6 +71,37 @@ static void host_fft_pow2(std::vector<double>& re, std::vector<double>& im) {
   }
 }
 
+// float64 O(m^2) DFT for the one non-power-of-two kernel length (table construction only)
+static void host_dft(std::vector<double>& re, std::vector<double>& im) {
+  const int m = (int)re.size();
+  std::vector<double> yr(m), yi(m);
+  for (int k = 0; k < m; ++k) {
+    double sr = 0.0, si = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const double ang = -2.0 * M_PI * (double)(((long long)j * k) % m) / (double)m;
+      const double c = cos(ang), sn = sin(ang);
+      sr += re[j] * c - im[j] * sn;
+      si += re[j] * sn + im[j] * c;
+    }
+    yr[k] = sr; yi[k] = si;
+  }
+  re.swap(yr); im.swap(yi);
+}
+
+// Kernel length of the chirp-z transform of n points: the next power of two >= 2n-1, or
+// (MVS_BLUESTEIN_SMOOTH=1 in the environment, read once) the 640-point kernel where it
+// fits -- 513 <= 2n-1 <= 640, i.e. 257 <= n <= 320 -- at 0.58x the flops of 1024 points.
+static int bluestein_length(int n) {
+  static const bool smooth = [] {
+    const char* e = getenv("MVS_BLUESTEIN_SMOOTH");
+    return e && e[0] == '1';
+  }();
+  int m = 1;
+  while (m < 2 * n - 1) m <<= 1;
+  if (smooth && m == 1024 && 2 * n - 1 <= 640) m = 640;
+  return m;
+}
+
 const AxisFft* get_axis_fft(int n) {
   std::lock_guard<std::mutex> lock(g_fft_mutex);
   auto it = g_fft_cache.find(n);
@@ -79,7 +110,7 @@ const AxisFft* get_axis_fft(int n) {
   AxisFft ax{};
   ax.n = n;
   if (is_pow2(n)) { ax.m = n; ax.bluestein = 0; }
-  else { int m = 1; while (m < 2 * n - 1) m <<= 1; ax.m = m; ax.bluestein = 1; }
+  else { ax.m = bluestein_length(n); ax.bluestein = 1; }
   if (ax.m > 8192) {
     set_error("axis length %d needs a %d-point FFT (max 8192)", n, ax.m);
     return nullptr;
@@ -110,7 +141,7 @@ const AxisFft* get_axis_fft(int n) {
       br[k] = cr[k]; bi[k] = -ci[k];
       if (k) { br[m - k] = cr[k]; bi[m - k] = -ci[k]; }
     }
-    host_fft_pow2(br, bi);
+    if (is_pow2(m)) host_fft_pow2(br, bi); else host_dft(br, bi);
     for (int k = 0; k < m; ++k)
       bhat[k] = make_float2((float)(br[k] / m), (float)(bi[k] / m));
     ok = up(&d_chirp, chirp) && up(&d_bhat, bhat);
@@ -130,7 +161,7 @@ const AxisFft* get_axis_fft(int n) {
 struct PassGeom { int L, line_stride, threads; size_t smem; };
 
 static PassGeom pass_geom(int m, bool contiguous, bool paired, long long nlines) {
-  const int E = m < 16 ? m : 16, T = m / E;
+  const int E = fft_values_per_thread(m), T = m / E;
   int L;
   if (contiguous) {
     L = T >= 128 ? 1 : 128 / T;  // ~128 threads per CTA: several CTAs per SM in different phases
@@ -139,6 +170,7 @@ static PassGeom pass_geom(int m, bool contiguous, bool paired, long long nlines)
     L = T <= 32 ? 256 / T : (T <= 64 ? 8 : (T <= 128 ? 4 : (T <= 256 ? 2 : 1)));
   }
   if (L > 32) L = 32;
+  if (m == 640 && L > 8) L = 8;  // 256-thread CTAs (the kernel's launch bound)
   while (L > 1 && (long long)(L / 2) >= nlines) L >>= 1;  // few lines: smaller CTAs
   if (paired && L < 2) L = 2;
   while (L * T < 32) L <<= 1;  // whole warps
@@ -673,6 +705,7 @@ static int launch_pass(mvs_pc_plan* p, int n, int axis, int sign, PassKind kind,
     case 128: return launch_pass_m<128>(a, blue, grid, g.threads, g.smem, st);
     case 256: return launch_pass_m<256>(a, blue, grid, g.threads, g.smem, st);
     case 512: return launch_pass_m<512>(a, blue, grid, g.threads, g.smem, st);
+    case 640: return launch_pass_m<640>(a, blue, grid, g.threads, g.smem, st);
     case 1024: return launch_pass_m<1024>(a, blue, grid, g.threads, g.smem, st);
     case 2048: return launch_pass_m<2048>(a, blue, grid, g.threads, g.smem, st);
     case 4096: return launch_pass_m<4096>(a, blue, grid, g.threads, g.smem, st);

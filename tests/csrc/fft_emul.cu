@@ -69,6 +69,7 @@ int main() {
   worst = fmax(worst, check<128>());
   worst = fmax(worst, check<256>());
   worst = fmax(worst, check<512>());
+  worst = fmax(worst, check<640>());
   worst = fmax(worst, check<1024>());
   worst = fmax(worst, check<2048>());
   worst = fmax(worst, check<4096>());

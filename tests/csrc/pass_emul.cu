@@ -31,11 +31,17 @@ static void dft(std::vector<cd>& x, int sign) {
   x = y;
 }
 
+static bool g_smooth = false;  // use the 640-point kernel where it fits (MVS_BLUESTEIN_SMOOTH)
+
 static Axis make_axis(int n) {
   Axis a;
   a.n = n;
   if (is_pow2(n)) { a.m = n; a.blue = 0; }
-  else { int m = 1; while (m < 2 * n - 1) m <<= 1; a.m = m; a.blue = 1; }
+  else {
+    int m = 1; while (m < 2 * n - 1) m <<= 1;
+    if (g_smooth && m == 1024 && 2 * n - 1 <= 640) m = 640;
+    a.m = m; a.blue = 1;
+  }
   a.tw.resize(a.m);
   for (int k = 0; k < a.m; ++k) a.tw[k] = make_float2((float)cos(-2 * M_PI * k / a.m), (float)sin(-2 * M_PI * k / a.m));
   if (a.blue) {
@@ -122,7 +128,7 @@ static void pass(Vol& V, int axis, int sign, Kind kind, const float2* src, float
   a.contig = axis == 2;
   a.keys = V.keys.data();
   a.tw = ax.tw.data(); a.chirp = ax.chirp.data(); a.bhat = ax.bhat.data();
-  const int m = ax.m, E = m < 16 ? m : 16, T = m / E;
+  const int m = ax.m, E = fft_values_per_thread(m), T = m / E;
   int L = Lreq;
   if (a.paired && L < 2) L = 2;
   a.L = L; a.line_stride = m + (m >> 4) + (a.contig ? 0 : (L <= 16 ? 16 / L : 1));
@@ -147,6 +153,7 @@ static void pass(Vol& V, int axis, int sign, Kind kind, const float2* src, float
     case 128: emulate_m<128>(a, blue, threads, gx, V.npairs); break;
     case 256: emulate_m<256>(a, blue, threads, gx, V.npairs); break;
     case 512: emulate_m<512>(a, blue, threads, gx, V.npairs); break;
+    case 640: emulate_m<640>(a, blue, threads, gx, V.npairs); break;
     case 1024: emulate_m<1024>(a, blue, threads, gx, V.npairs); break;
     case 2048: emulate_m<2048>(a, blue, threads, gx, V.npairs); break;
     default: printf("unsupported m %d\n", m); exit(2);
@@ -253,6 +260,14 @@ int main(int argc, char** argv) {
   bad += run_case(4, 6, 8, 4, 4);      // 3-D
   bad += run_case(3, 5, 9, 2, 8);      // 3-D all Bluestein
   bad += run_case(2, 33, 4, 8, 16);
+  // the smooth 640-point Bluestein kernel on the 257..320 range (C2's 307-px overlap): as the
+  // contiguous axis, as the first (paired) axis, and next to a 1024-point neighbour
+  g_smooth = true;
+  bad += run_case(1, 8, 307, 4, 4);
+  bad += run_case(1, 307, 8, 2, 8);
+  bad += run_case(2, 260, 6, 2, 4);
+  bad += run_case(1, 6, 321, 1, 4);    // just outside: falls back to 1024
+  g_smooth = false;
   printf(bad ? "FAIL\n" : "OK\n");
   return bad != 0;
 }
