@@ -51,3 +51,34 @@ def test_optimal_binning_heuristic():
     assert opairs.optimal_registration_binning(v((256, 512, 512), (1, 1, 1)), v((256, 512, 512), (1, 1, 1))) == {"z": 2, "y": 1, "x": 1}
     assert opairs.optimal_registration_binning(v((256, 512, 512), (2, 1, 1)), v((256, 512, 512), (2, 1, 1))) == {"z": 1, "y": 2, "x": 2}
     assert opairs.optimal_registration_binning(v((100, 100, 100), (1, 1, 1)), v((100, 100, 100), (1, 1, 1))) == {"z": 1, "y": 1, "x": 1}
+
+
+def test_binning_heuristic_matches_reference_source():
+    """Runs the reference's own ``get_optimal_registration_binning`` body (registration.py:114-191,
+    extracted by name; only needs shapes and spacings) next to the oracle and the engine."""
+    import ast
+    import types
+
+    path = "/root/reference/src/multiview_stitcher/registration.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_optimal_registration_binning")
+    si = types.SimpleNamespace(
+        get_spatial_dims_from_sim=lambda sim: list(sim.dims),
+        get_spacing_from_sim=lambda sim, asarray=False: dict(sim.spacing),
+    )
+    ns = {"np": np, "spatial_image_utils": si}
+    exec(compile(ast.Module([fn], []), path, "exec"), ns)
+    from multiview_stitcher_b200 import pairs as epairs
+
+    for shape, sp in (((256, 512, 512), (1, 1, 1)), ((256, 512, 512), (2, 1, 1)), ((512, 2048, 2048), (1, 0.5, 0.5)),
+                      ((2048, 2048), (1, 1)), ((9000, 9000), (0.5, 0.5)), ((100, 100, 100), (1, 1, 1)),
+                      ((800, 400, 400), (0.3, 1, 1))):
+        dims = opairs.SPATIAL_DIMS[-len(shape):]
+        sim = types.SimpleNamespace(dims=dims, shape=shape, spacing=dict(zip(dims, map(float, sp))))
+        want = ns["get_optimal_registration_binning"](sim, sim)
+        v = opairs.with_coords({"data": np.broadcast_to(np.zeros((1,) * len(shape), np.uint8), shape),
+                                "origin": dict(zip(dims, (0.0,) * len(shape))), "spacing": dict(zip(dims, map(float, sp)))})
+        assert opairs.optimal_registration_binning(v, v) == want
+        assert epairs.optimal_registration_binning(shape, shape, sp, sp, dims) == want
