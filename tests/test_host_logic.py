@@ -234,3 +234,31 @@ def test_batch_block_geometry_is_the_regular_chunk_grid():
     for _, st, sh in table.values():
         covered[tuple(slice(a, a + n) for a, n in zip(st, sh))] += 1
     assert (covered == 1).all()
+
+
+def test_hook_argument_errors_are_raised_before_any_device_work():
+    """Error behaviour of hooks A and C that does not need a GPU: unsupported registration
+    functions / register kwargs / backends are refused up front, an empty edge list is fine."""
+    import functools
+
+    from multiview_stitcher_b200 import pairs, registration
+    from multiview_stitcher_b200._lib import EngineError
+    from multiview_stitcher_b200.batch import BatchFuser
+
+    assert pairs.pairwise_executor([], [], {"transform_key": "stage"}) == []
+    assert registration.pairwise_executor([], [], {"transform_key": "stage"}) == []
+    with pytest.raises(EngineError, match="phase_correlation_registration only"):
+        pairs.pairwise_executor([], [(0, 1)], {"transform_key": "k", "pairwise_reg_func": lambda fixed_data, moving_data: None})
+    with pytest.raises(EngineError, match="reg_res_level"):
+        pairs.pairwise_executor([], [(0, 1)], {"transform_key": "k", "reg_res_level": 2})
+    with pytest.raises(EngineError, match="unsupported register kwargs"):
+        pairs.pairwise_executor([], [(0, 1)], {"transform_key": "k", "made_up_option": 1})
+    with pytest.raises(KeyError):
+        pairs.pairwise_executor([], [(0, 1)], {})  # transform_key is mandatory, like in register()
+
+    osp = {"origin": {"y": 0.0, "x": 0.0}, "spacing": {"y": 1.0, "x": 1.0}, "shape": {"y": 8, "x": 8}}
+    part = functools.partial(lambda block_id, **kw: None, output_stack_properties=osp, ns_shape={}, nsdims=[],
+                             fuse_kwargs={"images": [], "transform_key": "k", "backend": "cupy"},
+                             output_chunksize={"y": 8, "x": 8}, output_zarr_array=np.zeros((8, 8)))
+    with pytest.raises(EngineError, match="own backend"):
+        BatchFuser()(part, [(0, 0)])
