@@ -160,3 +160,21 @@ def test_blending_weights_cover_views():
         s = np.nansum(bw, axis=0)
         assert np.all((np.abs(s) < 1e-5) | (np.abs(s - 1) < 1e-5))
         assert np.all(bw[~np.isnan(tv)] > 0)
+
+
+def test_kat_fused_field_slice_is_aligned():
+    """_tests/test_fusion.py:932-987 (arithmetic half): a one-plane output stack placed on the
+    view's z index 1 (anisotropic spacing, translated view, order 1) reproduces the input value
+    exactly -- the slice is aligned with the input grid, nothing is interpolated across planes."""
+    spacing = {"z": 3.5, "y": 2.5, "x": 4.5}
+    trans = {"z": 1.3, "y": 1.0, "x": 2.0}
+    data = np.zeros((5, 50, 100), dtype=np.float32)
+    data[1] = 1.0  # only the plane the output slice coincides with carries the value
+    view = {"data": data, "origin": {d: 0.0 for d in DIMS}, "spacing": spacing}
+    param = np.eye(4)
+    param[:3, 3] = [trans[d] for d in DIMS]
+    osp = {"spacing": spacing, "origin": {d: trans[d] + 1 * spacing[d] for d in DIMS},
+           "shape": {"z": 1, "y": 40, "x": 70}}
+    fused, _ = of.fuse([view], [param], output_stack_properties=osp, interpolation_order=1)
+    assert fused.shape == (1, 40, 70)
+    assert not np.any(fused - 1.0)
