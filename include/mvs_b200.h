@@ -129,6 +129,13 @@ int mvs_fuse_plan_destroy(mvs_fuse_plan* plan);
 int mvs_fuse_finalize(const float* acc_num, const float* acc_den, void* out,
                       int out_dtype, int64_t n, void* stream);
 
+/* Same for a list of boxes (HOST array of mvs_chunk): box i divides its packed,
+ * C-ordered accumulators acc_num / acc_den (shape[0]*shape[1]*shape[2] floats
+ * each) into the strided output window `out` (element strides `stride`).  The
+ * owner of a border chunk calls this after summing the partial sums its
+ * neighbours sent (distributed.fuse_tile_partitioned). */
+int mvs_fuse_finalize_boxes(const mvs_chunk* boxes, int n_boxes, void* stream);
+
 /* ------------------------------------------------------------------------
  * Post-resample stage on (V, *chunk) float32 stacks (NaN = outside): the
  * arithmetic behind the reference's fusion_func / weights_func hooks
@@ -271,6 +278,17 @@ int mvs_bin_mean(const void* d_in, int dtype, const int32_t shape[3],
 int mvs_synth_tile(void* d_out, int dtype, const int32_t shape[3],
                    const int64_t stride[3], const int64_t origin[3], uint32_t seed,
                    void* stream);
+
+/* Band-limited analytic ground truth for SUB-PIXEL tile positions: the tile is
+ * f(origin + index) for f(p) = base + sum_k a_k sin(2 pi w_k.p + phi_k), clamped to
+ * [0, 1) and scaled by out_scale (float32: 1, uint16: 4095), plus per-tile hash noise
+ * of amplitude noise_amp.  The caller tabulates the per-axis factors in float64:
+ * d_e{z,y,x}[k * n_axis + i] = exp(2 pi i w_k[axis] (origin[axis] + i)) as float2 and
+ * d_coef[k] = a_k exp(i phi_k)  (device pointers; n_terms <= 128). */
+int mvs_synth_field(void* d_out, int dtype, const int32_t shape[3], const int64_t stride[3],
+                    const float* d_ez, const float* d_ey, const float* d_ex,
+                    const float* d_coef, int n_terms, float base, float out_scale,
+                    float noise_amp, uint32_t noise_seed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,7 @@ _SIGNATURES = {
     ),
     "mvs_fuse_plan_destroy": (ctypes.c_int, [_P]),
     "mvs_fuse_finalize": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, _P]),
+    "mvs_fuse_finalize_boxes": (ctypes.c_int, [_P, ctypes.c_int, _P]),
     "mvs_resample_views": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int, _P, _P, _P]),
     "mvs_normalize_weights": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, _P]),
     "mvs_gaussian_filter": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _P, ctypes.c_int, _P]),
@@ -118,6 +119,11 @@ _SIGNATURES = {
     "mvs_synth_tile": (
         ctypes.c_int,
         [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.c_uint32, _P],
+    ),
+    "mvs_synth_field": (
+        ctypes.c_int,
+        [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, ctypes.c_int,
+         ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint32, _P],
     ),
 }
 

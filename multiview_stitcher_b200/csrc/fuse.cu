@@ -382,6 +382,27 @@ __global__ void finalize_kernel(const float* __restrict__ num, const float* __re
   }
 }
 
+// One block column per box: out[box voxel] = cast(num / den) from the box's packed
+// (C-order) accumulators; 4 consecutive x voxels per thread.
+__global__ void __launch_bounds__(256)
+finalize_boxes_kernel(const mvs_chunk* __restrict__ boxes) {
+  const mvs_chunk& b = boxes[blockIdx.y];
+  const int nx = b.shape[2], ny = b.shape[1];
+  const int64_t n = (int64_t)b.shape[0] * ny * nx;
+  const float* __restrict__ num = b.acc_num;
+  const float* __restrict__ den = b.acc_den;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % nx);
+    const int64_t r = i / nx;
+    const int y = (int)(r % ny), z = (int)(r / ny);
+    float d = den[i];
+    if (d == 0.0f) d = 1.0f;
+    store_from_float(b.out, b.out_dtype, z * b.stride[0] + y * b.stride[1] + x * b.stride[2],
+                     __fdiv_rn(num[i], d));
+  }
+}
+
 }  // namespace mvs
 
 struct mvs_fuse_plan {
@@ -815,6 +836,36 @@ extern "C" int mvs_fuse_finalize(const float* acc_num, const float* acc_den, voi
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(acc_num, acc_den, out, out_dtype, n);
   MVS_CHECK_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+extern "C" int mvs_fuse_finalize_boxes(const mvs_chunk* boxes, int n_boxes, void* stream) {
+  MVS_REQUIRE(n_boxes >= 0, MVS_ERR_INVALID, "negative n_boxes");
+  if (n_boxes == 0) return MVS_OK;
+  MVS_REQUIRE(boxes != nullptr, MVS_ERR_INVALID, "boxes is NULL");
+  MVS_REQUIRE(n_boxes <= 65535, MVS_ERR_UNSUPPORTED, "%d boxes (max 65535 per call)", n_boxes);
+  int64_t biggest = 0;
+  for (int i = 0; i < n_boxes; ++i) {
+    const mvs_chunk& b = boxes[i];
+    MVS_REQUIRE(b.out && b.acc_num && b.acc_den, MVS_ERR_INVALID, "box %d: NULL pointer", i);
+    MVS_REQUIRE(b.out_dtype >= MVS_U8 && b.out_dtype <= MVS_F32, MVS_ERR_INVALID,
+                "box %d: bad out dtype", i);
+    MVS_REQUIRE(b.shape[0] >= 0 && b.shape[1] >= 0 && b.shape[2] >= 0, MVS_ERR_INVALID,
+                "box %d: negative extent", i);
+    biggest = std::max<int64_t>(biggest, (int64_t)b.shape[0] * b.shape[1] * b.shape[2]);
+  }
+  if (biggest == 0) return MVS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  mvs_chunk* d_boxes = nullptr;
+  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_boxes, sizeof(mvs_chunk) * n_boxes, st));
+  // pageable source: staged before the call returns
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_boxes, boxes, sizeof(mvs_chunk) * n_boxes,
+                                 cudaMemcpyHostToDevice, st));
+  const unsigned gx = (unsigned)std::min<int64_t>((biggest + 255) / 256, 148 * 8);
+  finalize_boxes_kernel<<<dim3(gx, (unsigned)n_boxes), 256, 0, st>>>(d_boxes);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(d_boxes, st);
+  if (e != cudaSuccess) { set_error("finalize launch: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
   return MVS_OK;
 }
 

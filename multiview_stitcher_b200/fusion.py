@@ -199,12 +199,17 @@ def _required_overlap(func, kwargs):
 
 def build_work_list(
     views, params, osp, chunksize, halo=0, sample_origin=None, full_view_bbs=None, spacings=None,
-    blending_widths=None, shrink_distance=0, chunk_subset=None,
+    blending_widths=None, shrink_distance=0, chunk_subset=None, chunk_list=None,
 ):
     """Host geometry of a fusion job: for every output chunk the views that can
     touch it and, per (chunk, view) pairing, exactly the matrix / offset
     ``transform_sim`` would hand to scipy for the view (transformation.py:31-83)
     and for its blending-support table (weights.py:465-481).
+
+    ``chunk_subset`` picks chunks of the regular grid by linear index;
+    ``chunk_list`` replaces the grid by explicit ``(start, shape)`` boxes of the
+    output stack (the tile-partitioned multi-GPU path cuts border chunks into
+    boxes, distributed.py).
 
     Returns ``{"chunks": [(start, shape, first_xform, n_xforms)], "xforms":
     VIEW_XFORM_DTYPE array, "tables": (V, 125) float32, "halo": int array}``.
@@ -231,7 +236,7 @@ def build_work_list(
         inv_params.append(np.linalg.inv(np.asarray(p, dtype=np.float64)))
         aabbs.append(geometry.transformed_aabb(v.bb(), p, dims))
 
-    grid = geometry.chunk_grid(osp, chunksize)
+    grid = geometry.chunk_grid(osp, chunksize) if chunk_list is None else [(tuple(a), tuple(b)) for a, b in chunk_list]
     if sample_origin is not None and len(grid) != 1:
         raise EngineError("sample_origin needs a single-chunk plan")
     if chunk_subset is not None:
@@ -302,7 +307,16 @@ class FusionPlan:
         halo=0,
         sample_origin=None,
         device="cuda",
+        chunk_list=None,
+        out_start=None,
+        out_shape=None,
+        chunk_targets=None,
     ):
+        """``out`` may cover only a box of the output stack: ``out_start`` is the
+        stack index of its first voxel and ``out_shape`` its extent (sharded jobs
+        allocate their slab only).  ``chunk_targets`` (partial mode): per chunk
+        ``(acc_num ptr, acc_den ptr, element strides (z, y, x))`` of caller-owned
+        float32 accumulators, e.g. packed send buffers."""
         import torch
 
         lib = _lib.load(require_device=True)
@@ -324,6 +338,11 @@ class FusionPlan:
         osp = output_stack_properties
         self.osp = osp
         full_shape = tuple(int(osp["shape"][d]) for d in dims)
+        if out_shape is not None:
+            full_shape = tuple(int(n) for n in out_shape)
+        elif out is not None and out_start is not None:
+            full_shape = tuple(out.shape)
+        out_start = np.zeros(ndim, dtype=np.int64) if out_start is None else np.asarray(out_start, dtype=np.int64)
         if output_chunksize is None:
             output_chunksize = (
                 geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
@@ -339,21 +358,27 @@ class FusionPlan:
         if out is None and not partial:
             out = torch.zeros(full_shape, dtype=_np_to_torch(self.out_np_dtype), device=device)
         self.out = out
-        if partial:
-            self.acc_num = torch.zeros(full_shape, dtype=torch.float32, device=device)
-            self.acc_den = torch.zeros(full_shape, dtype=torch.float32, device=device)
+        if partial and chunk_targets is not None:
+            self.acc_num = self.acc_den = None
+            ref = None
+        elif partial:
+            # one (2, *stack) buffer: the whole-volume reduce sums it in place
+            self.acc = torch.zeros((2,) + full_shape, dtype=torch.float32, device=device)
+            self.acc_num, self.acc_den = self.acc[0], self.acc[1]
             ref = self.acc_num
         else:
             if tuple(out.shape) != full_shape:
                 raise EngineError(f"out has shape {tuple(out.shape)}, expected {full_shape}")
             ref = out
-        ostride = [0] * (3 - ndim) + [int(s) for s in ref.stride()]
-        elem = ref.element_size()
+        ostride = [0] * (3 - ndim) + [int(s) for s in ref.stride()] if ref is not None else [0, 0, 0]
+        elem = ref.element_size() if ref is not None else 4
 
         work = build_work_list(
             self.views, self.params, osp, self.chunksize, halo, sample_origin, full_view_bbs,
-            spacings, blending_widths, shrink_distance, chunk_subset,
+            spacings, blending_widths, shrink_distance, chunk_subset, chunk_list,
         )
+        if chunk_targets is not None and len(chunk_targets) != len(work["chunks"]):
+            raise EngineError("need one accumulator target per chunk")
         self.work = work
         tables, xarr = work["tables"], work["xforms"]
         n_chunks = len(work["chunks"])
@@ -361,7 +386,17 @@ class FusionPlan:
         halo_v = work["halo"]
         for ci, (start, shape, first, count) in enumerate(work["chunks"]):
             c = carr[ci]
-            off_elems = int(np.dot(start, ostride[3 - ndim :]))
+            off_elems = int(np.dot(np.asarray(start, dtype=np.int64) - out_start, ostride[3 - ndim :]))
+            if partial and chunk_targets is not None:
+                c["out"] = 0
+                c["acc_num"], c["acc_den"] = int(chunk_targets[ci][0]), int(chunk_targets[ci][1])
+                c["out_dtype"] = _lib.mvs_dtype(self.out_np_dtype)
+                c["shape"] = [1] * (3 - ndim) + list(map(int, shape))
+                c["stride"] = [0] * (3 - ndim) + [int(v) for v in chunk_targets[ci][2]][-ndim:]
+                c["halo"] = [0] * (3 - ndim) + [int(h) for h in halo_v]
+                c["first_xform"] = first
+                c["n_xforms"] = count
+                continue
             if partial:
                 c["out"] = 0
                 c["acc_num"] = self.acc_num.data_ptr() + off_elems * 4

@@ -19,15 +19,35 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ws = dist.get_world_size()
-    views, stage, true = synthetic.make_grid((2, 4), (192, 256), (40, 48), np.float32, jitter=2, seed=7)
+    views, stage, true = synthetic.make_grid((2, 4), (192, 256), (40, 48), np.float32, jitter=2, seed=7, subpixel=True)
     osp = geometry.union_stack_props([v.bb() for v in views], true, views[0].spacing)
     ref, _ = fusion.fuse(views, true, output_stack_properties=osp, output_on_backend=True)
+
+    # tiles partitioned by grid column blocks: border boxes only cross NVLink
+    owners = [(i % 4) * ws // 4 for i in range(len(views))]
+    bbs = [v.bb() for v in views]
+    local = {i: views[i] for i in range(len(views)) if owners[i] == rank}
+    slab, start, info = distributed.fuse_tile_partitioned(local, bbs, true, owners, osp, {"y": 96, "x": 128})
+    part = info["partition"]
+    got = torch.zeros_like(ref)
+    got[tuple(slice(a, a + n) for a, n in zip(start, slab.shape))] = slab
+    mask = torch.zeros_like(ref, dtype=torch.bool)
+    for ci, (cs_, cn_) in enumerate(part.grid):
+        if part.owner_of[ci] == rank:
+            mask[tuple(slice(a, a + n) for a, n in zip(cs_, cn_))] = True
+    err = ((got - ref).abs() * mask).max().item()
+    assert err <= 1e-4 * ref.abs().max().item(), f"fuse_tile_partitioned mismatch {err}"
+    cover = mask.to(torch.int32)
+    dist.all_reduce(cover)
+    assert int(cover.min()) == 1 and int(cover.max()) == 1, "chunk ownership does not tile the stack"
+    assert ws == 1 or part.exchanged_bytes() > 0
+    assert part.exchanged_bytes() < 0.5 * 8 * ref.numel(), "border exchange should be a fraction of the stack"
 
     # slab-sharded chunks, no data-path communication until the optional gather
     out, owned = distributed.fuse_sharded(views, true, osp, output_chunksize={"y": 96, "x": 128}, gather=True)
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6), "fuse_sharded mismatch"
 
-    # tile-partitioned: this rank only holds views rank, rank+ws, ...
+    # whole-volume variant: this rank only holds views rank, rank+ws, ...
     mine = list(range(rank, len(views), ws))
     part = distributed.fuse_partial([views[i] for i in mine], [true[i] for i in mine], osp)
     assert torch.allclose(part, ref, rtol=1e-4, atol=1e-5), "fuse_partial mismatch"

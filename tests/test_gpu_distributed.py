@@ -42,6 +42,47 @@ def test_partial_sums_reduce_to_full_fusion():
     assert (d != 0).mean() < 0.02
 
 
+def test_tile_partition_boxes_on_one_gpu_match_full_fusion():
+    """Plays every rank of a 3-rank tile partition in-process on one GPU: direct boxes +
+    packed partial sums + box finalisation must rebuild the single-plan result."""
+    import torch
+
+    from multiview_stitcher_b200 import distributed as D, fusion, geometry, synthetic
+
+    for dtype, grid, tile, ov, cs in ((np.uint16, (1, 2, 3), (24, 96, 112), (0, 20, 24), {"z": 16, "y": 64, "x": 64}),
+                                      (np.float32, (2, 3), (160, 200), (36, 44), {"y": 96, "x": 128})):
+        views, stage, true = synthetic.make_grid(grid, tile, ov, dtype, jitter=2, seed=4, subpixel=True)
+        bbs = [v.bb() for v in views]
+        osp = geometry.union_stack_props(bbs, true, views[0].spacing)
+        full, _ = fusion.fuse(views, true, output_stack_properties=osp, output_chunksize=cs, output_on_backend=True)
+        ws = 3
+        owners = [i % ws for i in range(len(views))]
+        part = D.TilePartition(bbs, true, owners, osp, cs, ws)
+        eng = D._CudaEngine()
+        out = torch.zeros_like(full)
+        zero = [0] * full.ndim
+        accs = {}
+        for r in range(ws):
+            lv = [views[i] for i in range(len(views)) if owners[i] == r]
+            lp = [true[i] for i in range(len(views)) if owners[i] == r]
+            eng.fuse_direct(lv, lp, osp, cs, part.direct[r], out, zero)
+            # every entry r takes part in, accumulated into one buffer per entry
+            es = [e for e in part.entries if e["owner"] == r or r in e["contrib"]]
+            bufs = [torch.zeros(2 * e["nvox"], device="cuda") for e in es]
+            eng.fuse_partial(lv, lp, osp, cs, [(e["start"], e["shape"]) for e in es],
+                             [(b, 0, e["nvox"]) for b, e in zip(bufs, es)])
+            for e, b in zip(es, bufs):
+                accs[e["chunk"]] = accs.get(e["chunk"], 0) + b
+        for e in part.entries:
+            eng.finalize(accs[e["chunk"]], [(0, e["nvox"], e["start"], e["shape"])], out, zero, np.dtype(dtype))
+        a, b = out.cpu().numpy().astype(np.float64), full.cpu().numpy().astype(np.float64)
+        if dtype == np.uint16:
+            assert np.abs(a - b).max() <= 1
+        else:
+            assert np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-6 * np.abs(b).max())
+        assert part.entries and part.exchanged_bytes() < 8 * full.numel()
+
+
 def test_fuse_partial_single_rank_equals_fuse():
     from multiview_stitcher_b200 import distributed, fusion, geometry
 
