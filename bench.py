@@ -2,28 +2,44 @@
 """Benchmark of the registration-and-fusion hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--only c2,c3,c4,c5] [--no-cpu]
 
-One "step" = one pass of the hot path over BASELINE config 1 (5x5 grid of
-2048x2048 float32 tiles, 15 % overlap): every overlap pair registered by phase
-correlation and the whole stack fused with cosine-edge blending.  Prints ONE JSON line (see DESIGN.md "Measurement").
+Prints ONE JSON line (DESIGN.md "Measurement").  All inputs are tiles of the
+band-limited analytic field at FRACTIONAL positions (jitter ~ U(-2, 2) px,
+SURVEY.md 8d), so every interpolation fraction is non-zero.
+
+Headline (`value`, `roofline`, `e2e`, `cpu_baseline`): BASELINE config 1 ("C2"),
+5x5 grid of 2048x2048 float32 tiles, 15 % overlap -- one step = the whole stack
+fused with cosine-edge blending (and, reported beside it, all 40 overlap pairs
+registered by phase correlation).
 
 * ``value``     fused Mvoxels/s, tiles resident in HBM, CUDA-event timed.
-* ``e2e``       same metric through the public API with HOST buffers (pinned
-                H2D of every tile + D2H of the fused stack inside the timing).
-* ``roofline``  algorithmic bytes of the fused resample-blend kernel / its
-                measured duration vs the measured HBM peak.
-* ``cpu_baseline`` the oracle (numpy/scipy restatement of the reference's
-                path) on a bounded sample of the same workload on host cores.
-* ``--impl reference`` times that CPU path alone (the reference itself is pure
-                Python on scipy and cannot be imported in this image).
+* ``e2e``       same metric through the reference's hook C (`batch_func`:
+                `BatchFuser.__call__` on the partial `fuse()` builds, fusion/_core.py:1133-1141)
+                with PAGEABLE numpy tiles in and a numpy destination array out; staging
+                through pinned memory, H2D, fusion and D2H are all inside the timing.
+* ``roofline``  algorithmic bytes of the fused resample-blend kernel / its measured
+                duration vs the measured HBM peak.
+* ``cpu_baseline`` the oracle (numpy/scipy restatement of the reference's path) on a
+                bounded sample of the same workload on the host cores.
+* ``configs``   the other BASELINE configs: C3 (4x4x2 grid of 256x512x512 uint16, blend /
+                content-weighted fusion, 64 pairs), C4 (4 affine views of 512x1024x1024),
+                C5 (8x8 grid of 512x2048x2048 uint16, one tile row per GPU).
 
-N > 1 (torchrun): every rank fuses its own replica of the workload (output
-chunks are independent units; no data-path collective) -> weak scaling.
+N > 1 (torchrun, one rank per GPU): `value` stays C2 with one replica per rank (chunks
+and pairs are independent units -> "weak").  The sharded jobs are in ``configs``:
+C3 as ONE job strong-scaled over the ranks (pairs round-robin, chunk bands with tile
+replication, and the tile-partitioned run whose border boxes cross NVLink as NCCL
+send/recv of partial (sum w*v, sum w)); C5 weak-scaled: every rank holds one tile row
+of the 8x8 grid, N ranks fuse N rows, only the row-overlap boxes are exchanged.
+``--impl reference`` times the CPU path alone (the reference is pure Python on scipy
+and cannot be imported in this image; the oracle port makes the same library calls).
 """
 
 from __future__ import annotations
 
 import argparse
+import functools
 import json
 import os
 import subprocess
@@ -38,29 +54,35 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = {
-    "workload": "C2: 5x5 grid of 2-D tiles 2048x2048 float32, 15% overlap (307 px), "
-    "phase-correlation registration + cosine-edge weighted-average fusion",
+    "workload": "C2: 5x5 grid of 2-D tiles 2048x2048 float32, 15% overlap (307 px), sub-pixel tile positions "
+    "(jitter U(-2,2) px), phase-correlation registration + cosine-edge weighted-average fusion",
     "grid": [5, 5],
     "tile": [2048, 2048],
     "overlap_px": 307,
     "tile_dtype": "float32",
     "output_chunks": "2048x2048 (reference default)",
     "interpolation_order": 1,
+    "jitter": "U(-2, 2) px per axis on a 1/64 px grid (fractional: every lerp fraction non-zero)",
     "l2": "inputs+outputs (744 MB/step) exceed the 126 MB L2; no explicit flush",
 }
 GRID, TILE, OVERLAP = (5, 5), (2048, 2048), (307, 307)
+C3 = {"grid": (2, 4, 4), "tile": (256, 512, 512), "overlap": (26, 51, 51)}
+C5 = {"grid": (1, 8, 8), "tile": (512, 2048, 2048), "overlap": (0, 205, 205)}
 METRIC = "fused_Mvoxels_per_sec"
 UNIT = "Mvoxel/s"
+SEED = 0
 
 
 def _ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
-    try:
-        with open(p) as f:
-            return int(json.load(f)["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01c_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(p) as f:
+                return int(json.load(f)["traffic_bytes_per_launch"]), f"profiles/{name}"
+        except Exception:
+            continue
+    return None, None
 
 
 def _peaks():
@@ -124,31 +146,21 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------
-# CPU arm: the oracle on a bounded sample
+# CPU arm: the oracle on a bounded sample.  Nothing here touches the CUDA library:
+# tiles come from the numpy mirror of the generator (synthetic.field_tile_host).
 # ----------------------------------------------------------------------------
 
 
-def _host_c2_views(seed):
-    """C2's 25 tiles on the host.  Generated by the engine's synthetic kernel
-    when a GPU is present (so both arms see identical inputs), else by a numpy
-    smooth-noise stand-in of the same shape/dtype (CPU timing does not depend
-    on the values)."""
+def _host_c2_views(seed=SEED):
+    """C2's 25 tiles on the host (numpy mirror of the analytic field; equal to the GPU
+    generator's tiles up to float32 rounding)."""
     from multiview_stitcher_b200 import synthetic
 
-    true, stage, idx = synthetic.grid_layout(GRID, TILE, OVERLAP, jitter=2, seed=seed)
-    try:
-        import torch
-
-        if not torch.cuda.is_available():
-            raise RuntimeError
-        tiles = [synthetic.make_tile(TILE, o, np.float32, seed).cpu().numpy() for o in true]
-    except Exception:
-        rng = np.random.default_rng(seed)
-        base = rng.random((TILE[0] + 8, TILE[1] + 8), dtype=np.float32)
-        tiles = [base[: TILE[0], : TILE[1]].copy() for _ in true]
+    true, stage, idx = synthetic.grid_layout(GRID, TILE, OVERLAP, jitter=2, seed=seed, subpixel=True)
     views, params = [], []
-    for t, s_org, t_org in zip(tiles, stage, true):
-        views.append({"data": t, "origin": {"y": float(s_org[0]), "x": float(s_org[1])}, "spacing": {"y": 1.0, "x": 1.0}})
+    for k, (s_org, t_org) in enumerate(zip(stage, true)):
+        data = synthetic.field_tile_host(TILE, t_org, np.float32, seed, tile_id=k)
+        views.append({"data": data, "origin": {"y": float(s_org[0]), "x": float(s_org[1])}, "spacing": {"y": 1.0, "x": 1.0}})
         p = np.eye(3)
         p[:2, 2] = t_org - s_org
         params.append(p)
@@ -162,32 +174,27 @@ def _cpu_fuse_chunk(args):
     return of.fuse_np(views, params, hbb, full_view_bbs=bbs).shape
 
 
-def cpu_fusion_sample(seed=0, n_chunks=None, n_jobs=None):
-    """Oracle fuse_np over a sample of C2's 2048^2 output chunks, one chunk per
-    worker process (joblib), each handed only the views that touch it.
-    Returns (Mvoxel/s, cores, sample description)."""
+def cpu_fusion_sample(views, params, n_jobs=None):
+    """Oracle fuse_np over ALL of C2's 25 output chunks (2048^2, the reference's default
+    chunking), one chunk per worker process (joblib), each handed only the views that
+    touch it.  Returns (Mvoxel/s, cores, sample description)."""
     from joblib import Parallel, delayed
 
     from oracle import fusion as of
 
-    views, params = _host_c2_views(seed)
     bbs = [of.view_bb(v) for v in views]
     osp = of.calc_stack_properties(bbs, params, views[0]["spacing"])
     cores = n_jobs or os.cpu_count() or 1
     chunks = of.chunk_bbs(osp, {"y": 2048, "x": 2048})
-    # interior chunks first (they carry the typical 4-9 views)
-    order = sorted(range(len(chunks)), key=lambda i: -min(chunks[i][0]["shape"].values()))
-    n_chunks = n_chunks or min(len(chunks), max(cores, 4))
     jobs, vox = [], 0
-    for i in order[:n_chunks]:
-        cbb, _ = chunks[i]
+    for cbb, _ in chunks:
         sel = [k for k in range(len(views)) if of._view_touches(bbs[k], params[k], cbb, 2)]
         jobs.append(([views[k] for k in sel], [params[k] for k in sel], [bbs[k] for k in sel], cbb))
         vox += int(np.prod([cbb["shape"][d] for d in "yx"]))
     t0 = time.perf_counter()
     Parallel(n_jobs=cores)(delayed(_cpu_fuse_chunk)(j) for j in jobs)
     dt = time.perf_counter() - t0
-    return vox / dt / 1e6, cores, f"{n_chunks} of {len(chunks)} output chunks (2048x2048) of C2, oracle fuse_np, joblib x{cores}"
+    return vox / dt / 1e6, cores, f"all {len(chunks)} output chunks (2048x2048) of C2, oracle fuse_np, joblib x{cores}"
 
 
 def c2_pairs():
@@ -225,12 +232,11 @@ def _cpu_register_pair(args):
     return oreg.phase_correlation_registration(f, m)["quality"]
 
 
-def cpu_registration_sample(seed=0, n_pairs=None, n_jobs=None):
+def cpu_registration_sample(views, n_pairs=None, n_jobs=None):
     """Oracle phase_correlation_registration on a sample of C2's pairs, one pair
     per worker process.  Returns (pairs/s, cores, sample description)."""
     from joblib import Parallel, delayed
 
-    views, _ = _host_c2_views(seed)
     tiles = [v["data"] for v in views]
     pairs = c2_pairs()
     cores = n_jobs or os.cpu_count() or 1
@@ -247,16 +253,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    sample = ""
-    cores = 1
-    pvals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_fusion_sample(seed=0)
-        pv, _, psample = cpu_registration_sample(seed=0)
-        if i >= args.warmup:
-            vals.append(v)
-            pvals.append(pv)
+    views, params = _host_c2_views()
+    vals, pvals = [], []
+    # a step is seconds of CPU work on every host core: one warm-up pass, at most three timed
+    cpu_fusion_sample(views, params)
+    for _ in range(max(1, min(args.steps, 3))):
+        v, cores, sample = cpu_fusion_sample(views, params)
+        pv, _, psample = cpu_registration_sample(views)
+        vals.append(v)
+        pvals.append(pv)
     value = float(np.mean(vals))
     line = {
         "impl": "reference",
@@ -264,9 +269,9 @@ def run_reference(args):
         "value": value,
         "unit": UNIT,
         "n_gpus": args.gpus,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": None,
+        "steps": len(vals),
+        "warmup": min(args.warmup, 1),
+        "ms_per_step": 81261210 / value / 1e3 if value else None,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -287,34 +292,90 @@ def run_reference(args):
 # ----------------------------------------------------------------------------
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Rank / world plumbing and max-over-ranks CUDA-event timing."""
 
-    from multiview_stitcher_b200 import fusion, synthetic
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    seed = rank  # every rank fuses its own replica (weak scaling)
-    views, stage, true = synthetic.make_grid(GRID, TILE, OVERLAP, np.float32, jitter=2, seed=seed)
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup=1):
+        """ms per step of fn(): barrier + synchronize on both sides, CUDA events on the
+        current stream, MAX over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1) / steps)
+
+
+def _roof(bytes_per_launch, ms, kernel=None):
+    peak, src = _peaks()
+    ach = bytes_per_launch / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms": ms}
+    if kernel:
+        r["kernel"] = kernel
+    return r
+
+
+def _fake_partial(msims, osp, chunksize, out, **fuse_kwargs):
+    """The functools.partial `fuse(output_zarr_url=...)` hands a batch_func
+    (fusion/_core.py:1133-1141, 2285-2293): keywords of _fuse_chunk_to_zarr."""
+
+    def _never(block_id, **kw):
+        raise AssertionError("the per-block CPU path must not run")
+
+    fk = {"images": msims, "transform_key": "reg", "fusion_func": None, "weights_func": None,
+          "interpolation_order": 1, "blending_widths": None, "backend": None, "output_chunksize": chunksize}
+    fk.update(fuse_kwargs)
+    return functools.partial(_never, output_stack_properties=osp, ns_shape={}, nsdims=[], fuse_kwargs=fk,
+                             output_chunksize=chunksize, output_zarr_array=out)
+
+
+def bench_c2(cx, args):
+    torch = cx.torch
+    from multiview_stitcher_b200 import fusion, geometry, pairs as pairs_mod, registration, synthetic
+    from multiview_stitcher_b200.batch import BatchFuser, block_geometry
+
+    world = cx.world
+    seed = SEED + cx.rank  # every rank fuses its own replica (weak scaling)
+    views, stage, true = synthetic.make_grid(GRID, TILE, OVERLAP, np.float32, jitter=2, seed=seed, subpixel=True)
     bbs = [v.bb() for v in views]
-    from multiview_stitcher_b200 import geometry
-
     osp = geometry.union_stack_props(bbs, true, bbs[0]["spacing"])
     plan = fusion.FusionPlan(views, true, osp)
     launches_per_step = plan.launches_per_run
-
-    from multiview_stitcher_b200 import registration
 
     pairs = c2_pairs()
     tiles = [v.tensor for v in views]
@@ -326,232 +387,470 @@ def run_ours(args):
     def reg_step():
         return registration.register_pairs(fixed, moving, plans=pc_plans)
 
-    def step():
-        plan.run()
-
     for _ in range(max(args.warmup, 3)):
-        step()
-        reg_res = reg_step()
-    barrier()
-    # true pairwise shift = jitter difference (integer px): parity gate before timing
+        plan.run()
+    reg_res = reg_step()
+    reg_step()
+    # true pairwise shift = jitter difference (fractional): accuracy of the algorithm on this data
     true_t = np.array([t[:2, 2] for t in true])
-    reg_err = max(
-        float(np.abs(r["affine_matrix"][:2, 2] + (true_t[b] - true_t[a])).max())
-        for r, (a, b, _) in zip(reg_res, pairs)
-    )
+    reg_err = max(float(np.abs(r["affine_matrix"][:2, 2] + (true_t[b] - true_t[a])).max())
+                  for r, (a, b, _) in zip(reg_res, pairs))
     launches0 = sum(p.launch_count for p in pc_plans.values())
-    rev0, rev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_reg = max(2, min(args.steps, 5))
-    # clocks / throttle reasons are sampled across ALL timed regions (registration,
-    # phase-correlation stage, fusion steps, end-to-end steps)
-    clocks = ClockSampler(local_rank)
-    clocks.__enter__()
-    rev0.record()
-    for _ in range(n_reg):
-        reg_step()
-    rev1.record()
-    barrier()
-    reg_ms = rev0.elapsed_time(rev1) / n_reg
-    tr = torch.tensor([reg_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-    reg_ms = float(tr.item())
+    reg_ms = cx.timed(reg_step, n_reg, 0)
     reg_launches = (sum(p.launch_count for p in pc_plans.values()) - launches0) // n_reg
-    # the same 40 pairs from the resident TILES: overlap boxes, crop windows and the
-    # resampling onto the fixed tile's grid run in the engine (pairs.register_views =
-    # register_pair_of_msims for all edges); the host geometry is planned once
-    from multiview_stitcher_b200 import pairs as pairs_mod
 
-    import time as _time
-
-    t_plan = _time.perf_counter()
+    # the same 40 pairs from the resident TILES (hook A's work): overlap boxes, crop windows,
+    # resampling onto the fixed tile's grid, registration, physical transform
+    t_plan = time.perf_counter()
     pair_plan = pairs_mod.PairPlan(views, stage, [(a, b) for a, b, _ in pairs], registration_binning={"y": 1, "x": 1})
-    plan_ms = (_time.perf_counter() - t_plan) * 1e3
-    for _ in range(2):
-        rv = pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans)
-    rv_err = max(
-        float(np.abs(r["transform"][:2, 2] + (true_t[b] - true_t[a])).max()) for r, (a, b, _) in zip(rv, pairs)
-    )
-    torch.cuda.synchronize()
-    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    v0.record()
-    for _ in range(n_reg):
-        pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans)
-    v1.record()
-    torch.cuda.synchronize()
-    rv_ms = v0.elapsed_time(v1) / n_reg
-    trv = torch.tensor([rv_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(trv, op=dist.ReduceOp.MAX)
-    rv_ms = float(trv.item())
+    plan_ms = (time.perf_counter() - t_plan) * 1e3
+    rv = pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans)
+    rv_err = max(float(np.abs(r["transform"][:2, 2] + (true_t[b] - true_t[a])).max()) for r, (a, b, _) in zip(rv, pairs))
+    rv_ms = cx.timed(lambda: pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans), n_reg, 1)
+
     # phase-correlation stage alone (FFT -> cross power -> IFFT -> peak -> upsampled DFT):
     # algorithmic bytes (32*ndim + 8) * N per pair over its CUDA-event time
-    pc_bytes, pc_ms = 0, 0.0
-    for pcp in pc_plans.values():
-        for _ in range(2):
-            pcp.correlate()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(3):
-            pcp.correlate()
-        c1.record()
-        torch.cuda.synchronize()
-        pc_ms += c0.elapsed_time(c1) / 3
-        pc_bytes += (32 * pcp.ndim + 8) * pcp.voxels * pcp.n
-    # the same stage on power-of-two crops (2048 x 256): C2's 307-px overlap is prime,
-    # so its transforms run Bluestein's chirp-z (two 1024-point FFTs per 307-point line)
-    # and are instruction-bound; this figure shows the plain register-FFT passes
+    def pc_time(plans):
+        b, ms = 0, 0.0
+        for pcp in plans:
+            for _ in range(2):
+                pcp.correlate()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                pcp.correlate()
+            c1.record()
+            torch.cuda.synchronize()
+            ms += c0.elapsed_time(c1) / 3
+            b += (32 * pcp.ndim + 8) * pcp.voxels * pcp.n
+        return b, ms
+
+    pc_bytes, pc_ms = pc_time(pc_plans.values())
     p2_pairs = [(a, b) for a, b, ax in pairs if ax == 1]
     p2_fixed = [tiles[a][:, TILE[1] - 256:].contiguous() for a, b in p2_pairs]
     p2_moving = [tiles[b][:, :256].contiguous() for a, b in p2_pairs]
     p2_plan = registration.PhaseCorrPlan((TILE[0], 256), len(p2_pairs), 10)
     p2_plan.load_pairs(p2_fixed, p2_moving)
-    for _ in range(2):
-        p2_plan.correlate()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(3):
-        p2_plan.correlate()
-    c1.record()
-    torch.cuda.synchronize()
-    p2_ms = c0.elapsed_time(c1) / 3
-    p2_bytes = (32 * 2 + 8) * p2_plan.voxels * len(p2_pairs)
+    p2_bytes, p2_ms = pc_time([p2_plan])
     p2_plan.close()
     del p2_fixed, p2_moving
+
+    # ---- the headline: K fused steps, each step also timed on its own ----
+    cx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
     for i in range(args.steps):
         kev[i][0].record()
-        step()
+        plan.run()
         kev[i][1].record()
     ev1.record()
-    barrier()
-    total_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    cx.barrier()
+    total_ms = cx.max_over_ranks(ev0.elapsed_time(ev1))
     fuse_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     vox_per_step = plan.out_voxels
     value = vox_per_step * world * args.steps / (total_ms * 1e-3) / 1e6
 
-    # ---- end to end through the public API with host buffers ----
-    host_views = [
-        {"data": v.tensor.cpu().numpy(), "origin": v.origin, "spacing": v.spacing} for v in views
-    ]
-    pinned = []
-    for hv in host_views:
-        t_pin = torch.from_numpy(hv["data"]).pin_memory()
-        pinned.append({"data": t_pin, "origin": hv["origin"], "spacing": hv["spacing"]})
-    h2d = sum(p["data"].numel() * p["data"].element_size() for p in pinned)
-    out_host = torch.empty(tuple(int(osp["shape"][d]) for d in "yx"), dtype=torch.float32).pin_memory()
-    d2h = out_host.numel() * 4
-
-    # public API for repeated fusion of one tile geometry (time points / channels):
-    # geometry planned once, every call moves host tiles in and the fused stack out
-    fuser = fusion.HostFuser(pinned, true, output_stack_properties=osp)
+    # ---- end to end through hook C with pageable numpy buffers ----
+    host_tiles = [v.tensor.cpu().numpy() for v in views]  # plain (pageable) numpy, as a reader hands them over
+    msims = [{"data": d, "origin": v.origin, "spacing": v.spacing, "transforms": {"reg": p}}
+             for d, v, p in zip(host_tiles, views, true)]
+    out_shape = tuple(int(osp["shape"][d]) for d in "yx")
+    out_host = np.zeros(out_shape, dtype=np.float32)  # the destination "zarr" array: plain numpy
+    chunksize = {"y": 2048, "x": 2048}
+    fuse_chunk = _fake_partial(msims, osp, chunksize, out_host)
+    block_ids = sorted(block_geometry(osp, chunksize))
+    bf = BatchFuser()
 
     def e2e_step():
-        # H2D of every tile (pinned), fusion and D2H of the fused stack all inside
-        # this call, pipelined band by band
-        fuser(pinned, out_host)
-        torch.cuda.synchronize()
+        bf.reset()  # tiles cross PCIe again every step
+        bf(fuse_chunk, block_ids)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
+    e2e_step()
+    dev_ref = plan.out.cpu().numpy()
+    e2e_ok = bool(np.array_equal(out_host, dev_ref))
+    h0, d0 = bf.h2d_bytes, bf.d2h_bytes
+    e2e_step()
+    h2d, d2h = bf.h2d_bytes - h0, bf.d2h_bytes - d0
+    cx.barrier()
     n_e2e = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(n_e2e):
         e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    clocks.__exit__(None, None, None)
-    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = vox_per_step * world / float(te.item()) / 1e6
+    torch.cuda.synchronize()
+    e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    cx.barrier()
+    e2e_value = vox_per_step * world / e2e_s / 1e6
+    e2e_launches = bf.launches
 
-    if rank == 0:
-        peak, peak_src = _peaks()
-        bytes_per_launch = plan.algorithmic_bytes()
-        achieved = bytes_per_launch / (fuse_kernel_ms * 1e-3) / 1e9
+    # secondary: the engine's own host API with PRE-PINNED buffers (round-1 figure)
+    pinned = [{"data": torch.from_numpy(d).pin_memory(), "origin": v.origin, "spacing": v.spacing}
+              for d, v in zip(host_tiles, views)]
+    out_pin = torch.empty(out_shape, dtype=torch.float32).pin_memory()
+    fuser = fusion.HostFuser(pinned, true, output_stack_properties=osp)
+
+    def pinned_step():
+        fuser(pinned, out_pin)
+        torch.cuda.synchronize()
+
+    pinned_step()
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        pinned_step()
+    pin_s = cx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    fuser.close()
+    bf.close()
+    del pinned, out_pin
+
+    # registration end to end: host crops in (pageable numpy) -> transforms out
+    hf, hm = pair_crops(host_tiles, pairs)
+    hf = [np.ascontiguousarray(a) for a in hf]
+    hm = [np.ascontiguousarray(a) for a in hm]
+    registration.register_pairs(hf, hm, plans=pc_plans)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        registration.register_pairs(hf, hm, plans=pc_plans)
+    torch.cuda.synchronize()
+    reg_e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / 2)
+
+    traffic, traffic_src = _ncu_traffic()
+    roof = _roof(plan.algorithmic_bytes(), fuse_kernel_ms, "fuse_stencil_kernel<2,float,WAVG> (TMA-staged translation path)")
+    roof.update({"peak_source": _peaks()[1], "frac_of_nominal_8TBps": roof["achieved"] / 8000.0,
+                 "traffic": traffic, "traffic_source": traffic_src})
+    rec = {
+        "value": value,
+        "ms_per_step": total_ms / args.steps,
+        "vox_per_step": vox_per_step,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "path": "hook C: BatchFuser.__call__(fuse_chunk partial, all 25 block ids) -- pageable numpy tiles in, "
+                        "numpy destination array out; pinned staging + H2D + fusion + D2H inside the timing",
+                "ms_per_step": e2e_s * 1e3, "equals_device_result": e2e_ok, "gpu_launches_per_step": e2e_launches // (n_e2e + 2),
+                "pre_pinned_HostFuser": {"value": vox_per_step * world / pin_s / 1e6, "ms_per_step": pin_s * 1e3,
+                                         "what": "fusion.HostFuser with buffers pinned outside the timing (round-1 e2e)"}},
+        "registration": {
+            "pairs_per_sec": len(pairs) * world / (reg_ms * 1e-3),
+            "unit": "pairs/s",
+            "pairs_per_step": len(pairs),
+            "ms_per_step": reg_ms,
+            "crop": "2048x307 / 307x2048 float32",
+            "max_abs_shift_error_px": reg_err,
+            "shift_error_note": "vs the generator's fractional jitter difference; the algorithm's sub-pixel grid is 0.1 px (upsample_factor 10)",
+            "gpu_launches_per_step": reg_launches,
+            "e2e": {"pairs_per_sec": len(pairs) * world / reg_e2e_s, "ms_per_step": reg_e2e_s * 1e3,
+                    "path": "registration.register_pairs: pageable numpy crops in (2 x 40 x 2.5 MB H2D), affine + quality out"},
+            "from_tiles": {
+                "what": "pairs.register_views (hook A's work): crop to the overlap box + resample onto the fixed tile's grid "
+                        "(1 launch per crop shape) + registration + physical transform, tiles resident",
+                "pairs_per_sec": len(pairs) * world / (rv_ms * 1e-3),
+                "ms_per_step": rv_ms,
+                "max_abs_shift_error_px": rv_err,
+                "host_geometry_plan_ms_once": plan_ms,
+            },
+            "phasecorr_roofline": dict(_roof(pc_bytes, pc_ms), stage="mvs_pc_correlate on C2's 40 crops (307 is prime: Bluestein axes)"),
+            "phasecorr_roofline_pow2": dict(_roof(p2_bytes, p2_ms), stage="mvs_pc_correlate on 20 crops of 2048x256 (power-of-two axes)"),
+        },
+        "gpu_launches": launches_per_step * args.steps + reg_launches * n_reg,
+        "roofline": roof,
+    }
+    plan.close()
+    for p in pc_plans.values():
+        p.close()
+    return rec
+
+
+def _c3_pairs(grid):
+    idx = list(np.ndindex(*grid))
+    pos = {c: i for i, c in enumerate(idx)}
+    pairs = []
+    for c in idx:
+        for ax in range(3):
+            n = list(c)
+            n[ax] += 1
+            if tuple(n) in pos:
+                pairs.append((pos[c], pos[tuple(n)]))
+    return pairs
+
+
+def bench_c3(cx, args):
+    """C3 as ONE job: at N ranks the 64 pairs are dealt round-robin, the 128 output chunks
+    go to the ranks in bands (tiles replicated), and the tile-partitioned run keeps 32/N
+    tiles per rank and exchanges border boxes over NVLink.  Strong scaling."""
+    torch = cx.torch
+    from multiview_stitcher_b200 import content, distributed, fusion, geometry, synthetic
+
+    grid, tile, ov = C3["grid"], C3["tile"], C3["overlap"]
+    views, stage, true = synthetic.make_grid(grid, tile, ov, np.uint16, jitter=2, seed=SEED, subpixel=True)
+    bbs = [v.bb() for v in views]
+    osp = geometry.union_stack_props(bbs, true, bbs[0]["spacing"])
+    vox = int(np.prod([osp["shape"][d] for d in "zyx"]))
+    b_fuse = sum(v.tensor.numel() * 2 for v in views) + vox * 2
+    n_steps = max(3, min(args.steps, 10))
+    rec = {"workload": "C3: 4x4x2 grid of 3-D tiles (z256,y512,x512) uint16, 10% overlap, sub-pixel positions; "
+                       f"output {[osp['shape'][d] for d in 'zyx']}", "scaling": "strong" if cx.world > 1 else None}
+
+    # (1) blend fusion, whole stack on this GPU (N = 1 figure; at N > 1 every rank runs it too)
+    plan = fusion.FusionPlan(views, true, osp)
+    ms = cx.timed(plan.run, n_steps, 2)
+    rec["fuse_blend_one_gpu"] = {"ms": ms, "Mvoxel_per_s": vox / ms / 1e3, "roofline": _roof(b_fuse, ms, "fuse_stencil 3-D uint16"),
+                                 "launches": plan.launches_per_run}
+    ref_out = plan.out
+    launches = plan.launches_per_run * n_steps
+
+    if cx.world > 1:
+        # (2) chunk bands per rank, tiles replicated, no communication
+        cs = geometry.DEFAULT_CHUNKSIZE_3D
+        holder = {}
+
+        def sharded():
+            holder["out"], holder["owned"] = distributed.fuse_sharded(views, true, osp, cs)
+
+        ms_sh = cx.timed(sharded, 3, 1)
+        rec["fuse_sharded"] = {"ms": ms_sh, "Mvoxel_per_s": vox / ms_sh / 1e3, "chunks_this_rank": len(holder["owned"]),
+                               "what": "distributed.fuse_sharded: chunk bands per rank, plan built + run per step, no collective"}
+        # (3) tiles partitioned: each tile lives on one rank; border boxes cross NVLink
+        idx = list(np.ndindex(*grid))
+        cols = grid[1] * grid[2]
+        owners = [((c[1] * grid[2] + c[2]) * cx.world) // cols for c in idx]
+        local = {i: views[i] for i in range(len(views)) if owners[i] == cx.rank}
+        for mode in ("halo", "partial"):
+            tp = distributed.TilePartitionedFuser(local, bbs, true, owners, osp, cs, mode=mode)
+            ms_tp = cx.timed(tp.run, 3, 1)
+            # parity vs the one-GPU result on the chunks this rank owns (uint16: <= 1 LSB; halo: equal)
+            part = tp.partition
+            sl = tuple(slice(a, a + n) for a, n in zip(tp.out_start, tp.out.shape))
+            diff = (tp.out.to(torch.int32) - ref_out[sl].to(torch.int32)).abs()
+            mask = torch.zeros_like(diff, dtype=torch.bool)
+            for ci, (cs_, cn_) in enumerate(part.grid):
+                if part.owner_of[ci] == cx.rank:
+                    mask[tuple(slice(a - o, a - o + n) for a, o, n in zip(cs_, tp.out_start, cn_))] = True
+            max_lsb = cx.max_over_ranks(float((diff * mask).max().item()))
+            xbytes = part.halo_bytes(2) if mode == "halo" else part.exchanged_bytes()
+            rec["fuse_tile_partitioned_" + mode] = {
+                "ms": ms_tp, "Mvoxel_per_s": vox / ms_tp / 1e3, "tiles_per_rank": len(local),
+                "nvlink_bytes_per_job": int(xbytes), "sent_bytes_all_ranks": int(cx.sum_over_ranks(tp.sent_bytes)),
+                "border_boxes": len(part.entries),
+                "full_stack_reduce_bytes": int(8 * vox), "exchange_fraction_of_full_reduce": xbytes / (8.0 * vox),
+                "max_abs_diff_vs_one_gpu_lsb": max_lsb, "launches_per_step": tp.launches,
+                "what": ("raw uint16 windows of the foreign tiles -> owner (NCCL send/recv, hidden behind the direct launch), "
+                         "border boxes fused by the ordinary kernel" if mode == "halo" else
+                         "partial (sum w*v, sum w) float32 of the border boxes -> owner (NCCL send/recv), add + divide + cast"),
+            }
+            tp.close()
+            del tp, diff, mask
+            torch.cuda.empty_cache()
+    plan.close()
+    del ref_out
+
+    # (4) registration of all 64 face pairs from the resident tiles (pairs round-robin over ranks)
+    from multiview_stitcher_b200 import pairs as pairs_mod
+
+    pairs = _c3_pairs(grid)
+    binning = {"z": 1, "y": 1, "x": 1}
+    owned = distributed.shard_round_robin(len(pairs), cx.rank, cx.world)
+    my_pairs = [pairs[i] for i in owned]
+    pc_plans = {}
+    pplan = pairs_mod.PairPlan(views, stage, my_pairs, registration_binning=binning)
+    res = pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans)
+    tt = np.array([t[:3, 3] for t in true])
+    err = max(float(np.abs(r["transform"][:3, 3] + (tt[b] - tt[a])).max()) for r, (a, b) in zip(res, my_pairs))
+    ms_reg = cx.timed(lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 2, 0)
+    rec["registration_from_tiles"] = {"pairs": len(pairs), "pairs_this_rank": len(my_pairs), "ms": ms_reg,
+                                      "pairs_per_sec": len(pairs) / (ms_reg * 1e-3),
+                                      "max_abs_shift_error_px": cx.max_over_ranks(err),
+                                      "shift_error_note": "3-D default upsample_factor 2: the algorithm's sub-pixel grid is 0.5 px"}
+    for p in pc_plans.values():
+        p.close()
+
+    # (5) content-weighted fusion (the mode C3 names): chunks of 256^3 + 22 px halo, sigma 5 / 11
+    n_chunks = len(geometry.chunk_grid(osp, geometry.DEFAULT_CHUNKSIZE_3D))
+    mine = distributed.shard_slabs(n_chunks, cx.rank, cx.world)
+
+    def content_run():
+        return content.fuse_with_weights(views, true, osp, None, fusion.weighted_average_fusion, fusion.content_based,
+                                         None, 1, None, chunk_subset=mine)
+
+    ms_c = cx.timed(content_run, 1, 1)
+    n_halo = sum(int(np.prod([min(s + 44, 10**9) for s in shape])) for _, shape in geometry.chunk_grid(osp, geometry.DEFAULT_CHUNKSIZE_3D))
+    rec["fuse_content_weighted"] = {"ms": ms_c, "Mvoxel_per_s": vox / ms_c / 1e3, "chunks_this_rank": len(mine),
+                                    "algorithmic_bytes_note": "B_fuse + 108 B per contributing view-voxel incl. the 22 px halo (SURVEY 8d)",
+                                    "halo_voxels_all_chunks": n_halo}
+    rec["gpu_launches"] = launches
+    del views
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_c4(cx, args):
+    """C4: 4 views of (512,1024,1024) uint16, rotations 0/90/180/270 deg about y with a +-2 deg tilt
+    and 0.5 % anisotropic scale, spacing z=2: general-affine path.  One GPU (rank 0's figure)."""
+    torch = cx.torch
+    from multiview_stitcher_b200 import content, fusion, geometry, synthetic
+    from multiview_stitcher_b200.fusion import DeviceView
+
+    shape = (512, 1024, 1024)
+    spacing = {"z": 2.0, "y": 1.0, "x": 1.0}
+    ext = np.array([shape[0] * 2.0, shape[1] * 1.0, shape[2] * 1.0])
+    centre = ext / 2
+    views, params = [], []
+    for k in range(4):
+        t = synthetic.make_tile_field(shape, (0.0, 0.0, 0.0), np.uint16, seed=SEED + 10 + k, tile_id=k)
+        views.append(DeviceView(t, {"z": 0.0, "y": 0.0, "x": 0.0}, spacing))
+        a = np.deg2rad(90.0 * k)
+        tilt = np.deg2rad(2.0 if k % 2 else -2.0)
+        ry = np.array([[np.cos(a), 0, -np.sin(a)], [0, 1, 0], [np.sin(a), 0, np.cos(a)]])
+        rx = np.array([[np.cos(tilt), np.sin(tilt), 0], [-np.sin(tilt), np.cos(tilt), 0], [0, 0, 1]])
+        m = ry @ rx @ np.diag([1.0, 1.005, 0.995])
+        p = np.eye(4)
+        p[:3, :3] = m
+        p[:3, 3] = centre - m @ centre
+        params.append(p)
+    bbs = [v.bb() for v in views]
+    osp = geometry.union_stack_props(bbs, params, spacing)
+    vox = int(np.prod([osp["shape"][d] for d in "zyx"]))
+    plan = fusion.FusionPlan(views, params, osp)
+    ms = cx.timed(plan.run, 3, 1)
+    b = plan.algorithmic_bytes()
+    rec = {"workload": "C4: 4 views (z512,y1024,x1024) uint16, spacing z=2, rotations about y + tilt + 0.5% scale; "
+                       f"output {[osp['shape'][d] for d in 'zyx']}",
+           "fuse_blend": {"ms": ms, "Mvoxel_per_s": vox / ms / 1e3, "roofline": _roof(b, ms, "fuse_kernel<3,1,WAVG> (general affine)")},
+           "gpu_launches": plan.launches_per_run * 3}
+    plan.close()
+
+    def content_run():
+        return content.fuse_with_weights(views, params, osp, None, fusion.weighted_average_fusion, fusion.content_based, None, 1, None)
+
+    ms_c = cx.timed(content_run, 1, 1)
+    rec["fuse_content_weighted"] = {"ms": ms_c, "Mvoxel_per_s": vox / ms_c / 1e3}
+    del views
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_c5(cx, args):
+    """C5 weak-scaled: rank r holds tile row r of the 8x8 grid (8 tiles of 512x2048x2048 uint16
+    = 34 GB); N ranks fuse the first N rows as one tile-partitioned job (N = 8: the whole 137 Gvoxel
+    stack).  Only the row-overlap boxes cross NVLink."""
+    torch = cx.torch
+    from multiview_stitcher_b200 import distributed, geometry, synthetic
+
+    grid = (1, cx.world, C5["grid"][2])
+    tile, ov = C5["tile"], C5["overlap"]
+    owners = [c[1] for c in np.ndindex(*grid)]
+    mine = {i for i, o in enumerate(owners) if o == cx.rank}
+    t0 = time.perf_counter()
+    views, stage, true = synthetic.make_grid(grid, tile, ov, np.uint16, jitter=2, seed=SEED, subpixel=True, only=mine)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    dims = ["z", "y", "x"]
+    sp = {d: 1.0 for d in dims}
+    bbs = []
+    for k, c in enumerate(np.ndindex(*grid)):
+        s_org = np.array(c) * (np.array(tile) - np.array(ov))
+        bbs.append({"origin": dict(zip(dims, map(float, s_org))), "spacing": dict(sp), "shape": dict(zip(dims, tile))})
+    osp = geometry.union_stack_props(bbs, true, sp)
+    vox = int(np.prod([osp["shape"][d] for d in dims]))
+    local = {i: views[i] for i in mine}
+    n_steps = max(2, min(args.steps, 5))
+    rec = {
+        "workload": f"C5: {cx.world} row(s) of the 8x8 grid of 3-D tiles (z512,y2048,x2048) uint16, 10% overlap, one row of 8 tiles "
+                    f"(34 GB) per GPU; output {[osp['shape'][d] for d in dims]}",
+        "scaling": "weak", "out_voxels": vox, "tiles_per_rank": len(mine),
+        "input_bytes_all_ranks": int(len(owners) * np.prod(tile) * 2), "generate_tiles_s": gen_s, "gpu_launches": 0,
+    }
+    for mode in ("halo", "partial") if cx.world > 1 else ("halo",):
+        tp = distributed.TilePartitionedFuser(local, bbs, true, owners, osp, geometry.DEFAULT_CHUNKSIZE_3D, mode=mode)
+        ms = cx.timed(tp.run, n_steps, 1)
+        part = tp.partition
+        xbytes = part.halo_bytes(2) if mode == "halo" else part.exchanged_bytes()
+        sub = {"ms": ms, "Mvoxel_per_s": vox / ms / 1e3, "nvlink_bytes_per_job": int(xbytes),
+               "sent_bytes_all_ranks": int(cx.sum_over_ranks(tp.sent_bytes)), "border_boxes": len(part.entries),
+               "launches_per_step": tp.launches}
+        rec["gpu_launches"] += tp.launches * (n_steps + 1)
+        if mode == "halo":
+            # kernel-only figure of this rank's direct boxes (the fused stencil launch)
+            ms_direct = cx.timed(tp.direct.run, n_steps, 0)
+            own_vox = sum(int(np.prod(n)) for ci, (s_, n) in enumerate(part.grid) if part.owner_of[ci] == cx.rank)
+            b_local = len(mine) * int(np.prod(tile)) * 2 + own_vox * 2
+            rec.update({"ms": ms, "Mvoxel_per_s": vox / ms / 1e3})
+            rec["direct_launch"] = {
+                "ms": ms_direct, "roofline": _roof(b_local, ms_direct, "fuse_stencil 3-D uint16, this rank's direct boxes"),
+                "note": "algorithmic bytes = this rank's tiles + the chunks it owns (the border boxes are in the bytes but "
+                        "not in this launch, so the fraction is a slight over-estimate at N > 1)"}
+        rec["exchange_" + mode] = sub
+        tp.close()
+        del tp
+        torch.cuda.empty_cache()
+    del views, local
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_ours(args):
+    cx = Ctx()
+    torch = cx.torch
+    only = set((args.only or "c2,c3,c4,c5").split(","))
+    clocks = ClockSampler(cx.local_rank)
+    clocks.__enter__()
+    c2 = bench_c2(cx, args)
+    torch.cuda.empty_cache()
+    configs = {}
+    errors = {}
+    for name, fn in (("C3", bench_c3), ("C4", bench_c4), ("C5", bench_c5)):
+        if name.lower() not in only:
+            continue
+        if name == "C4" and cx.world > 1:
+            continue  # single-GPU config; measured at N = 1
+        try:
+            configs[name] = fn(cx, args)
+        except Exception as e:  # a sub-record must not take the headline down with it
+            import traceback
+
+            errors[name] = f"{type(e).__name__}: {e}"
+            if cx.rank == 0:
+                traceback.print_exc()
+            if cx.world > 1:
+                raise
+        torch.cuda.empty_cache()
+    clocks.__exit__(None, None, None)
+
+    if cx.rank == 0:
         line = {
             "metric": METRIC,
-            "value": value,
+            "value": c2["value"],
             "unit": UNIT,
-            "n_gpus": world,
+            "n_gpus": cx.world,
             "steps": args.steps,
             "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps,
+            "ms_per_step": c2["ms_per_step"],
             "higher_is_better": True,
             "scaling": "weak",
+            "scaling_note": "value = C2, one replica per rank (independent units, no data-path collective); the sharded jobs "
+                            "(C3 strong, C5 weak with border exchange over NVLink) are under configs",
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": WORKLOAD,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "registration": {
-                "pairs_per_sec": len(pairs) * world / (reg_ms * 1e-3),
-                "unit": "pairs/s",
-                "pairs_per_step": len(pairs),
-                "ms_per_step": reg_ms,
-                "crop": "2048x307 / 307x2048 float32",
-                "max_abs_shift_error_px": reg_err,
-                "gpu_launches_per_step": reg_launches,
-                "from_tiles": {
-                    "what": "pairs.register_views: crop to the overlap box + resample onto the fixed tile's grid (1 launch per crop shape) + registration + physical transform, tiles resident",
-                    "pairs_per_sec": len(pairs) * world / (rv_ms * 1e-3),
-                    "ms_per_step": rv_ms,
-                    "max_abs_shift_error_px": rv_err,
-                    "host_geometry_plan_ms_once": plan_ms,
-                },
-                "phasecorr_roofline": {
-                    "stage": "mvs_pc_correlate (fft_reg_pass_kernel x 2*ndim incl. fused cross power and argmax, updft)",
-                    "bound": "hbm",
-                    "algorithmic_bytes_per_step": pc_bytes,
-                    "ms_per_step": pc_ms,
-                    "achieved": pc_bytes / (pc_ms * 1e-3) / 1e9,
-                    "unit": "GB/s",
-                    "frac": pc_bytes / (pc_ms * 1e-3) / 1e9 / _peaks()[0],
-                    "note": "C2's 307-px overlap is prime: those axes run Bluestein (2 x 1024-point FFT per line), instruction-bound",
-                },
-                "phasecorr_roofline_pow2": {
-                    "stage": "mvs_pc_correlate on 20 crops of 2048x256 (power-of-two axes, no Bluestein)",
-                    "bound": "hbm",
-                    "algorithmic_bytes": p2_bytes,
-                    "ms": p2_ms,
-                    "achieved": p2_bytes / (p2_ms * 1e-3) / 1e9,
-                    "unit": "GB/s",
-                    "frac": p2_bytes / (p2_ms * 1e-3) / 1e9 / _peaks()[0],
-                },
-            },
-            "gpu_launches": launches_per_step * args.steps + reg_launches * n_reg,
+            "e2e": c2["e2e"],
+            "registration": c2["registration"],
+            "gpu_launches": c2["gpu_launches"] + sum(c.get("gpu_launches", 0) for c in configs.values()),
             "clocks": clocks.summary(),
-            "roofline": {
-                "kernel": "fuse_stencil_kernel<2,float,WAVG> (TMA-staged translation path)",
-                "bound": "hbm",
-                "achieved": achieved,
-                "peak": peak,
-                "peak_source": peak_src,
-                "unit": "GB/s",
-                "frac": achieved / peak,
-                "frac_of_nominal_8TBps": achieved / 8000.0,
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel_ms": fuse_kernel_ms,
-                "traffic": _ncu_traffic(),
-                "traffic_source": "profiles/r01c_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
-            },
+            "roofline": c2["roofline"],
+            "configs": configs,
         }
-        if world == 1 and not args.no_cpu:
-            v, cores, sample = cpu_fusion_sample(seed=0)
-            pv, _, psample = cpu_registration_sample(seed=0)
+        if errors:
+            line["config_errors"] = errors
+        if cx.world == 1 and not args.no_cpu:
+            views, params = _host_c2_views()
+            v, cores, sample = cpu_fusion_sample(views, params)
+            pv, _, psample = cpu_registration_sample(views)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "pairs_per_sec": pv, "pairs_sample": psample}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 def main():
@@ -561,6 +860,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only", default=None, help="comma list of configs to run beside C2 (c3,c4,c5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -252,6 +252,21 @@ int mvs_pc_spearman_batch(mvs_pc_plan* plan, int n, const int32_t* pairs, const 
                           const int64_t* n_mask, double* rho_host, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Host <-> device movement of PAGEABLE host arrays: what the reference's hooks hand
+ * over are plain numpy arrays (view slices, fusion/_core.py:1579-1587; the zarr
+ * region a fused block is written to, :2130-2150).  `rows` rows of `width` bytes
+ * travel through a ring of pinned staging buffers filled / drained by worker
+ * threads while the DMA engine moves the previous piece.
+ * mvs_copy_h2d_2d returns once h_src has been staged (the device copy is ordered on
+ * `stream`); mvs_copy_d2h_2d returns once h_dst is filled (work on `stream` enqueued
+ * before the call is waited for).  Pitches in bytes.
+ * ---------------------------------------------------------------------- */
+int mvs_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
+                    size_t width, size_t rows, void* stream);
+int mvs_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
+                    size_t width, size_t rows, void* stream);
+
+/* ------------------------------------------------------------------------
  * Pair preparation (register_pair_of_msims, registration.py:1732-1968): the
  * views are mean-binned (`sim.coarsen(binning, boundary="trim").mean()
  * .astype(dtype)`, :1732-1743), cropped to the overlap box plus one pixel

@@ -120,6 +120,8 @@ _SIGNATURES = {
         ctypes.c_int,
         [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.c_uint32, _P],
     ),
+    "mvs_copy_h2d_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
+    "mvs_copy_d2h_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_synth_field": (
         ctypes.c_int,
         [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, ctypes.c_int,
@@ -192,3 +194,53 @@ def current_stream_ptr():
     import torch
 
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _pitched(shape, strides_bytes, itemsize):
+    """(outer index tuples, rows, width bytes, pitch bytes) of an array window whose last
+    axis is contiguous: the window is a stack of pitched 2-D copies."""
+    if len(shape) == 1:
+        return [()], 1, shape[0] * itemsize, shape[0] * itemsize
+    if strides_bytes[-1] != itemsize:
+        raise EngineError("staged copies need a contiguous last axis")
+    outer = list(np.ndindex(*shape[:-2])) if len(shape) > 2 else [()]
+    return outer, int(shape[-2]), int(shape[-1]) * itemsize, int(strides_bytes[-2])
+
+
+def copy_h2d(dst_tensor, src_array, stream_ptr=None):
+    """Pageable numpy window -> CUDA tensor window (same shape, contiguous last axis)
+    through the engine's pinned staging ring.  Returns the bytes moved."""
+    lib = load(require_device=True)
+    if tuple(dst_tensor.shape) != tuple(src_array.shape) or dst_tensor.element_size() != src_array.itemsize:
+        raise EngineError("copy_h2d: shape / item size mismatch")
+    es = src_array.itemsize
+    outer, rows, width, hp = _pitched(src_array.shape, src_array.strides, es)
+    dstr = [s * es for s in dst_tensor.stride()]
+    _, _, _, dp = _pitched(tuple(dst_tensor.shape), dstr, es)
+    st = stream_ptr if stream_ptr is not None else current_stream_ptr()
+    for idx in outer:
+        ho = sum(i * s for i, s in zip(idx, src_array.strides))
+        do = sum(i * s for i, s in zip(idx, dstr))
+        check(lib.mvs_copy_h2d_2d(ctypes.c_void_p(dst_tensor.data_ptr() + do), dp,
+                                  ctypes.c_void_p(src_array.ctypes.data + ho), hp, width, rows, st), "mvs_copy_h2d_2d")
+    return int(src_array.size) * es
+
+
+def copy_d2h(dst_array, src_tensor, stream_ptr=None):
+    """CUDA tensor window -> pageable numpy window (blocking)."""
+    lib = load(require_device=True)
+    if tuple(src_tensor.shape) != tuple(dst_array.shape) or src_tensor.element_size() != dst_array.itemsize:
+        raise EngineError("copy_d2h: shape / item size mismatch")
+    if not dst_array.flags.writeable:
+        raise EngineError("copy_d2h: destination is read-only")
+    es = dst_array.itemsize
+    outer, rows, width, hp = _pitched(dst_array.shape, dst_array.strides, es)
+    sstr = [s * es for s in src_tensor.stride()]
+    _, _, _, dp = _pitched(tuple(src_tensor.shape), sstr, es)
+    st = stream_ptr if stream_ptr is not None else current_stream_ptr()
+    for idx in outer:
+        ho = sum(i * s for i, s in zip(idx, dst_array.strides))
+        do = sum(i * s for i, s in zip(idx, sstr))
+        check(lib.mvs_copy_d2h_2d(ctypes.c_void_p(dst_array.ctypes.data + ho), hp,
+                                  ctypes.c_void_p(src_tensor.data_ptr() + do), dp, width, rows, st), "mvs_copy_d2h_2d")
+    return int(dst_array.size) * es

@@ -187,10 +187,12 @@ def fuse_np_with_weights(
 
 
 def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weights_func, weights_func_kwargs,
-                      interpolation_order, blending_widths, overlap_in_pixels=None):
+                      interpolation_order, blending_widths, overlap_in_pixels=None, chunk_subset=None):
     """Chunked multi-pass fusion of whole views: one ``fuse_np_with_weights`` per
     output chunk with the halo the hooks ask for (fusion/_core.py:1194-1254) and
-    the views restricted to those that can touch the chunk (:582-653)."""
+    the views restricted to those that can touch the chunk (:582-653).
+    ``chunk_subset``: linear indices of the chunks to fuse (sharded jobs); the rest of
+    the returned stack stays zero."""
     import torch
 
     from .fusion import _required_overlap
@@ -213,7 +215,10 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
     o_org, o_sp, _ = geometry.bb_arrays(osp, dims)
     aabbs = [geometry.transformed_aabb(bb, p, dims) for bb, p in zip(bbs, params)]
     out = torch.zeros(full_shape, dtype=dviews[0].tensor.dtype, device="cuda")
-    for start, shape in geometry.chunk_grid(osp, output_chunksize):
+    grid = geometry.chunk_grid(osp, output_chunksize)
+    if chunk_subset is not None:
+        grid = [grid[i] for i in chunk_subset]
+    for start, shape in grid:
         start_a = np.array(start)
         c_org = (o_org + o_sp * start_a) - ov * o_sp
         hbb = {

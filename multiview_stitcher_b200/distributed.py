@@ -15,13 +15,21 @@ Both stages shard into independent units:
     exactly one GPU; this is how a stack larger than one GPU's HBM is fused).
     Every output chunk has an owner rank.  Chunks fed by one rank only are fused
     straight into the owner's slab.  For a chunk that draws from tiles on
-    several GPUs only the box the foreign tiles can reach is exchanged: every
-    contributing rank produces un-normalised partial sums (sum_i v_i*b_i,
-    sum_i b_i) of ITS tiles over that box, sends them to the owner (NCCL
-    send/recv over NVLink), and the owner adds them to its own partial sums,
-    divides and casts.  Valid because normalisation is linear:
-    sum_i v_i b_i / sum_i b_i (the per-view normalisers of weights.py:340-345
-    cancel).  The rest of the chunk is fused directly.
+    several GPUs only the box the foreign tiles can reach is exchanged, in one
+    of two ways (one NCCL send/recv message per rank pair over NVLink, issued
+    BEFORE the direct launch so the transfer hides behind it):
+      mode="partial"  every contributing rank produces un-normalised partial
+        sums (sum_i v_i*b_i, sum_i b_i) of ITS tiles over that box (8 bytes per
+        voxel) and the owner adds them to its own, divides and casts.  Valid
+        because normalisation is linear: sum_i v_i b_i / sum_i b_i (the per-view
+        normalisers of weights.py:340-345 cancel).  Within 1 LSB / 1e-6 of the
+        one-GPU result.
+      mode="halo" (default)  the contributing rank sends the raw WINDOW of each
+        of its tiles that the box can sample (input dtype: 2 bytes per voxel for
+        uint16, a quarter of the partial sums) and the owner fuses the box with
+        the ordinary fused kernel from local tiles + received windows, in global
+        view order -- bit-identical to the one-GPU result, no extra passes.
+    The rest of the chunk is fused directly.
   - ``fuse_partial``: whole-volume variant (all-reduce of full accumulators;
     small stacks, ``max_fusion``).
 """
@@ -246,7 +254,8 @@ class TilePartition:
             contrib = tuple(sorted({owners[vi] for vi, _, _ in foreign}))
             ushape = uhi - ulo + 1
             entries.append({"chunk": ci, "owner": owner, "contrib": contrib, "start": tuple(int(v) for v in ulo),
-                            "shape": tuple(int(v) for v in ushape), "nvox": int(np.prod(ushape))})
+                            "shape": tuple(int(v) for v in ushape), "nvox": int(np.prod(ushape)),
+                            "foreign": [vi for vi, _, _ in foreign]})
         entries.sort(key=lambda e: (e["owner"], e["contrib"], e["chunk"]))
         self.entries = entries
         self.slab = []
@@ -259,6 +268,38 @@ class TilePartition:
             hi = np.max([np.array(s) + np.array(n) for s, n in mine], axis=0)
             self.slab.append((tuple(int(v) for v in lo), tuple(int(v) for v in hi - lo)))
         self.full_shape = tuple(int(v) for v in full)
+        # halo mode: per (owner rank, foreign view) the window of the view (its own pixel
+        # indices, inclusive) that can be sampled from the owner's border boxes
+        self.windows = {}
+        for e in entries:
+            c_org = o_org + o_sp * np.array(e["start"], dtype=np.float64)
+            corners = np.array(list(np.ndindex(*([2] * ndim))), dtype=np.float64) * (np.array(e["shape"], dtype=np.float64) - 1)
+            for vi in e["foreign"]:
+                bb = view_bbs[vi]
+                in_org, in_sp, in_n = geometry.bb_arrays(bb, dims)
+                m, off = geometry.pixel_affine(np.linalg.inv(np.asarray(params[vi], dtype=np.float64)), c_org, o_sp, in_org, in_sp)
+                pts = corners @ m.T + off
+                lo = np.maximum(np.floor(pts.min(0)).astype(np.int64) - 2, 0)
+                hi = np.minimum(np.ceil(pts.max(0)).astype(np.int64) + 2, in_n.astype(np.int64) - 1)
+                if np.any(hi < lo):
+                    continue
+                lo[-1] = (lo[-1] // 16) * 16  # rows start 16-byte aligned for every dtype (TMA)
+                key = (e["owner"], vi)
+                if key in self.windows:
+                    plo, phi = self.windows[key]
+                    lo, hi = np.minimum(lo, plo), np.maximum(hi, phi)
+                self.windows[key] = (lo, hi)
+        self.view_owner = owners
+
+    def halo_sends(self, src, dst):
+        """Windows ``(view index, lo, hi)`` of ``src``'s tiles that ``dst`` needs for the
+        border boxes it owns (halo mode), in view order."""
+        return [(vi, lo, hi) for (o, vi), (lo, hi) in sorted(self.windows.items(), key=lambda kv: kv[0])
+                if o == dst and self.view_owner[vi] == src]
+
+    def halo_bytes(self, itemsize):
+        """Raw tile bytes crossing NVLink per job in halo mode."""
+        return sum(int(np.prod(hi - lo + 1)) * itemsize for (lo, hi) in self.windows.values())
 
     def own_entries(self, rank):
         return [e for e in self.entries if e["owner"] == rank]
@@ -272,8 +313,25 @@ class TilePartition:
         return sum(8 * e["nvox"] * len(e["contrib"]) for e in self.entries)
 
 
+class _Runner:
+    """A prepared launch: ``run()`` enqueues it, ``launches`` kernels per run."""
+
+    def __init__(self, plan=None):
+        self.plan = plan
+        self.launches = plan.launches_per_run if plan is not None else 0
+
+    def run(self):
+        if self.plan is not None:
+            self.plan.run()
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.close()
+            self.plan = None
+
+
 class _CudaEngine:
-    """Device half of ``fuse_tile_partitioned`` (the CPU test substitutes an oracle-backed
+    """Device half of ``TilePartitionedFuser`` (the CPU test substitutes an oracle-backed
     engine to exercise the exchange protocol over gloo)."""
 
     def __init__(self, **plan_kwargs):
@@ -286,36 +344,46 @@ class _CudaEngine:
 
         return torch.zeros(n, dtype=_np_to_torch(np.dtype(np_dtype)), device="cuda")
 
-    def fuse_direct(self, views, params, osp, chunksize, boxes, out, out_start):
+    def direct_plan(self, views, params, osp, chunksize, boxes, out, out_start):
         from .fusion import FusionPlan
 
-        if not boxes:
-            return 0
-        plan = FusionPlan(views, params, osp, output_chunksize=chunksize, chunk_list=boxes, out=out,
-                          out_start=out_start, **self.kw)
-        plan.run()
-        n = plan.launches_per_run
-        plan.close()
-        return n
+        if not boxes or not views:
+            return _Runner()
+        return _Runner(FusionPlan(views, params, osp, output_chunksize=chunksize, chunk_list=boxes, out=out,
+                                  out_start=out_start, **self.kw))
 
-    def fuse_partial(self, views, params, osp, chunksize, boxes, targets):
+    def border_plan(self, views, params, full_bbs, osp, chunksize, boxes, out, out_start):
+        """Border boxes fused from local views and received windows of foreign views
+        (``full_bbs``: the bounding boxes of the WHOLE views, for the blending weights)."""
+        from .fusion import FusionPlan
+
+        if not boxes or not views:
+            return _Runner()
+        return _Runner(FusionPlan(views, params, osp, output_chunksize=chunksize, chunk_list=boxes, out=out,
+                                  out_start=out_start, full_view_bbs=full_bbs, **self.kw))
+
+    def view_tensor(self, view):
+        return view.tensor
+
+    def make_view(self, tensor, origin, spacing):
+        from .fusion import DeviceView
+
+        return DeviceView(tensor, origin, spacing)
+
+    def partial_plan(self, views, params, osp, chunksize, boxes, targets):
         """boxes[i] accumulated into the packed float32 (num, den) windows targets[i] =
         (buffer tensor, element offset of num, element offset of den)."""
         from .fusion import FusionPlan
 
-        if not boxes:
-            return 0
+        if not boxes or not views:
+            return _Runner()
         tg = []
         for (start, shape), (buf, o_num, o_den) in zip(boxes, targets):
             strides = [int(np.prod(shape[i + 1:])) for i in range(len(shape))]
             tg.append((buf.data_ptr() + 4 * o_num, buf.data_ptr() + 4 * o_den, strides))
         kw = {k: v for k, v in self.kw.items() if k != "fusion_func"}
-        plan = FusionPlan(views, params, osp, output_chunksize=chunksize, chunk_list=boxes, partial=True,
-                          chunk_targets=tg, **kw)
-        plan.run()
-        n = plan.launches_per_run
-        plan.close()
-        return n
+        return _Runner(FusionPlan(views, params, osp, output_chunksize=chunksize, chunk_list=boxes, partial=True,
+                                  chunk_targets=tg, **kw))
 
     def finalize(self, buf, items, out, out_start, np_dtype):
         """items: (element offset of num, of den, start, shape) per box."""
@@ -338,114 +406,226 @@ class _CudaEngine:
         return 1
 
 
-def fuse_tile_partitioned(local_views, view_bbs, params, owners, output_stack_properties, output_chunksize=None,
-                          out_dtype=None, engine=None, partition=None, **plan_kwargs):
-    """Fusion of a stack whose tiles are partitioned over the ranks.
+class TilePartitionedFuser:
+    """Fusion of a stack whose tiles are partitioned over the ranks (see module docstring).
 
     ``local_views``: {global view index: view} for the views THIS rank holds (exactly the
     indices ``i`` with ``owners[i] == rank``); ``view_bbs`` / ``params`` / ``owners``: bounding
     box, affine and owner rank of EVERY view of the job (metadata, identical on all ranks).
     Weighted-average fusion with blending weights only.
 
-    Returns ``(out, out_start, info)``: this rank's slab of the fused stack (a CUDA tensor
-    covering the chunks it owns), the stack index of its first voxel and ``info`` =
-    {"partition", "sent_bytes", "recv_bytes", "border_boxes", "launches"}.
+    Construction plans the partition, allocates this rank's slab ``out`` (the chunks it
+    owns; ``out_start`` = stack index of its first voxel), the packed partial-sum buffers
+    and the launches; ``run()`` fuses: direct boxes -> partial sums of the border boxes ->
+    one NCCL message per (contributor -> owner) pair -> add, divide, cast.
     """
-    import torch
-    import torch.distributed as dist
 
-    rank, ws = world()
-    osp = output_stack_properties
-    ndim = len(osp["shape"])
-    dims = geometry.spatial_dims(ndim)
-    if output_chunksize is None:
-        output_chunksize = geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
-    cs = {d: int(output_chunksize[d]) for d in dims}
-    ff = plan_kwargs.get("fusion_func")
-    if ff is not None and getattr(ff, "__name__", None) != "weighted_average_fusion":
-        raise EngineError("tile-partitioned fusion supports weighted_average_fusion (use fuse_partial for max_fusion)")
-    mine = sorted(i for i, o in enumerate(owners) if int(o) == rank)
-    if sorted(local_views) != mine:
-        raise EngineError(f"rank {rank} must hold exactly the views it owns: {mine}, got {sorted(local_views)}")
-    if engine is None:
-        engine = _CudaEngine(**plan_kwargs)
-    part = partition or TilePartition(view_bbs, params, owners, osp, cs, ws)
-    lviews = [local_views[i] for i in mine]
-    lparams = [params[i] for i in mine]
-    if out_dtype is None:
-        t = getattr(lviews[0], "tensor", None) if lviews else None
-        if t is not None:
-            from .fusion import _torch_to_np
+    def __init__(self, local_views, view_bbs, params, owners, output_stack_properties, output_chunksize=None,
+                 out_dtype=None, engine=None, partition=None, mode="halo", **plan_kwargs):
+        if mode not in ("halo", "partial"):
+            raise EngineError(f"unknown exchange mode {mode!r} (halo, partial)")
+        self.mode = mode
+        rank, ws = world()
+        self.rank, self.ws = rank, ws
+        osp = output_stack_properties
+        ndim = len(osp["shape"])
+        dims = geometry.spatial_dims(ndim)
+        if output_chunksize is None:
+            output_chunksize = geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
+        cs = {d: int(output_chunksize[d]) for d in dims}
+        ff = plan_kwargs.get("fusion_func")
+        if ff is not None and getattr(ff, "__name__", None) != "weighted_average_fusion":
+            raise EngineError("tile-partitioned fusion supports weighted_average_fusion (use fuse_partial for max_fusion)")
+        mine = sorted(i for i, o in enumerate(owners) if int(o) == rank)
+        if sorted(local_views) != mine:
+            raise EngineError(f"rank {rank} must hold exactly the views it owns: {mine}, got {sorted(local_views)}")
+        self.engine = engine = engine or _CudaEngine(**plan_kwargs)
+        self.partition = part = partition or TilePartition(view_bbs, params, owners, osp, cs, ws)
+        lviews = [local_views[i] for i in mine]
+        lparams = [params[i] for i in mine]
+        if out_dtype is None:
+            t = getattr(lviews[0], "tensor", None) if lviews else None
+            if t is not None:
+                from .fusion import _torch_to_np
 
-            out_dtype = _torch_to_np(t.dtype)
-        else:
-            out_dtype = np.asarray(lviews[0]["data"]).dtype if lviews else np.float32
-    np_dt = np.dtype(out_dtype)
-    slab_start, slab_shape = part.slab[rank]
-    out = engine.zeros(int(np.prod(slab_shape)), np_dt).reshape(slab_shape)
-    launches = 0
-    if lviews:
-        launches += engine.fuse_direct(lviews, lparams, osp, cs, part.direct[rank], out, slab_start)
-    # packed (num | den) windows: my own border boxes first, then one send buffer per owner
-    own = part.own_entries(rank)
-    own_off, n = [], 0
-    for e in own:
-        own_off.append(n)
-        n += 2 * e["nvox"]
-    acc = engine.zeros(n)
-    send, send_off = {}, {}
-    for dst in range(ws):
-        es = part.send_entries(rank, dst) if dst != rank else []
-        if es:
-            offs, m = [], 0
+                out_dtype = _torch_to_np(t.dtype)
+            else:
+                out_dtype = np.asarray(lviews[0]["data"]).dtype if lviews else np.float32
+        self.np_dtype = np.dtype(out_dtype)
+        self.out_start, slab_shape = part.slab[rank]
+        self.out = engine.zeros(int(np.prod(slab_shape)), self.np_dtype).reshape(slab_shape)
+        self.direct = engine.direct_plan(lviews, lparams, osp, cs, part.direct[rank], self.out, self.out_start)
+        self.own = own = part.own_entries(rank)
+        self.launches = 0
+        if mode == "halo":
+            self._init_halo(engine, part, local_views, mine, view_bbs, params, osp, cs)
+            return
+        # packed (num | den) windows: my own border boxes first, then one send buffer per owner
+        self.own_off, n = [], 0
+        for e in own:
+            self.own_off.append(n)
+            n += 2 * e["nvox"]
+        self.acc = engine.zeros(n)
+        self.send = {}
+        boxes = [(e["start"], e["shape"]) for e in own]
+        targets = [(self.acc, o, o + e["nvox"]) for e, o in zip(own, self.own_off)]
+        for dst in range(ws):
+            es = part.send_entries(rank, dst) if dst != rank else []
+            if not es:
+                continue
+            m = sum(2 * e["nvox"] for e in es)
+            buf = engine.zeros(m)
+            self.send[dst] = buf
+            o = 0
             for e in es:
-                offs.append(m)
-                m += 2 * e["nvox"]
-            send[dst], send_off[dst] = engine.zeros(m), (es, offs)
-    boxes, targets = [], []
-    for e, o in zip(own, own_off):
-        boxes.append((e["start"], e["shape"]))
-        targets.append((acc, o, o + e["nvox"]))
-    for dst, (es, offs) in send_off.items():
-        for e, o in zip(es, offs):
-            boxes.append((e["start"], e["shape"]))
-            targets.append((send[dst], o, o + e["nvox"]))
-    if lviews:
-        launches += engine.fuse_partial(lviews, lparams, osp, cs, boxes, targets)
-    # exchange: one message per (contributor -> owner) pair
-    recv = {}
-    for src in range(ws):
-        if src == rank:
-            continue
-        es = part.send_entries(src, rank)
-        if es:
-            recv[src] = (engine.zeros(sum(2 * e["nvox"] for e in es)), es)
-    sent_bytes = sum(4 * b.numel() for b in send.values())
-    recv_bytes = sum(4 * b.numel() for b, _ in recv.values())
-    if ws > 1 and (send or recv):
-        ops = [dist.P2POp(dist.isend, send[dst], dst) for dst in sorted(send)]
-        ops += [dist.P2POp(dist.irecv, recv[src][0], src) for src in sorted(recv)]
-        for w in dist.batch_isend_irecv(ops):
+                boxes.append((e["start"], e["shape"]))
+                targets.append((buf, o, o + e["nvox"]))
+                o += 2 * e["nvox"]
+        self.partial = engine.partial_plan(lviews, lparams, osp, cs, boxes, targets)
+        self.recv = {}
+        for src in range(ws):
+            es = part.send_entries(src, rank) if src != rank else []
+            if es:
+                self.recv[src] = (engine.zeros(sum(2 * e["nvox"] for e in es)), es)
+        # owner-side adds: runs of consecutive own boxes per source -> one flat add each
+        own_index = {e["chunk"]: k for k, e in enumerate(own)}
+        self.adds = []  # (src, acc offset, recv offset, length)
+        for src in sorted(self.recv):
+            es = self.recv[src][1]
+            k, pos = 0, 0
+            while k < len(es):
+                j = k
+                first = own_index[es[k]["chunk"]]
+                while j + 1 < len(es) and own_index[es[j + 1]["chunk"]] == first + (j + 1 - k):
+                    j += 1
+                length = sum(2 * e["nvox"] for e in es[k : j + 1])
+                self.adds.append((src, self.own_off[first], pos, length))
+                pos += length
+                k = j + 1
+        self.final_items = [(o, o + e["nvox"], e["start"], e["shape"]) for e, o in zip(own, self.own_off)]
+        self.sent_bytes = int(sum(4 * b.numel() for b in self.send.values()))
+        self.recv_bytes = int(sum(4 * b.numel() for b, _ in self.recv.values()))
+        self.launches = 0
+
+    # -- halo mode: raw windows of the foreign tiles travel, the owner fuses its border
+    #    boxes from local views + received windows with the ordinary fused kernel ------
+    def _init_halo(self, engine, part, local_views, mine, view_bbs, params, osp, cs):
+        import torch
+
+        rank, ws = self.rank, self.ws
+        self.partial = _Runner()
+        self.adds, self.final_items = [], []
+
+        def layout(items, itemsize):
+            offs, n = [], 0
+            for vi, lo, hi in items:
+                offs.append(n)
+                n += -(-int(np.prod(hi - lo + 1)) * itemsize // 16) * 16
+            return offs, n
+
+        self.send, self.packs = {}, []  # packs: (buffer window tensor, source window tensor)
+        for dst in range(ws):
+            items = part.halo_sends(rank, dst) if dst != rank else []
+            if not items:
+                continue
+            t0 = engine.view_tensor(local_views[items[0][0]])
+            offs, n = layout(items, t0.element_size())
+            buf = engine.zeros(n, np.uint8)
+            self.send[dst] = buf
+            for (vi, lo, hi), o in zip(items, offs):
+                t = engine.view_tensor(local_views[vi])
+                shape = tuple(int(v) for v in hi - lo + 1)
+                nb = int(np.prod(shape)) * t.element_size()
+                dstw = buf[o : o + nb].view(t.dtype).view(shape)
+                self.packs.append((dstw, t[tuple(slice(int(a), int(b) + 1) for a, b in zip(lo, hi))]))
+        self.recv = {}
+        border_views = [(i, local_views[i]) for i in mine]
+        dims = geometry.spatial_dims(len(osp["shape"]))
+        tdt = engine.view_tensor(local_views[mine[0]]).dtype if mine else torch.uint8
+        es = torch.empty(0, dtype=tdt).element_size()
+        for src in range(ws):
+            items = part.halo_sends(src, rank) if src != rank else []
+            if not items:
+                continue
+            offs, n = layout(items, es)
+            buf = engine.zeros(n, np.uint8)
+            self.recv[src] = (buf, items)
+            for (vi, lo, hi), o in zip(items, offs):
+                shape = tuple(int(v) for v in hi - lo + 1)
+                nb = int(np.prod(shape)) * es
+                win = buf[o : o + nb].view(tdt).view(shape)
+                bb = view_bbs[vi]
+                origin = {d: bb["origin"][d] + float(lo[k]) * bb["spacing"][d] for k, d in enumerate(dims)}
+                border_views.append((vi, engine.make_view(win, origin, bb["spacing"])))
+        border_views.sort(key=lambda kv: kv[0])  # global view order = the one-GPU summation order
+        boxes = [(e["start"], e["shape"]) for e in self.own]
+        self.border = engine.border_plan([v for _, v in border_views], [params[i] for i, _ in border_views],
+                                         [view_bbs[i] for i, _ in border_views], osp, cs, boxes, self.out, self.out_start)
+        self.sent_bytes = int(sum(b.numel() for b in self.send.values()))
+        self.recv_bytes = int(sum(b.numel() for b, _ in self.recv.values()))
+
+    def _run_halo(self):
+        import torch.distributed as dist
+
+        for dstw, src in self.packs:
+            dstw.copy_(src)
+        works = []
+        if self.ws > 1 and (self.send or self.recv):
+            ops = [dist.P2POp(dist.isend, self.send[dst], dst) for dst in sorted(self.send)]
+            ops += [dist.P2POp(dist.irecv, self.recv[src][0], src) for src in sorted(self.recv)]
+            works = dist.batch_isend_irecv(ops)
+        self.direct.run()  # overlaps the exchange
+        for w in works:
             w.wait()
-    # owner: add the neighbours' partial sums (runs of consecutive boxes -> one add each)
-    own_index = {e["chunk"]: k for k, e in enumerate(own)}
-    for src in sorted(recv):
-        buf, es = recv[src]
-        k, pos = 0, 0
-        while k < len(es):
-            j = k
-            first = own_index[es[k]["chunk"]]
-            while j + 1 < len(es) and own_index[es[j + 1]["chunk"]] == first + (j + 1 - k):
-                j += 1
-            length = sum(2 * e["nvox"] for e in es[k : j + 1])
-            acc[own_off[first] : own_off[first] + length] += buf[pos : pos + length]
-            pos += length
-            k = j + 1
-    launches += engine.finalize(acc, [(o, o + e["nvox"], e["start"], e["shape"]) for e, o in zip(own, own_off)],
-                                out, slab_start, np_dt)
-    info = {"partition": part, "sent_bytes": int(sent_bytes), "recv_bytes": int(recv_bytes),
-            "border_boxes": len(own), "launches": int(launches)}
-    return out, slab_start, info
+        self.border.run()
+        self.launches = len(self.packs) + self.direct.launches + self.border.launches
+        return self.out
+
+    def run(self):
+        import torch.distributed as dist
+
+        if self.mode == "halo":
+            return self._run_halo()
+        n = self.direct.launches + self.partial.launches
+        self.partial.run()
+        works = []
+        if self.ws > 1 and (self.send or self.recv):
+            ops = [dist.P2POp(dist.isend, self.send[dst], dst) for dst in sorted(self.send)]
+            ops += [dist.P2POp(dist.irecv, self.recv[src][0], src) for src in sorted(self.recv)]
+            works = dist.batch_isend_irecv(ops)
+        self.direct.run()  # overlaps the exchange
+        for w in works:
+            w.wait()
+        for src, a_off, r_off, length in self.adds:
+            self.acc[a_off : a_off + length] += self.recv[src][0][r_off : r_off + length]
+        n += len(self.adds)
+        n += self.engine.finalize(self.acc, self.final_items, self.out, self.out_start, self.np_dtype)
+        self.launches = n
+        return self.out
+
+    def info(self):
+        return {"partition": self.partition, "mode": self.mode, "sent_bytes": self.sent_bytes,
+                "recv_bytes": self.recv_bytes, "border_boxes": len(self.own), "launches": int(self.launches)}
+
+    def close(self):
+        self.direct.close()
+        self.partial.close()
+        if self.mode == "halo":
+            self.border.close()
+
+
+def fuse_tile_partitioned(local_views, view_bbs, params, owners, output_stack_properties, output_chunksize=None,
+                          out_dtype=None, engine=None, partition=None, mode="halo", **plan_kwargs):
+    """One-shot ``TilePartitionedFuser``.  Returns ``(out, out_start, info)``: this rank's
+    slab of the fused stack (covering the chunks it owns), the stack index of its first
+    voxel and ``info`` = {"partition", "sent_bytes", "recv_bytes", "border_boxes", "launches"}."""
+    f = TilePartitionedFuser(local_views, view_bbs, params, owners, output_stack_properties, output_chunksize,
+                             out_dtype, engine, partition, mode, **plan_kwargs)
+    try:
+        out = f.run()
+        return out, f.out_start, f.info()
+    finally:
+        f.close()
 
 
 def fuse_partial(local_views, local_params, output_stack_properties, output_chunksize=None, fusion_func=None,

@@ -158,7 +158,10 @@ def _view_fields(view):
             c = np.asarray(view.coords[d].values if hasattr(view.coords[d], "values") else view.coords[d])
             origin[d] = float(c[0])
             spacing[d] = float(c[1] - c[0]) if len(c) > 1 else 1.0
-        return np.asarray(view.data), origin, spacing
+        data = view.data
+        if not (hasattr(data, "__cuda_array_interface__") or type(data).__module__.startswith("torch")):
+            data = np.asarray(data)
+        return data, origin, spacing
     raise EngineError(f"cannot interpret view of type {type(view)}")
 
 
@@ -171,6 +174,10 @@ def to_device_view(view, device="cuda", non_blocking=True):
     data, origin, spacing = _view_fields(view)
     if isinstance(data, torch.Tensor):
         t = data.to(device, non_blocking=non_blocking)
+    elif hasattr(data, "__cuda_array_interface__"):
+        # device arrays of another library (the CuPy arrays of fuse(backend="cupy"),
+        # fusion/_core.py:1579-1587): zero-copy
+        t = torch.as_tensor(data, device=device)
     else:
         data = np.ascontiguousarray(data)
         _lib.mvs_dtype(data.dtype)

@@ -141,7 +141,7 @@ class _OracleEngine:
     fusion computed with the oracle (numpy / scipy) on CPU tensors."""
 
     def zeros(self, n, np_dtype=np.float32):
-        return torch.zeros(n, dtype={np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.uint16}[np.dtype(np_dtype)])
+        return torch.zeros(n, dtype={np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.uint16, np.dtype(np.uint8): torch.uint8}[np.dtype(np_dtype)])
 
     @staticmethod
     def _props(osp, start, shape):
@@ -149,17 +149,40 @@ class _OracleEngine:
         return {"origin": {d: osp["origin"][d] + a * osp["spacing"][d] for d, a in zip(dims, start)},
                 "spacing": dict(osp["spacing"]), "shape": {d: int(n) for d, n in zip(dims, shape)}}
 
-    def fuse_direct(self, views, params, osp, chunksize, boxes, out, out_start):
+    class _Run:
+        launches = 1
+
+        def __init__(self, fn):
+            self.run = fn
+
+        def close(self):
+            pass
+
+    def direct_plan(self, views, params, osp, chunksize, boxes, out, out_start):
+        return self._Run(lambda: self._direct(views, params, osp, boxes, out, out_start))
+
+    def border_plan(self, views, params, full_bbs, osp, chunksize, boxes, out, out_start):
+        return self._Run(lambda: self._direct(views, params, osp, boxes, out, out_start, full_bbs))
+
+    def view_tensor(self, view):
+        return torch.from_numpy(view["data"])
+
+    def make_view(self, tensor, origin, spacing):
+        return {"data": tensor.numpy(), "origin": dict(origin), "spacing": dict(spacing)}
+
+    def partial_plan(self, views, params, osp, chunksize, boxes, targets):
+        return self._Run(lambda: self._partial(views, params, osp, boxes, targets))
+
+    def _direct(self, views, params, osp, boxes, out, out_start, full_bbs=None):
         from oracle import fusion as of
 
-        bbs = [of.view_bb(v) for v in views]
+        bbs = full_bbs or [of.view_bb(v) for v in views]
         for start, shape in boxes:
             res = of.fuse_np(views, params, self._props(osp, start, shape), full_view_bbs=bbs)
             sl = tuple(slice(a - o, a - o + n) for a, o, n in zip(start, out_start, shape))
             out[sl] = torch.from_numpy(res.astype(np.float32))
-        return len(boxes)
 
-    def fuse_partial(self, views, params, osp, chunksize, boxes, targets):
+    def _partial(self, views, params, osp, boxes, targets):
         from oracle import fusion as of
 
         for (start, shape), (buf, o_num, o_den) in zip(boxes, targets):
@@ -174,7 +197,6 @@ class _OracleEngine:
             n = int(np.prod(shape))
             buf[o_num : o_num + n] = torch.from_numpy(num.reshape(-1))
             buf[o_den : o_den + n] = torch.from_numpy(den.reshape(-1))
-        return len(boxes)
 
     def finalize(self, buf, items, out, out_start, np_dtype):
         for o_num, o_den, start, shape in items:
@@ -198,9 +220,24 @@ def _tp_worker(rank, ws, port, q):
         osp = of.calc_stack_properties(bbs, params, views[0]["spacing"])
         owners = [0, 0, 1, 0, 1, 1]  # ragged split: corner chunks draw from both ranks
         local = {i: views[i] for i in range(len(views)) if owners[i] == rank}
-        out, start, info = D.fuse_tile_partitioned(local, bbs, params, owners, osp, {"y": 32, "x": 32},
-                                                   out_dtype=np.float32, engine=_OracleEngine())
         ref, _ = of.fuse(views, params)
+        # halo mode: raw windows of the foreign tiles travel and the owner fuses its border boxes
+        # from local views + received windows
+        out_h, start_h, info_h = D.fuse_tile_partitioned(local, bbs, params, owners, osp, {"y": 32, "x": 32},
+                                                         out_dtype=np.float32, engine=_OracleEngine(), mode="halo")
+        part_h = info_h["partition"]
+        got_h = np.zeros(ref.shape, dtype=np.float32)
+        got_h[tuple(slice(a, a + n) for a, n in zip(start_h, out_h.shape))] = out_h.numpy()
+        mask_h = np.zeros(ref.shape, dtype=bool)
+        for ci, (cs_, cn_) in enumerate(part_h.grid):
+            if part_h.owner_of[ci] == rank:
+                mask_h[tuple(slice(a, a + n) for a, n in zip(cs_, cn_))] = True
+        # (numpy's reduction order depends on how many views a box / chunk stacks: 1 ulp)
+        halo_ok = bool(np.abs(got_h - ref)[mask_h].max() <= 1e-6 * np.abs(ref).max()) and info_h["sent_bytes"] > 0
+        halo_ok = halo_ok and info_h["sent_bytes"] == sum(
+            -(-int(np.prod(hi - lo + 1)) * 4 // 16) * 16 for (o, vi), (lo, hi) in part_h.windows.items() if owners[vi] == rank)
+        out, start, info = D.fuse_tile_partitioned(local, bbs, params, owners, osp, {"y": 32, "x": 32},
+                                                   out_dtype=np.float32, engine=_OracleEngine(), mode="partial")
         sl = tuple(slice(a, a + n) for a, n in zip(start, out.shape))
         part = info["partition"]
         # compare only the chunks this rank owns inside its slab's bounding box
@@ -212,7 +249,7 @@ def _tp_worker(rank, ws, port, q):
         got[sl] = out.numpy()
         err = np.abs(got - ref)[mask].max() if mask.any() else 0.0
         tol = 1e-4 * np.abs(ref).max()
-        ok = bool(err <= tol) and info["sent_bytes"] == sum(8 * e["nvox"] for e in part.entries if rank in e["contrib"])
+        ok = halo_ok and bool(err <= tol) and info["sent_bytes"] == sum(8 * e["nvox"] for e in part.entries if rank in e["contrib"])
         ok = ok and info["recv_bytes"] == sum(8 * e["nvox"] * len(e["contrib"]) for e in part.own_entries(rank))
         q.put((rank, ok, float(err), int(mask.sum()), info["sent_bytes"]))
     finally:

@@ -65,12 +65,14 @@ def test_tile_partition_boxes_on_one_gpu_match_full_fusion():
         for r in range(ws):
             lv = [views[i] for i in range(len(views)) if owners[i] == r]
             lp = [true[i] for i in range(len(views)) if owners[i] == r]
-            eng.fuse_direct(lv, lp, osp, cs, part.direct[r], out, zero)
+            r_ = eng.direct_plan(lv, lp, osp, cs, part.direct[r], out, zero)
+            r_.run(); r_.close()
             # every entry r takes part in, accumulated into one buffer per entry
             es = [e for e in part.entries if e["owner"] == r or r in e["contrib"]]
             bufs = [torch.zeros(2 * e["nvox"], device="cuda") for e in es]
-            eng.fuse_partial(lv, lp, osp, cs, [(e["start"], e["shape"]) for e in es],
-                             [(b, 0, e["nvox"]) for b, e in zip(bufs, es)])
+            r_ = eng.partial_plan(lv, lp, osp, cs, [(e["start"], e["shape"]) for e in es],
+                                  [(b, 0, e["nvox"]) for b, e in zip(bufs, es)])
+            r_.run(); r_.close()
             for e, b in zip(es, bufs):
                 accs[e["chunk"]] = accs.get(e["chunk"], 0) + b
         for e in part.entries:
