@@ -40,6 +40,7 @@ constexpr int kMaxXforms = 1024;  // per chunk
 
 }  // namespace mvs
 #include "fuse_stencil.cuh"
+#include "fuse_stencil3.cuh"
 namespace mvs {
 
 struct ViewEval {
@@ -426,6 +427,7 @@ struct mvs_fuse_plan {
   int n_chunks_total = 0;
   int64_t run_st[2] = {0, 0}, run_gen[2] = {0, 0};  // block ranges of the current run
   int stencil_dtype = MVS_F32;
+  bool s3 = false;  // 3-D chunks run the z-marching column kernel (fuse_stencil3.cuh)
   int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
   float* d_tables = nullptr;
@@ -457,19 +459,21 @@ static PFN_tensorMapEncodeTiled get_tensor_map_encoder() {
   return fn;
 }
 
-// TMA descriptor of one view window: box = one stencil block footprint.
-static bool make_tensor_map(const mvs_view_xform& X, int ndim, CUtensorMap* out) {
+// TMA descriptor of one view window: box = one stencil block footprint (bz == 0), or
+// the z-marching kernel's boxes of bz planes (fuse_stencil3.cuh).
+static bool make_tensor_map(const mvs_view_xform& X, int ndim, CUtensorMap* out, int bz = 0) {
   PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
   if (!enc) return false;
   const cuuint64_t es = (cuuint64_t)dtype_size(X.dtype);
   const CUtensorMapDataType dt = X.dtype == MVS_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : X.dtype == MVS_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
                                                       : CU_TENSOR_MAP_DATA_TYPE_UINT8;
-  const cuuint32_t bw = (cuuint32_t)((ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX) + 16 / es);
+  const cuuint32_t bw = (cuuint32_t)((bz ? S3::BX : (ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX)) + 16 / es);
   cuuint64_t gdim[3] = {(cuuint64_t)X.shape[2], (cuuint64_t)X.shape[1], (cuuint64_t)X.shape[0]};
   cuuint64_t gstr[2] = {(cuuint64_t)X.stride[1] * es, (cuuint64_t)X.stride[0] * es};
   cuuint32_t box[3] = {bw, (cuuint32_t)(ndim == 3 ? SBlock<3>::ROWS_Y : SBlock<2>::ROWS_Y),
                        (cuuint32_t)(ndim == 3 ? SBlock<3>::ROWS_Z : 1)};
+  if (bz) { box[1] = S3::ROWS; box[2] = (cuuint32_t)bz; }
   cuuint32_t estr[3] = {1, 1, 1};
   // a rank-2 map needs a sane stride even for single-row windows
   if (X.shape[1] == 1) gstr[0] = ((gdim[0] * es + 15) / 16) * 16;
@@ -539,8 +543,34 @@ static cudaError_t launch_stencil(const mvs_fuse_plan* p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <typename T, int MODE, bool PARTIAL>
+static cudaError_t launch_stencil3(const mvs_fuse_plan* p, cudaStream_t st) {
+  const int64_t nb = p->run_st[1] - p->run_st[0];
+  auto kern = fuse_stencil3_kernel<T, MODE, PARTIAL>;
+  const size_t smem = stencil3_smem_bytes<T>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
+  const int grid = (int)std::min<int64_t>(nb, (int64_t)p->sm_count * 2);  // persistent, 2 CTAs per SM
+  kern<<<grid, S3::THREADS, smem, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st, p->d_xforms,
+                                        p->d_sxf, p->d_tables, p->d_tmaps, p->d_recs, p->d_counter,
+                                        p->run_st[0], p->run_st[1]);
+  return cudaGetLastError();
+}
+
 template <int NDIM, typename T>
 static cudaError_t dispatch_stencil_mode(const mvs_fuse_plan* p, cudaStream_t st) {
+  if (NDIM == 3 && p->s3) {
+    switch (p->mode) {
+      case MVS_FUSE_WAVG:
+        return p->partial ? launch_stencil3<T, MVS_FUSE_WAVG, true>(p, st)
+                          : launch_stencil3<T, MVS_FUSE_WAVG, false>(p, st);
+      case MVS_FUSE_MAX:
+        return launch_stencil3<T, MVS_FUSE_MAX, false>(p, st);
+      default:
+        return launch_stencil3<T, MVS_FUSE_MEAN, false>(p, st);
+    }
+  }
   switch (p->mode) {
     case MVS_FUSE_WAVG:
       return p->partial ? launch_stencil<NDIM, T, MVS_FUSE_WAVG, true>(p, st)
@@ -647,6 +677,10 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
 
   // classify pairings / chunks: translation stencil path vs general affine path
   const bool allow_stencil = getenv("MVS_FUSE_GENERIC") == nullptr;
+  // 3-D: the z-marching column kernel (fuse_stencil3.cuh) is an experiment that measured
+  // SLOWER than the block kernel on the B200 (C3: 12.0 vs 7.2 ms, profiles/r02_stencil3_*):
+  // opt-in with MVS_STENCIL3=1
+  const bool s3 = ndim == 3 && getenv("MVS_STENCIL3") != nullptr;
   const int stencil_dtype = n_xforms ? xforms[0].dtype : MVS_F32;
   std::vector<StencilXform> sxf(n_xforms);
   std::vector<char> xf_ok(n_xforms, 0);
@@ -667,10 +701,21 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
       }
       if (found < 0) {
         CUtensorMap m;
-        if (!make_tensor_map(xforms[i], ndim, &m)) { xf_ok[i] = 0; continue; }
-        tmaps.push_back(m);
+        if (s3) {
+          // two boxes per view: the step's 4 new planes and the single plane below them
+          CUtensorMap m1;
+          if (!make_tensor_map(xforms[i], ndim, &m, S3::PZ) || !make_tensor_map(xforms[i], ndim, &m1, 1)) {
+            xf_ok[i] = 0;
+            continue;
+          }
+          tmaps.push_back(m);
+          tmaps.push_back(m1);
+        } else {
+          if (!make_tensor_map(xforms[i], ndim, &m)) { xf_ok[i] = 0; continue; }
+          tmaps.push_back(m);
+        }
         owner.push_back(i);
-        found = (int)tmaps.size() - 1;
+        found = (int)owner.size() - 1;
       }
       sxf[i].tmap = found;
     }
@@ -683,7 +728,9 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
     bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
     if (ok) {
-      const int BX = ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX, BY = ndim == 3 ? SBlock<3>::BY : SBlock<2>::BY, BZ = ndim == 3 ? SBlock<3>::BZ : 1;
+      const int BX = s3 ? S3::BX : (ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX);
+      const int BY = s3 ? S3::BY : (ndim == 3 ? SBlock<3>::BY : SBlock<2>::BY);
+      const int BZ = s3 ? std::max(ck.shape[0], 1) : (ndim == 3 ? SBlock<3>::BZ : 1);  // s3: one unit per column
       const int64_t nb = (int64_t)((ck.shape[2] + BX - 1) / BX) * ((ck.shape[1] + BY - 1) / BY) *
                          ((ck.shape[0] + BZ - 1) / BZ);
       ch_st.push_back(ck);
@@ -704,6 +751,7 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   p->ndim = ndim; p->order = order; p->mode = fusion_mode; p->partial = partial;
   p->total_blocks = bs_gen.back(); p->total_blocks_st = bs_st.back();
   p->stencil_dtype = stencil_dtype;
+  p->s3 = s3;
   p->prefix_st = prefix_st; p->h_bs_st = bs_st; p->h_bs_gen = bs_gen; p->n_chunks_total = n_chunks;
   {
     int dev = 0;
@@ -755,7 +803,10 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
       return fail(e, "allocate block counter");
     const float* tabs = fusion_mode == MVS_FUSE_WAVG ? p->d_tables : nullptr;
     const unsigned grid = (unsigned)((p->total_blocks_st + 7) / 8);
-    if (ndim == 3)
+    if (s3)
+      stencil3_classify_kernel<<<grid, 256, 0, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
+                                                     p->d_xforms, p->d_sxf, tabs, p->d_recs);
+    else if (ndim == 3)
       stencil_classify_kernel<3><<<grid, 256, 0, st>>>(p->d_chunks_st, p->d_block_start_st, p->n_chunks_st,
                                                      p->d_xforms, p->d_sxf, tabs, p->d_recs);
     else

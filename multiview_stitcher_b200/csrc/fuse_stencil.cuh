@@ -177,6 +177,37 @@ __device__ __forceinline__ unsigned to_u8(float v) {
   return (unsigned)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
+// float32 -> integer like np.nan_to_num(x).astype(dtype) for in-range values, in ONE
+// instruction: PTX float-to-integer conversion truncates (rzi), maps NaN to 0 and saturates
+__device__ __forceinline__ unsigned cvt_u16_sat(float v) {
+  unsigned short r;
+  asm("cvt.rzi.u16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned cvt_u8_sat(float v) {
+  unsigned r;
+  asm("{\n\t.reg .u8 t;\n\tcvt.rzi.u8.f32 t, %1;\n\tcvt.u32.u8 %0, t;\n\t}" : "=r"(r) : "f"(v));
+  return r;
+}
+// (cos((1 - x) pi) + 1) / 2 == sin^2(pi x / 2) for x in [0, 1): the square of an odd
+// near-minimax polynomial of sin(pi/2 t) (4e-7 relative in float32), i.e. WITHOUT the
+// cancellation of the reference's float32 (cos + 1) / 2 near x = 0, whose own rounding noise
+// there (6e-8 absolute) is larger than this error.  Callers use it where several views are
+// blended (tolerance 1e-4 relative) and fall back to the reference's formula right at a view
+// border (x < 0.02), where that formula underflows to an exact 0 and the view is ignored.
+__device__ __forceinline__ float cosine_ramp(float x) {
+  const float t = fminf(fmaxf(x, 0.f), 1.f);
+  const float t2 = t * t;
+  float p = -3.431829309e-6f;
+  p = fmaf(p, t2, 1.602546911e-4f);
+  p = fmaf(p, t2, -4.681657796e-3f);
+  p = fmaf(p, t2, 7.969260372e-2f);
+  p = fmaf(p, t2, -6.459640956e-1f);
+  p = fmaf(p, t2, 1.570796327f);
+  const float sn = p * t;
+  return sn * sn;
+}
+
 // stores 4 consecutive outputs of one row; `nvalid` = how many lie inside the chunk
 __device__ __forceinline__ void store_row4(void* out, int dtype, int64_t o, const float* v,
                                            int nvalid) {
@@ -314,11 +345,10 @@ template <int NDIM, typename OT, bool CHECK_NAN>
 __device__ __forceinline__ void store_column(OT* __restrict__ p, int64_t sy, int64_t sz, int ylim,
                                              int zlim, const float* v) {
   auto conv = [](float x) -> OT {
-    if (CHECK_NAN) x = fix_nan(x);
-    if (sizeof(OT) == 4) return (OT)x;
-    int q = __float2int_rz(x);
-    const int hi = sizeof(OT) == 2 ? 65535 : 255;
-    return (OT)(q < 0 ? 0 : (q > hi ? hi : q));
+    if (sizeof(OT) == 4) return (OT)(CHECK_NAN ? fix_nan(x) : x);
+    // one saturating convert: truncation toward zero, NaN -> 0, clamped to the type's range
+    if (sizeof(OT) == 2) return (OT)cvt_u16_sat(x);
+    return (OT)cvt_u8_sat(x);
   };
   if (NDIM == 2) {
     constexpr int NR = SBlock<2>::OUTS;
@@ -697,9 +727,13 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
               }
             }
             if (__any_sync(0xffffffffu, valid && w < 1.0f)) {
-              // weights.py:502-507 cosine ramp (float32), only near view borders
-              const float a = __fmul_rn(__fsub_rn(1.0f, w), 3.14159274101257324f);
-              const float cw = __fmul_rn(__fadd_rn(cosf(a), 1.0f), 0.5f);
+              // weights.py:502-507 cosine ramp, only near view borders
+              float cw = cosine_ramp(w);
+              if (__any_sync(0xffffffffu, valid && w < 0.02f)) {
+                const float a = __fmul_rn(__fsub_rn(1.0f, w), 3.14159274101257324f);
+                const float ce = __fmul_rn(__fadd_rn(cosf(a), 1.0f), 0.5f);
+                cw = w < 0.02f ? ce : cw;
+              }
               w = w < 1.0f ? cw : w;
             }
             w = fminf(fmaxf(w, 0.0f), 1.0f);
