@@ -81,16 +81,21 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// suspend-time hint of try_wait: a waiting warp sleeps in hardware instead of spinning through
+// issue slots the working warps need (the kernels are issue-bound)
+#ifndef MVS_MBAR_SUSPEND_NS
+#define MVS_MBAR_SUSPEND_NS 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t done = 0;
   unsigned spins = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MVS_MBAR_SUSPEND_NS)
         : "memory");
     if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU on a lost copy
   }
@@ -113,6 +118,26 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+// staged element -> float.  Integer samples avoid the quarter-rate I2F pipe: the value is
+// OR-ed into the mantissa of 2^23 and 2^23 is subtracted (exact for < 2^23; LOP3 + FADD)
+#ifndef MVS_MAGIC_CVT
+#define MVS_MAGIC_CVT 0  // measured: no difference (the kernels are not I2F-bound)
+#endif
+__device__ __forceinline__ float tofl(float v) { return v; }
+__device__ __forceinline__ float tofl(unsigned short v) {
+#if MVS_MAGIC_CVT
+  return __uint_as_float(0x4B000000u | (unsigned)v) - 8388608.0f;
+#else
+  return (float)v;
+#endif
+}
+__device__ __forceinline__ float tofl(unsigned char v) {
+#if MVS_MAGIC_CVT
+  return __uint_as_float(0x4B000000u | (unsigned)v) - 8388608.0f;
+#else
+  return (float)v;
+#endif
+}
 __device__ __forceinline__ float lerp_s(float a, float b, float t) {
   return fmaf(t, b, fmaf(-t, a, a));
 }
@@ -387,9 +412,15 @@ struct alignas(128) StencilSlot {
 
 constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 
+#ifndef MVS_NS3
+#define MVS_NS3 3
+#endif
+#ifndef MVS_STATIC_SCHED
+#define MVS_STATIC_SCHED 0  // measured: static round-robin loses L2 locality (C5 row 35 -> 70 ms)
+#endif
 template <int NDIM, typename T>
 struct StencilStages {
-  static constexpr int value = NDIM == 3 ? 3 : 4;
+  static constexpr int value = NDIM == 3 ? MVS_NS3 : 4;
 };
 
 template <int NDIM, typename T, int MODE, bool PARTIAL>
@@ -430,12 +461,24 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     // so CTAs stay busy whatever the mix of single- and multi-view blocks, and
     // concurrently processed blocks are neighbours (halo rows hit in L2)
     const int4* recs4 = reinterpret_cast<const int4*>(recs);
+#if MVS_STATIC_SCHED
+    // static round-robin schedule: block ids are known ahead, so the NEXT block's record is
+    // requested while the current block is being issued (the dependent chain atomic ->
+    // record -> view constants otherwise costs the lone producer warp ~2 us per block)
+    int64_t bid = block_begin + blockIdx.x, bid_n = 0;
+    int4 ra = make_int4(0, 0, 0, 0), rb = ra, ra_n = ra, rb_n = ra;
+    if (bid < nblocks) { ra = __ldg(recs4 + 2 * bid); rb = __ldg(recs4 + 2 * bid + 1); }
+    for (; bid < nblocks; bid = bid_n, ra = ra_n, rb = rb_n) {
+      bid_n = bid + gridDim.x;
+      if (bid_n < nblocks) { ra_n = __ldg(recs4 + 2 * bid_n); rb_n = __ldg(recs4 + 2 * bid_n + 1); }
+#else
     for (;;) {
       unsigned long long nb = 0;
       if (lane == 0) nb = atomicAdd(next_block, 1ull);
       const int64_t bid = block_begin + (int64_t)__shfl_sync(0xffffffffu, nb, 0);
       if (bid >= nblocks) break;
       const int4 ra = __ldg(recs4 + 2 * bid), rb = __ldg(recs4 + 2 * bid + 1);
+#endif
       const int ci = ra.x, first = ra.y, x0 = ra.z, y0 = ra.w, z0 = rb.x;
       const unsigned active = (unsigned)rb.y;
       const unsigned long long codes = (unsigned long long)(unsigned)rb.z | ((unsigned long long)(unsigned)rb.w << 32);
@@ -613,11 +656,11 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       float val[B::OUTS];
       if (NDIM == 2) {
         const T* p = sl.stage + yoff * BW;
-        float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
+        float hprev = lerp_s(tofl(p[c0]), tofl(p[c1]), tx);
 #pragma unroll
         for (int k = 0; k < B::OUTS; ++k) {
           p += BW;
-          const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
+          const float hn = lerp_s(tofl(p[c0]), tofl(p[c1]), tx);
           val[k] = dy ? lerp_s(hprev, hn, ty) : hprev;
           hprev = hn;
         }
@@ -627,11 +670,11 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
 #pragma unroll
         for (int pz = 0; pz < 2; ++pz) {
           const T* p = sl.stage + ((zpl + pz) * B::ROWS_Y + yoff) * BW;
-          float hprev = lerp_s((float)p[c0], (float)p[c1], tx);
+          float hprev = lerp_s(tofl(p[c0]), tofl(p[c1]), tx);
 #pragma unroll
           for (int y = 0; y < 8; ++y) {
             p += BW;
-            const float hn = lerp_s((float)p[c0], (float)p[c1], tx);
+            const float hn = lerp_s(tofl(p[c0]), tofl(p[c1]), tx);
             const float g = dy ? lerp_s(hprev, hn, ty) : hprev;
             if (pz == 0) g0[y] = g;
             else val[y] = dz ? lerp_s(g0[y], g, tz) : g0[y];
