@@ -715,7 +715,7 @@ def bench_c4(cx, args):
     b = plan.algorithmic_bytes()
     rec = {"workload": "C4: 4 views (z512,y1024,x1024) uint16, spacing z=2, rotations about y + tilt + 0.5% scale; "
                        f"output {[osp['shape'][d] for d in 'zyx']}",
-           "fuse_blend": {"ms": ms, "Mvoxel_per_s": vox / ms / 1e3, "roofline": _roof(b, ms, "fuse_kernel<3,1,WAVG> (general affine)")},
+           "fuse_blend": {"ms": ms, "Mvoxel_per_s": vox / ms / 1e3, "roofline": _roof(b, ms, "fuse_affine_kernel<3,1,WAVG> (general affine, TMA-staged bricks)")},
            "gpu_launches": plan.launches_per_run * 3}
     plan.close()
 

@@ -194,6 +194,10 @@ __device__ bool view_touches_box(const mvs_view_xform& X, const double lo[3],
   return true;
 }
 
+}  // namespace mvs
+#include "fuse_affine.cuh"
+namespace mvs {
+
 template <int NDIM, int ORDER, int MODE, bool PARTIAL>
 __global__ void __launch_bounds__(kThreads)
 fuse_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restrict__ block_start,
@@ -427,6 +431,17 @@ struct mvs_fuse_plan {
   int n_chunks_total = 0;
   int64_t run_st[2] = {0, 0}, run_gen[2] = {0, 0};  // block ranges of the current run
   int stencil_dtype = MVS_F32;
+  // general affine with TMA-staged bricks (fuse_affine.cuh)
+  mvs_chunk* d_chunks_aff = nullptr;
+  int64_t* d_block_start_aff = nullptr;
+  int n_chunks_aff = 0;
+  int64_t total_blocks_aff = 0;
+  mvs::AffInfo* d_ainfo = nullptr;
+  CUtensorMap* d_tmaps_aff = nullptr;
+  size_t aff_smem = 0;
+  std::vector<int> prefix_aff;
+  std::vector<int64_t> h_bs_aff;
+  int64_t run_aff[2] = {0, 0};
   bool s3 = false;  // 3-D chunks run the z-marching column kernel (fuse_stencil3.cuh)
   int sm_count = 148;
   mvs_view_xform* d_xforms = nullptr;
@@ -482,6 +497,55 @@ static bool make_tensor_map(const mvs_view_xform& X, int ndim, CUtensorMap* out,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// TMA descriptor of a view with an explicit box (z, y, x elements): affine bricks.
+static bool make_tensor_map_box(const mvs_view_xform& X, int ndim, const int box_zyx[3], CUtensorMap* out) {
+  PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t es = (cuuint64_t)dtype_size(X.dtype);
+  const CUtensorMapDataType dt = X.dtype == MVS_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : X.dtype == MVS_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                                      : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  cuuint64_t gdim[3] = {(cuuint64_t)X.shape[2], (cuuint64_t)X.shape[1], (cuuint64_t)X.shape[0]};
+  cuuint64_t gstr[2] = {(cuuint64_t)X.stride[1] * es, (cuuint64_t)X.stride[0] * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_zyx[2], (cuuint32_t)box_zyx[1], (cuuint32_t)box_zyx[0]};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (X.shape[1] == 1) gstr[0] = ((gdim[0] * es + 15) / 16) * 16;
+  if (ndim == 3 && X.shape[0] == 1) gstr[1] = gstr[0] * gdim[1];
+  CUresult r = enc(out, dt, (cuuint32_t)ndim, const_cast<void*>(X.data), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// Brick extent of pairing X for the affine path's output block; false when the view cannot
+// be staged (alignment, brick too large for shared memory).
+static bool affine_box(const mvs_view_xform& X, int ndim, int box_zyx[3]) {
+  const int64_t es = (int64_t)dtype_size(X.dtype);
+  if (X.stride[2] != 1 || ((uintptr_t)X.data) % 16 || (X.stride[1] * es) % 16) return false;
+  if (ndim == 3 && (X.stride[0] * es) % 16) return false;
+  const int A = (int)(16 / es);
+  const int bz = ndim == 3 ? ABlock<3>::BZ : 1, by = ndim == 3 ? ABlock<3>::BY : ABlock<2>::BY,
+            bx = ndim == 3 ? ABlock<3>::BX : ABlock<2>::BX;
+  int64_t bytes = es;
+  for (int d = 0; d < 3; ++d) {
+    if (ndim == 2 && d == 0) { box_zyx[0] = 1; continue; }
+    double ext = fabs(X.matrix[3 * d + 1]) * (by - 1) + fabs(X.matrix[3 * d + 2]) * (bx - 1);
+    if (ndim == 3) ext += fabs(X.matrix[3 * d + 0]) * (bz - 1);
+    if (!(ext < 1000.0)) return false;
+    int n = (int)ceil(ext) + 4;  // -1 margin below, second tap, rounding slack
+    if (d == 2) {
+      n = ((n + A - 1 + A - 1) / A) * A;  // + alignment slack, whole 16-byte units
+      if (((n / A) & 1) == 0) n += A;     // odd number of 16-byte units per row ...
+    } else if (d == 1 && (n & 1) == 0) {
+      ++n;                                // ... and an odd row count: lanes that step along y or z
+    }                                     // of the brick (rotated views) spread over 8 banks, not 4
+    if (n > 256) return false;
+    box_zyx[d] = n;
+    bytes *= n;
+  }
+  return bytes <= kAffMaxBrickBytes;
 }
 
 // Fills S and returns true when pairing X is a pure translation that the
@@ -603,6 +667,33 @@ static cudaError_t launch_fuse(const mvs_fuse_plan* p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <int NDIM, int ORDER, int MODE, bool PARTIAL>
+static cudaError_t launch_affine(const mvs_fuse_plan* p, cudaStream_t st) {
+  const int64_t nb = p->run_aff[1] - p->run_aff[0];
+  const int64_t gx = std::min<int64_t>(nb, 1 << 30);
+  const int64_t gy = (nb + gx - 1) / gx;
+  auto kern = fuse_affine_kernel<NDIM, ORDER, MODE, PARTIAL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * p->aff_smem));
+  if (e != cudaSuccess) return e;
+  kern<<<dim3((unsigned)gx, (unsigned)gy), ABlock<NDIM>::THREADS, 2 * p->aff_smem, st>>>(
+      p->d_chunks_aff, p->d_block_start_aff, p->n_chunks_aff, p->d_xforms, p->d_ainfo, p->d_tables,
+      p->d_tmaps_aff, p->run_aff[0], p->run_aff[1], (int)p->aff_smem);
+  return cudaGetLastError();
+}
+
+template <int NDIM, int ORDER>
+static cudaError_t dispatch_affine(const mvs_fuse_plan* p, cudaStream_t st) {
+  switch (p->mode) {
+    case MVS_FUSE_WAVG:
+      return p->partial ? launch_affine<NDIM, ORDER, MVS_FUSE_WAVG, true>(p, st)
+                        : launch_affine<NDIM, ORDER, MVS_FUSE_WAVG, false>(p, st);
+    case MVS_FUSE_MAX:
+      return launch_affine<NDIM, ORDER, MVS_FUSE_MAX, false>(p, st);
+    default:
+      return launch_affine<NDIM, ORDER, MVS_FUSE_MEAN, false>(p, st);
+  }
+}
+
 template <int NDIM, int ORDER>
 static cudaError_t dispatch_mode(const mvs_fuse_plan* p, cudaStream_t st) {
   switch (p->mode) {
@@ -720,13 +811,58 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
       sxf[i].tmap = found;
     }
   }
-  std::vector<mvs_chunk> ch_st, ch_gen;
-  std::vector<int64_t> bs_st(1, 0), bs_gen(1, 0);
-  std::vector<int> prefix_st(n_chunks + 1, 0);
+  // affine pairings: brick extents, tensor maps (one per distinct view + box), float32 matrices
+  const bool allow_affine = getenv("MVS_FUSE_GATHER") == nullptr;
+  std::vector<AffInfo> ainfo(n_xforms);
+  std::vector<char> af_ok(n_xforms, 0);
+  std::vector<CUtensorMap> tmaps_aff;
+  {
+    struct Key { const void* data; int32_t shape[3]; int64_t stride[3]; int dtype; int box[3]; };
+    std::vector<Key> keys;
+    for (int i = 0; i < n_xforms; ++i) {
+      AffInfo& a = ainfo[i];
+      memset(&a, 0, sizeof(a));
+      a.tmap = -1;
+      for (int q = 0; q < 9; ++q) { a.m[q] = (float)xforms[i].matrix[q]; a.wm[q] = (float)xforms[i].wmatrix[q]; }
+      if (!allow_affine || xf_ok[i]) continue;  // translations take the stencil path
+      int box[3];
+      if (!affine_box(xforms[i], ndim, box)) continue;
+      const mvs_view_xform& X = xforms[i];
+      int found = -1;
+      for (size_t k = 0; k < keys.size() && found < 0; ++k)
+        if (keys[k].data == X.data && !memcmp(keys[k].shape, X.shape, sizeof(X.shape)) &&
+            !memcmp(keys[k].stride, X.stride, sizeof(X.stride)) && keys[k].dtype == X.dtype &&
+            !memcmp(keys[k].box, box, sizeof(box)))
+          found = (int)k;
+      if (found < 0) {
+        CUtensorMap m;
+        if (!make_tensor_map_box(X, ndim, box, &m)) continue;
+        Key k;
+        k.data = X.data; memcpy(k.shape, X.shape, sizeof(X.shape)); memcpy(k.stride, X.stride, sizeof(X.stride));
+        k.dtype = X.dtype; memcpy(k.box, box, sizeof(box));
+        keys.push_back(k);
+        tmaps_aff.push_back(m);
+        found = (int)keys.size() - 1;
+      }
+      a.tmap = found;
+      memcpy(a.box, box, sizeof(box));
+      af_ok[i] = 1;
+    }
+  }
+  std::vector<mvs_chunk> ch_st, ch_gen, ch_aff;
+  std::vector<int64_t> bs_st(1, 0), bs_gen(1, 0), bs_aff(1, 0);
+  std::vector<int> prefix_st(n_chunks + 1, 0), prefix_aff(n_chunks + 1, 0);
+  size_t aff_smem = 0;
   for (int c = 0; c < n_chunks; ++c) {
     const mvs_chunk& ck = chunks[c];
     bool ok = allow_stencil && ck.n_xforms <= 32 && ck.stride[2] == 1;
     for (int i = 0; ok && i < ck.n_xforms; ++i) ok = xf_ok[ck.first_xform + i];
+    // affine-staged: every pairing stageable (translations of a mixed chunk included: they
+    // were skipped above, so a chunk mixing both kinds falls through to the gather kernel)
+    bool aok = !ok && allow_affine && ck.n_xforms > 0;
+    for (int i = 0; aok && i < ck.n_xforms; ++i) aok = af_ok[ck.first_xform + i];
+    prefix_st[c + 1] = prefix_st[c] + (ok ? 1 : 0);
+    prefix_aff[c + 1] = prefix_aff[c] + (aok ? 1 : 0);
     if (ok) {
       const int BX = s3 ? S3::BX : (ndim == 3 ? SBlock<3>::BX : SBlock<2>::BX);
       const int BY = s3 ? S3::BY : (ndim == 3 ? SBlock<3>::BY : SBlock<2>::BY);
@@ -735,14 +871,24 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
                          ((ck.shape[0] + BZ - 1) / BZ);
       ch_st.push_back(ck);
       bs_st.push_back(bs_st.back() + nb);
-      prefix_st[c + 1] = prefix_st[c] + 1;
+    } else if (aok) {
+      const int BX = ndim == 3 ? ABlock<3>::BX : ABlock<2>::BX, BY = ndim == 3 ? ABlock<3>::BY : ABlock<2>::BY,
+                BZ = ndim == 3 ? ABlock<3>::BZ : 1;
+      const int64_t nb = (int64_t)((ck.shape[2] + BX - 1) / BX) * ((ck.shape[1] + BY - 1) / BY) *
+                         ((ck.shape[0] + BZ - 1) / BZ);
+      ch_aff.push_back(ck);
+      bs_aff.push_back(bs_aff.back() + nb);
+      for (int i = 0; i < ck.n_xforms; ++i) {
+        const AffInfo& a = ainfo[ck.first_xform + i];
+        aff_smem = std::max(aff_smem, (size_t)a.box[0] * a.box[1] * a.box[2] * dtype_size(xforms[ck.first_xform + i].dtype));
+      }
     } else {
-      prefix_st[c + 1] = prefix_st[c];
       const int64_t nbx = (ck.shape[2] + kBX - 1) / kBX, nby = (ck.shape[1] + kBY - 1) / kBY;
       ch_gen.push_back(ck);
       bs_gen.push_back(bs_gen.back() + nbx * nby * (int64_t)ck.shape[0]);
     }
   }
+  aff_smem = ((aff_smem + 127) / 128) * 128;
 
   cudaStream_t st = (cudaStream_t)stream;
   mvs_fuse_plan* p = new mvs_fuse_plan();
@@ -753,6 +899,8 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   p->stencil_dtype = stencil_dtype;
   p->s3 = s3;
   p->prefix_st = prefix_st; p->h_bs_st = bs_st; p->h_bs_gen = bs_gen; p->n_chunks_total = n_chunks;
+  p->prefix_aff = prefix_aff; p->h_bs_aff = bs_aff; p->n_chunks_aff = (int)ch_aff.size();
+  p->total_blocks_aff = bs_aff.back(); p->aff_smem = aff_smem;
   {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -795,6 +943,16 @@ extern "C" int mvs_fuse_plan_create(mvs_fuse_plan** plan, const mvs_chunk* chunk
   if ((e = upload((void**)&p->d_block_start, bs_gen.data(), sizeof(int64_t) * bs_gen.size())) !=
       cudaSuccess)
     return fail(e, "upload block schedule");
+  if (!ch_aff.empty()) {
+    if ((e = upload((void**)&p->d_chunks_aff, ch_aff.data(), sizeof(mvs_chunk) * ch_aff.size())) != cudaSuccess)
+      return fail(e, "upload affine chunks");
+    if ((e = upload((void**)&p->d_block_start_aff, bs_aff.data(), sizeof(int64_t) * bs_aff.size())) != cudaSuccess)
+      return fail(e, "upload affine block schedule");
+    if ((e = upload((void**)&p->d_ainfo, ainfo.data(), sizeof(AffInfo) * ainfo.size())) != cudaSuccess)
+      return fail(e, "upload affine pairings");
+    if ((e = upload((void**)&p->d_tmaps_aff, tmaps_aff.data(), sizeof(CUtensorMap) * tmaps_aff.size())) != cudaSuccess)
+      return fail(e, "upload affine tensor maps");
+  }
   // per-block schedule of the stencil path (views touching each block + weight classes)
   if (p->total_blocks_st > 0) {
     if ((e = cudaMalloc((void**)&p->d_recs, sizeof(BlockRec) * p->total_blocks_st)) != cudaSuccess)
@@ -828,13 +986,21 @@ extern "C" int mvs_fuse_plan_run_chunks(mvs_fuse_plan* p, int first_chunk, int n
               first_chunk + n_chunks, p->n_chunks_total);
   const int c0 = first_chunk, c1 = first_chunk + n_chunks;
   const int s0 = p->prefix_st[c0], s1 = p->prefix_st[c1];
-  const int g0 = c0 - s0, g1 = c1 - s1;
+  const int a0 = p->prefix_aff[c0], a1 = p->prefix_aff[c1];
+  const int g0 = c0 - s0 - a0, g1 = c1 - s1 - a1;
+  p->run_aff[0] = p->h_bs_aff[a0]; p->run_aff[1] = p->h_bs_aff[a1];
   p->run_st[0] = p->h_bs_st[s0]; p->run_st[1] = p->h_bs_st[s1];
   p->run_gen[0] = p->h_bs_gen[g0]; p->run_gen[1] = p->h_bs_gen[g1];
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   if (p->run_st[1] > p->run_st[0])
     e = p->ndim == 2 ? dispatch_stencil<2>(p, st) : dispatch_stencil<3>(p, st);
+  if (e == cudaSuccess && p->run_aff[1] > p->run_aff[0]) {
+    if (p->ndim == 2)
+      e = p->order == 0 ? dispatch_affine<2, 0>(p, st) : dispatch_affine<2, 1>(p, st);
+    else
+      e = p->order == 0 ? dispatch_affine<3, 0>(p, st) : dispatch_affine<3, 1>(p, st);
+  }
   if (e == cudaSuccess && p->run_gen[1] > p->run_gen[0]) {
     if (p->ndim == 2)
       e = p->order == 0 ? dispatch_mode<2, 0>(p, st) : dispatch_mode<2, 1>(p, st);
@@ -856,8 +1022,8 @@ extern "C" int mvs_fuse_plan_run(mvs_fuse_plan* p, void* stream) {
 extern "C" int mvs_fuse_plan_info(const mvs_fuse_plan* p, int* launches, int64_t* blocks,
                                   int64_t* out_voxels) {
   MVS_REQUIRE(p != nullptr, MVS_ERR_INVALID, "plan is NULL");
-  if (launches) *launches = (p->total_blocks > 0 ? 1 : 0) + (p->total_blocks_st > 0 ? 1 : 0);
-  if (blocks) *blocks = p->total_blocks + p->total_blocks_st;
+  if (launches) *launches = (p->total_blocks > 0 ? 1 : 0) + (p->total_blocks_st > 0 ? 1 : 0) + (p->total_blocks_aff > 0 ? 1 : 0);
+  if (blocks) *blocks = p->total_blocks + p->total_blocks_st + p->total_blocks_aff;
   if (out_voxels) *out_voxels = p->out_voxels;
   return MVS_OK;
 }
@@ -874,6 +1040,10 @@ extern "C" int mvs_fuse_plan_destroy(mvs_fuse_plan* p) {
   cudaFree(p->d_xforms);
   cudaFree(p->d_tables);
   cudaFree(p->d_block_start);
+  cudaFree(p->d_chunks_aff);
+  cudaFree(p->d_block_start_aff);
+  cudaFree(p->d_ainfo);
+  cudaFree(p->d_tmaps_aff);
   delete p;
   return MVS_OK;
 }

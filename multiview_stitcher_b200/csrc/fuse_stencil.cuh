@@ -169,6 +169,25 @@ __device__ float raw_table_value(const float* __restrict__ tab, double uz, doubl
                 lerp_s(__ldg(tab + iy1 * 5 + ix), __ldg(tab + iy1 * 5 + ix1), tx), ty);
 }
 
+// same with plain loads (table staged in shared memory)
+template <int NDIM>
+__device__ float raw_table_value_s(const float* __restrict__ tab, double uz, double uy, double ux) {
+  if (ux < 0.0 || ux > 4.0 || uy < 0.0 || uy > 4.0) return 0.f;
+  if (NDIM == 3 && (uz < 0.0 || uz > 4.0)) return 0.f;
+  const double fx = floor(ux), fy = floor(uy), fz = floor(uz);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const float tx = (float)(ux - fx), ty = (float)(uy - fy), tz = (float)(uz - fz);
+  const int ix1 = min(ix + 1, 4), iy1 = min(iy + 1, 4), iz1 = min(iz + 1, 4);
+  if (NDIM == 3) {
+    const float* p0 = tab + iz * 25;
+    const float* p1 = tab + iz1 * 25;
+    float a0 = lerp_s(lerp_s(p0[iy * 5 + ix], p0[iy * 5 + ix1], tx), lerp_s(p0[iy1 * 5 + ix], p0[iy1 * 5 + ix1], tx), ty);
+    float a1 = lerp_s(lerp_s(p1[iy * 5 + ix], p1[iy * 5 + ix1], tx), lerp_s(p1[iy1 * 5 + ix], p1[iy1 * 5 + ix1], tx), ty);
+    return lerp_s(a0, a1, tz);
+  }
+  return lerp_s(lerp_s(tab[iy * 5 + ix], tab[iy * 5 + ix1], tx), lerp_s(tab[iy1 * 5 + ix], tab[iy1 * 5 + ix1], tx), ty);
+}
+
 // Smallest pre-cosine table value x for which (cos((1-x)*pi)+1)/2 is safely > 0
 // in float32 (delta^2/2 >= ~3 ulp of 2^-24 with delta = pi*x).
 #define MVS_POSITIVE_X 1.8e-4f

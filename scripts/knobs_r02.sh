@@ -1,7 +1,5 @@
-set -e
-python -m pytest tests/test_gpu_fusion.py -m gpu -x -q 2>&1 | tail -2
-python scripts/probe_r02c.py C3 C5row 2>&1 | tail -2
-for v in "-DMVS_MAGIC_CVT=0"; do
+python scripts/probe_c4.py 2>&1 | grep -A1 "staged_order"
+for v in "-DMVS_AFF_MINB=2" "-DMVS_AFF_MINB=5"; do
   MVS_EXTRA_NVCC="$v" python -m multiview_stitcher_b200.build --force > /dev/null 2>&1
-  echo "== $v"; python scripts/probe_r02c.py C3 C5row 2>&1 | tail -2
+  echo "== $v"; python scripts/probe_c4.py 2>&1 | grep -A1 "staged_order"
 done
