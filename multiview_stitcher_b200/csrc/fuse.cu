@@ -162,8 +162,13 @@ __device__ __forceinline__ ViewEval eval_view(const mvs_view_xform& X,
     // one (warp-uniform) dtype switch per view instead of one per tap
     const int dt = X.dtype;
     if (dt == MVS_U16) r.v = sample_view<NDIM, ORDER, unsigned short>(X, xz, xy, xx);
-    else if (dt == MVS_F32) r.v = sample_view<NDIM, ORDER, float>(X, xz, xy, xx);
-    else r.v = sample_view<NDIM, ORDER, unsigned char>(X, xz, xy, xx);
+    else if (dt == MVS_F32) {
+      r.v = sample_view<NDIM, ORDER, float>(X, xz, xy, xx);
+      // NaN data inside a float view counts as "outside" for this voxel: the reference zeroes
+      // the weight where the transformed view is NaN (fusion/_core.py:1648) and its fusion
+      // functions are nan-aware, so another view's valid data survives
+      if (r.v != r.v) { r.valid = false; return r; }
+    } else r.v = sample_view<NDIM, ORDER, unsigned char>(X, xz, xy, xx);
   }
   if (WANT_B) {
     const double* w = X.wmatrix;
@@ -1109,27 +1114,14 @@ extern "C" int mvs_resample_views(const mvs_view_xform* xforms, int n_views, con
   const long long N = (long long)shape[0] * shape[1] * shape[2];
   if (N <= 0) return MVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  // Parameter buffers are cached (grow-only) and reused stream-ordered: calls are
-  // serialised while they enqueue; a call on another stream first waits for the
-  // previous user's stream.  The host arrays are pageable, so the async copies
-  // have staged them when they return.
-  static std::mutex mtx;
-  static void* d_buf = nullptr;
-  static size_t d_bytes = 0;
-  static cudaStream_t last_stream = nullptr;
-  static bool used = false;
-  std::lock_guard<std::mutex> lock(mtx);
-  if (used && last_stream != st) cudaStreamSynchronize(last_stream);
-  last_stream = st;
-  used = true;
+  // Parameter buffer from the stream-ordered pool of the CURRENT device: nothing is shared
+  // between devices, streams or threads (per-group streams of register_pairs run
+  // concurrently).  The host arrays are pageable, so the async copies have staged them when
+  // they return.
   const size_t xbytes = ((sizeof(mvs_view_xform) * n_views + 255) / 256) * 256;
   const size_t tbytes = d_weights ? sizeof(float) * 125 * n_tables : 0;
-  if (d_bytes < xbytes + tbytes) {
-    if (d_buf) cudaFree(d_buf);
-    d_buf = nullptr; d_bytes = 0;
-    MVS_CHECK_CUDA(cudaMalloc(&d_buf, 2 * (xbytes + tbytes)));
-    d_bytes = 2 * (xbytes + tbytes);
-  }
+  void* d_buf = nullptr;
+  MVS_CHECK_CUDA(cudaMallocAsync(&d_buf, xbytes + tbytes, st));
   mvs_view_xform* d_x = (mvs_view_xform*)d_buf;
   float* d_t = d_weights ? (float*)((char*)d_buf + xbytes) : nullptr;
   if (d_weights)
@@ -1144,6 +1136,7 @@ extern "C" int mvs_resample_views(const mvs_view_xform* xforms, int n_views, con
     else resample_views_kernel<3, 1><<<grid, 256, 0, st>>>(ck, d_x, n_views, d_t, d_views, d_weights);
   }
   cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(d_buf, st);
   if (e != cudaSuccess) { set_error("resample launch: %s", cudaGetErrorString(e)); return MVS_ERR_CUDA; }
   return MVS_OK;
 }

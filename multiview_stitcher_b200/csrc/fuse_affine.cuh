@@ -314,8 +314,10 @@ fuse_affine_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restri
           return lerp_s(a0, lerp_s(a10, a11, ty), tz);
         };
         if (dt == MVS_U16) v = fetch(reinterpret_cast<const unsigned short*>(brick));
-        else if (dt == MVS_F32) v = fetch(reinterpret_cast<const float*>(brick));
-        else v = fetch(reinterpret_cast<const unsigned char*>(brick));
+        else if (dt == MVS_F32) {
+          v = fetch(reinterpret_cast<const float*>(brick));
+          if (v != v) continue;  // NaN data = outside for this voxel (fusion/_core.py:1648)
+        } else v = fetch(reinterpret_cast<const unsigned char*>(brick));
       }
       if (MODE == MVS_FUSE_MAX) {
         res[k] = npos[k] ? fmaxf(res[k], v) : v;

@@ -668,8 +668,12 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       }
       const float tx = S.t[2], ty = S.t[1], tz = NDIM == 3 ? S.t[0] : 0.f;
       const int c0 = sl.xoff + jx;
-      const int c1 = c0 + S.d1[2];
-      const bool dy = S.d1[1] != 0, dz = NDIM == 3 && S.d1[0] != 0;
+      // float32 views: the second tap always takes part, like in scipy, whose order-1 spline
+      // multiplies a NaN neighbour by its zero weight at integer positions (NaN data spreads
+      // one voxel towards lower indices); integer views skip it when the fraction is 0
+      constexpr bool kF = sizeof(T) == 4;
+      const int c1 = c0 + (kF ? 1 : S.d1[2]);
+      const bool dy = kF || S.d1[1] != 0, dz = NDIM == 3 && (kF || S.d1[0] != 0);
 
       // ---- interpolate this thread's outputs from shared memory ----
       float val[B::OUTS];
@@ -700,6 +704,14 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
             hprev = hn;
           }
         }
+      }
+
+      // NaN data inside a float view counts as "outside" for that voxel (the reference zeroes
+      // the weight where the transformed view is NaN, fusion/_core.py:1648; nan-aware fusion)
+      if (sizeof(T) == 4) {
+#pragma unroll
+        for (int k = 0; k < B::OUTS; ++k)
+          if (val[k] != val[k]) vm &= ~(1u << k);
       }
 
       // ---- combine ----

@@ -474,7 +474,6 @@ fuse_stencil3_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __rest
         vm = ((vzm & 1u) ? rc : 0u) | ((vzm & 2u) ? rc << 4 : 0u) | ((vzm & 4u) ? rc << 8 : 0u) | ((vzm & 8u) ? rc << 12 : 0u);
       }
       const float tx = sl.tx, ty = sl.ty, tz = sl.tz;
-      const bool dxf = sl.d1x != 0, dyf = sl.d1y != 0, dzf = sl.d1z != 0;
       const int c0 = sl.xoff + jx;
 
       // ---- interpolate: x/y per plane, z against the previous plane ----
@@ -485,19 +484,16 @@ fuse_stencil3_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __rest
         for (int rr = 0; rr < 3; ++rr) {
           float a, b, c;
           load3(base + (jy + rr) * BW, c0, a, b, c);
-          if (kNan) {
-            h[rr][0] = dxf ? lerp_s(a, b, tx) : a;
-            h[rr][1] = dxf ? lerp_s(b, c, tx) : b;
-          } else {
-            h[rr][0] = lerp_s(a, b, tx);
-            h[rr][1] = lerp_s(b, c, tx);
-          }
+          // the second tap always takes part (scipy multiplies a NaN neighbour by its zero
+          // weight at integer positions; for finite data lerp(a, b, 0) == a exactly)
+          h[rr][0] = lerp_s(a, b, tx);
+          h[rr][1] = lerp_s(b, c, tx);
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int c = 0; c < 2; ++c)
-            g[r * 2 + c] = (kNan && !dyf) ? h[r][c] : lerp_s(h[r][c], h[r + 1][c], ty);
+            g[r * 2 + c] = lerp_s(h[r][c], h[r + 1][c], ty);
       };
       if (!(flags & ITEM_CARRY)) plane_g(sl.prime, gc);
 #pragma unroll
@@ -506,9 +502,15 @@ fuse_stencil3_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __rest
         plane_g(sl.main + p * (S3::ROWS * BW), g);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          val[p * 4 + k] = (kNan && !dzf) ? gc[k] : lerp_s(gc[k], g[k], tz);
+          val[p * 4 + k] = lerp_s(gc[k], g[k], tz);
           gc[k] = g[k];
         }
+      }
+
+      if (kNan) {  // NaN data = outside for that voxel (fusion/_core.py:1648)
+#pragma unroll
+        for (int k = 0; k < OUTS; ++k)
+          if (val[k] != val[k]) vm &= ~(1u << k);
       }
 
       // ---- combine ----

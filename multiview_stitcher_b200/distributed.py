@@ -653,21 +653,22 @@ def fuse_partial(local_views, local_params, output_stack_properties, output_chun
     full_shape = tuple(int(output_stack_properties["shape"][d]) for d in dims)
     np_dtype = np.dtype(out_dtype or (_torch_to_np(dviews[0].tensor.dtype) if dviews else np.float32))
     if mode == _lib.MVS_FUSE_MAX:
-        # float32 max of the per-rank maxima; uncovered voxels carry -inf
+        # max of the per-rank maxima.  A voxel no local view covers is 0 in the per-rank result
+        # (like the reference's nan_to_num of an all-NaN nanmax), which is neutral under MAX
+        # for non-negative data -- the only kind this path accepts (validity is decided by the
+        # coordinate predicate inside the kernel, not by a blending weight).
+        for v in dviews:
+            if v.tensor.dtype == torch.float32 and bool((torch.nan_to_num(v.tensor) < 0).any()):
+                raise EngineError("fuse_partial(max_fusion) needs non-negative data (uncovered voxels are 0)")
         if dviews:
             plan = FusionPlan(dviews, local_params, output_stack_properties, output_chunksize=output_chunksize,
                               fusion_func=fusion_func, out_dtype=np.float32, **plan_kwargs)
             part = plan.run()
-            cov = FusionPlan(dviews, local_params, output_stack_properties, output_chunksize=output_chunksize,
-                             partial=True, **plan_kwargs)
-            cov.run()
-            part = torch.where(cov.acc_den > 0, part, torch.full_like(part, float("-inf")))
-            plan.close(); cov.close()
+            plan.close()
         else:
-            part = torch.full(full_shape, float("-inf"), dtype=torch.float32, device="cuda")
+            part = torch.zeros(full_shape, dtype=torch.float32, device="cuda")
         if ws > 1:
             dist.all_reduce(part, op=dist.ReduceOp.MAX)
-        part = torch.where(torch.isinf(part), torch.zeros_like(part), part)
         return part.to(_np_to_torch(np_dtype)) if np_dtype != np.float32 else part
     if dviews:
         plan = FusionPlan(dviews, local_params, output_stack_properties, output_chunksize=output_chunksize,

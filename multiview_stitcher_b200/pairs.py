@@ -466,6 +466,24 @@ def _n_timepoints(msim):
     return int(sim.sizes["t"]) if hasattr(sim, "dims") and "t" in sim.dims else None
 
 
+def _t_coords(msim, nt):
+    """Time coordinate VALUES of an msim (the reference assigns them to the results,
+    registration.py:2091; its groupwise resolution selects per time point by these labels,
+    param_resolution/utils.py:23-39).  An msim without "t" gets ``ensure_dim``'s single
+    coordinate 0 (msi_utils.ensure_dim, registration.py:2070-2071)."""
+    if nt is None:
+        return np.array([0])
+    sim = msim["scale0/image"]
+    try:
+        c = sim.coords["t"]
+        vals = np.asarray(c.values if hasattr(c, "values") else c)
+        if vals.shape == (nt,):
+            return vals
+    except Exception:
+        pass
+    return np.arange(nt)
+
+
 def _view_and_affine(msim, transform_key, it=None):
     """(view, affine) of one element of ``msims`` at time index ``it``: a
     MultiscaleSpatialImage-like mapping (``msim["scale0/image"]``,
@@ -527,14 +545,16 @@ def pairwise_executor(msims, edges, register_kwargs):
         xr = None
     n = plan_affines[0].shape[0] - 1
     labels = geometry.spatial_dims(n) + ["1"]
+    tvals = _t_coords(msims[0], nt)
     out = []
     for k in range(len(edges)):
         tr = np.stack([r[k]["transform"] for r in per_t])
         q = np.array([r[k]["quality"] for r in per_t], dtype=float)
         bb = np.stack([r[k]["bbox"] for r in per_t])
         if xr is not None:
-            tr = xr.DataArray(tr, dims=["t", "x_in", "x_out"], coords={"x_in": labels, "x_out": labels})
-            q = xr.DataArray(q, dims=["t"])
-            bb = xr.DataArray(bb, dims=["t", "point_index", "dim"])
+            tr = xr.DataArray(tr, dims=["t", "x_in", "x_out"], coords={"t": tvals, "x_in": labels, "x_out": labels})
+            q = xr.DataArray(q, dims=["t"], coords={"t": tvals})
+            bb = xr.DataArray(bb, dims=["t", "point_index", "dim"], coords={"t": tvals})
         out.append({"transform": tr, "quality": q, "bbox": bb})
+    pairwise_executor.last_t_coords = tvals
     return out

@@ -327,3 +327,37 @@ def test_host_fuser_reuse(eng):
         got = fuser(views, out).numpy()
         assert np.array_equal(got, ref)
     fuser.close()
+
+
+@pytest.mark.parametrize("kind", ["translation", "affine"])
+@pytest.mark.parametrize("func", ["weighted_average_fusion", "max_fusion", "simple_average_fusion"])
+def test_nan_data_inside_float_views_is_masked_per_voxel(kind, func):
+    """float32 views carrying NaN DATA (not just NaN outside): the reference zeroes the blending
+    weight where the transformed view is NaN (fusion/_core.py:1648) and its fusion functions are
+    nan-aware, so the other view's data survives in the overlap and a lone NaN voxel becomes 0."""
+    from multiview_stitcher_b200 import fusion
+    from oracle import fusion as of
+
+    rng = np.random.default_rng(3)
+    views, params = [], []
+    for k in range(2):
+        data = (rng.random((48, 64)) * 100 + 10).astype(np.float32)
+        views.append({"data": data, "origin": {"y": 0.0, "x": 40.0 * k}, "spacing": {"y": 1.0, "x": 1.0}})
+        p = np.eye(3)
+        p[:2, 2] = (0.3 * k, -0.45 * k)
+        if kind == "affine":
+            a = np.deg2rad(3.0 * (k + 1))
+            p[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        params.append(p)
+    views[0]["data"][10:20, 45:60] = np.nan   # inside the overlap: view 1 must fill it
+    views[0]["data"][30:34, 5:9] = np.nan     # where view 0 is alone: fused 0
+    views[1]["data"][25, 3] = np.nan
+    ofunc = getattr(of, func)
+    efunc = getattr(fusion, func)
+    ref, osp = of.fuse(views, params, fusion_func=ofunc)
+    got, _ = fusion.fuse(views, params, output_stack_properties=osp, fusion_func=efunc)
+    assert not np.isnan(got).any()
+    tol = 1e-4 * np.abs(ref) + 1e-6 * np.abs(ref).max()
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), (int(bad.sum()), float(np.abs(got - ref).max()))
+    assert (ref[12:18, 48:56] > 0).all()  # the hole in view 0 was filled by view 1

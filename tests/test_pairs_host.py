@@ -190,3 +190,52 @@ def test_plan_pair_fuzz_vs_oracle():
             np.testing.assert_array_equal(got.astype(np.float32), want[key])
         n_done += 1
     assert n_done >= 45
+
+
+def test_pairwise_executor_assigns_time_coordinates(monkeypatch):
+    """Hook A's results carry the "t" coordinate VALUES of the input (registration.py:2091):
+    the reference's groupwise resolution looks time points up by label
+    (param_resolution/utils.py:23-39).  xarray is not installed here, so a minimal stand-in
+    records what the executor constructs; the device work is stubbed."""
+    import sys
+    import types
+
+    from multiview_stitcher_b200 import pairs as P
+
+    class DataArray:
+        def __init__(self, data, dims=None, coords=None):
+            self.data, self.dims, self.coords = np.asarray(data), tuple(dims), dict(coords or {})
+
+    monkeypatch.setitem(sys.modules, "xarray", types.SimpleNamespace(DataArray=DataArray))
+
+    class Coord:
+        def __init__(self, v):
+            self.values = np.asarray(v)
+
+    class Sim:
+        def __init__(self, nt):
+            self.dims = ("t", "y", "x")
+            self.sizes = {"t": nt, "y": 8, "x": 8}
+            self.coords = {"t": Coord([10.0, 20.5, 31.0][:nt])}
+
+        def isel(self, t=0):
+            return {"data": np.zeros((8, 8), np.float32), "origin": {"y": 0.0, "x": 0.0}, "spacing": {"y": 1.0, "x": 1.0}}
+
+    msims = [{"scale0/image": Sim(3), "scale0": {"reg": np.eye(3)}} for _ in range(2)]
+
+    class FakePlan:
+        def __init__(self, *a, **k):
+            pass
+
+    def fake_register_views(views, plan=None, **kw):
+        return [{"transform": np.eye(3), "quality": 0.5, "bbox": np.zeros((2, 2))}]
+
+    monkeypatch.setattr(P, "PairPlan", FakePlan)
+    monkeypatch.setattr(P, "register_views", fake_register_views)
+    out = P.pairwise_executor(msims, [(0, 1)], {"transform_key": "reg"})
+    assert len(out) == 1
+    for key, dims in (("transform", ("t", "x_in", "x_out")), ("quality", ("t",)), ("bbox", ("t", "point_index", "dim"))):
+        da = out[0][key]
+        assert da.dims == dims and da.data.shape[0] == 3
+        np.testing.assert_array_equal(da.coords["t"], [10.0, 20.5, 31.0])
+    assert out[0]["transform"].coords["x_in"] == ["y", "x", "1"]
