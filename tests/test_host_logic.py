@@ -258,7 +258,8 @@ def test_hook_argument_errors_are_raised_before_any_device_work():
 
     osp = {"origin": {"y": 0.0, "x": 0.0}, "spacing": {"y": 1.0, "x": 1.0}, "shape": {"y": 8, "x": 8}}
     part = functools.partial(lambda block_id, **kw: None, output_stack_properties=osp, ns_shape={}, nsdims=[],
-                             fuse_kwargs={"images": [], "transform_key": "k", "backend": "cupy"},
+                             fuse_kwargs={"images": [], "transform_key": "k", "backend": "jax"},
                              output_chunksize={"y": 8, "x": 8}, output_zarr_array=np.zeros((8, 8)))
-    with pytest.raises(EngineError, match="own backend"):
+    # backend="numpy" / "cupy" are accepted (host arrays are staged, device arrays used in place)
+    with pytest.raises(EngineError, match="unknown backend"):
         BatchFuser()(part, [(0, 0)])
