@@ -133,3 +133,38 @@ def test_weights_func_blocks_match_per_chunk_fuse():
                           fusion_func=efusion.weighted_average_fusion)
     BatchFuser()(fuse_chunk, sorted(block_geometry(osp, chunksize)))
     _close(out, ref)
+
+
+class _CudaArray:
+    """CuPy-like device array: only ``__cuda_array_interface__``, shape, dtype, ndim (what the
+    views of ``fuse(backend="cupy")`` expose, fusion/_core.py:1579-1587)."""
+
+    def __init__(self, t):
+        self._t = t
+        self.__cuda_array_interface__ = t.__cuda_array_interface__
+        self.shape, self.ndim = tuple(t.shape), t.ndim
+        self.dtype = np.dtype(str(t.dtype).replace("torch.", ""))
+
+
+def test_device_array_inputs_at_the_hooks():
+    """backend="cupy": hook C and fuse_np take device arrays of another library in place."""
+    import torch
+
+    from multiview_stitcher_b200 import fusion as efusion
+    from multiview_stitcher_b200.batch import BatchFuser, block_geometry
+
+    case = cases.fusion_cases()["2d_f32_quad_lin"]
+    views, params = case["views"], case["params"]
+    ref, osp = of.fuse(views, params)
+    dev = [dict(v, data=_CudaArray(torch.from_numpy(np.ascontiguousarray(v["data"])).cuda())) for v in views]
+    chunksize = {d: max(8, int(osp["shape"][d]) // 2 + 1) for d in "yx"}
+    msims = [dict(v, transforms={"reg": p}) for v, p in zip(dev, params)]
+    out = np.zeros(ref.shape, dtype=ref.dtype)
+    bf = BatchFuser()
+    bf(_partial(msims, osp, chunksize, out, backend="cupy"), sorted(block_geometry(osp, chunksize)))
+    _close(out, ref)
+    assert bf.h2d_bytes == 0  # nothing was uploaded: the device arrays were used in place
+    # fuse_np on device slices
+    cprops = osp
+    got = efusion.fuse_np(dev, params, cprops, full_view_bbs=[of.view_bb(v) for v in views])
+    _close(got, ref)
