@@ -169,6 +169,17 @@ int mvs_content_based(const float* d_views, const float* d_blending, int V,
                       const int32_t shape[3], int ndim, const double* w1, int r1,
                       const double* w2, int r2, float* d_out_weights, void* stream);
 
+/* weights.content_based_dct (weights.py:77-290): per view and block of block[0..2] voxels
+ * (<= 32 per axis; z = 1 in 2-D) the Shannon entropy of the orthonormal DCT-II coefficients
+ * with L1 frequency index < r_o, normalised by the block's L2 norm and scaled by 2 / r_o^2
+ * (r_o < 0: every coefficient, L1-mean normalisation, weights.py:232-243), raised to
+ * `exponent`; blocks with < 20 % valid voxels score 0, NaNs are filled with the block's
+ * minimum.  Scores are normalised over the views, interpolated to voxel resolution
+ * (order 1, mode "nearest") and normalised again.  d_out_weights: (V, *shape) float32. */
+int mvs_content_based_dct(const float* d_views, int V, const int32_t shape[3], int ndim,
+                          const int32_t block[3], float r_o, float exponent, float* d_out_weights,
+                          void* stream);
+
 /* fusion_func on stacks: MVS_FUSE_WAVG = weighted_average_fusion(views, blending,
  * fusion_weights or NULL) (_core.py:61-94), MVS_FUSE_MAX (_core.py:42-58),
  * MVS_FUSE_MEAN (_core.py:97-131).  d_out: float32 volume (NaN where the

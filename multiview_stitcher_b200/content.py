@@ -28,6 +28,7 @@ _ENGINE_FUNCS = {
     "max_fusion": hooks.max_fusion,
     "simple_average_fusion": hooks.simple_average_fusion,
     "content_based": hooks.content_based,
+    "content_based_dct": hooks.content_based_dct,
 }
 
 
@@ -204,13 +205,17 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
         output_chunksize = geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
     wfunc, _ = _resolve(weights_func)
     ffunc, _ = _resolve(fusion_func)
+    # per-axis halo: the maximum over what the hooks ask for (fusion/_core.py:1194-1219)
+    ov = np.zeros(ndim, dtype=np.int64)
     if overlap_in_pixels is None:
-        ov = 0
         for f, kw in ((wfunc if weights_func is not None else None, weights_func_kwargs), (ffunc, None)):
-            o = _required_overlap(f, kw)
-            ov = max(ov, max(o.values()) if isinstance(o, dict) else o)
+            o = _required_overlap(f, kw, output_chunksize)
+            o = np.array([o[d] for d in dims] if isinstance(o, dict) else [o] * ndim, dtype=np.int64)
+            ov = np.maximum(ov, o)
+    elif isinstance(overlap_in_pixels, dict):
+        ov = np.array([int(overlap_in_pixels[d]) for d in dims], dtype=np.int64)
     else:
-        ov = int(overlap_in_pixels)
+        ov = np.full(ndim, int(overlap_in_pixels), dtype=np.int64)
     bbs = [v.bb() for v in dviews]
     o_org, o_sp, _ = geometry.bb_arrays(osp, dims)
     aabbs = [geometry.transformed_aabb(bb, p, dims) for bb, p in zip(bbs, params)]
@@ -224,7 +229,7 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
         hbb = {
             "origin": dict(zip(dims, map(float, c_org))),
             "spacing": osp["spacing"],
-            "shape": {d: int(s) + 2 * ov for d, s in zip(dims, shape)},
+            "shape": {d: int(s) + 2 * int(h) for d, s, h in zip(dims, shape, ov)},
         }
         lo, hi = c_org, c_org + (np.array(shape) + 2 * ov - 1) * o_sp
         sel = [i for i, (alo, ahi) in enumerate(aabbs) if not (np.any(ahi < lo - 1e-6) or np.any(alo > hi + 1e-6))]
@@ -232,7 +237,8 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
             continue
         res = fuse_np_with_weights(
             [dviews[i] for i in sel], [params[i] for i in sel], hbb, fusion_func=fusion_func,
-            weights_func=weights_func, weights_func_kwargs=weights_func_kwargs, trim_overlap_in_pixels=ov,
+            weights_func=weights_func, weights_func_kwargs=weights_func_kwargs,
+            trim_overlap_in_pixels={d: int(h) for d, h in zip(dims, ov)},
             interpolation_order=interpolation_order, full_view_bbs=[bbs[i] for i in sel],
             blending_widths=blending_widths, output_on_backend=True,
         )

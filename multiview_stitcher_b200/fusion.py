@@ -37,6 +37,7 @@ __all__ = [
     "max_fusion",
     "simple_average_fusion",
     "content_based",
+    "content_based_dct",
     "build_work_list",
 ]
 
@@ -75,6 +76,22 @@ def content_based(transformed_views, blending_weights, sigma_1=5, sigma_2=11):
 
 
 content_based.required_overlap = lambda kwargs: 2 * kwargs["sigma_2"]
+
+
+def content_based_dct(transformed_views, dct_size=32, exponent=1.0, otf_support_fraction=0.5, output_chunksize=None):
+    """weights.content_based_dct (weights.py:77-290) on the GPU; pass as ``weights_func``."""
+    from . import hooks
+
+    return hooks.content_based_dct(transformed_views, dct_size, exponent, otf_support_fraction, output_chunksize)
+
+
+def _dct_overlap(kwargs):
+    from . import hooks
+
+    return hooks._clamp_overlap(kwargs["dct_size"], kwargs["output_chunksize"])
+
+
+content_based_dct.required_overlap = _dct_overlap
 
 
 _MODE_BY_NAME = {
@@ -188,17 +205,18 @@ def to_device_view(view, device="cuda", non_blocking=True):
 # --- planning -----------------------------------------------------------------
 
 
-def _required_overlap(func, kwargs):
+def _required_overlap(func, kwargs, output_chunksize=None):
     """Halo a hook asks for via its ``required_overlap`` attribute
-    (misc_utils.py:69-105, consumed at fusion/_core.py:1199-1222)."""
+    (misc_utils.py:69-105, consumed at fusion/_core.py:1199-1222; ``output_chunksize`` is
+    injected for hooks that declare it so they can clamp the halo, :1205-1213)."""
     if func is None or not hasattr(func, "required_overlap"):
         return 0
-    defaults = {
-        k: v.default
-        for k, v in inspect.signature(func).parameters.items()
-        if v.default is not inspect.Parameter.empty
-    }
-    ov = func.required_overlap({**defaults, **(kwargs or {})})
+    params = inspect.signature(func).parameters
+    defaults = {k: v.default for k, v in params.items() if v.default is not inspect.Parameter.empty}
+    merged = {**defaults, **(kwargs or {})}
+    if "output_chunksize" in params and output_chunksize is not None and (kwargs or {}).get("output_chunksize") is None:
+        merged["output_chunksize"] = dict(output_chunksize)
+    ov = func.required_overlap(merged)
     if isinstance(ov, dict):
         return {d: int(np.ceil(v)) for d, v in ov.items()}
     return int(np.ceil(ov))

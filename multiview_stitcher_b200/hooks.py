@@ -139,6 +139,47 @@ def content_based(transformed_views, blending_weights, sigma_1=5, sigma_2=11):
 content_based.required_overlap = lambda kwargs: 2 * kwargs["sigma_2"]
 
 
+def _clamp_overlap(overlap, output_chunksize):
+    """weights._clamp_overlap (weights.py:514-524)."""
+    sdims = sorted(output_chunksize.keys())[::-1]
+    if not isinstance(overlap, dict):
+        overlap = {dim: int(overlap) for dim in sdims}
+    return {dim: min(overlap[dim], output_chunksize[dim]) for dim in sdims}
+
+
+def content_based_dct(transformed_views, dct_size=32, exponent=1.0, otf_support_fraction=0.5, output_chunksize=None):
+    """weights.content_based_dct (weights.py:77-290) on the GPU: DCT Shannon-entropy quality per
+    block of ``dct_size`` voxels, normalised over the views and interpolated back to voxel
+    resolution.  Same arguments and defaults as the reference; block edges up to 32."""
+    import torch
+
+    lib = _lib.load(require_device=True)
+    tv, was_np = _to_stack(transformed_views)
+    spatial = tuple(tv.shape[1:])
+    ndim = len(spatial)
+    sdims = ["z", "y", "x"][-ndim:]
+    sizes = tuple(dct_size[d] for d in sdims) if isinstance(dct_size, dict) else (dct_size,) * ndim
+    if output_chunksize is not None:
+        sizes = tuple(int(min(ds, output_chunksize[dim], s)) for ds, dim, s in zip(sizes, sdims, spatial))
+    else:
+        sizes = tuple(int(min(ds, s)) for ds, s in zip(sizes, spatial))
+    if max(sizes) > 32:
+        raise EngineError(f"content_based_dct: dct_size {sizes} exceeds the engine's block limit of 32")
+    r_o = -1.0 if otf_support_fraction is None else float(otf_support_fraction) * min(sizes)
+    out = torch.empty_like(tv)
+    blk = (ctypes.c_int32 * 3)(*((1,) * (3 - ndim) + sizes))
+    _lib.check(
+        lib.mvs_content_based_dct(ctypes.c_void_p(tv.data_ptr()), tv.shape[0], _shape3(spatial), ndim, blk,
+                                  ctypes.c_float(r_o), ctypes.c_float(float(exponent)), ctypes.c_void_p(out.data_ptr()),
+                                  _lib.current_stream_ptr()),
+        "mvs_content_based_dct",
+    )
+    return _back(out, was_np)
+
+
+content_based_dct.required_overlap = lambda kwargs: _clamp_overlap(kwargs["dct_size"], kwargs["output_chunksize"])
+
+
 def gaussian_filter(stack, sigma):
     """scipy.ndimage.gaussian_filter(mode="reflect") of every volume of a stack."""
     import torch
