@@ -180,6 +180,26 @@ int mvs_content_based_dct(const float* d_views, int V, const int32_t shape[3], i
                           const int32_t block[3], float r_o, float exponent, float* d_out_weights,
                           void* stream);
 
+/* scipy.ndimage.convolve(input, kernel, mode, cval) of one float32 volume with a small
+ * dense kernel (HOST float32, odd extents <= 15; z extent 1 in 2-D): mode 0 = "mirror",
+ * 1 = "constant".  float32 accumulation.  d_in != d_out. */
+int mvs_convolve(const float* d_in, float* d_out, const int32_t shape[3], const float* kernel,
+                 const int32_t kshape[3], int mode, float cval, void* stream);
+
+/* fusion.mv_deconv.multi_view_deconvolution (fusion/mv_deconv.py:251-500) as a fusion_func on
+ * (V, *shape) float32 stacks: psi0 = clip(nansum(views * weights)), then n_iterations of the
+ * sequential per-view Richardson-Lucy update (forward convolution with kernels1[v], mode
+ * mirror; ratio gated by the view's coverage and blending weight; back-projection with the
+ * compound kernel kernels2[v], mode constant 1; optional Tikhonov regularisation; clamp to
+ * min_value), optional erosion of the union coverage mask by erosion_px face-neighbour
+ * steps.  kernels1 / kernels2: HOST arrays of V kernels of kshape (odd, <= 15) -- the PSFs
+ * and compound kernels are tiny and built on the host exactly like the reference (:173-245,
+ * :373-415).  d_out: float32 volume. */
+int mvs_mv_deconvolution(const float* d_views, const float* d_weights, int V, const int32_t shape[3],
+                         int ndim, const float* kernels1, const float* kernels2,
+                         const int32_t kshape[3], int n_iterations, float lambda_reg, float min_value,
+                         int erosion_px, float* d_out, void* stream);
+
 /* fusion_func on stacks: MVS_FUSE_WAVG = weighted_average_fusion(views, blending,
  * fusion_weights or NULL) (_core.py:61-94), MVS_FUSE_MAX (_core.py:42-58),
  * MVS_FUSE_MEAN (_core.py:97-131).  d_out: float32 volume (NaN where the

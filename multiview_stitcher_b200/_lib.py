@@ -102,6 +102,9 @@ _SIGNATURES = {
     "mvs_gaussian_filter": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _P, ctypes.c_int, _P]),
     "mvs_content_based": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _P, ctypes.c_int, _P, ctypes.c_int, _P, _P]),
     "mvs_content_based_dct": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_float, ctypes.c_float, _P, _P]),
+    "mvs_convolve": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_int32), _P, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_float, _P]),
+    "mvs_mv_deconvolution": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _P, _P, ctypes.POINTER(ctypes.c_int32),
+                                            ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, _P, _P]),
     "mvs_fuse_stack": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _P, _P]),
     "mvs_trim_cast": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), _P]),
     "mvs_pc_plan_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int]),

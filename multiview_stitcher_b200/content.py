@@ -20,7 +20,7 @@ import inspect
 
 import numpy as np
 
-from . import _lib, geometry, hooks
+from . import _lib, deconv, geometry, hooks
 from ._lib import EngineError
 
 _ENGINE_FUNCS = {
@@ -29,6 +29,7 @@ _ENGINE_FUNCS = {
     "simple_average_fusion": hooks.simple_average_fusion,
     "content_based": hooks.content_based,
     "content_based_dct": hooks.content_based_dct,
+    "multi_view_deconvolution": deconv.multi_view_deconvolution,
 }
 
 

@@ -38,6 +38,7 @@ __all__ = [
     "simple_average_fusion",
     "content_based",
     "content_based_dct",
+    "multi_view_deconvolution",
     "build_work_list",
 ]
 
@@ -92,6 +93,26 @@ def _dct_overlap(kwargs):
 
 
 content_based_dct.required_overlap = _dct_overlap
+
+
+def multi_view_deconvolution(transformed_views, blending_weights, psfs=None, psf_type="EFFICIENT_BAYESIAN", n_iterations=10,
+                             lambda_reg=0.0, min_value=1e-4, output_spacing=None, na=0.8, wavelength_um=0.5,
+                             sample_boundary_erosion_px=0):
+    """fusion.mv_deconv.multi_view_deconvolution (fusion/mv_deconv.py:251-500) on the GPU; pass as
+    ``fusion_func``."""
+    from . import deconv
+
+    return deconv.multi_view_deconvolution(transformed_views, blending_weights, psfs, psf_type, n_iterations, lambda_reg,
+                                           min_value, output_spacing, na, wavelength_um, sample_boundary_erosion_px)
+
+
+def _deconv_overlap(kwargs):
+    from . import deconv
+
+    return deconv._required_overlap_for_deconvolution(kwargs)
+
+
+multi_view_deconvolution.required_overlap = _deconv_overlap
 
 
 _MODE_BY_NAME = {
