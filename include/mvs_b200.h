@@ -297,6 +297,33 @@ int mvs_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pit
 int mvs_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
                     size_t width, size_t rows, void* stream);
 
+/* Chunk files of a Zarr directory store (output side of fuse(output_zarr_url=...),
+ * fusion/_core.py:1160-1168, :2130-2150; input tiles likewise): n independent files written
+ * from (write != 0) or read into host buffers by a pool of threads. */
+int mvs_io_files(const char* const* paths, void* const* bufs, const size_t* sizes, int n, int write);
+
+/* Zarr v2 chunk encode / decode (what zarr-python does under `da.to_zarr(region=...)`,
+ * fusion/_core.py:2130-2150, and under `write_sim_to_ome_zarr`, ngff_utils.py:1353-1362; the
+ * reference's own statement of the encoding is VirtualOMEZarr.read_chunk / _pad_edge_chunk,
+ * ngff_utils.py:372-395, :425-436): a chunk is the C-order bytes of a chunk[0] x chunk[1] x
+ * chunk[2] box, edge chunks padded with the fill value 0.  mvs_chunks_pack gathers a dense
+ * level (element strides, x contiguous; 2-D uses z extent / chunk 1) into chunk-major order --
+ * chunk (iz, iy, ix) at ((iz*gy + iy)*gx + ix) * prod(chunk) items, g = ceil(shape / chunk) --
+ * and mvs_chunks_unpack scatters it back (bytes beyond the dense extent are dropped).
+ * mvs_chunks_store writes n consecutive packed chunks of chunk_bytes each to paths[i]
+ * (device -> per-thread pinned buffer -> file, pipelined over the copy pool; work enqueued on
+ * `stream` before the call is waited for); mvs_chunks_load reads them back (a missing file
+ * reads as zeros = the fill value; a short file is an error) and returns when all chunks are
+ * resident. */
+int mvs_chunks_pack(const void* d_dense, int item_size, const int32_t shape[3],
+                    const int64_t stride[3], const int32_t chunk[3], void* d_packed, void* stream);
+int mvs_chunks_unpack(const void* d_packed, int item_size, const int32_t shape[3],
+                      const int64_t stride[3], const int32_t chunk[3], void* d_dense, void* stream);
+int mvs_chunks_store(const void* d_packed, size_t chunk_bytes, int n, const char* const* paths,
+                     void* stream);
+int mvs_chunks_load(void* d_packed, size_t chunk_bytes, int n, const char* const* paths,
+                    void* stream);
+
 /* ------------------------------------------------------------------------
  * Pair preparation (register_pair_of_msims, registration.py:1732-1968): the
  * views are mean-binned (`sim.coarsen(binning, boundary="trim").mean()

@@ -126,6 +126,11 @@ _SIGNATURES = {
     ),
     "mvs_copy_h2d_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_copy_d2h_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
+    "mvs_io_files": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int]),
+    "mvs_chunks_pack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), _P, _P]),
+    "mvs_chunks_unpack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), _P, _P]),
+    "mvs_chunks_store": (ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_int, _P, _P]),
+    "mvs_chunks_load": (ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_int, _P, _P]),
     "mvs_synth_field": (
         ctypes.c_int,
         [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _P, _P, _P, _P, ctypes.c_int,

@@ -243,6 +243,12 @@ class BatchFuser:
                               chunk_subset=[b[0] for b in blocks], out=out, out_start=lo)
             self._plans[pkey] = plan
         host_out = zarr_out if isinstance(zarr_out, np.ndarray) else None
+        from .ngff_io import ZarrArray
+
+        # the engine's own Zarr v2 array: blocks are chunk-encoded on the device and go from HBM to
+        # their chunk files without a dense host copy (raw chunks; the output chunk grid is the array's)
+        dev_store = (isinstance(zarr_out, ZarrArray) and zarr_out._codec is None
+                     and tuple(zarr_out.chunks) == (1,) * n_ns + tuple(int(chunksize[d]) for d in dims))
         h2d.wait_stream(cur)
         d2h_ptr = ctypes.c_void_p(d2h.cuda_stream)
         futures = []
@@ -256,6 +262,9 @@ class BatchFuser:
                 region = tuple(int(i) for i in ns_idx) + tuple(slice(int(a), int(a) + int(m)) for a, m in zip(start, shape))
                 if host_out is not None:
                     n += _lib.copy_d2h(host_out[region], win, d2h_ptr)
+                elif dev_store:
+                    with torch.cuda.stream(d2h):
+                        n += zarr_out.write_device(win, lead=ns_idx, start=start)
                 else:
                     with torch.cuda.stream(d2h):
                         arr = win.cpu().numpy()

@@ -22,6 +22,8 @@ from __future__ import annotations
 import ctypes
 import inspect
 
+import os
+
 import numpy as np
 
 from . import _lib, geometry
@@ -707,6 +709,8 @@ def fuse(
     blending_widths=None,
     output_on_backend=False,
     out_host=None,
+    output_zarr_url=None,
+    zarr_options=None,
 ):
     """Fuse whole in-memory views (host or device) into one stack.
 
@@ -718,7 +722,38 @@ def fuse(
     With host views and a preallocated ``out_host`` (pinned array / CPU tensor of
     the fused shape and dtype) uploads, fusion and download are pipelined band
     by band and ``out_host`` is returned.
+
+    ``output_zarr_url`` (+ ``zarr_options``: ``ome_zarr``, ``ngff_version``, ``overwrite``,
+    ``zarr_array_creation_kwargs``; fusion/_core.py:1068-1168): the fused stack is chunk-encoded
+    on the device and written as a Zarr v2 array -- under ``<url>/0`` with the resolution pyramid
+    and NGFF 0.4 metadata when ``ome_zarr`` is set (``ngff_io.write_sim_to_ome_zarr``).
     """
+    if output_zarr_url is not None:
+        import shutil
+
+        from . import ngff_io
+
+        zo = dict(zarr_options or {})
+        if out_host is not None:
+            raise EngineError("out_host and output_zarr_url are mutually exclusive")
+        fused, osp = fuse(views, params, output_stack_properties, output_spacing, output_stack_mode, output_chunksize,
+                          fusion_func, weights_func, weights_func_kwargs, interpolation_order, blending_widths,
+                          output_on_backend=True)
+        dims = geometry.spatial_dims(fused.ndim)
+        default = {"z": 256, "y": 256, "x": 256} if fused.ndim == 3 else {"y": 2048, "x": 2048}
+        chunks = {d: int((output_chunksize or default)[d]) for d in dims}
+        if zo.get("overwrite", True) and os.path.exists(str(output_zarr_url)):
+            shutil.rmtree(str(output_zarr_url))
+        kw = zo.get("zarr_array_creation_kwargs") or {}
+        if zo.get("ome_zarr", False):
+            ngff_io.write_sim_to_ome_zarr(DeviceView(fused, osp["origin"], osp["spacing"]), output_zarr_url,
+                                          overwrite=False, ngff_version=zo.get("ngff_version", "0.4"),
+                                          zarr_array_creation_kwargs=kw, chunks=chunks)
+        else:
+            arr = ngff_io.ZarrArray.create(output_zarr_url, tuple(fused.shape), [chunks[d] for d in dims],
+                                           _torch_to_np(fused.dtype), compressor=kw.get("compressor"))
+            arr.write_device(fused)
+        return (fused if output_on_backend else fused.cpu().numpy()), osp
     builtin = getattr(fusion_func, "__name__", None) in _MODE_BY_NAME
     if out_host is not None and weights_func is None and builtin and all(_is_host_view(v) for v in views):
         host_bbs = []
