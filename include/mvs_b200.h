@@ -286,8 +286,9 @@ int mvs_pc_spearman_batch(mvs_pc_plan* plan, int n, const int32_t* pairs, const 
  * Host <-> device movement of PAGEABLE host arrays: what the reference's hooks hand
  * over are plain numpy arrays (view slices, fusion/_core.py:1579-1587; the zarr
  * region a fused block is written to, :2130-2150).  `rows` rows of `width` bytes
- * travel through a ring of pinned staging buffers filled / drained by worker
- * threads while the DMA engine moves the previous piece.
+ * are cut into 2 MiB pieces; every thread of a small pool moves its pieces end to end
+ * through its own two pinned buffers and its own stream (fill + DMA, or DMA + drain with
+ * cache-bypassing stores), so uploads, downloads and the host copies all overlap.
  * mvs_copy_h2d_2d returns once h_src has been staged (the device copy is ordered on
  * `stream`); mvs_copy_d2h_2d returns once h_dst is filled (work on `stream` enqueued
  * before the call is waited for).  Pitches in bytes.
@@ -296,6 +297,11 @@ int mvs_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pit
                     size_t width, size_t rows, void* stream);
 int mvs_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
                     size_t width, size_t rows, void* stream);
+/* The same for `planes` planes `*_plane` bytes apart (3-D windows of tiles and fused blocks). */
+int mvs_copy_h2d_3d(void* d_dst, size_t d_pitch, size_t d_plane, const void* h_src, size_t h_pitch,
+                    size_t h_plane, size_t width, size_t rows, size_t planes, void* stream);
+int mvs_copy_d2h_3d(void* h_dst, size_t h_pitch, size_t h_plane, const void* d_src, size_t d_pitch,
+                    size_t d_plane, size_t width, size_t rows, size_t planes, void* stream);
 
 /* Chunk files of a Zarr directory store (output side of fuse(output_zarr_url=...),
  * fusion/_core.py:1160-1168, :2130-2150; input tiles likewise): n independent files written

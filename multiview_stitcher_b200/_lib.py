@@ -126,6 +126,8 @@ _SIGNATURES = {
     ),
     "mvs_copy_h2d_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_copy_d2h_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
+    "mvs_copy_h2d_3d": (ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
+    "mvs_copy_d2h_3d": (ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_io_files": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int]),
     "mvs_chunks_pack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), _P, _P]),
     "mvs_chunks_unpack": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), _P, _P]),
@@ -206,50 +208,55 @@ def current_stream_ptr():
 
 
 def _pitched(shape, strides_bytes, itemsize):
-    """(outer index tuples, rows, width bytes, pitch bytes) of an array window whose last
-    axis is contiguous: the window is a stack of pitched 2-D copies."""
-    if len(shape) == 1:
-        return [()], 1, shape[0] * itemsize, shape[0] * itemsize
-    if strides_bytes[-1] != itemsize:
+    """(outer index tuples, planes, rows, width bytes, row pitch, plane pitch) of an array window
+    whose last axis is contiguous: a stack of pitched 3-D copies (one for up to 3 axes)."""
+    if len(shape) == 0:
+        return [()], 1, 1, itemsize, itemsize, itemsize
+    if strides_bytes[-1] != itemsize and shape[-1] > 1:
         raise EngineError("staged copies need a contiguous last axis")
-    outer = list(np.ndindex(*shape[:-2])) if len(shape) > 2 else [()]
-    return outer, int(shape[-2]), int(shape[-1]) * itemsize, int(strides_bytes[-2])
+    width = int(shape[-1]) * itemsize
+    if len(shape) == 1:
+        return [()], 1, 1, width, width, width
+    rows, pitch = int(shape[-2]), int(strides_bytes[-2])
+    if len(shape) == 2:
+        return [()], 1, rows, width, pitch, pitch * rows
+    outer = list(np.ndindex(*shape[:-3])) if len(shape) > 3 else [()]
+    return outer, int(shape[-3]), rows, width, pitch, int(strides_bytes[-3])
+
+
+def _staged(fn_name, dev_tensor, host_array, stream_ptr):
+    lib = load(require_device=True)
+    if tuple(dev_tensor.shape) != tuple(host_array.shape) or dev_tensor.element_size() != host_array.itemsize:
+        raise EngineError(f"{fn_name}: shape / item size mismatch")
+    es = host_array.itemsize
+    outer, planes, rows, width, hp, hpl = _pitched(host_array.shape, host_array.strides, es)
+    dstr = [s * es for s in dev_tensor.stride()]
+    _, _, _, _, dp, dpl = _pitched(tuple(dev_tensor.shape), dstr, es)
+    if min(hp, dp) < width or (planes > 1 and (hpl < hp * rows or dpl < dp * rows)) or (rows > 1 and (hp <= 0 or dp <= 0)):
+        raise EngineError(f"{fn_name}: overlapping / negative strides are not supported")
+    st = stream_ptr if stream_ptr is not None else current_stream_ptr()
+    fn = getattr(lib, fn_name)
+    no = len(outer[0])
+    for idx in outer:
+        ho = sum(i * s for i, s in zip(idx, host_array.strides[:no]))
+        do = sum(i * s for i, s in zip(idx, dstr[:no]))
+        d = ctypes.c_void_p(dev_tensor.data_ptr() + do)
+        h = ctypes.c_void_p(host_array.ctypes.data + ho)
+        if fn_name == "mvs_copy_h2d_3d":
+            check(fn(d, dp, dpl, h, hp, hpl, width, rows, planes, st), fn_name)
+        else:
+            check(fn(h, hp, hpl, d, dp, dpl, width, rows, planes, st), fn_name)
+    return int(host_array.size) * es
 
 
 def copy_h2d(dst_tensor, src_array, stream_ptr=None):
     """Pageable numpy window -> CUDA tensor window (same shape, contiguous last axis)
-    through the engine's pinned staging ring.  Returns the bytes moved."""
-    lib = load(require_device=True)
-    if tuple(dst_tensor.shape) != tuple(src_array.shape) or dst_tensor.element_size() != src_array.itemsize:
-        raise EngineError("copy_h2d: shape / item size mismatch")
-    es = src_array.itemsize
-    outer, rows, width, hp = _pitched(src_array.shape, src_array.strides, es)
-    dstr = [s * es for s in dst_tensor.stride()]
-    _, _, _, dp = _pitched(tuple(dst_tensor.shape), dstr, es)
-    st = stream_ptr if stream_ptr is not None else current_stream_ptr()
-    for idx in outer:
-        ho = sum(i * s for i, s in zip(idx, src_array.strides))
-        do = sum(i * s for i, s in zip(idx, dstr))
-        check(lib.mvs_copy_h2d_2d(ctypes.c_void_p(dst_tensor.data_ptr() + do), dp,
-                                  ctypes.c_void_p(src_array.ctypes.data + ho), hp, width, rows, st), "mvs_copy_h2d_2d")
-    return int(src_array.size) * es
+    through the engine's pinned staging lanes.  Returns the bytes moved."""
+    return _staged("mvs_copy_h2d_3d", dst_tensor, src_array, stream_ptr)
 
 
 def copy_d2h(dst_array, src_tensor, stream_ptr=None):
     """CUDA tensor window -> pageable numpy window (blocking)."""
-    lib = load(require_device=True)
-    if tuple(src_tensor.shape) != tuple(dst_array.shape) or src_tensor.element_size() != dst_array.itemsize:
-        raise EngineError("copy_d2h: shape / item size mismatch")
     if not dst_array.flags.writeable:
         raise EngineError("copy_d2h: destination is read-only")
-    es = dst_array.itemsize
-    outer, rows, width, hp = _pitched(dst_array.shape, dst_array.strides, es)
-    sstr = [s * es for s in src_tensor.stride()]
-    _, _, _, dp = _pitched(tuple(src_tensor.shape), sstr, es)
-    st = stream_ptr if stream_ptr is not None else current_stream_ptr()
-    for idx in outer:
-        ho = sum(i * s for i, s in zip(idx, dst_array.strides))
-        do = sum(i * s for i, s in zip(idx, sstr))
-        check(lib.mvs_copy_d2h_2d(ctypes.c_void_p(dst_array.ctypes.data + ho), hp,
-                                  ctypes.c_void_p(src_tensor.data_ptr() + do), dp, width, rows, st), "mvs_copy_d2h_2d")
-    return int(dst_array.size) * es
+    return _staged("mvs_copy_d2h_3d", src_tensor, dst_array, stream_ptr)

@@ -257,6 +257,13 @@ class BatchFuser:
             torch.cuda.set_device(out.device)
             d2h.wait_event(done)
             n = 0
+            if host_out is not None and len(band_blocks) > 1:
+                # blocks that tile a box (a band of a regular chunk grid) go down as ONE pitched copy:
+                # long rows and a deep pipeline instead of a short transfer per block
+                b_lo = np.min([b[1] for b in band_blocks], axis=0)
+                b_hi = np.max([np.add(b[1], b[2]) for b in band_blocks], axis=0)
+                if int(np.prod(b_hi - b_lo)) == sum(int(np.prod(b[2])) for b in band_blocks):
+                    band_blocks = [(None, b_lo, b_hi - b_lo)]
             for lin, start, shape in band_blocks:
                 win = out[tuple(slice(int(a - o), int(a - o + m)) for a, o, m in zip(start, lo, shape))]
                 region = tuple(int(i) for i in ns_idx) + tuple(slice(int(a), int(a) + int(m)) for a, m in zip(start, shape))

@@ -3,22 +3,37 @@
 // The reference's hooks hand the engine plain numpy arrays (fuse_np's view slices,
 // fusion/_core.py:1579-1587; the destination zarr region of _fuse_chunk_to_zarr,
 // :2130-2150).  A cudaMemcpy from pageable memory is staged by the driver through a
-// small bounce buffer at a fraction of the link rate.  Here a ring of pinned staging
-// buffers is filled (H2D) or drained (D2H) by a pool of worker threads while the DMA
-// engine moves the previous piece, so pageable arrays travel at close to the rate of
-// pinned ones and the pinning cost is paid once, by the engine.
+// small bounce buffer at a fraction of the link rate.  Here a transfer is cut into 2 MiB
+// pieces that travel through a ring of pinned slots: a pool of threads copies between the
+// user's array and the slots (several pieces at a time; downloads with cache-bypassing
+// stores) while the calling thread alone enqueues the DMAs and waits for their events, so
+// pageable arrays travel at close to the rate of pinned ones, uploads and downloads overlap,
+// and the pinning cost is paid once, by the engine.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "common.cuh"
 
 namespace mvs {
+
+static inline void cpu_relax() {
+#if defined(__SSE2__)
+  _mm_pause();
+#else
+  std::this_thread::yield();
+#endif
+}
 
 class CopyPool {
  public:
@@ -34,6 +49,15 @@ class CopyPool {
     for (auto& t : workers_) t.join();
   }
   int size() const { return (int)workers_.size(); }
+  // fire-and-forget job (the caller tracks completion itself)
+  void submit(std::function<void()> job) {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      q_.push_back(std::move(job));
+      pending_.fetch_add(1, std::memory_order_release);
+    }
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_one();
+  }
   // runs fn(0..n-1) on the pool and the calling thread; returns when all are done
   void parallel_for(int n, const std::function<void(int)>& fn) {
     if (n <= 1 || workers_.empty()) {
@@ -66,6 +90,7 @@ class CopyPool {
             dcv.notify_all();
           }
         });
+      pending_.fetch_add(helpers, std::memory_order_release);
     }
     cv_.notify_all();
     body();
@@ -74,19 +99,41 @@ class CopyPool {
   }
 
  private:
+  // A worker that has just run a job keeps polling for the next one for a while before it goes
+  // to sleep: the pieces of a transfer arrive every few tens of microseconds, and waking a
+  // sleeping thread costs more than copying a piece (measured on the B200 box: a transfer whose
+  // workers sleep between pieces runs at a third of the rate).
   void loop() {
     for (;;) {
       std::function<void()> job;
-      {
-        std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [this] { return stop_ || !q_.empty(); });
-        if (stop_ && q_.empty()) return;
-        job = std::move(q_.front());
-        q_.erase(q_.begin());
+      const auto t0 = std::chrono::steady_clock::now();
+      for (;;) {
+        if (pending_.load(std::memory_order_acquire) > 0) {
+          std::lock_guard<std::mutex> l(m_);
+          if (!q_.empty()) {
+            job = std::move(q_.front());
+            q_.erase(q_.begin());
+            pending_.fetch_sub(1, std::memory_order_relaxed);
+            break;
+          }
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) {
+          std::unique_lock<std::mutex> l(m_);
+          sleepers_.fetch_add(1);
+          cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+          sleepers_.fetch_sub(1);
+          if (stop_ && q_.empty()) return;
+          job = std::move(q_.front());
+          q_.erase(q_.begin());
+          pending_.fetch_sub(1, std::memory_order_relaxed);
+          break;
+        }
+        cpu_relax();
       }
       job();
     }
   }
+  std::atomic<int> pending_{0}, sleepers_{0};
   std::vector<std::thread> workers_;
   std::vector<std::function<void()>> q_;
   std::mutex m_;
@@ -94,67 +141,291 @@ class CopyPool {
   bool stop_ = false;
 };
 
-constexpr size_t kPiece = 8u << 20;  // staging piece: 8 MiB
-constexpr int kRing = 4;
+// staging piece (default 2 MiB; MVS_COPY_PIECE_KB overrides it for experiments)
+static size_t piece_bytes() {
+  static const size_t v = [] {
+    const char* e = getenv("MVS_COPY_PIECE_KB");
+    const long kb = e ? atol(e) : 0;
+    return kb >= 64 && kb <= (64 << 10) ? (size_t)kb << 10 : (size_t)2 << 20;
+  }();
+  return v;
+}
+#define kPiece (piece_bytes())
+static bool stream_stores_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("MVS_COPY_NT");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
 
-struct Stager {
+static CopyPool& pool() {
+  static CopyPool p([] {
+    const char* e = getenv("MVS_COPY_THREADS");
+    const int want = e ? atoi(e) : 0;
+    const int hw = (int)std::thread::hardware_concurrency();
+    return want > 0 ? std::min(want, 64) : std::max(1, std::min(8, hw - 1));
+  }());
+  return p;
+}
+
+// memcpy whose stores bypass the cache (the destination of a download is written once and
+// not read by this thread again: no read-for-ownership traffic on the host memory bus)
+static void copy_stream_stores(char* dst, const char* src, size_t n) {
+#if defined(__SSE2__)
+  if (n >= 256 && stream_stores_enabled()) {
+    const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (head) {
+      memcpy(dst, src, head);
+      dst += head, src += head, n -= head;
+    }
+    const size_t body = n & ~(size_t)63;
+    for (size_t i = 0; i < body; i += 64) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+      const __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+      const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32));
+      const __m128i d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+      _mm_stream_si128((__m128i*)(dst + i), a);
+      _mm_stream_si128((__m128i*)(dst + i + 16), b);
+      _mm_stream_si128((__m128i*)(dst + i + 32), c);
+      _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    dst += body, src += body, n -= body;
+  }
+#endif
+  if (n) memcpy(dst, src, n);
+}
+
+// One staging ring per direction: kSlots pinned pieces.  ONE thread -- the caller -- talks to
+// the CUDA driver (DMA enqueue, event waits); the pool's threads only run the host copies
+// between the user's pageable array and the pinned pieces, several pieces at a time, and
+// report back through a flag per slot.  (Measured on the B200 box: letting every worker
+// enqueue its own DMAs and poll its own events makes an upload and a download that run side
+// by side 8x slower than either alone -- the driver serialises the calls.)
+constexpr int kSlots = 16;
+constexpr int kFillAhead = 12;  // upload: pieces being filled by the pool (the other slots hold DMAs in flight)
+constexpr int kDmaAhead = 6;    // download: DMAs in flight (the other slots are being drained by the pool)
+
+struct Ring {
   std::mutex mtx;  // one transfer per direction at a time
-  void* buf[kRing] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev[kRing];
-  bool used[kRing] = {false, false, false, false};
-  bool ready = false;
+  void* buf[kSlots] = {};
+  size_t cap = 0;
+  cudaEvent_t ev[kSlots] = {};
+  bool dma_pending[kSlots] = {};
+  size_t pos = 0;  // first slot of the next transfer: consecutive calls keep rotating through the ring
   int device = -1;
-  int pos = 0;  // next ring slot (persists across calls so small copies pipeline too)
-  cudaError_t init() {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (ready && dev == device) return cudaSuccess;
-    if (!ready) {
-      for (int i = 0; i < kRing; ++i) {
-        if ((e = cudaHostAlloc(&buf[i], kPiece, cudaHostAllocPortable)) != cudaSuccess) return e;
+  // host-copy completion, signalled by pool threads (the caller polls: see CopyPool::loop)
+  std::atomic<int> host_done[kSlots] = {};
+
+  cudaError_t prepare(int dev, size_t bytes) {
+    cudaError_t e;
+    if (device != dev) {
+      for (int i = 0; i < kSlots; ++i) {
+        if (dma_pending[i]) cudaEventSynchronize(ev[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+        if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        dma_pending[i] = false;
       }
-    } else {
-      for (int i = 0; i < kRing; ++i) cudaEventDestroy(ev[i]);
+      device = dev;
     }
-    for (int i = 0; i < kRing; ++i) {
-      if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-      used[i] = false;
+    if (cap < bytes) {
+      for (int i = 0; i < kSlots; ++i) {
+        if (dma_pending[i]) cudaEventSynchronize(ev[i]);
+        dma_pending[i] = false;
+        if (buf[i]) cudaFreeHost(buf[i]);
+        buf[i] = nullptr;
+      }
+      cap = 0;
+      for (int i = 0; i < kSlots; ++i)
+        if ((e = cudaHostAlloc(&buf[i], bytes + 4096, cudaHostAllocPortable)) != cudaSuccess) return e;
+      cap = bytes;
     }
-    device = dev;
-    ready = true;
     return cudaSuccess;
+  }
+  // The piece's place inside slot k: half a page away (mod 4 KiB) from the user's address, so
+  // that the loads and stores of the host copy never share their low 12 address bits (when they
+  // do -- e.g. 2 MiB pieces of a page-aligned array -- every load falsely depends on the store
+  // before it and the copy runs at half speed; measured on the B200 box).
+  char* at(int k, const void* user) const {
+    const uintptr_t want = (((uintptr_t)user & 4095) + 2048) & 4095 & ~(uintptr_t)63;
+    return (char*)buf[k] + want;
+  }
+  void mark(int slot) { host_done[slot].store(1, std::memory_order_release); }
+  void wait_host(int slot) {
+    for (int spins = 0; host_done[slot].load(std::memory_order_acquire) == 0; ++spins) {
+      if (spins < (1 << 16)) cpu_relax();
+      else std::this_thread::yield();
+    }
+  }
+  void clear(int slot) { host_done[slot].store(0, std::memory_order_relaxed); }
+};
+
+static Ring& ring(int dir) {
+  static Ring r[2];
+  return r[dir];
+}
+
+// a transfer of `planes` planes of `rows` rows of `width` bytes cut into pieces: byte ranges
+// when both sides are contiguous, else runs of whole rows inside one plane
+struct Pieces {
+  bool flat;
+  size_t width, rows, planes, unit, per_plane, n, buf_bytes;
+  Pieces(size_t width_, size_t rows_, size_t planes_, size_t d_pitch, size_t d_plane, size_t h_pitch,
+         size_t h_plane)
+      : width(width_), rows(rows_), planes(planes_) {
+    flat = d_pitch == width && h_pitch == width &&
+           (planes == 1 || (d_plane == width * rows && h_plane == width * rows));
+    if (flat) {
+      unit = kPiece;
+      per_plane = 0;
+      n = (width * rows * planes + unit - 1) / unit;
+      buf_bytes = kPiece;
+    } else {
+      unit = std::max<size_t>(1, kPiece / width);  // rows per piece
+      per_plane = (rows + unit - 1) / unit;
+      n = per_plane * planes;
+      buf_bytes = std::max(kPiece, width);
+    }
+  }
+  // piece p: byte offsets on both sides and its extent (flat: n_rows == 0 and `bytes` valid)
+  void locate(size_t p, size_t d_pitch, size_t d_plane, size_t h_pitch, size_t h_plane, size_t* d_off,
+              size_t* h_off, size_t* n_rows, size_t* bytes) const {
+    if (flat) {
+      *d_off = *h_off = p * unit;
+      *n_rows = 0;
+      *bytes = std::min(unit, width * rows * planes - p * unit);
+      return;
+    }
+    const size_t pl = p / per_plane, r0 = (p % per_plane) * unit;
+    *d_off = pl * d_plane + r0 * d_pitch;
+    *h_off = pl * h_plane + r0 * h_pitch;
+    *n_rows = std::min(unit, rows - r0);
+    *bytes = *n_rows * width;
   }
 };
 
-static CopyPool& pool() {
-  static CopyPool p(std::max(1, std::min(8, (int)std::thread::hardware_concurrency() - 1)));
-  return p;
-}
-static Stager& stager(int dir) {
-  static Stager s[2];
-  return s[dir];
-}
-
-// memcpy of `rows` rows of `width` bytes between pitched layouts, split over the pool
-static void pitched_copy(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width,
-                         size_t rows) {
+// memcpy of `rows` rows of `width` bytes between pitched layouts
+template <bool STREAM>
+static void rows_copy(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows) {
   if (dpitch == width && spitch == width) {
-    const size_t total = width * rows;
-    const int parts = (int)std::min<size_t>(pool().size() + 1, std::max<size_t>(1, total >> 20));
-    const size_t per = ((total + parts - 1) / parts + 63) & ~(size_t)63;
-    pool().parallel_for(parts, [&](int i) {
-      const size_t a = std::min(total, per * i), b = std::min(total, per * (i + 1));
-      if (b > a) memcpy(dst + a, src + a, b - a);
-    });
+    if (STREAM) copy_stream_stores(dst, src, width * rows);
+    else memcpy(dst, src, width * rows);
     return;
   }
-  const int parts = (int)std::min<size_t>(pool().size() + 1, std::max<size_t>(1, (width * rows) >> 20));
-  const size_t per = (rows + parts - 1) / parts;
-  pool().parallel_for(parts, [&](int i) {
-    const size_t a = std::min(rows, per * i), b = std::min(rows, per * (i + 1));
-    for (size_t r = a; r < b; ++r) memcpy(dst + r * dpitch, src + r * spitch, width);
-  });
+  for (size_t r = 0; r < rows; ++r) {
+    if (STREAM) copy_stream_stores(dst + r * dpitch, src + r * spitch, width);
+    else memcpy(dst + r * dpitch, src + r * spitch, width);
+  }
+}
+
+static int staged_upload(char* d_dst, size_t d_pitch, size_t d_plane, const char* h_src, size_t h_pitch,
+                         size_t h_plane, size_t width, size_t rows, size_t planes, cudaStream_t st) {
+  if (width == 0 || rows == 0 || planes == 0) return MVS_OK;
+  MVS_REQUIRE(d_dst && h_src, MVS_ERR_INVALID, "NULL pointer");
+  MVS_REQUIRE(d_pitch >= width && h_pitch >= width, MVS_ERR_INVALID, "pitch smaller than width");
+  int dev = 0;
+  MVS_CHECK_CUDA(cudaGetDevice(&dev));
+  const Pieces P(width, rows, planes, d_pitch, d_plane, h_pitch, h_plane);
+  Ring& R = ring(0);
+  std::lock_guard<std::mutex> lock(R.mtx);
+  MVS_CHECK_CUDA(R.prepare(dev, P.buf_bytes));
+  // pieces are handed to the pool as slots free up (a slot is free once the DMA that last read it
+  // has completed) and their DMAs are enqueued on `stream`, in order, as the fills complete
+  size_t dispatched = 0, issued = 0;
+  const size_t base = R.pos;
+  R.pos = (R.pos + P.n) % kSlots;
+  cudaError_t e = cudaSuccess;
+  while (issued < P.n && e == cudaSuccess) {
+    while (dispatched < P.n && dispatched < issued + kFillAhead) {
+      const int k = (int)((base + dispatched) % kSlots);
+      if (R.dma_pending[k]) {
+        if ((e = cudaEventSynchronize(R.ev[k])) != cudaSuccess) break;
+        R.dma_pending[k] = false;
+      }
+      R.clear(k);
+      const size_t p = dispatched++;
+      pool().submit([&R, &P, k, p, h_src, d_pitch, d_plane, h_pitch, h_plane, width] {
+        size_t d_off, h_off, n_rows, bytes;
+        P.locate(p, d_pitch, d_plane, h_pitch, h_plane, &d_off, &h_off, &n_rows, &bytes);
+        char* stage = R.at(k, h_src + h_off);
+        if (n_rows == 0) memcpy(stage, h_src + h_off, bytes);
+        else rows_copy<false>(stage, width, h_src + h_off, h_pitch, width, n_rows);
+        R.mark(k);
+      });
+    }
+    if (e != cudaSuccess) break;
+    const int k = (int)((base + issued) % kSlots);
+    R.wait_host(k);
+    size_t d_off, h_off, n_rows, bytes;
+    P.locate(issued, d_pitch, d_plane, h_pitch, h_plane, &d_off, &h_off, &n_rows, &bytes);
+    const char* stage = R.at(k, h_src + h_off);
+    if (n_rows == 0) e = cudaMemcpyAsync(d_dst + d_off, stage, bytes, cudaMemcpyHostToDevice, st);
+    else e = cudaMemcpy2DAsync(d_dst + d_off, d_pitch, stage, width, width, n_rows, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(R.ev[k], st);
+    R.dma_pending[k] = true;
+    ++issued;
+  }
+  for (size_t p = issued; p < dispatched; ++p) R.wait_host((int)((base + p) % kSlots));  // error path: no job may outlive the call
+  MVS_REQUIRE(e == cudaSuccess, MVS_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString(e));
+  return MVS_OK;
+}
+
+static int staged_download(char* h_dst, size_t h_pitch, size_t h_plane, const char* d_src, size_t d_pitch,
+                           size_t d_plane, size_t width, size_t rows, size_t planes, cudaStream_t st) {
+  if (width == 0 || rows == 0 || planes == 0) return MVS_OK;
+  MVS_REQUIRE(h_dst && d_src, MVS_ERR_INVALID, "NULL pointer");
+  MVS_REQUIRE(d_pitch >= width && h_pitch >= width, MVS_ERR_INVALID, "pitch smaller than width");
+  int dev = 0;
+  MVS_CHECK_CUDA(cudaGetDevice(&dev));
+  const Pieces P(width, rows, planes, d_pitch, d_plane, h_pitch, h_plane);
+  Ring& R = ring(1);
+  std::lock_guard<std::mutex> lock(R.mtx);
+  MVS_CHECK_CUDA(R.prepare(dev, P.buf_bytes));
+  // DMAs run up to kDmaAhead pieces ahead on `stream`; a piece that has landed is drained to the
+  // user's array by a pool thread (cache-bypassing stores) and its slot is reused afterwards
+  size_t issued = 0, drained = 0;  // drained = pieces handed to the pool
+  bool draining[kSlots] = {};
+  cudaError_t e = cudaSuccess;
+  while (drained < P.n && e == cudaSuccess) {
+    while (issued < P.n && issued < drained + kDmaAhead) {
+      const int k = (int)(issued % kSlots);
+      if (draining[k]) {
+        R.wait_host(k);
+        draining[k] = false;
+      }
+      size_t d_off, h_off, n_rows, bytes;
+      P.locate(issued, d_pitch, d_plane, h_pitch, h_plane, &d_off, &h_off, &n_rows, &bytes);
+      char* stage = R.at(k, h_dst + h_off);
+      if (n_rows == 0) e = cudaMemcpyAsync(stage, d_src + d_off, bytes, cudaMemcpyDeviceToHost, st);
+      else e = cudaMemcpy2DAsync(stage, width, d_src + d_off, d_pitch, width, n_rows, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaEventRecord(R.ev[k], st);
+      if (e != cudaSuccess) break;
+      ++issued;
+    }
+    if (e != cudaSuccess) break;
+    const int k = (int)(drained % kSlots);
+    if ((e = cudaEventSynchronize(R.ev[k])) != cudaSuccess) break;
+    R.clear(k);
+    draining[k] = true;
+    const size_t p = drained++;
+    pool().submit([&R, &P, k, p, h_dst, d_pitch, d_plane, h_pitch, h_plane, width] {
+      size_t d_off, h_off, n_rows, bytes;
+      P.locate(p, d_pitch, d_plane, h_pitch, h_plane, &d_off, &h_off, &n_rows, &bytes);
+      const char* stage = R.at(k, h_dst + h_off);
+      if (n_rows == 0) copy_stream_stores(h_dst + h_off, stage, bytes);
+      else rows_copy<true>(h_dst + h_off, h_pitch, stage, width, width, n_rows);
+#if defined(__SSE2__)
+      _mm_sfence();
+#endif
+      R.mark(k);
+    });
+  }
+  for (int k = 0; k < kSlots; ++k)
+    if (draining[k]) R.wait_host(k);
+  if (e != cudaSuccess) cudaStreamSynchronize(st);  // pending DMAs must not write the ring after an error return
+  for (int k = 0; k < kSlots; ++k) R.dma_pending[k] = false;
+  MVS_REQUIRE(e == cudaSuccess, MVS_ERR_CUDA, "staged download failed: %s", cudaGetErrorString(e));
+  return MVS_OK;
 }
 
 }  // namespace mvs
@@ -163,61 +434,24 @@ using namespace mvs;
 
 extern "C" int mvs_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
                                size_t width, size_t rows, void* stream) {
-  if (width == 0 || rows == 0) return MVS_OK;
-  MVS_REQUIRE(d_dst && h_src, MVS_ERR_INVALID, "NULL pointer");
-  MVS_REQUIRE(d_pitch >= width && h_pitch >= width, MVS_ERR_INVALID, "pitch smaller than width");
-  MVS_REQUIRE(width <= kPiece, MVS_ERR_UNSUPPORTED, "row of %zu bytes exceeds the staging piece", width);
-  Stager& S = stager(0);
-  std::lock_guard<std::mutex> lock(S.mtx);
-  MVS_CHECK_CUDA(S.init());
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t rows_per = std::max<size_t>(1, kPiece / width);
-  for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
-    const int k = S.pos;
-    S.pos = (S.pos + 1) % kRing;
-    const size_t n = std::min(rows_per, rows - r0);
-    if (S.used[k]) MVS_CHECK_CUDA(cudaEventSynchronize(S.ev[k]));
-    pitched_copy((char*)S.buf[k], width, (const char*)h_src + r0 * h_pitch, h_pitch, width, n);
-    MVS_CHECK_CUDA(cudaMemcpy2DAsync((char*)d_dst + r0 * d_pitch, d_pitch, S.buf[k], width, width, n,
-                                     cudaMemcpyHostToDevice, st));
-    MVS_CHECK_CUDA(cudaEventRecord(S.ev[k], st));
-    S.used[k] = true;
-  }
-  return MVS_OK;
+  return staged_upload((char*)d_dst, d_pitch, 0, (const char*)h_src, h_pitch, 0, width, rows, 1, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
                                size_t width, size_t rows, void* stream) {
-  if (width == 0 || rows == 0) return MVS_OK;
-  MVS_REQUIRE(h_dst && d_src, MVS_ERR_INVALID, "NULL pointer");
-  MVS_REQUIRE(d_pitch >= width && h_pitch >= width, MVS_ERR_INVALID, "pitch smaller than width");
-  MVS_REQUIRE(width <= kPiece, MVS_ERR_UNSUPPORTED, "row of %zu bytes exceeds the staging piece", width);
-  Stager& S = stager(1);
-  std::lock_guard<std::mutex> lock(S.mtx);
-  MVS_CHECK_CUDA(S.init());
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t rows_per = std::max<size_t>(1, kPiece / width);
-  const size_t pieces = (rows + rows_per - 1) / rows_per;
-  auto issue = [&](size_t p) -> cudaError_t {
-    const int k = (int)(p % kRing);
-    const size_t r0 = p * rows_per, n = std::min(rows_per, rows - r0);
-    cudaError_t e = cudaMemcpy2DAsync(S.buf[k], width, (const char*)d_src + r0 * d_pitch, d_pitch,
-                                      width, n, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    return cudaEventRecord(S.ev[k], st);
-  };
-  // keep kRing - 1 DMA pieces in flight ahead of the CPU drain
-  size_t issued = 0;
-  for (; issued < std::min<size_t>(pieces, kRing - 1); ++issued) MVS_CHECK_CUDA(issue(issued));
-  for (size_t p = 0; p < pieces; ++p) {
-    const int k = (int)(p % kRing);
-    MVS_CHECK_CUDA(cudaEventSynchronize(S.ev[k]));
-    if (issued < pieces) { MVS_CHECK_CUDA(issue(issued)); ++issued; }
-    const size_t r0 = p * rows_per, n = std::min(rows_per, rows - r0);
-    pitched_copy((char*)h_dst + r0 * h_pitch, h_pitch, (const char*)S.buf[k], width, width, n);
-  }
-  for (int i = 0; i < kRing; ++i) S.used[i] = false;
-  return MVS_OK;
+  return staged_download((char*)h_dst, h_pitch, 0, (const char*)d_src, d_pitch, 0, width, rows, 1, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_copy_h2d_3d(void* d_dst, size_t d_pitch, size_t d_plane, const void* h_src, size_t h_pitch,
+                               size_t h_plane, size_t width, size_t rows, size_t planes, void* stream) {
+  return staged_upload((char*)d_dst, d_pitch, d_plane, (const char*)h_src, h_pitch, h_plane, width, rows, planes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int mvs_copy_d2h_3d(void* h_dst, size_t h_pitch, size_t h_plane, const void* d_src, size_t d_pitch,
+                               size_t d_plane, size_t width, size_t rows, size_t planes, void* stream) {
+  return staged_download((char*)h_dst, h_pitch, h_plane, (const char*)d_src, d_pitch, d_plane, width, rows, planes,
+                         (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -411,7 +411,12 @@ def _to_device_f32(a):
         return a.to("cuda", dtype=torch.float32).contiguous()
     if hasattr(a, "data") and not isinstance(a, np.ndarray):
         a = a.data  # xr.DataArray-like (registration.py:377-378)
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to("cuda")
+    if hasattr(a, "__cuda_array_interface__"):
+        return torch.as_tensor(a, device="cuda").to(torch.float32).contiguous()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    t = torch.empty(a.shape, dtype=torch.float32, device="cuda")
+    _lib.copy_h2d(t, a)  # pageable host crop -> device through the pinned staging ring
+    return t
 
 
 def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsample_factor=None, return_details=False, plans=None):
