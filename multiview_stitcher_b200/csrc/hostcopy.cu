@@ -163,8 +163,12 @@ static CopyPool& pool() {
   static CopyPool p([] {
     const char* e = getenv("MVS_COPY_THREADS");
     const int want = e ? atoi(e) : 0;
-    const int hw = (int)std::thread::hardware_concurrency();
-    return want > 0 ? std::min(want, 64) : std::max(1, std::min(8, hw - 1));
+    // one process per GPU shares the host's cores with its node-local peers (torchrun exports
+    // LOCAL_WORLD_SIZE): polling workers must not oversubscribe them
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    const int peers = std::max(1, lw ? atoi(lw) : 1);
+    const int hw = std::max(1, (int)std::thread::hardware_concurrency() / peers);
+    return want > 0 ? std::min(want, 64) : std::max(2, std::min(8, hw - 1));
   }());
   return p;
 }
