@@ -516,6 +516,39 @@ def bench_c2(cx, args):
     torch.cuda.synchronize()
     reg_e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / 2)
 
+    # ---- output side: fused stack -> OME-Zarr 0.4 (pyramid levels binned on the device,
+    # chunks encoded on the device, raw chunk files written through pinned staging) and read back ----
+    zrec = None
+    if cx.rank == 0:
+        import shutil
+        import tempfile
+
+        from multiview_stitcher_b200 import ngff_io
+
+        zdir = tempfile.mkdtemp(prefix="mvs_b200_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            dv = fusion.DeviceView(plan.out, osp["origin"], osp["spacing"])
+            url = os.path.join(zdir, "fused.zarr")
+            ngff_io.write_sim_to_ome_zarr(dv, url, overwrite=True, chunks=chunksize)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            wres = ngff_io.write_sim_to_ome_zarr(dv, url, overwrite=True, chunks=chunksize)
+            torch.cuda.synchronize()
+            w_s = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            back = ngff_io.read_sim_from_ome_zarr(url, 0)
+            torch.cuda.synchronize()
+            r_s = time.perf_counter() - t0
+            zrec = {"what": "ngff_io.write_sim_to_ome_zarr(fused C2 stack): mvs_bin_mean per level + mvs_chunks_pack + "
+                            "mvs_chunks_store (raw Zarr v2 chunks of 2048x2048, store in " + os.path.dirname(zdir) + "), "
+                            "then read_sim_from_ome_zarr level 0 (mvs_chunks_load + mvs_chunks_unpack)",
+                    "levels": len(wres["shapes"]), "bytes_written": int(wres["bytes_written"]),
+                    "write_ms": w_s * 1e3, "write_Mvoxel_per_s": vox_per_step / w_s / 1e6,
+                    "read_level0_ms": r_s * 1e3, "read_back_equal": bool(torch.equal(back.tensor, plan.out))}
+            del back
+        finally:
+            shutil.rmtree(zdir, ignore_errors=True)
+
     traffic, traffic_src = _ncu_traffic()
     roof = _roof(plan.algorithmic_bytes(), fuse_kernel_ms, "fuse_stencil_kernel<2,float,WAVG> (TMA-staged translation path)")
     roof.update({"peak_source": _peaks()[1], "frac_of_nominal_8TBps": roof["achieved"] / 8000.0,
@@ -554,6 +587,7 @@ def bench_c2(cx, args):
         },
         "gpu_launches": launches_per_step * args.steps + reg_launches * n_reg,
         "roofline": roof,
+        "output_zarr": zrec,
     }
     plan.close()
     for p in pc_plans.values():
@@ -838,6 +872,7 @@ def run_ours(args):
             "gpu_launches": c2["gpu_launches"] + sum(c.get("gpu_launches", 0) for c in configs.values()),
             "clocks": clocks.summary(),
             "roofline": c2["roofline"],
+            "output_zarr": c2["output_zarr"],
             "configs": configs,
         }
         if errors:

@@ -279,13 +279,16 @@ struct Pieces {
       : width(width_), rows(rows_), planes(planes_) {
     flat = d_pitch == width && h_pitch == width &&
            (planes == 1 || (d_plane == width * rows && h_plane == width * rows));
+    // small transfers are cut finer (>= 256 KiB) so that all pool threads work on them
+    const size_t total = width * rows * planes;
+    const size_t piece = std::min<size_t>(kPiece, std::max<size_t>((size_t)256 << 10, ((total / 16) + 65535) & ~(size_t)65535));
     if (flat) {
-      unit = kPiece;
+      unit = piece;
       per_plane = 0;
-      n = (width * rows * planes + unit - 1) / unit;
+      n = (total + unit - 1) / unit;
       buf_bytes = kPiece;
     } else {
-      unit = std::max<size_t>(1, kPiece / width);  // rows per piece
+      unit = std::max<size_t>(1, piece / width);  // rows per piece
       per_plane = (rows + unit - 1) / unit;
       n = per_plane * planes;
       buf_bytes = std::max(kPiece, width);

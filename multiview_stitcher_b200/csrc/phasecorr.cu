@@ -290,7 +290,8 @@ updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, 
   if (blockIdx.y == 0 && threadIdx.x < 3) peaks[pn * 3 + threadIdx.x] = sh[threadIdx.x];
   float2* e = E + (long long)pn * e_stride;
   {
-    const double off = (double)(R / 2) - (double)sh[2] * u;
+    // off - R/2: the x contraction runs over centred powers g^(a - R/2) (updft_x_kernel)
+    const double off = (double)(R / 2) - (double)sh[2] * u - (double)(R / 2);
     for (int k = tid; k < n2; k += nth) {
       const int ks = (k <= (n2 - 1) / 2) ? k : k - n2;
       double s, c;
@@ -317,8 +318,14 @@ updft_setup_kernel(const unsigned long long* __restrict__ keys, int n0, int n1, 
   }
 }
 
-// Contract the x axis for both normalisations: T[pn][line][a] = sum_x P_pn[line, x] H_pn[x] g[x]^a.
-// One warp per line; float partials per lane, combined in float64 in lane order.
+// Contract the x axis for both normalisations: T[pn][line][a] = sum_x P_pn[line, x] H_pn[x] g[x]^(a - R/2)
+// (the setup kernel folds g^(R/2) into H, so the powers are centred).  |g| = 1, hence
+// g^-j = conj(g^j): with w = P H and g^j = c + i s the four real sums
+//   A = sum wr c, B = sum wi s, C = sum wr s, D = sum wi c
+// give BOTH outputs of a +-j pair -- (A - B) + i (C + D) and (A + B) + i (D - C) -- for four
+// FMAs per element and norm, against the twelve instructions per output of a plain
+// accumulate-and-rotate loop.  One warp per line; float partials per lane, combined in float64
+// in lane order.
 constexpr int kUpWarps = 4;
 
 template <int R>
@@ -326,6 +333,7 @@ __global__ void __launch_bounds__(kUpWarps * 32)
 updft_x_kernel(const float2* __restrict__ Pg, int n0, int n1, int n2, long long N,
                const float2* __restrict__ E, long long e_stride, const float2* __restrict__ G,
                double2* __restrict__ T) {
+  constexpr int C0 = R / 2, JP = R - 1 - C0, JM = C0 > JP ? C0 : JP;  // negative side reaches C0
   __shared__ float2 s_part[kUpWarps][2 * R][33];
   const int pair = blockIdx.y;
   const long long nlines = (long long)n0 * n1;
@@ -336,31 +344,53 @@ updft_x_kernel(const float2* __restrict__ Pg, int n0, int n1, int n2, long long 
     const float2* h0 = E + (long long)(2 * pair) * e_stride;
     const float2* h1 = h0 + e_stride;
     const float tiny = 100.0f * 1.1920929e-07f;  // 100 * eps(float32)
-    float2 acc0[R], acc1[R];
+    float2 cen0 = make_float2(0.f, 0.f), cen1 = make_float2(0.f, 0.f);
+    float A0[JM > 0 ? JM : 1], B0[JM > 0 ? JM : 1], C0s[JM > 0 ? JM : 1], D0[JM > 0 ? JM : 1];
+    float A1[JM > 0 ? JM : 1], B1[JM > 0 ? JM : 1], C1s[JM > 0 ? JM : 1], D1[JM > 0 ? JM : 1];
 #pragma unroll
-    for (int a = 0; a < R; ++a) { acc0[a] = make_float2(0.f, 0.f); acc1[a] = make_float2(0.f, 0.f); }
-    // two x per iteration: the g-power chains of the two elements are independent
+    for (int j = 0; j < JM; ++j) { A0[j] = B0[j] = C0s[j] = D0[j] = 0.f; A1[j] = B1[j] = C1s[j] = D1[j] = 0.f; }
+    // two x per iteration: the power chains of the two elements are independent
     for (int x = lane; x < n2; x += 64) {
       const int x2 = x + 32;
       const bool has2 = x2 < n2;
+      const int xb = has2 ? x2 : x;
       const float2 PsA = row[x];
       const float2 PsB = has2 ? row[x2] : make_float2(0.f, 0.f);
       const float magA = fmaxf(hypotf(PsA.x, PsA.y), tiny), magB = fmaxf(hypotf(PsB.x, PsB.y), tiny);
       const float2 PnA = make_float2(__fdiv_rn(PsA.x, magA), __fdiv_rn(PsA.y, magA));
       const float2 PnB = make_float2(__fdiv_rn(PsB.x, magB), __fdiv_rn(PsB.y, magB));
-      const float2 gA = __ldg(G + x), gB = __ldg(G + (has2 ? x2 : x));
-      float2 w0A = cmul(PsA, __ldg(h0 + x)), w1A = cmul(PnA, __ldg(h1 + x));
-      float2 w0B = cmul(PsB, __ldg(h0 + (has2 ? x2 : x))), w1B = cmul(PnB, __ldg(h1 + (has2 ? x2 : x)));
+      const float2 gA = __ldg(G + x), gB = __ldg(G + xb);
+      const float2 w0A = cmul(PsA, __ldg(h0 + x)), w1A = cmul(PnA, __ldg(h1 + x));
+      const float2 w0B = cmul(PsB, __ldg(h0 + xb)), w1B = cmul(PnB, __ldg(h1 + xb));
+      cen0 = cadd(cen0, cadd(w0A, w0B));
+      cen1 = cadd(cen1, cadd(w1A, w1B));
+      float2 qA = gA, qB = gB;
 #pragma unroll
-      for (int b = 0; b < R; ++b) {
-        acc0[b] = cadd(acc0[b], cadd(w0A, w0B));
-        acc1[b] = cadd(acc1[b], cadd(w1A, w1B));
-        w0A = cmul(w0A, gA); w1A = cmul(w1A, gA);
-        w0B = cmul(w0B, gB); w1B = cmul(w1B, gB);
+      for (int j = 0; j < JM; ++j) {
+        A0[j] = fmaf(w0A.x, qA.x, A0[j]); A0[j] = fmaf(w0B.x, qB.x, A0[j]);
+        B0[j] = fmaf(w0A.y, qA.y, B0[j]); B0[j] = fmaf(w0B.y, qB.y, B0[j]);
+        C0s[j] = fmaf(w0A.x, qA.y, C0s[j]); C0s[j] = fmaf(w0B.x, qB.y, C0s[j]);
+        D0[j] = fmaf(w0A.y, qA.x, D0[j]); D0[j] = fmaf(w0B.y, qB.x, D0[j]);
+        A1[j] = fmaf(w1A.x, qA.x, A1[j]); A1[j] = fmaf(w1B.x, qB.x, A1[j]);
+        B1[j] = fmaf(w1A.y, qA.y, B1[j]); B1[j] = fmaf(w1B.y, qB.y, B1[j]);
+        C1s[j] = fmaf(w1A.x, qA.y, C1s[j]); C1s[j] = fmaf(w1B.x, qB.y, C1s[j]);
+        D1[j] = fmaf(w1A.y, qA.x, D1[j]); D1[j] = fmaf(w1B.y, qB.x, D1[j]);
+        if (j + 1 < JM) { qA = cmul(qA, gA); qB = cmul(qB, gB); }
       }
     }
+    s_part[warp][C0][lane] = cen0;
+    s_part[warp][R + C0][lane] = cen1;
 #pragma unroll
-    for (int b = 0; b < R; ++b) { s_part[warp][b][lane] = acc0[b]; s_part[warp][R + b][lane] = acc1[b]; }
+    for (int j = 0; j < JM; ++j) {
+      if (j < JP) {
+        s_part[warp][C0 + 1 + j][lane] = make_float2(A0[j] - B0[j], C0s[j] + D0[j]);
+        s_part[warp][R + C0 + 1 + j][lane] = make_float2(A1[j] - B1[j], C1s[j] + D1[j]);
+      }
+      if (j < C0) {
+        s_part[warp][C0 - 1 - j][lane] = make_float2(A0[j] + B0[j], D0[j] - C0s[j]);
+        s_part[warp][R + C0 - 1 - j][lane] = make_float2(A1[j] + B1[j], D1[j] - C1s[j]);
+      }
+    }
   }
   __syncwarp();
   if (line < nlines) {

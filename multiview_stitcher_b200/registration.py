@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import itertools
+import os
 import warnings
 
 import numpy as np
@@ -419,6 +420,9 @@ def _to_device_f32(a):
     return t
 
 
+_SPLIT = int(os.environ.get("MVS_REG_SPLIT", "1"))
+
+
 def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsample_factor=None, return_details=False, plans=None):
     """Batched phase-correlation registration.  ``fixed_list[i]`` /
     ``moving_list[i]`` are same-shape float arrays (host or CUDA, NaN = outside);
@@ -439,10 +443,10 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
         groups.setdefault(tuple(f.shape), []).append(i)
     results = [None] * n
 
-    def run_group(shape, idx):
+    def run_group(shape, idx, part=0):
         ndim = len(shape)
         u = upsample_factor if upsample_factor is not None else (10 if ndim == 2 else 2)
-        key = (shape, u)
+        key = (shape, u) if part == 0 else (shape, u, part)
         plan = plans.get(key) if plans is not None else None
         if plan is None or plan.max_pairs < len(idx):
             plan = PhaseCorrPlan(shape, len(idx), u)
@@ -472,7 +476,14 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
         if plans is None:
             plan.close()
 
-    items = list(groups.items())
+    # large groups are cut into sub-batches that run side by side (own plan, stream and thread):
+    # the stages of one batch return to the host between launches, and another batch's kernels
+    # fill those gaps
+    items = []
+    for shape, idx in groups.items():
+        parts = max(1, min(_SPLIT, len(idx) // 8))
+        for k in range(parts):
+            items.append((shape, idx[k::parts], k))
     if len(items) == 1:
         run_group(*items[0])
         return results
@@ -496,7 +507,7 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
             run_group(*item)
         st.synchronize()
 
-    with ThreadPoolExecutor(max_workers=min(len(items), 4)) as pool:
+    with ThreadPoolExecutor(max_workers=min(len(items), 8)) as pool:
         for f in [pool.submit(worker, it) for it in items]:
             f.result()
     return results
