@@ -690,7 +690,7 @@ def bench_c3(cx, args):
     res = pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans)
     tt = np.array([t[:3, 3] for t in true])
     err = max(float(np.abs(r["transform"][:3, 3] + (tt[b] - tt[a])).max()) for r, (a, b) in zip(res, my_pairs))
-    ms_reg = cx.timed(lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 2, 0)
+    ms_reg = cx.timed(lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 3, 1)
     rec["registration_from_tiles"] = {"pairs": len(pairs), "pairs_this_rank": len(my_pairs), "ms": ms_reg,
                                       "pairs_per_sec": len(pairs) / (ms_reg * 1e-3),
                                       "max_abs_shift_error_px": cx.max_over_ranks(err),

@@ -317,10 +317,10 @@ int mvs_io_files(const char* const* paths, void* const* bufs, const size_t* size
  * chunk (iz, iy, ix) at ((iz*gy + iy)*gx + ix) * prod(chunk) items, g = ceil(shape / chunk) --
  * and mvs_chunks_unpack scatters it back (bytes beyond the dense extent are dropped).
  * mvs_chunks_store writes n consecutive packed chunks of chunk_bytes each to paths[i]
- * (device -> per-thread pinned buffer -> file, pipelined over the copy pool; work enqueued on
- * `stream` before the call is waited for); mvs_chunks_load reads them back (a missing file
- * reads as zeros = the fill value; a short file is an error) and returns when all chunks are
- * resident. */
+ * (device -> ring of pinned chunk slots on `stream` -> files written by the copy pool while the
+ * next DMAs run; returns when every file is written); mvs_chunks_load reads them back (a missing
+ * file reads as zeros = the fill value; a short file is an error) and returns when all chunks
+ * are resident. */
 int mvs_chunks_pack(const void* d_dense, int item_size, const int32_t shape[3],
                     const int64_t stride[3], const int32_t chunk[3], void* d_packed, void* stream);
 int mvs_chunks_unpack(const void* d_packed, int item_size, const int32_t shape[3],

@@ -522,7 +522,10 @@ struct ChunkGeom {
   int es;                       // item size in bytes
 };
 
-template <int VEC, bool PACK>  // VEC = bytes per thread along x (16, or the item size)
+// VEC = bytes per thread along x on the packed side (16, or the item size); DV: the dense side is
+// 16-byte aligned too (one vector access), else it is touched item by item (ES bytes each) while the
+// packed side still moves as one 16-byte vector
+template <int VEC, bool PACK, bool DV = true, int ES = 1>
 __global__ void __launch_bounds__(256) chunks_copy_kernel(char* dense, char* packed, ChunkGeom g,
                                                           int64_t n_units) {
   const int64_t row_units = (int64_t)g.chunk[2] * g.es / VEC;  // units per chunk row
@@ -544,7 +547,35 @@ __global__ void __launch_bounds__(256) chunks_copy_kernel(char* dense, char* pac
     const bool in_zy = z < g.shape[0] && y < g.shape[1];
     char* d = dense + z * g.stride[0] + y * g.stride[1] + xb;
     char* p = packed + u * VEC;
-    if (VEC == 16) {
+    if (VEC == 16 && !DV) {
+      union { uint4 v; unsigned char b[16]; } u16;
+      if (PACK) {
+        u16.v = make_uint4(0, 0, 0, 0);
+        if (in_zy) {
+#pragma unroll
+          for (int i = 0; i < 16 / ES; ++i) {
+            if (xb + (i + 1) * ES <= row_bytes) {
+              if (ES == 1) u16.b[i] = *reinterpret_cast<const unsigned char*>(d + i);
+              else if (ES == 2) reinterpret_cast<unsigned short*>(u16.b)[i] = *reinterpret_cast<const unsigned short*>(d + 2 * i);
+              else if (ES == 4) reinterpret_cast<unsigned*>(u16.b)[i] = *reinterpret_cast<const unsigned*>(d + 4 * i);
+              else reinterpret_cast<unsigned long long*>(u16.b)[i] = *reinterpret_cast<const unsigned long long*>(d + 8 * i);
+            }
+          }
+        }
+        *reinterpret_cast<uint4*>(p) = u16.v;
+      } else if (in_zy && xb < row_bytes) {
+        u16.v = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < 16 / ES; ++i) {
+          if (xb + (i + 1) * ES <= row_bytes) {
+            if (ES == 1) *reinterpret_cast<unsigned char*>(d + i) = u16.b[i];
+            else if (ES == 2) *reinterpret_cast<unsigned short*>(d + 2 * i) = reinterpret_cast<unsigned short*>(u16.b)[i];
+            else if (ES == 4) *reinterpret_cast<unsigned*>(d + 4 * i) = reinterpret_cast<unsigned*>(u16.b)[i];
+            else *reinterpret_cast<unsigned long long*>(d + 8 * i) = reinterpret_cast<unsigned long long*>(u16.b)[i];
+          }
+        }
+      }
+    } else if (VEC == 16) {
       if (PACK) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (in_zy && xb + 16 <= row_bytes) {
@@ -591,12 +622,19 @@ static int chunks_copy(void* dense, int item_size, const int32_t shape[3], const
     n_bytes *= (int64_t)g.grid[d] * chunk[d];
   }
   MVS_REQUIRE(stride[2] == 1, MVS_ERR_UNSUPPORTED, "the x axis must be contiguous");
-  const bool vec = ((int64_t)chunk[2] * item_size) % 16 == 0 && g.stride[0] % 16 == 0 && g.stride[1] % 16 == 0 &&
-                   ((uintptr_t)dense % 16) == 0 && ((uintptr_t)packed % 16) == 0;
-  const int64_t units = n_bytes / (vec ? 16 : item_size);
+  const bool pvec = ((int64_t)chunk[2] * item_size) % 16 == 0 && ((uintptr_t)packed % 16) == 0;
+  const bool dvec = g.stride[0] % 16 == 0 && g.stride[1] % 16 == 0 && ((uintptr_t)dense % 16) == 0;
+  const bool ialigned = ((uintptr_t)dense % item_size) == 0;
+  const int64_t units = n_bytes / (pvec && (dvec || ialigned) ? 16 : item_size);
   const int blocks = (int)std::min<int64_t>((units + 255) / 256, 148 * 32);
-  if (vec) {
+  if (pvec && dvec) {
     chunks_copy_kernel<16, PACK><<<blocks, 256, 0, st>>>((char*)dense, (char*)packed, g, units);
+  } else if (pvec && ialigned) {
+    // rows of arbitrary length (e.g. 9015 floats): 16-byte vectors on the packed side only
+    if (item_size == 1) chunks_copy_kernel<16, PACK, false, 1><<<blocks, 256, 0, st>>>((char*)dense, (char*)packed, g, units);
+    else if (item_size == 2) chunks_copy_kernel<16, PACK, false, 2><<<blocks, 256, 0, st>>>((char*)dense, (char*)packed, g, units);
+    else if (item_size == 4) chunks_copy_kernel<16, PACK, false, 4><<<blocks, 256, 0, st>>>((char*)dense, (char*)packed, g, units);
+    else chunks_copy_kernel<16, PACK, false, 8><<<blocks, 256, 0, st>>>((char*)dense, (char*)packed, g, units);
   } else if (item_size == 1) {
     chunks_copy_kernel<1, PACK><<<blocks, 256, 0, st>>>((char*)dense, (char*)packed, g, units);
   } else if (item_size == 2) {
@@ -610,33 +648,50 @@ static int chunks_copy(void* dense, int item_size, const int32_t shape[3], const
   return MVS_OK;
 }
 
-// per-thread staging for the chunk store / load pipeline: one pinned buffer (grow-only) and
-// one stream per pool thread, so the DMA of one chunk overlaps the file I/O of the others
-struct ChunkLane {
-  void* pinned = nullptr;
+// Pinned slots of one chunk each for the chunk store / load pipeline.  As with the staged copies
+// above, only the calling thread talks to the driver; the pool's threads do the file I/O.
+constexpr int kChunkSlots = 8;
+
+struct ChunkRing {
+  std::mutex mtx;
+  void* buf[kChunkSlots] = {};
   size_t cap = 0;
-  cudaStream_t st = nullptr;
+  cudaEvent_t ev[kChunkSlots] = {};
   int device = -1;
+  std::atomic<int> host_done[kChunkSlots] = {};
   cudaError_t prepare(int dev, size_t bytes) {
-    cudaError_t e = cudaSetDevice(dev);
-    if (e != cudaSuccess) return e;
-    if (st == nullptr || device != dev) {
-      if (st) cudaStreamDestroy(st);
-      if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    cudaError_t e;
+    if (device != dev) {
+      for (int i = 0; i < kChunkSlots; ++i) {
+        if (ev[i]) cudaEventDestroy(ev[i]);
+        if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+      }
       device = dev;
     }
     if (cap < bytes) {
-      if (pinned) cudaFreeHost(pinned);
-      pinned = nullptr;
+      for (int i = 0; i < kChunkSlots; ++i) {
+        if (buf[i]) cudaFreeHost(buf[i]);
+        buf[i] = nullptr;
+      }
       cap = 0;
-      if ((e = cudaHostAlloc(&pinned, bytes, cudaHostAllocPortable)) != cudaSuccess) return e;
+      for (int i = 0; i < kChunkSlots; ++i)
+        if ((e = cudaHostAlloc(&buf[i], bytes, cudaHostAllocPortable)) != cudaSuccess) return e;
       cap = bytes;
     }
     return cudaSuccess;
   }
+  void wait_host(int k) {
+    for (int spins = 0; host_done[k].load(std::memory_order_acquire) == 0; ++spins) {
+      if (spins < (1 << 16)) cpu_relax();
+      else std::this_thread::yield();
+    }
+  }
 };
 
-static thread_local ChunkLane t_lane;
+static ChunkRing& chunk_ring() {
+  static ChunkRing r;
+  return r;
+}
 
 }  // namespace mvs
 
@@ -660,30 +715,46 @@ extern "C" int mvs_chunks_store(const void* d_packed, size_t chunk_bytes, int n,
   MVS_REQUIRE(d_packed && paths && chunk_bytes > 0, MVS_ERR_INVALID, "NULL pointer / empty chunk");
   int dev = 0;
   MVS_CHECK_CUDA(cudaGetDevice(&dev));
-  cudaEvent_t ready;
-  MVS_CHECK_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  MVS_CHECK_CUDA(cudaEventRecord(ready, (cudaStream_t)stream));
-  std::atomic<int> failed(-1), cuda_err(0);
-  pool().parallel_for(n, [&](int i) {
-    ChunkLane& L = t_lane;
-    cudaError_t e = L.prepare(dev, chunk_bytes);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(L.st, ready, 0);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(L.pinned, (const char*)d_packed + (size_t)i * chunk_bytes, chunk_bytes,
-                          cudaMemcpyDeviceToHost, L.st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(L.st);
-    if (e != cudaSuccess) {
-      cuda_err.store((int)e);
-      return;
+  cudaStream_t st = (cudaStream_t)stream;
+  ChunkRing& R = chunk_ring();
+  std::lock_guard<std::mutex> lock(R.mtx);
+  MVS_CHECK_CUDA(R.prepare(dev, chunk_bytes));
+  constexpr int kAhead = 3;  // DMAs in flight; the other slots are being written out by the pool
+  std::atomic<int> failed(-1);
+  bool writing[kChunkSlots] = {};
+  int issued = 0, handed = 0;
+  cudaError_t e = cudaSuccess;
+  while (handed < n && e == cudaSuccess) {
+    while (issued < n && issued < handed + kAhead) {
+      const int k = issued % kChunkSlots;
+      if (writing[k]) {
+        R.wait_host(k);
+        writing[k] = false;
+      }
+      e = cudaMemcpyAsync(R.buf[k], (const char*)d_packed + (size_t)issued * chunk_bytes, chunk_bytes,
+                          cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaEventRecord(R.ev[k], st);
+      if (e != cudaSuccess) break;
+      ++issued;
     }
-    if (!file_rw(paths[i], (char*)L.pinned, chunk_bytes, true)) {
-      int expect = -1;
-      failed.compare_exchange_strong(expect, i);
-    }
-  });
-  cudaEventDestroy(ready);
-  MVS_REQUIRE(cuda_err.load() == 0, MVS_ERR_CUDA, "chunk download failed: %s",
-              cudaGetErrorString((cudaError_t)cuda_err.load()));
+    if (e != cudaSuccess) break;
+    const int k = handed % kChunkSlots;
+    if ((e = cudaEventSynchronize(R.ev[k])) != cudaSuccess) break;
+    R.host_done[k].store(0, std::memory_order_relaxed);
+    writing[k] = true;
+    const int i = handed++;
+    pool().submit([&R, &failed, k, i, paths, chunk_bytes] {
+      if (!file_rw(paths[i], (char*)R.buf[k], chunk_bytes, true)) {
+        int expect = -1;
+        failed.compare_exchange_strong(expect, i);
+      }
+      R.host_done[k].store(1, std::memory_order_release);
+    });
+  }
+  for (int k = 0; k < kChunkSlots; ++k)
+    if (writing[k]) R.wait_host(k);
+  if (e != cudaSuccess) cudaStreamSynchronize(st);
+  MVS_REQUIRE(e == cudaSuccess, MVS_ERR_CUDA, "chunk download failed: %s", cudaGetErrorString(e));
   const int f = failed.load();
   MVS_REQUIRE(f < 0, MVS_ERR_INVALID, "write failed for %s", paths[f]);
   return MVS_OK;
@@ -695,31 +766,55 @@ extern "C" int mvs_chunks_load(void* d_packed, size_t chunk_bytes, int n, const 
   MVS_REQUIRE(d_packed && paths && chunk_bytes > 0, MVS_ERR_INVALID, "NULL pointer / empty chunk");
   int dev = 0;
   MVS_CHECK_CUDA(cudaGetDevice(&dev));
-  cudaEvent_t ready;
-  MVS_CHECK_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  MVS_CHECK_CUDA(cudaEventRecord(ready, (cudaStream_t)stream));
-  std::atomic<int> failed(-1), cuda_err(0);
-  pool().parallel_for(n, [&](int i) {
-    ChunkLane& L = t_lane;
-    cudaError_t e = L.prepare(dev, chunk_bytes);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(L.st, ready, 0);
-    if (e == cudaSuccess) {
-      char* dst = (char*)d_packed + (size_t)i * chunk_bytes;
-      if (access(paths[i], F_OK) != 0) {
-        e = cudaMemsetAsync(dst, 0, chunk_bytes, L.st);  // a missing chunk reads as the fill value
-      } else if (file_rw(paths[i], (char*)L.pinned, chunk_bytes, false)) {
-        e = cudaMemcpyAsync(dst, L.pinned, chunk_bytes, cudaMemcpyHostToDevice, L.st);
-      } else {
-        int expect = -1;
-        failed.compare_exchange_strong(expect, i);
+  cudaStream_t st = (cudaStream_t)stream;
+  ChunkRing& R = chunk_ring();
+  std::lock_guard<std::mutex> lock(R.mtx);
+  MVS_CHECK_CUDA(R.prepare(dev, chunk_bytes));
+  constexpr int kReadAhead = 6;  // files being read by the pool; the other slots hold DMAs in flight
+  std::atomic<int> failed(-1);
+  int status[kChunkSlots] = {};  // written by the reader of the slot: 1 data, 2 missing file
+  bool dma_pending[kChunkSlots] = {};
+  int dispatched = 0, issued = 0;
+  cudaError_t e = cudaSuccess;
+  while (issued < n && e == cudaSuccess) {
+    while (dispatched < n && dispatched < issued + kReadAhead) {
+      const int k = dispatched % kChunkSlots;
+      if (dma_pending[k]) {
+        if ((e = cudaEventSynchronize(R.ev[k])) != cudaSuccess) break;
+        dma_pending[k] = false;
       }
+      R.host_done[k].store(0, std::memory_order_relaxed);
+      const int i = dispatched++;
+      pool().submit([&R, &failed, &status, k, i, paths, chunk_bytes] {
+        if (access(paths[i], F_OK) != 0) {
+          status[k] = 2;  // a missing chunk reads as the fill value
+        } else if (file_rw(paths[i], (char*)R.buf[k], chunk_bytes, false)) {
+          status[k] = 1;
+        } else {
+          status[k] = 2;
+          int expect = -1;
+          failed.compare_exchange_strong(expect, i);
+        }
+        R.host_done[k].store(1, std::memory_order_release);
+      });
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(L.st);
-    if (e != cudaSuccess) cuda_err.store((int)e);
-  });
-  cudaEventDestroy(ready);
-  MVS_REQUIRE(cuda_err.load() == 0, MVS_ERR_CUDA, "chunk upload failed: %s",
-              cudaGetErrorString((cudaError_t)cuda_err.load()));
+    if (e != cudaSuccess) break;
+    const int k = issued % kChunkSlots;
+    R.wait_host(k);
+    char* dst = (char*)d_packed + (size_t)issued * chunk_bytes;
+    if (status[k] == 1) {
+      e = cudaMemcpyAsync(dst, R.buf[k], chunk_bytes, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaEventRecord(R.ev[k], st);
+      dma_pending[k] = true;
+    } else {
+      e = cudaMemsetAsync(dst, 0, chunk_bytes, st);
+    }
+    ++issued;
+  }
+  for (int p = issued; p < dispatched; ++p) R.wait_host(p % kChunkSlots);
+  // the ring is reused by the next call: its DMAs must have read the slots by then
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  MVS_REQUIRE(e == cudaSuccess, MVS_ERR_CUDA, "chunk upload failed: %s", cudaGetErrorString(e));
   const int f = failed.load();
   MVS_REQUIRE(f < 0, MVS_ERR_INVALID, "read failed for %s (short or unreadable chunk file)", paths[f]);
   return MVS_OK;
