@@ -10,8 +10,10 @@ Public surface mirrors the reference's names for this path:
   ``pairs.PairPlan`` / ``pairs.register_views`` underneath
 * ``hooks.*`` (``fusion_func`` / ``weights_func`` on resampled stacks),
   ``batch.BatchFuser`` (``batch_options["batch_func"]``, hook C)
-* ``pyramid.build_pyramid`` (output resolution levels), ``distributed.*`` (one process
-  per GPU)
+* ``hooks.content_based_dct`` / ``fusion.multi_view_deconvolution`` (the other built-in
+  weights / fusion methods)
+* ``pyramid.build_pyramid`` (output resolution levels), ``ngff_io.*`` (Zarr v2 / OME-Zarr 0.4
+  chunk encode + write and read + decode on the device), ``distributed.*`` (one process per GPU)
 
 Everything computes on the GPU through ``libmvs_b200.so`` (C ABI,
 include/mvs_b200.h); there is no CPU fallback.

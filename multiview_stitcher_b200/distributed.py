@@ -28,7 +28,8 @@ Both stages shard into independent units:
         of its tiles that the box can sample (input dtype: 2 bytes per voxel for
         uint16, a quarter of the partial sums) and the owner fuses the box with
         the ordinary fused kernel from local tiles + received windows, in global
-        view order -- bit-identical to the one-GPU result, no extra passes.
+        view order -- the one-GPU result up to float32 rounding of the box origin
+        (<= 1e-6 relative, <= 1 LSB for uint16), no extra passes.
     The rest of the chunk is fused directly.
   - ``fuse_partial``: whole-volume variant (all-reduce of full accumulators;
     small stacks, ``max_fusion``).
