@@ -434,6 +434,9 @@ constexpr int kStencilMaxViews = 32;  // views per chunk on this path
 #ifndef MVS_NS3
 #define MVS_NS3 3
 #endif
+#ifndef MVS_PREFETCH
+#define MVS_PREFETCH 0  // measured: C2 0.197 -> 0.200 ms, C3 unchanged, C5 row 34.8 -> 33.4 ms: the producer is not the bottleneck
+#endif
 #ifndef MVS_STATIC_SCHED
 #define MVS_STATIC_SCHED 0  // measured: static round-robin loses L2 locality (C5 row 35 -> 70 ms)
 #endif
@@ -490,6 +493,20 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
     for (; bid < nblocks; bid = bid_n, ra = ra_n, rb = rb_n) {
       bid_n = bid + gridDim.x;
       if (bid_n < nblocks) { ra_n = __ldg(recs4 + 2 * bid_n); rb_n = __ldg(recs4 + 2 * bid_n + 1); }
+#elif MVS_PREFETCH
+    // dynamic schedule, two deep: the id of block k+2 is requested and the record of block k+1 is
+    // loaded while block k is issued, so the dependent chain atomic -> record -> view constants
+    // (~2 us for the lone producer warp) is off the critical path; a CTA over-grabs at most two
+    // ids past the end (ids only grow, so an id past the end is never followed by a valid one)
+    unsigned long long nb0 = 0, nb1 = 0, nb2 = 0;
+    if (lane == 0) { nb0 = atomicAdd(next_block, 1ull); nb1 = atomicAdd(next_block, 1ull); }
+    int64_t bid = block_begin + (int64_t)__shfl_sync(0xffffffffu, nb0, 0), bid1 = 0;
+    int4 ra = make_int4(0, 0, 0, 0), rb = ra, ra1 = ra, rb1 = ra;
+    if (bid < nblocks) { ra = __ldg(recs4 + 2 * bid); rb = __ldg(recs4 + 2 * bid + 1); }
+    for (; bid < nblocks; bid = bid1, ra = ra1, rb = rb1, nb1 = nb2) {
+      bid1 = block_begin + (int64_t)__shfl_sync(0xffffffffu, nb1, 0);
+      if (lane == 0) nb2 = atomicAdd(next_block, 1ull);
+      if (bid1 < nblocks) { ra1 = __ldg(recs4 + 2 * bid1); rb1 = __ldg(recs4 + 2 * bid1 + 1); }
 #else
     for (;;) {
       unsigned long long nb = 0;

@@ -190,9 +190,15 @@ def test_synthetic_3d_pair_matches_oracle(reg):
     moving = tiles[1][:, :, : ov[2]].contiguous()
     res = reg.register_pairs([fixed], [moving], return_details=True)[0]
     ref = oreg.phase_correlation_registration(fixed.cpu().numpy(), moving.cpu().numpy(), return_details=True)
-    assert np.abs(res["affine_matrix"] - ref["affine_matrix"]).max() <= 0.5 + 1e-6, (res["affine_matrix"][:3, 3], ref["affine_matrix"][:3, 3])
+    # upsample_factor 2: every shift lies on the 0.5 px grid.  Integer jitter puts the true peak ON a grid
+    # node, where the two neighbouring upsampled-DFT samples tie to within float32 rounding: the only
+    # admissible difference is such an adjacent-bin tie (exactly one bin), everything else must be equal
+    # (the fractional-shift cases in test_gpu_subpixel.py hold 0.1 px)
     for a, b in zip(res["shift_candidates"], ref["shift_candidates"]):
-        assert np.abs(np.asarray(a) - np.asarray(b)).max() <= 0.5 + 1e-6
+        d = np.abs(np.asarray(a) - np.asarray(b))
+        assert np.all((d <= 1e-6) | (np.abs(d - 0.5) <= 1e-6)), (a, b)
+    d = np.abs(res["affine_matrix"][:3, 3] - ref["affine_matrix"][:3, 3])
+    assert np.all((d <= 1e-6) | (np.abs(d - 0.5) <= 1e-6)), (res["affine_matrix"][:3, 3], ref["affine_matrix"][:3, 3])
     d = (true[1] - stage[1].astype(np.int64)) - (true[0] - stage[0].astype(np.int64))
     # both implementations land within one upsampling bin (0.5 px) of the true jitter
     assert np.abs(ref["affine_matrix"][:3, 3] + d).max() <= 0.5 + 1e-6
