@@ -546,6 +546,8 @@ def bench_c2(cx, args):
                     "write_ms": w_s * 1e3, "write_Mvoxel_per_s": vox_per_step / w_s / 1e6,
                     "read_level0_ms": r_s * 1e3, "read_back_equal": bool(torch.equal(back.tensor, plan.out))}
             del back
+        except Exception as e:  # a full or missing scratch directory must not take the headline down
+            zrec = {"error": f"{type(e).__name__}: {e}"}
         finally:
             shutil.rmtree(zdir, ignore_errors=True)
 

@@ -103,7 +103,10 @@ gauss1d_kernel(const float* __restrict__ in, float* __restrict__ out, int nz, in
 // outside are not produced (they are exact zeros that nobody reads,
 // weights.py:314-320 divides only where the view exists).
 
-constexpr int kGTA = 128;     // outputs per tile along the filter axis
+#ifndef MVS_GTA
+#define MVS_GTA 128
+#endif
+constexpr int kGTA = MVS_GTA;  // outputs per tile along the filter axis (= threads per CTA)
 constexpr int kGSub = 32;     // ... per warp
 constexpr int kGWarps = kGTA / kGSub;
 constexpr int kGPitch = 33;
@@ -212,11 +215,11 @@ __global__ void __launch_bounds__(kGWarps * 32) gauss_tile_kernel(const GaussArg
       // consecutive threads read consecutive x of one row: coalesced; transposed into [k][row]
       const int spad = (span + 31) & ~31;
       const int total = 32 * spad;
-      for (int e0 = 0; e0 < total; e0 += kGB * 128) {
+      for (int e0 = 0; e0 < total; e0 += kGB * kGTA) {
         float tv[kGB];
 #pragma unroll
         for (int u = 0; u < kGB; ++u) {
-          const int e = e0 + u * 128 + tid;
+          const int e = e0 + u * kGTA + tid;
           const int row = e / spad, kk = e - row * spad;
           const int y = l0 + row;
           const int a = reflect_idx(a0 - rp + kk, nA);
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(kGWarps * 32) gauss_tile_kernel(const GaussArg
         if (e0 == 0) first = tv[0];
 #pragma unroll
         for (int u = 0; u < kGB; ++u) {
-          const int e = e0 + u * 128 + tid;
+          const int e = e0 + u * kGTA + tid;
           const int row = e / spad, kk = e - row * spad;
           if (e < total && kk < span) {
             strip[kk * kGPitch + row] = tv[u];

@@ -158,8 +158,18 @@ cand_stats_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
 //        of the (32+6) x (8+6) input columns; each plane then gets its y and x
 //        passes through shared memory.
 constexpr int kMaxWin = 7;
-constexpr int kS2TX = 128, kS2TY = 64, kS2Threads = 160, kS2Cols = kS2TX + kMaxWin - 1;
-constexpr int kS3TX = 32, kS3TY = 8, kS3TZ = 32, kS3Threads = 256;
+// 2-D tile width (knob).  Measured: 150 output columns (156 of 160 threads busy, 2 instead of 3 tiles across
+// C2's 305-px slices) is no faster than 128 (1145 vs 1108 us per 20-pair batch): the kernel is bound by the
+// per-row barrier / shared-memory latency chain, not by lane utilisation
+#ifndef MVS_S2_TX
+#define MVS_S2_TX 128
+#endif
+constexpr int kS2TX = MVS_S2_TX, kS2TY = 64, kS2Threads = 160, kS2Cols = kS2TX + kMaxWin - 1;
+static_assert(kS2Cols <= kS2Threads, "one thread per input column");
+#ifndef MVS_S3_THREADS
+#define MVS_S3_THREADS 288  // 9 warps: the (32+6) x (8+6) = 532 input columns of a tile take 2 per thread (3 with 256)
+#endif
+constexpr int kS3TX = 32, kS3TY = 8, kS3TZ = 32, kS3Threads = MVS_S3_THREADS;
 constexpr int kS3WX = kS3TX + kMaxWin - 1, kS3WY = kS3TY + kMaxWin - 1, kS3P = kS3WX + 1;
 
 // im1t[slices] of every candidate, packed one after the other (offset mat_off)
@@ -170,11 +180,18 @@ materialize_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
   const Cand c = cands[blockIdx.y];
   const long long n = (long long)c.len[0] * c.len[1] * c.len[2];
   float* out = mat + c.mat_off;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % c.len[2]), y = (int)((i / c.len[2]) % c.len[1]),
-              z = (int)(i / ((long long)c.len[2] * c.len[1]));
-    out[i] = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, c.lo[0] + z, c.lo[1] + y, c.lo[2] + x);
+  // rows of the slice are walked with 32-bit arithmetic (a 64-bit division per voxel costs more than
+  // the interpolation itself)
+  const unsigned rows = (unsigned)c.len[0] * (unsigned)c.len[1];  // < 2^31: the slice fits the crop
+  const unsigned lenx = (unsigned)c.len[2], leny = (unsigned)c.len[1];
+  const unsigned xt = (lenx + 31) / 32;  // 32-voxel segments per row: one warp each
+  const unsigned nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned w = blockIdx.x * nwarps + (threadIdx.x >> 5); w < rows * xt; w += gridDim.x * nwarps) {
+    const unsigned row = w / xt, x = (w - row * xt) * 32 + lane;
+    if (x >= lenx) continue;
+    const unsigned z = row / leny, y = row - z * leny;
+    out[(long long)row * lenx + x] =
+        shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, c.lo[0] + (int)z, c.lo[1] + (int)y, c.lo[2] + (int)x);
   }
 }
 
@@ -309,8 +326,12 @@ ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
   ssim_block_reduce<kS2Threads>(sum, vmax, tile, tile_sum, tile_max);
 }
 
+// 3 CTAs of 9 warps per SM (72 registers, no spills): 12 C3 face pairs 67 -> 48 ms against 2 CTAs at 96
+#ifndef MVS_S3_MINB
+#define MVS_S3_MINB 3
+#endif
 template <int WIN>
-__global__ void __launch_bounds__(kS3Threads)
+__global__ void __launch_bounds__(kS3Threads, MVS_S3_MINB)
 ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
               const float* __restrict__ mat, double* __restrict__ tile_sum,
               float* __restrict__ tile_max) {
