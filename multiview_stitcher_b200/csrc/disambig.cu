@@ -247,6 +247,8 @@ __device__ __forceinline__ void ssim_block_reduce(double sum, float vmax, long l
   }
 }
 
+// (occupancy hints measured on the B200: minBlocks 8 / 10 -> 1295 / 1438 us against 1108 us for the
+// compiler's own choice of 56 registers)
 template <int WIN>
 __global__ void __launch_bounds__(kS2Threads)
 ssim2d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
@@ -469,38 +471,56 @@ ssim3d_kernel(const Cand* __restrict__ cands, int n_cand, int n1, int n2,
 }
 
 // ---- stage E: Spearman ---------------------------------------------------------
-// Ranks of several pairs are computed with ONE radix sort per image: the key is
-// (pair slot << 32) | order-preserving bits of the float, so every pair occupies
+// Ranks of up to four pairs are computed with ONE radix sort per image: the key is
+// (pair slot << 30) | 30 order-preserving bits of the float, so every pair occupies
 // its own N-element segment of the sorted array.
 
-__device__ __forceinline__ unsigned sortable_bits(float v) {
-  const unsigned u = __float_as_uint(v + 0.0f);  // -0 -> +0
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+// Both ranked images live in a known interval -- im0 is rescaled to [0, 1] and the reference ranks
+// im1t - 1, i.e. [-1, 0] -- so an order-preserving key needs 30 bits: the float's bits for [0, 1],
+// 0x3F800000 minus the bits of |v| for [-1, 0] (-0 and +0 coincide).  With the slot of a pair in the
+// bits above, four pairs sort together on 32-bit keys (4 radix passes over 8 bytes per element
+// instead of 5 over 12 with 64-bit keys).
+constexpr unsigned kKeyOne = 0x3F800000u;     // bits of 1.0f: the largest valid key
+constexpr unsigned kKeyMasked = 0x3FFFFFFFu;  // sorts behind every valid key of its slot
+constexpr int kKeyBits = 30;
+constexpr int kSortSlots = 4;
+
+__device__ __forceinline__ unsigned key_unit(float v) {  // v in [0, 1]
+  return min(__float_as_uint(v + 0.0f) & 0x7fffffffu, kKeyOne);
+}
+__device__ __forceinline__ unsigned key_neg_unit(float v) {  // v in [-1, 0]
+  return kKeyOne - min(__float_as_uint(v) & 0x7fffffffu, kKeyOne);
 }
 
-// Stage E without scatters: sort (a-key, b-bits) by a; the position in the sorted
+// Stage E without scatters: sort (a-key, b-key) by a; the position in the sorted
 // segment is a's rank, written (doubled, so tie averages stay integers) as the
 // payload of a second sort by b; in b-sorted order both ranks are at hand and the
 // Pearson sums stream out.
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
-                     unsigned long long* __restrict__ ka, unsigned* __restrict__ vb) {
+                     unsigned* __restrict__ ka, unsigned* __restrict__ vb) {
   const int slot = blockIdx.y;
   const Cand c = cands[slot];
   const long long N = (long long)n0 * n1 * n2;
-  const unsigned long long hi = (unsigned long long)slot << 32;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(i % n2), y = (int)((i / n2) % n1), z = (int)(i / ((long long)n1 * n2));
+  const unsigned hi = (unsigned)slot << kKeyBits;
+  // rows are walked with 32-bit arithmetic, one warp per 32-voxel segment (see materialize_kernel)
+  const unsigned rows = (unsigned)n0 * (unsigned)n1, xt = ((unsigned)n2 + 31) / 32;
+  const unsigned nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned w = blockIdx.x * nwarps + (threadIdx.x >> 5); w < rows * xt; w += gridDim.x * nwarps) {
+    const unsigned row = w / xt, xu = (w - row * xt) * 32 + lane;
+    if (xu >= (unsigned)n2) continue;
+    const unsigned zu = row / (unsigned)n1;
+    const int x = (int)xu, y = (int)(row - zu * (unsigned)n1), z = (int)zu;
+    const long long i = (long long)row * n2 + x;
     float b = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, z, y, x);
     float a = __ldg(c.r0 + i);
     const bool m = (a == a) && (b == b);
     // the reference ranks `im1t[mask] - 1` in float32 (registration.py:551-553):
     // the subtraction merges values below ~3e-8 into ties, which changes ranks
     const long long e = (long long)slot * N + i;
-    ka[e] = hi | (m ? sortable_bits(a) : 0xffffffffu);
-    vb[e] = m ? sortable_bits(__fsub_rn(b, 1.0f)) : 0xffffffffu;
+    ka[e] = hi | (m ? key_unit(a) : kKeyMasked);
+    vb[e] = m ? key_neg_unit(__fsub_rn(b, 1.0f)) : kKeyMasked;
   }
 }
 
@@ -510,11 +530,11 @@ spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
 // (Integer-valued microscopy data is tie-heavy; a binary search per element
 // costs ~40 dependent L2 reads.)
 __global__ void __launch_bounds__(256)
-run_flags_kernel(const unsigned long long* __restrict__ sorted, long long E,
+run_flags_kernel(const unsigned* __restrict__ sorted, long long E,
                  unsigned* __restrict__ head, unsigned* __restrict__ tail_rev) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < E;
        j += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long v = sorted[j];
+    const unsigned v = sorted[j];
     head[j] = (j == 0 || sorted[j - 1] != v) ? (unsigned)j : 0u;
     tail_rev[E - 1 - j] = (j == E - 1 || sorted[j + 1] != v) ? (unsigned)j : 0xffffffffu;
   }
@@ -528,12 +548,12 @@ struct MinOp { __device__ __forceinline__ unsigned operator()(unsigned a, unsign
 __global__ void __launch_bounds__(256)
 rank_a_kernel(const unsigned* __restrict__ first, const unsigned* __restrict__ last_rev,
               const unsigned* __restrict__ vb_sorted, long long N, long long E,
-              const long long* __restrict__ nmask, unsigned long long* __restrict__ kb,
+              const long long* __restrict__ nmask, unsigned* __restrict__ kb,
               unsigned* __restrict__ ra2) {
   const int slot = blockIdx.y;
   const long long n = nmask[slot];
   const long long base = (long long)slot * N;
-  const unsigned long long hi = (unsigned long long)slot << 32;
+  const unsigned hi = (unsigned)slot << kKeyBits;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N;
        j += (long long)gridDim.x * blockDim.x) {
     const long long e = base + j;
@@ -542,7 +562,7 @@ rank_a_kernel(const unsigned* __restrict__ first, const unsigned* __restrict__ l
       kb[e] = hi | vb_sorted[e];
       ra2[e] = (unsigned)(f + l + 2);  // 2 * ((f + l) / 2 + 1)
     } else {
-      kb[e] = hi | 0xffffffffu;
+      kb[e] = hi | kKeyMasked;
       ra2[e] = 0u;
     }
   }
@@ -555,7 +575,7 @@ __global__ void __launch_bounds__(256)
 pearson_sorted_kernel(const unsigned* __restrict__ first, const unsigned* __restrict__ last_rev,
                       const unsigned* __restrict__ ra2, long long N, long long E,
                       const long long* __restrict__ nmask,
-                      double* __restrict__ partial /* [slot][block][3] */) {
+                      double* __restrict__ partial /* [slot][block][3] of this sub-batch */) {
   const int slot = blockIdx.y;
   const long long n = nmask[slot];
   const double mean = 0.5 * (double)(n + 1);
@@ -752,16 +772,13 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
   const int ndim = pc_ndim(p);
   const int* sh = pc_shape(p);
   const long long N = (long long)sh[0] * sh[1] * sh[2];
-  // sub-batches of B pairs sorted together (<= 2^26 elements)
-  int B = (int)std::max<long long>(1, std::min<long long>(n, (1LL << 26) / N));
+  // sub-batches of up to kSortSlots pairs sorted together on 32-bit keys (<= 2^26 elements)
+  int B = (int)std::max<long long>(1, std::min<long long>(std::min(n, kSortSlots), (1LL << 26) / N));
   MVS_REQUIRE((long long)B * N < (1LL << 31), MVS_ERR_UNSUPPORTED, "pair volume too large for the rank sort");
   const long long E = (long long)B * N;
-  int seg_bits = 1;
-  while ((1 << seg_bits) < B) ++seg_bits;
   size_t temp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned long long*)nullptr,
-                                  (unsigned long long*)nullptr, (const unsigned*)nullptr,
-                                  (unsigned*)nullptr, (int)E, 0, 32 + seg_bits, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                  (const unsigned*)nullptr, (unsigned*)nullptr, (int)E, 0, 32, st);
   {
     size_t scan_bytes = 0;
     cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
@@ -769,39 +786,41 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
     temp_bytes = std::max(temp_bytes, scan_bytes);
   }
   auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
-  const size_t kbytes = al(sizeof(unsigned long long) * E), ub = al(sizeof(unsigned) * E),
-               pb = al(sizeof(double) * 3 * kPearsonBlocks * B),
-               cb = al(sizeof(Cand) * B), nb = al(sizeof(long long) * B);
+  const size_t ub = al(sizeof(unsigned) * E), pb = al(sizeof(double) * 3 * kPearsonBlocks * n),
+               cb = al(sizeof(Cand) * n), nb = al(sizeof(long long) * n);
   void* scratch;
-  if ((rc = pc_scratch(p, 2 * kbytes + 6 * ub + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
+  if ((rc = pc_scratch(p, 8 * ub + pb + cb + nb + al(temp_bytes), &scratch))) return rc;
   char* w = (char*)scratch;
-  unsigned long long* k1 = (unsigned long long*)w; w += kbytes;   // keys in
-  unsigned long long* k2 = (unsigned long long*)w; w += kbytes;   // keys sorted
-  unsigned* v1 = (unsigned*)w; w += ub;                           // payload in
-  unsigned* v2 = (unsigned*)w; w += ub;                           // payload sorted
-  unsigned* f_in = (unsigned*)w; w += ub;                         // run-head flags / scanned
+  unsigned* k1 = (unsigned*)w; w += ub;     // keys in
+  unsigned* k2 = (unsigned*)w; w += ub;     // keys sorted
+  unsigned* v1 = (unsigned*)w; w += ub;     // payload in
+  unsigned* v2 = (unsigned*)w; w += ub;     // payload sorted
+  unsigned* f_in = (unsigned*)w; w += ub;   // run-head flags / scanned
   unsigned* f_out = (unsigned*)w; w += ub;
-  unsigned* l_in = (unsigned*)w; w += ub;                         // run-tail flags (reversed) / scanned
+  unsigned* l_in = (unsigned*)w; w += ub;   // run-tail flags (reversed) / scanned
   unsigned* l_out = (unsigned*)w; w += ub;
-  double* part = (double*)w; w += pb;
+  double* part = (double*)w; w += pb;       // [n][kPearsonBlocks][3]
   Cand* d_c = (Cand*)w; w += cb;
   long long* d_n = (long long*)w; w += nb;
   void* temp = w;
   const int gx = (int)std::min<long long>((N + 255) / 256, 148 * 4);
-  std::vector<double> hp((size_t)3 * kPearsonBlocks * B);
-  std::vector<long long> hn(B);
+  std::vector<long long> hn(n_mask, n_mask + n);
+  // everything is enqueued for all sub-batches (the scratch buffers are reused in stream order);
+  // the host waits once, for the partial sums of all pairs
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data(), sizeof(Cand) * n, cudaMemcpyHostToDevice, st));
+  MVS_CHECK_CUDA(cudaMemcpyAsync(d_n, hn.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
   for (int b0 = 0; b0 < n; b0 += B) {
     const int nb_ = std::min(B, n - b0);
-    for (int i = 0; i < nb_; ++i) hn[i] = n_mask[b0 + i];
-    MVS_CHECK_CUDA(cudaMemcpyAsync(d_c, cands.data() + b0, sizeof(Cand) * nb_, cudaMemcpyHostToDevice, st));
-    MVS_CHECK_CUDA(cudaMemcpyAsync(d_n, hn.data(), sizeof(long long) * nb_, cudaMemcpyHostToDevice, st));
+    int seg_bits = 0;
+    while ((1 << seg_bits) < nb_) ++seg_bits;
+    const int end_bit = kKeyBits + seg_bits;
     dim3 grid(gx, nb_);
-    if (ndim == 3) spearman_keys_kernel<3><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], k1, v1);
-    else spearman_keys_kernel<2><<<grid, 256, 0, st>>>(d_c, sh[0], sh[1], sh[2], k1, v1);
+    if (ndim == 3) spearman_keys_kernel<3><<<grid, 256, 0, st>>>(d_c + b0, sh[0], sh[1], sh[2], k1, v1);
+    else spearman_keys_kernel<2><<<grid, 256, 0, st>>>(d_c + b0, sh[0], sh[1], sh[2], k1, v1);
     MVS_CHECK_CUDA(cudaGetLastError());
     const int items = (int)((long long)nb_ * N);
-    // by a: (a key, b bits) -> k2, v2
-    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, 32 + seg_bits, st));
+    // by a: (a key, b key) -> k2, v2
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, end_bit, st));
     auto run_bounds = [&]() -> int {  // ties of k2 -> f_out (first), l_out (last, reversed order)
       run_flags_kernel<<<148 * 8, 256, 0, st>>>(k2, items, f_in, l_in);
       MVS_CHECK_CUDA(cub::DeviceScan::InclusiveScan(temp, temp_bytes, f_in, f_out, MaxOp(), items, st));
@@ -809,22 +828,24 @@ extern "C" int mvs_pc_spearman_batch(mvs_pc_plan* p, int n, const int32_t* pairs
       return MVS_OK;
     };
     if ((rc = run_bounds())) return rc;
-    rank_a_kernel<<<grid, 256, 0, st>>>(f_out, l_out, v2, N, items, d_n, k1, v1);  // -> (b key, 2 rank_a)
+    rank_a_kernel<<<grid, 256, 0, st>>>(f_out, l_out, v2, N, items, d_n + b0, k1, v1);  // -> (b key, 2 rank_a)
     // by b: -> k2, v2
-    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, 32 + seg_bits, st));
+    MVS_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k1, k2, v1, v2, items, 0, end_bit, st));
     dim3 pg(kPearsonBlocks, nb_);
     if ((rc = run_bounds())) return rc;
-    pearson_sorted_kernel<<<pg, 256, 0, st>>>(f_out, l_out, v2, N, items, d_n, part);
+    pearson_sorted_kernel<<<pg, 256, 0, st>>>(f_out, l_out, v2, N, items, d_n + b0,
+                                              part + (size_t)3 * kPearsonBlocks * b0);
     MVS_CHECK_CUDA(cudaGetLastError());
-    MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * 3 * kPearsonBlocks * nb_, cudaMemcpyDeviceToHost, st));
-    MVS_CHECK_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < nb_; ++i) {
-      if (hn[i] < 2) { rho_host[b0 + i] = NAN; continue; }
-      double sab = 0, saa = 0, sbb = 0;
-      const double* q = hp.data() + (size_t)3 * kPearsonBlocks * i;
-      for (int k = 0; k < kPearsonBlocks; ++k) { sab += q[3 * k]; saa += q[3 * k + 1]; sbb += q[3 * k + 2]; }
-      rho_host[b0 + i] = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
-    }
+  }
+  std::vector<double> hp((size_t)3 * kPearsonBlocks * n);
+  MVS_CHECK_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * 3 * kPearsonBlocks * n, cudaMemcpyDeviceToHost, st));
+  MVS_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    if (hn[i] < 2) { rho_host[i] = NAN; continue; }
+    double sab = 0, saa = 0, sbb = 0;
+    const double* q = hp.data() + (size_t)3 * kPearsonBlocks * i;
+    for (int k = 0; k < kPearsonBlocks; ++k) { sab += q[3 * k]; saa += q[3 * k + 1]; sbb += q[3 * k + 2]; }
+    rho_host[i] = (saa > 0 && sbb > 0) ? sab / sqrt(saa * sbb) : NAN;
   }
   return MVS_OK;
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
-for v in gpurun_variants/a_tx150.so gpurun_variants/c_tx128.so; do
+for v in gpurun_variants/*.so; do
   cp $v multiview_stitcher_b200/libmvs_b200.so
   echo "== $v"
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ssim2d|materialize" -c 40 --csv --log-file gpurun_out/v.csv python scripts/prof_reg.py > /dev/null 2>&1
-  python scripts/summarize_launches.py gpurun_out/v.csv | tail -3
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ssim2d" -c 12 --csv --log-file gpurun_out/v.csv python scripts/prof_reg.py > /dev/null 2>&1
+  python scripts/summarize_launches.py gpurun_out/v.csv | tail -1
 done
