@@ -620,7 +620,9 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
   const int jx = cg * 32 + lane;
 
   // writes this thread's 16 outputs of the block at (x0, y0, z0)
-  auto store_block = [&](const mvs_chunk& ck, int x0, int y0, int z0, const float* v, const float* d) {
+  // clean: no output of this thread can be NaN (the lone-view path has already zeroed them)
+  auto store_block = [&](const mvs_chunk& ck, int x0, int y0, int z0, const float* v, const float* d,
+                         bool clean = false) {
     const int xo = x0 + jx;
     if (xo >= ck.shape[2]) return;
     const int64_t sy = ck.stride[1], sz = ck.stride[0];
@@ -634,7 +636,8 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
       store_column<NDIM, float, false>(ck.acc_num + o0, sy, sz, ylim, zlim, v);
       store_column<NDIM, float, false>(ck.acc_den + o0, sy, sz, ylim, zlim, d);
     } else if (ck.out_dtype == MVS_F32) {
-      store_column<NDIM, float, kNan>(reinterpret_cast<float*>(ck.out) + o0, sy, sz, ylim, zlim, v);
+      if (clean) store_column<NDIM, float, false>(reinterpret_cast<float*>(ck.out) + o0, sy, sz, ylim, zlim, v);
+      else store_column<NDIM, float, kNan>(reinterpret_cast<float*>(ck.out) + o0, sy, sz, ylim, zlim, v);
     } else if (ck.out_dtype == MVS_U16) {
       store_column<NDIM, unsigned short, kNan>(reinterpret_cast<unsigned short*>(ck.out) + o0, sy, sz, ylim, zlim, v);
     } else {
@@ -725,10 +728,17 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
 
       // NaN data inside a float view counts as "outside" for that voxel (the reference zeroes
       // the weight where the transformed view is NaN, fusion/_core.py:1648; nan-aware fusion)
+      // One test per thread finds the rare case: a NaN among the outputs makes their sum NaN (so may
+      // inf - inf: the exact per-output test below then finds nothing, which is harmless).
       if (sizeof(T) == 4) {
+        float nsum = val[0];
 #pragma unroll
-        for (int k = 0; k < B::OUTS; ++k)
-          if (val[k] != val[k]) vm &= ~(1u << k);
+        for (int k = 1; k < B::OUTS; ++k) nsum += val[k];
+        if (__any_sync(0xffffffffu, nsum != nsum)) {
+#pragma unroll
+          for (int k = 0; k < B::OUTS; ++k)
+            if (val[k] != val[k]) vm &= ~(1u << k);
+        }
       }
 
       // ---- combine ----
@@ -740,7 +750,7 @@ fuse_stencil_kernel(const mvs_chunk* __restrict__ chunks, const int64_t* __restr
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);  // slot consumed
-        store_block(ck, x0, y0, z0, val, nullptr);
+        store_block(ck, x0, y0, z0, val, nullptr, true);
         continue;
       } else if (MODE == MVS_FUSE_MAX) {
 #pragma unroll

@@ -1,7 +1,8 @@
 #!/bin/bash
+cp multiview_stitcher_b200/libmvs_b200.so /tmp/default.so
 for v in gpurun_variants/*.so; do
   cp $v multiview_stitcher_b200/libmvs_b200.so
   echo "== $v"
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ssim2d" -c 12 --csv --log-file gpurun_out/v.csv python scripts/prof_reg.py > /dev/null 2>&1
-  python scripts/summarize_launches.py gpurun_out/v.csv | tail -1
+  for i in 1 2; do python bench.py --no-cpu --only none --steps 20 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'])"; done
 done
+cp /tmp/default.so multiview_stitcher_b200/libmvs_b200.so
