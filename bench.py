@@ -340,6 +340,25 @@ class Ctx:
         return self.max_over_ranks(e0.elapsed_time(e1) / steps)
 
 
+def _median_ms(cx, fn, steps, warmup=1):
+    """Median wall time per call of a host-driven stage (each call synchronised), MAX over ranks.
+    The registration stages return to the host several times per call; on the shared boxes one call
+    in five can take twice as long (interpreter / scheduler hiccups), which a mean of 2-5 calls
+    turns into a number that changes by 50 % from run to run.  Returns (median, mean)."""
+    torch = cx.torch
+    for _ in range(warmup):
+        fn()
+    cx.barrier()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    cx.barrier()
+    return cx.max_over_ranks(float(np.median(ts))), cx.max_over_ranks(float(np.mean(ts)))
+
+
 def _roof(bytes_per_launch, ms, kernel=None):
     peak, src = _peaks()
     ach = bytes_per_launch / (ms * 1e-3) / 1e9
@@ -396,8 +415,8 @@ def bench_c2(cx, args):
     reg_err = max(float(np.abs(r["affine_matrix"][:2, 2] + (true_t[b] - true_t[a])).max())
                   for r, (a, b, _) in zip(reg_res, pairs))
     launches0 = sum(p.launch_count for p in pc_plans.values())
-    n_reg = max(2, min(args.steps, 5))
-    reg_ms = cx.timed(reg_step, n_reg, 0)
+    n_reg = 5
+    reg_ms, reg_ms_mean = _median_ms(cx, reg_step, n_reg, 0)
     reg_launches = (sum(p.launch_count for p in pc_plans.values()) - launches0) // n_reg
 
     # the same 40 pairs from the resident TILES (hook A's work): overlap boxes, crop windows,
@@ -407,7 +426,7 @@ def bench_c2(cx, args):
     plan_ms = (time.perf_counter() - t_plan) * 1e3
     rv = pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans)
     rv_err = max(float(np.abs(r["transform"][:2, 2] + (true_t[b] - true_t[a])).max()) for r, (a, b, _) in zip(rv, pairs))
-    rv_ms = cx.timed(lambda: pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans), n_reg, 1)
+    rv_ms, rv_ms_mean = _median_ms(cx, lambda: pairs_mod.register_views(views, plan=pair_plan, pc_plans=pc_plans), n_reg, 1)
 
     # phase-correlation stage alone (FFT -> cross power -> IFFT -> peak -> upsampled DFT):
     # algorithmic bytes (32*ndim + 8) * N per pair over its CUDA-event time
@@ -508,13 +527,8 @@ def bench_c2(cx, args):
     hf, hm = pair_crops(host_tiles, pairs)
     hf = [np.ascontiguousarray(a) for a in hf]
     hm = [np.ascontiguousarray(a) for a in hm]
-    registration.register_pairs(hf, hm, plans=pc_plans)
-    cx.barrier()
-    t0 = time.perf_counter()
-    for _ in range(2):
-        registration.register_pairs(hf, hm, plans=pc_plans)
-    torch.cuda.synchronize()
-    reg_e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / 2)
+    reg_e2e_ms, reg_e2e_mean = _median_ms(cx, lambda: registration.register_pairs(hf, hm, plans=pc_plans), 5, 1)
+    reg_e2e_s = reg_e2e_ms * 1e-3
 
     # ---- output side: fused stack -> OME-Zarr 0.4 (pyramid levels binned on the device,
     # chunks encoded on the device, raw chunk files written through pinned staging) and read back ----
@@ -570,17 +584,20 @@ def bench_c2(cx, args):
             "unit": "pairs/s",
             "pairs_per_step": len(pairs),
             "ms_per_step": reg_ms,
+            "ms_per_step_mean": reg_ms_mean,
+            "timing": "median of >= 5 synchronised calls (mean beside it); the fusion figures are means over K steps",
             "crop": "2048x307 / 307x2048 float32",
             "max_abs_shift_error_px": reg_err,
             "shift_error_note": "vs the generator's fractional jitter difference; the algorithm's sub-pixel grid is 0.1 px (upsample_factor 10)",
             "gpu_launches_per_step": reg_launches,
-            "e2e": {"pairs_per_sec": len(pairs) * world / reg_e2e_s, "ms_per_step": reg_e2e_s * 1e3,
+            "e2e": {"pairs_per_sec": len(pairs) * world / reg_e2e_s, "ms_per_step": reg_e2e_s * 1e3, "ms_per_step_mean": reg_e2e_mean,
                     "path": "registration.register_pairs: pageable numpy crops in (2 x 40 x 2.5 MB H2D), affine + quality out"},
             "from_tiles": {
                 "what": "pairs.register_views (hook A's work): crop to the overlap box + resample onto the fixed tile's grid "
                         "(1 launch per crop shape) + registration + physical transform, tiles resident",
                 "pairs_per_sec": len(pairs) * world / (rv_ms * 1e-3),
                 "ms_per_step": rv_ms,
+                "ms_per_step_mean": rv_ms_mean,
                 "max_abs_shift_error_px": rv_err,
                 "host_geometry_plan_ms_once": plan_ms,
             },
@@ -692,8 +709,8 @@ def bench_c3(cx, args):
     res = pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans)
     tt = np.array([t[:3, 3] for t in true])
     err = max(float(np.abs(r["transform"][:3, 3] + (tt[b] - tt[a])).max()) for r, (a, b) in zip(res, my_pairs))
-    ms_reg = cx.timed(lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 3, 1)
-    rec["registration_from_tiles"] = {"pairs": len(pairs), "pairs_this_rank": len(my_pairs), "ms": ms_reg,
+    ms_reg, ms_reg_mean = _median_ms(cx, lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 3, 1)
+    rec["registration_from_tiles"] = {"pairs": len(pairs), "pairs_this_rank": len(my_pairs), "ms": ms_reg, "ms_mean": ms_reg_mean,
                                       "pairs_per_sec": len(pairs) / (ms_reg * 1e-3),
                                       "max_abs_shift_error_px": cx.max_over_ranks(err),
                                       "shift_error_note": "3-D default upsample_factor 2: the algorithm's sub-pixel grid is 0.5 px"}

@@ -86,6 +86,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 #ifndef MVS_MBAR_SUSPEND_NS
 #define MVS_MBAR_SUSPEND_NS 20000u
 #endif
+#ifndef MVS_MBAR_SLEEP_NS
+#define MVS_MBAR_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t done = 0;
   unsigned spins = 0;
@@ -97,6 +100,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity), "r"(MVS_MBAR_SUSPEND_NS)
         : "memory");
+#if MVS_MBAR_SLEEP_NS > 0
+    if (!done) __nanosleep(MVS_MBAR_SLEEP_NS);  // free the issue slots for the warps that have data
+#endif
     if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU on a lost copy
   }
 }

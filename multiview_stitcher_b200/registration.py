@@ -164,7 +164,9 @@ class PhaseCorrPlan:
             ),
             "mvs_pc_spearman_batch",
         )
-        self.launch_count += 10 * n  # keys, 2 x (radix sort ~3 kernels + rank), pearson
+        # per sub-batch of <= 4 pairs: keys, 2 x (histogram + exclusive sum + 4 onesweep passes),
+        # 2 x (run flags + 2 x (scan init + scan)), rank, pearson  (ncu launch list: profiles/r02_reg_launches_summary.txt)
+        self.launch_count += 29 * ((n + 3) // 4)
         return rho
 
     def spearman(self, pair, t, n_mask):
