@@ -114,59 +114,89 @@ def _band_axis(n_per_axis):
     return max(cand, key=lambda a: (n_per_axis[a], -a))
 
 
+class ShardedFuser:
+    """This rank's band of output chunks, planned once and fused as often as needed (time lapses /
+    channels share the geometry, like ``fusion.HostFuser``): tiles are replicated where bands meet,
+    there is no communication.  ``out`` is the full-size output tensor with only the owned chunks
+    written; its memory is laid out with the band axis slowest, so a band is one contiguous range."""
+
+    def __init__(self, views, params, output_stack_properties, output_chunksize=None, band_axis=None, **plan_kwargs):
+        import torch
+
+        from .fusion import FusionPlan, _np_to_torch, _torch_to_np, to_device_view
+
+        self.rank, self.ws = world()
+        dviews = [to_device_view(v) for v in views]
+        ndim = dviews[0].ndim
+        dims = geometry.spatial_dims(ndim)
+        if output_chunksize is None:
+            output_chunksize = geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
+        cs = {d: int(output_chunksize[d]) for d in dims}
+        osp = output_stack_properties
+        full = [int(osp["shape"][d]) for d in dims]
+        counts = [-(-full[i] // cs[d]) for i, d in enumerate(dims)]
+        if band_axis is None:
+            band_axis = _band_axis(counts)
+        grid = geometry.chunk_grid(osp, cs)
+        self.bands = [shard_slabs(counts[band_axis], r, self.ws) for r in range(self.ws)]
+        mine = set(self.bands[self.rank])
+        self.owned = [i for i, (start, _) in enumerate(grid) if start[band_axis] // cs[dims[band_axis]] in mine]
+        # memory order: band axis first
+        self.perm = [band_axis] + [a for a in range(ndim) if a != band_axis]
+        inv = [self.perm.index(a) for a in range(ndim)]
+        np_dt = np.dtype(plan_kwargs.pop("out_dtype", None) or _torch_to_np(dviews[0].tensor.dtype))
+        self.out = torch.zeros([full[a] for a in self.perm], dtype=_np_to_torch(np_dt), device="cuda").permute(inv)
+        self.band_axis, self.band_size, self.full = band_axis, cs[dims[band_axis]], full
+        self.plan = None
+        if self.owned:
+            self.plan = FusionPlan(dviews, params, osp, output_chunksize=cs, chunk_subset=self.owned, out=self.out,
+                                   out_dtype=np_dt, **plan_kwargs)
+        self.last_gather_bytes = 0
+
+    def run(self):
+        if self.plan is not None:
+            self.plan.run()
+        return self.out
+
+    def gather(self):
+        """Broadcast every rank's band in the OUTPUT dtype (each rank ends up holding the whole
+        stack; bytes on the wire = stack bytes x (N-1)/N per rank, no float32 round trip)."""
+        import torch
+        import torch.distributed as dist
+
+        nbytes = 0
+        if self.ws > 1:
+            mem = self.out.permute(self.perm)  # contiguous, band axis leading
+            for r in range(self.ws):
+                if not self.bands[r]:
+                    continue
+                a = self.bands[r][0] * self.band_size
+                b = min((self.bands[r][-1] + 1) * self.band_size, self.full[self.band_axis])
+                slab = mem[a:b].view(torch.uint8)
+                dist.broadcast(slab, src=r)
+                if r != self.rank:
+                    nbytes += slab.numel()
+        self.last_gather_bytes = nbytes
+        return self.out
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.close()
+            self.plan = None
+
+
 def fuse_sharded(views, params, output_stack_properties, output_chunksize=None, gather=False, band_axis=None,
                  **plan_kwargs):
-    """Fuses this rank's band of output chunks (tiles replicated where bands meet, no
-    communication).  Returns ``(out, owned_chunks)``: ``out`` is the full-size output tensor
-    with only the owned chunks written; its memory is laid out with the band axis slowest,
-    so a band is one contiguous range.  ``gather=True`` broadcasts every rank's band in
-    the OUTPUT dtype (each rank ends up holding the whole stack; bytes on the wire =
-    stack bytes x (N-1)/N per rank, no float32 round trip)."""
-    import torch
-    import torch.distributed as dist
-
-    from .fusion import FusionPlan, _np_to_torch, _torch_to_np, to_device_view
-
-    rank, ws = world()
-    dviews = [to_device_view(v) for v in views]
-    ndim = dviews[0].ndim
-    dims = geometry.spatial_dims(ndim)
-    if output_chunksize is None:
-        output_chunksize = geometry.DEFAULT_CHUNKSIZE_2D if ndim == 2 else geometry.DEFAULT_CHUNKSIZE_3D
-    cs = {d: int(output_chunksize[d]) for d in dims}
-    osp = output_stack_properties
-    full = [int(osp["shape"][d]) for d in dims]
-    counts = [-(-full[i] // cs[d]) for i, d in enumerate(dims)]
-    if band_axis is None:
-        band_axis = _band_axis(counts)
-    grid = geometry.chunk_grid(osp, cs)
-    bands = [shard_slabs(counts[band_axis], r, ws) for r in range(ws)]
-    mine = set(bands[rank])
-    owned = [i for i, (start, _) in enumerate(grid) if start[band_axis] // cs[dims[band_axis]] in mine]
-    # memory order: band axis first
-    perm = [band_axis] + [a for a in range(ndim) if a != band_axis]
-    inv = [perm.index(a) for a in range(ndim)]
-    np_dt = np.dtype(plan_kwargs.pop("out_dtype", None) or _torch_to_np(dviews[0].tensor.dtype))
-    out = torch.zeros([full[a] for a in perm], dtype=_np_to_torch(np_dt), device="cuda").permute(inv)
-    if owned:
-        plan = FusionPlan(dviews, params, osp, output_chunksize=cs, chunk_subset=owned, out=out, out_dtype=np_dt,
-                          **plan_kwargs)
-        plan.run()
-        plan.close()
-    nbytes = 0
-    if gather and ws > 1:
-        mem = out.permute(perm)  # contiguous, band axis leading
-        c = cs[dims[band_axis]]
-        for r in range(ws):
-            if not bands[r]:
-                continue
-            a, b = bands[r][0] * c, min((bands[r][-1] + 1) * c, full[band_axis])
-            slab = mem[a:b].view(torch.uint8)
-            dist.broadcast(slab, src=r)
-            if r != rank:
-                nbytes += slab.numel()
-    fuse_sharded.last_gather_bytes = nbytes
-    return out, owned
+    """One-shot ``ShardedFuser``: fuses this rank's band of output chunks (tiles replicated where
+    bands meet, no communication).  Returns ``(out, owned_chunks)``; ``gather=True`` also
+    broadcasts every rank's band in the output dtype."""
+    f = ShardedFuser(views, params, output_stack_properties, output_chunksize, band_axis, **plan_kwargs)
+    out = f.run()
+    if gather:
+        f.gather()
+    fuse_sharded.last_gather_bytes = f.last_gather_bytes
+    f.close()
+    return out, f.owned
 
 
 # --- tile-partitioned fusion ---------------------------------------------------
