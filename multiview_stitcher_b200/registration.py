@@ -447,9 +447,10 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
             raise EngineError(f"pair {i}: shapes differ {_shape(f)} vs {_shape(m)}")
         groups.setdefault(_shape(f), []).append(i)
     results = [None] * n
-    # host crops go up first, through the staging ring (measured: uploading from the group threads so
-    # that one shape's upload overlaps the other's kernels is slower and erratic, 24-57 ms against
-    # 21.6 ms for C2's 40 pairs -- the threads fight over the interpreter and the copy pool)
+    # host crops go up first, through the staging ring (measured: overlapping one shape's upload with
+    # another's kernels is slower -- 24-57 ms when the group threads upload, 23-24 ms when this thread
+    # uploads group by group -- against 21.6 ms for C2's 40 pairs: the registration threads, the
+    # interpreter and the copy pool fight over the host's cores)
     fixed = [_to_device_f32(a) for a in fixed_list]
     moving = [_to_device_f32(a) for a in moving_list]
 
