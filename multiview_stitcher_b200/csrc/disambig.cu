@@ -96,6 +96,57 @@ __device__ __forceinline__ float shifted_value(const float* __restrict__ r1, int
   return (float)acc;
 }
 
+// The same value with the (z, y) part of the work hoisted: a warp that walks along x keeps the row's
+// validity, tap rows and weights in registers (identical arithmetic, so identical results).
+constexpr unsigned kRowSeg = 256;  // voxels of a row one warp walks with the hoisted (z, y) part
+
+template <int NDIM>
+struct ShiftRow {
+  bool valid;
+  long long base[4];  // offsets of the (z tap, y tap) rows: [a * 2 + b]
+  double wzy[4][2];   // wz[a], wy[b] per row tap
+  __device__ __forceinline__ void init(int n0, int n1, int n2, const double* t, int z, int y) {
+    const double cy = (double)y + t[1];
+    const double cz = NDIM == 3 ? (double)z + t[0] : 0.0;
+    valid = !(cy < 0.0 || cy > (double)(n1 - 1)) && !(NDIM == 3 && (cz < 0.0 || cz > (double)(n0 - 1)));
+    const double fy = floor(cy), fz = floor(cz);
+    const int iy = (int)fy, iz = (int)fz;
+    double wy[2], wz[2];
+    wy[0] = 1.0 - (cy - fy); wy[1] = 1.0 - wy[0];
+    wz[0] = 1.0 - (cz - fz); wz[1] = 1.0 - wz[0];
+    const int ys[2] = {iy, iy + 1 < n1 ? iy + 1 : mirror_idx(iy + 1, n1)};
+    const int zs[2] = {iz, iz + 1 < n0 ? iz + 1 : mirror_idx(iz + 1, n0)};
+#pragma unroll
+    for (int a = 0; a < (NDIM == 3 ? 2 : 1); ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        base[a * 2 + b] = valid ? ((long long)(NDIM == 3 ? zs[a] : 0) * n1 + ys[b]) * n2 : 0;
+        wzy[a * 2 + b][0] = wz[a];
+        wzy[a * 2 + b][1] = wy[b];
+      }
+  }
+  __device__ __forceinline__ float at(const float* __restrict__ r1, int n2, const double* t, int x) const {
+    const double cx = (double)x + t[2];
+    if (!valid || cx < 0.0 || cx > (double)(n2 - 1)) return NAN;
+    const double fx = floor(cx);
+    const int ix = (int)fx;
+    double wx[2];
+    wx[0] = 1.0 - (cx - fx); wx[1] = 1.0 - wx[0];
+    const int xs[2] = {ix, ix + 1 < n2 ? ix + 1 : mirror_idx(ix + 1, n2)};
+    double acc = 0.0;
+#pragma unroll
+    for (int ab = 0; ab < (NDIM == 3 ? 4 : 2); ++ab)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double v = (double)__ldg(r1 + base[ab] + xs[c]);
+        if (NDIM == 3) v = __dmul_rn(v, wzy[ab][0]);
+        v = __dmul_rn(__dmul_rn(v, wzy[ab][1]), wx[c]);
+        acc = __dadd_rn(acc, v);
+      }
+    return (float)acc;
+  }
+};
+
 // ---- stage C: mask statistics ------------------------------------------------
 
 constexpr int kStatBlocks = 32;
@@ -180,18 +231,21 @@ materialize_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
   const Cand c = cands[blockIdx.y];
   const long long n = (long long)c.len[0] * c.len[1] * c.len[2];
   float* out = mat + c.mat_off;
-  // rows of the slice are walked with 32-bit arithmetic (a 64-bit division per voxel costs more than
-  // the interpolation itself)
-  const unsigned rows = (unsigned)c.len[0] * (unsigned)c.len[1];  // < 2^31: the slice fits the crop
-  const unsigned lenx = (unsigned)c.len[2], leny = (unsigned)c.len[1];
-  const unsigned xt = (lenx + 31) / 32;  // 32-voxel segments per row: one warp each
+  // one warp per row of the slice (32-bit index arithmetic; the row's z / y taps and weights stay in
+  // registers while the lanes walk along x)
+  const unsigned rows = (unsigned)c.len[0] * (unsigned)c.len[1];
+  const unsigned leny = (unsigned)c.len[1];
+  const int lenx = c.len[2];
   const unsigned nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (unsigned w = blockIdx.x * nwarps + (threadIdx.x >> 5); w < rows * xt; w += gridDim.x * nwarps) {
-    const unsigned row = w / xt, x = (w - row * xt) * 32 + lane;
-    if (x >= lenx) continue;
+  const unsigned xt = ((unsigned)lenx + kRowSeg - 1) / kRowSeg;  // x segments per row: the units of work
+  for (unsigned u = blockIdx.x * nwarps + (threadIdx.x >> 5); u < rows * xt; u += gridDim.x * nwarps) {
+    const unsigned row = u / xt, x0 = (u - row * xt) * kRowSeg;
     const unsigned z = row / leny, y = row - z * leny;
-    out[(long long)row * lenx + x] =
-        shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, c.lo[0] + (int)z, c.lo[1] + (int)y, c.lo[2] + (int)x);
+    ShiftRow<NDIM> R;
+    R.init(n0, n1, n2, c.t, c.lo[0] + (int)z, c.lo[1] + (int)y);
+    float* orow = out + (long long)row * lenx;
+    const int x1 = min(lenx, (int)(x0 + kRowSeg));
+    for (int x = (int)(x0 + lane); x < x1; x += 32) orow[x] = R.at(c.r1, n2, c.t, c.lo[2] + x);
   }
 }
 
@@ -504,23 +558,27 @@ spearman_keys_kernel(const Cand* __restrict__ cands, int n0, int n1, int n2,
   const Cand c = cands[slot];
   const long long N = (long long)n0 * n1 * n2;
   const unsigned hi = (unsigned)slot << kKeyBits;
-  // rows are walked with 32-bit arithmetic, one warp per 32-voxel segment (see materialize_kernel)
-  const unsigned rows = (unsigned)n0 * (unsigned)n1, xt = ((unsigned)n2 + 31) / 32;
+  // one warp per row (see materialize_kernel)
+  const unsigned rows = (unsigned)n0 * (unsigned)n1;
   const unsigned nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (unsigned w = blockIdx.x * nwarps + (threadIdx.x >> 5); w < rows * xt; w += gridDim.x * nwarps) {
-    const unsigned row = w / xt, xu = (w - row * xt) * 32 + lane;
-    if (xu >= (unsigned)n2) continue;
+  const unsigned xt = ((unsigned)n2 + kRowSeg - 1) / kRowSeg;
+  for (unsigned u = blockIdx.x * nwarps + (threadIdx.x >> 5); u < rows * xt; u += gridDim.x * nwarps) {
+    const unsigned row = u / xt, x0 = (u - row * xt) * kRowSeg;
     const unsigned zu = row / (unsigned)n1;
-    const int x = (int)xu, y = (int)(row - zu * (unsigned)n1), z = (int)zu;
-    const long long i = (long long)row * n2 + x;
-    float b = shifted_value<NDIM>(c.r1, n0, n1, n2, c.t, z, y, x);
-    float a = __ldg(c.r0 + i);
-    const bool m = (a == a) && (b == b);
-    // the reference ranks `im1t[mask] - 1` in float32 (registration.py:551-553):
-    // the subtraction merges values below ~3e-8 into ties, which changes ranks
-    const long long e = (long long)slot * N + i;
-    ka[e] = hi | (m ? key_unit(a) : kKeyMasked);
-    vb[e] = m ? key_neg_unit(__fsub_rn(b, 1.0f)) : kKeyMasked;
+    ShiftRow<NDIM> R;
+    R.init(n0, n1, n2, c.t, (int)zu, (int)(row - zu * (unsigned)n1));
+    const int x1 = min(n2, (int)(x0 + kRowSeg));
+    for (int x = (int)(x0 + lane); x < x1; x += 32) {
+      const long long i = (long long)row * n2 + x;
+      const float b = R.at(c.r1, n2, c.t, x);
+      const float a = __ldg(c.r0 + i);
+      const bool m = (a == a) && (b == b);
+      // the reference ranks `im1t[mask] - 1` in float32 (registration.py:551-553):
+      // the subtraction merges values below ~3e-8 into ties, which changes ranks
+      const long long e = (long long)slot * N + i;
+      ka[e] = hi | (m ? key_unit(a) : kKeyMasked);
+      vb[e] = m ? key_neg_unit(__fsub_rn(b, 1.0f)) : kKeyMasked;
+    }
   }
 }
 
