@@ -310,14 +310,20 @@ box_kernel(const float* __restrict__ vols, int nz, int ny, int nx, int* __restri
   const long long N = (long long)nz * ny * nx;
   const float* v = vols + (long long)blockIdx.y * N;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float x = v[i];
-    if (x == x) {
-      const int c[3] = {(int)(i / ((long long)ny * nx)), (int)((i / nx) % ny), (int)(i % nx)};
-#pragma unroll
-      for (int d = 0; d < 3; ++d) { lo[d] = min(lo[d], c[d]); hi[d] = max(hi[d], c[d]); }
+  // one warp per 256-voxel row segment: (z, y) per segment, no per-voxel 64-bit divisions
+  const unsigned rows = (unsigned)nz * (unsigned)ny, xt = ((unsigned)nx + 255) / 256;
+  const unsigned nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned u = blockIdx.x * nwarps + (threadIdx.x >> 5); u < rows * xt; u += gridDim.x * nwarps) {
+    const unsigned row = u / xt, x0 = (u - row * xt) * 256;
+    const int z = (int)(row / (unsigned)ny), y = (int)(row - (unsigned)z * (unsigned)ny);
+    const float* rp = v + (long long)row * nx;
+    const int x1 = min(nx, (int)x0 + 256);
+    bool any = false;
+    for (int xi = (int)(x0 + lane); xi < x1; xi += 32) {
+      const float x = rp[xi];
+      if (x == x) { lo[2] = min(lo[2], xi); hi[2] = max(hi[2], xi); any = true; }
     }
+    if (any) { lo[0] = min(lo[0], z); hi[0] = max(hi[0], z); lo[1] = min(lo[1], y); hi[1] = max(hi[1], y); }
   }
 #pragma unroll
   for (int d = 0; d < 3; ++d)

@@ -7,4 +7,4 @@ timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
 head -c 600 gpurun_out/bench_r02.json; echo; tail -5 gpurun_out/bench_r02.err
 ( time timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r02_ref.json 2> gpurun_out/bench_r02_ref.err ) 2>&1 | grep real; echo "ref rc=$?"
 head -c 900 gpurun_out/bench_r02_ref.json; echo
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --only none > gpurun_out/b_ncu.log 2>&1; echo "ncu list rc=$?"
+timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --only none > gpurun_out/b_ncu.log 2>&1; echo "ncu list rc=$?"
