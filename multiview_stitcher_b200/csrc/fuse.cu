@@ -365,10 +365,15 @@ resample_views_kernel(mvs_chunk ck, const mvs_view_xform* __restrict__ xforms, i
   const long long N = (long long)ck.shape[0] * ck.shape[1] * ck.shape[2];
   const int v = blockIdx.y;
   const mvs_view_xform& X = xforms[v];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % ck.shape[2]), y = (int)((i / ck.shape[2]) % ck.shape[1]),
-              z = (int)(i / ((long long)ck.shape[2] * ck.shape[1]));
+  // one warp per 32-voxel row segment, 32-bit index arithmetic (no 64-bit divisions per voxel)
+  const unsigned rows = (unsigned)ck.shape[0] * (unsigned)ck.shape[1], nx = (unsigned)ck.shape[2];
+  const unsigned xt = (nx + 31) / 32, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned u = blockIdx.x * nwarps + (threadIdx.x >> 5); u < rows * xt; u += gridDim.x * nwarps) {
+    const unsigned row = u / xt, xu = (u - row * xt) * 32 + lane;
+    if (xu >= nx) continue;
+    const unsigned zu = row / (unsigned)ck.shape[1];
+    const int x = (int)xu, y = (int)(row - zu * (unsigned)ck.shape[1]), z = (int)zu;
+    const long long i = (long long)row * nx + x;
     ViewEval e;
     if (out_weights)
       e = eval_view<NDIM, ORDER, true, true>(X, tables, (double)(z + ck.halo[0]),

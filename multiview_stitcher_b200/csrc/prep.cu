@@ -17,13 +17,14 @@ template <typename T, bool SKIP>
 __global__ void __launch_bounds__(256)
 bin_mean_kernel(const T* __restrict__ in, int64_t sz, int64_t sy, int64_t sx, int nz, int ny,
                 int nx, int bz, int by, int bx, T* __restrict__ out) {
-  const int64_t N = (int64_t)nz * ny * nx;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += step) {
-    const int x = (int)(i % nx);
-    const int64_t r = i / nx;
-    const int y = (int)(r % ny);
-    const int z = (int)(r / ny);
+  // one warp per 32-output row segment, 32-bit index arithmetic (no 64-bit divisions per output)
+  const unsigned rows = (unsigned)nz * (unsigned)ny, xt = ((unsigned)nx + 31) / 32;
+  const unsigned nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned u = blockIdx.x * nwarps + (threadIdx.x >> 5); u < rows * xt; u += gridDim.x * nwarps) {
+    const unsigned row = u / xt, xu = (u - row * xt) * 32 + lane;
+    if (xu >= (unsigned)nx) continue;
+    const int z = (int)(row / (unsigned)ny), y = (int)(row - (unsigned)z * (unsigned)ny), x = (int)xu;
+    const int64_t i = (int64_t)row * nx + x;
     const T* p = in + (int64_t)z * bz * sz + (int64_t)y * by * sy + (int64_t)x * bx * sx;
     double acc = 0.0;
     int cnt = 0;
