@@ -238,8 +238,12 @@ struct PassThread {
 // runs at most 8 lines x 32 threads and gets the registers that frees (no spills; its
 // register budget / occupancy is untuned -- a second launch-bound argument changes the
 // code generated for every other length, so that tuning needs its own kernel entry)
+#ifndef MVS_FFT_MINB
+#define MVS_FFT_MINB 1
+#endif
 template <int M, bool BLUE>
-__global__ void __launch_bounds__(M == 640 ? 256 : 512) fft_reg_pass_kernel(const FftPassArgs P) {
+__global__ void __launch_bounds__(M == 640 ? 256 : 512, (!BLUE && M != 640) ? MVS_FFT_MINB : 1)
+fft_reg_pass_kernel(const FftPassArgs P) {
   extern __shared__ float2 fft_smem[];
   __shared__ unsigned long long s_keys[2][16];
   PassThread<M, BLUE> th;
