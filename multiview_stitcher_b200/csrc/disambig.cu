@@ -215,6 +215,10 @@ constexpr int kMaxWin = 7;
 #ifndef MVS_S2_TX
 #define MVS_S2_TX 128
 #endif
+// What bounds the kernel (ncu, profiles/r02_ssim2d_ncu.txt): the XU pipe at 62 % -- the 15 float32 -> float64 and
+// 10 float64 -> float32 conversions per thread and row that keep the window sums exact run at a quarter of the
+// ALU rate.  Measured and neutral: tile shapes 64..150 x 32..64 (1110-1165 us per 20-pair batch), two outputs per
+// thread in the x pass with 128-bit shared loads (14 -> 4 loads per output pair: 1132 us), occupancy hints.
 constexpr int kS2TX = MVS_S2_TX, kS2TY = 64, kS2Threads = 160, kS2Cols = kS2TX + kMaxWin - 1;
 static_assert(kS2Cols <= kS2Threads, "one thread per input column");
 #ifndef MVS_S3_THREADS
