@@ -238,12 +238,16 @@ struct PassThread {
 // runs at most 8 lines x 32 threads and gets the registers that frees (no spills; its
 // register budget / occupancy is untuned -- a second launch-bound argument changes the
 // code generated for every other length, so that tuning needs its own kernel entry)
-#ifndef MVS_FFT_MINB
-#define MVS_FFT_MINB 1
+// MVS_FFT_MINB (experiment): minimum CTAs per SM for the plain passes.  Measured with 2 (64 registers, a few
+// spilled bytes): power-of-two crops 4 % faster, C2's stage 3 % slower.  Left undefined by default: even an
+// explicit 1 changes the register allocation of every length (76 -> 113 for 2048 points).
+#ifdef MVS_FFT_MINB
+#define MVS_FFT_BOUNDS(M, BLUE) __launch_bounds__((M) == 640 ? 256 : 512, (!(BLUE) && (M) != 640) ? MVS_FFT_MINB : 1)
+#else
+#define MVS_FFT_BOUNDS(M, BLUE) __launch_bounds__((M) == 640 ? 256 : 512)
 #endif
 template <int M, bool BLUE>
-__global__ void __launch_bounds__(M == 640 ? 256 : 512, (!BLUE && M != 640) ? MVS_FFT_MINB : 1)
-fft_reg_pass_kernel(const FftPassArgs P) {
+__global__ void MVS_FFT_BOUNDS(M, BLUE) fft_reg_pass_kernel(const FftPassArgs P) {
   extern __shared__ float2 fft_smem[];
   __shared__ unsigned long long s_keys[2][16];
   PassThread<M, BLUE> th;
