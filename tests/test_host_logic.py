@@ -263,3 +263,22 @@ def test_hook_argument_errors_are_raised_before_any_device_work():
     # backend="numpy" / "cupy" are accepted (host arrays are staged, device arrays used in place)
     with pytest.raises(EngineError, match="unknown backend"):
         BatchFuser()(part, [(0, 0)])
+
+
+def test_pitched_decomposition_of_array_windows():
+    """_lib._pitched: how a numpy / tensor window maps onto the staged 3-D copies
+    (planes x rows x contiguous width, outer loop over the remaining axes)."""
+    from multiview_stitcher_b200 import _lib
+
+    a = np.zeros((5, 7, 11, 13), dtype=np.uint16)
+    outer, planes, rows, width, pitch, plane = _lib._pitched(a.shape, a.strides, a.itemsize)
+    assert (len(outer), planes, rows, width, pitch, plane) == (5, 7, 11, 26, 26, 11 * 26)
+    w = a[1:4, 2:6, 3:9, 4:12]  # a window: pitches stay those of the parent
+    outer, planes, rows, width, pitch, plane = _lib._pitched(w.shape, w.strides, w.itemsize)
+    assert (len(outer), planes, rows, width, pitch, plane) == (3, 4, 6, 16, 26, 11 * 26)
+    b = np.zeros((9, 20), dtype=np.float32)[:, 3:10]
+    assert _lib._pitched(b.shape, b.strides, 4) == ([()], 1, 9, 28, 80, 720)
+    c = np.zeros(17, dtype=np.uint8)
+    assert _lib._pitched(c.shape, c.strides, 1) == ([()], 1, 1, 17, 17, 17)
+    with pytest.raises(_lib.EngineError):
+        _lib._pitched((4, 6), (4, 24), 4)  # non-contiguous last axis
