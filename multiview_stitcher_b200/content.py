@@ -17,11 +17,15 @@ from __future__ import annotations
 
 import ctypes
 import inspect
+import os
 
 import numpy as np
 
 from . import _lib, deconv, geometry, hooks
 from ._lib import EngineError
+
+_N_STREAMS = max(1, min(3, int(os.environ.get("MVS_CONTENT_STREAMS", "2"))))  # the engine keeps 3 workspaces
+_TWO_STREAMS = _N_STREAMS > 1
 
 _ENGINE_FUNCS = {
     "weighted_average_fusion": hooks.weighted_average_fusion,
@@ -224,7 +228,39 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
     grid = geometry.chunk_grid(osp, output_chunksize)
     if chunk_subset is not None:
         grid = [grid[i] for i in chunk_subset]
-    for start, shape in grid:
+    # Consecutive chunks alternate between two streams: nothing in a chunk's pipeline returns to the
+    # host, so the FP64-bound Gaussian passes of one chunk run beside the HBM-bound resampling and
+    # element-wise passes of the next (each stream has its own engine workspace).
+    cur = torch.cuda.current_stream()
+    streams = _side_streams() if len(grid) > 1 and _TWO_STREAMS else [cur]
+    for st in streams:
+        st.wait_stream(cur)
+    for k, (start, shape) in enumerate(grid):
+        with torch.cuda.stream(streams[k % len(streams)]):
+            _fuse_one_chunk(dviews, params, osp, dims, start, shape, ov, o_org, o_sp, aabbs, bbs, fusion_func,
+                            weights_func, weights_func_kwargs, interpolation_order, blending_widths, out)
+    for st in streams:
+        cur.wait_stream(st)
+    return out
+
+
+_SIDE = {}
+
+
+def _side_streams():
+    """Two long-lived streams per device (the engine keeps one workspace per stream in use)."""
+    import torch
+
+    dev = torch.cuda.current_device()
+    if dev not in _SIDE:
+        _SIDE[dev] = [torch.cuda.Stream() for _ in range(_N_STREAMS)]
+    return _SIDE[dev]
+
+
+def _fuse_one_chunk(dviews, params, osp, dims, start, shape, ov, o_org, o_sp, aabbs, bbs, fusion_func, weights_func,
+                    weights_func_kwargs, interpolation_order, blending_widths, out):
+    """One output chunk of ``fuse_with_weights`` (enqueued on the current stream)."""
+    if True:
         start_a = np.array(start)
         c_org = (o_org + o_sp * start_a) - ov * o_sp
         hbb = {
@@ -235,7 +271,7 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
         lo, hi = c_org, c_org + (np.array(shape) + 2 * ov - 1) * o_sp
         sel = [i for i, (alo, ahi) in enumerate(aabbs) if not (np.any(ahi < lo - 1e-6) or np.any(alo > hi + 1e-6))]
         if not sel:
-            continue
+            return
         res = fuse_np_with_weights(
             [dviews[i] for i in sel], [params[i] for i in sel], hbb, fusion_func=fusion_func,
             weights_func=weights_func, weights_func_kwargs=weights_func_kwargs,
@@ -245,4 +281,3 @@ def fuse_with_weights(dviews, params, osp, output_chunksize, fusion_func, weight
         )
         sl = tuple(slice(int(s), int(s) + int(n)) for s, n in zip(start, shape))
         out[sl] = res
-    return out

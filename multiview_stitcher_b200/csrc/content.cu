@@ -506,33 +506,54 @@ static int gaussian_batch(const float* src, float* dst, float* tmp, int batch, c
   return MVS_OK;
 }
 
-// Grow-only device workspace shared by the multi-pass entry points.  Calls are
-// serialised by g_ws_mutex while they ENQUEUE; on one stream the work of two
-// calls is ordered by the stream itself, so nothing waits for the GPU.  A call on
-// another stream first waits for the previous user's stream; growing the buffer
-// frees it (cudaFree synchronises the device).
+// Grow-only device workspaces of the multi-pass entry points, one per stream in use (up to
+// kWsSlots; least recently used beyond that).  Calls are serialised by g_ws_mutex while they
+// ENQUEUE; on one stream the work of two calls is ordered by the stream itself, so nothing waits
+// for the GPU, and calls on different streams (e.g. the chunks of a content-weighted fusion
+// alternating between two streams, so that the FP64-bound Gaussian passes of one chunk overlap the
+// HBM-bound element-wise passes of the next) do not share a buffer.  A slot that changes hands first
+// waits for its previous stream; growing a buffer frees it (cudaFree synchronises the device).
 static std::mutex g_ws_mutex;
-static void* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-static cudaStream_t g_ws_stream = nullptr;
-static bool g_ws_used = false;
+constexpr int kWsSlots = 3;
+struct WsSlot {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st = nullptr;
+  bool used = false;
+  unsigned long long tick = 0;
+};
+static WsSlot g_ws[kWsSlots];
+static unsigned long long g_ws_tick = 0;
 
 static int workspace(size_t bytes, void** out, cudaStream_t st) {
-  if (g_ws_used && g_ws_stream != st) cudaStreamSynchronize(g_ws_stream);
-  g_ws_stream = st;
-  g_ws_used = true;
-  if (g_ws_bytes < bytes) {
-    if (g_ws) cudaFree(g_ws);
-    g_ws = nullptr;
-    g_ws_bytes = 0;
-    cudaError_t e = cudaMalloc(&g_ws, bytes);
-    if (e != cudaSuccess) {
-      set_error("workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+  WsSlot* e = nullptr;
+  for (auto& w : g_ws)
+    if (w.used && w.st == st) e = &w;
+  if (!e) {
+    for (auto& w : g_ws)
+      if (!w.used) { e = &w; break; }
+    if (!e) {
+      e = &g_ws[0];
+      for (auto& w : g_ws)
+        if (w.tick < e->tick) e = &w;
+      if (cudaStreamSynchronize(e->st) != cudaSuccess) cudaGetLastError();  // a stream that no longer exists
+    }
+    e->st = st;
+    e->used = true;
+  }
+  e->tick = ++g_ws_tick;
+  if (e->bytes < bytes) {
+    if (e->p) cudaFree(e->p);
+    e->p = nullptr;
+    e->bytes = 0;
+    cudaError_t err = cudaMalloc(&e->p, bytes);
+    if (err != cudaSuccess) {
+      set_error("workspace of %zu bytes: %s", bytes, cudaGetErrorString(err));
       return MVS_ERR_CUDA;
     }
-    g_ws_bytes = bytes;
+    e->bytes = bytes;
   }
-  *out = g_ws;
+  *out = e->p;
   return MVS_OK;
 }
 
