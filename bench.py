@@ -707,7 +707,9 @@ def bench_c3(cx, args):
     res = pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans)
     tt = np.array([t[:3, 3] for t in true])
     err = max(float(np.abs(r["transform"][:3, 3] + (tt[b] - tt[a])).max()) for r, (a, b) in zip(res, my_pairs))
-    ms_reg, ms_reg_mean = _median_ms(cx, lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 3, 1)
+    # the first calls grow the plans' scratch buffers (several GB per crop shape: cudaFree / cudaMalloc
+    # synchronise the device); measured call times 519 911 720 254 275 211 213 246 ms -> 3 warm-up calls
+    ms_reg, ms_reg_mean = _median_ms(cx, lambda: pairs_mod.register_views(views, plan=pplan, pc_plans=pc_plans), 5, 3)
     rec["registration_from_tiles"] = {"pairs": len(pairs), "pairs_this_rank": len(my_pairs), "ms": ms_reg, "ms_mean": ms_reg_mean,
                                       "pairs_per_sec": len(pairs) / (ms_reg * 1e-3),
                                       "max_abs_shift_error_px": cx.max_over_ranks(err),
