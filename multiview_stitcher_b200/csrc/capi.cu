@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <mutex>
 
 namespace mvs {
 
@@ -15,6 +16,27 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* get_error() { return g_err; }
+
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t st) {
+  static std::mutex m;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && !done[dev]) {
+    std::lock_guard<std::mutex> l(m);
+    if (!done[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      done[dev] = true;
+    }
+  }
+  return cudaMallocAsync(p, bytes, st);
+}
 
 }  // namespace mvs
 

@@ -16,6 +16,12 @@ namespace mvs {
 void set_error(const char* fmt, ...);
 const char* get_error();
 
+// cudaMallocAsync from the device's default pool, whose release threshold is raised once per device:
+// with the default of 0 the pool hands its memory back to the OS at every synchronisation, and the
+// unmap / re-map of even a few kilobytes was measured to stall the next launches for 250-570 ms
+// every few calls next to multi-GB allocations (the C3 pair-preparation launches).
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t st);
+
 #define MVS_CHECK_CUDA(expr)                                                        \
   do {                                                                              \
     cudaError_t _e = (expr);                                                        \

@@ -297,7 +297,7 @@ extern "C" int mvs_content_based_dct(const float* d_views, int V, const int32_t 
   MVS_REQUIRE(nblocks * V < (1ll << 31), MVS_ERR_UNSUPPORTED, "too many blocks");
   cudaStream_t st = (cudaStream_t)stream;
   float* d_q = nullptr;
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_q, sizeof(float) * nblocks * V, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_q, sizeof(float) * nblocks * V, st));
   a.quality = d_q;
   const size_t smem = sizeof(float) * (kDctMax * kDctMax * kDctPitch + 3 * kDctMax * kDctMax);
   MVS_CHECK_CUDA(cudaFuncSetAttribute(dct_quality_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

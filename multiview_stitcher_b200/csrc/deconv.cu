@@ -216,7 +216,7 @@ extern "C" int mvs_convolve(const float* d_in, float* d_out, const int32_t shape
   std::vector<float> flipped((size_t)kn);
   for (int64_t i = 0; i < kn; ++i) flipped[(size_t)i] = kernel[kn - 1 - i];
   float* d_w = nullptr;
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_w, sizeof(float) * kn, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_w, sizeof(float) * kn, st));
   MVS_CHECK_CUDA(cudaMemcpyAsync(d_w, flipped.data(), sizeof(float) * kn, cudaMemcpyHostToDevice, st));
   a.in = d_in; a.out = d_out; a.wcorr = d_w; a.mode = mode; a.cval = cval; a.epi = 0;
   cudaError_t e = launch_conv(a, st);
@@ -251,11 +251,11 @@ extern "C" int mvs_mv_deconvolution(const float* d_views, const float* d_weights
       flipped[(size_t)((V + v) * kn + i)] = kernels2[v * kn + (kn - 1 - i)];
     }
   float *d_w = nullptr, *d_psi = nullptr, *d_tmp = nullptr, *d_wr = nullptr;
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_w, sizeof(float) * 2 * V * kn, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_w, sizeof(float) * 2 * V * kn, st));
   MVS_CHECK_CUDA(cudaMemcpyAsync(d_w, flipped.data(), sizeof(float) * 2 * V * kn, cudaMemcpyHostToDevice, st));
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_psi, sizeof(float) * N, st));
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_tmp, sizeof(float) * N, st));
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_wr, sizeof(float) * N, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_psi, sizeof(float) * N, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_tmp, sizeof(float) * N, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_wr, sizeof(float) * N, st));
   const unsigned grid = (unsigned)std::min<int64_t>((N + 255) / 256, 148 * 16);
   deconv_init_kernel<<<grid, 256, 0, st>>>(d_views, d_weights, V, N, min_value, d_psi);
   MVS_CHECK_CUDA(cudaGetLastError());
@@ -285,8 +285,8 @@ extern "C" int mvs_mv_deconvolution(const float* d_views, const float* d_weights
   }
   if (e == cudaSuccess && erosion_px > 0) {
     unsigned char *m0 = nullptr, *m1 = nullptr;
-    MVS_CHECK_CUDA(cudaMallocAsync((void**)&m0, (size_t)N, st));
-    MVS_CHECK_CUDA(cudaMallocAsync((void**)&m1, (size_t)N, st));
+    MVS_CHECK_CUDA(mvs::pool_malloc((void**)&m0, (size_t)N, st));
+    MVS_CHECK_CUDA(mvs::pool_malloc((void**)&m1, (size_t)N, st));
     deconv_union_kernel<<<grid, 256, 0, st>>>(d_views, V, N, m0);
     for (int k = 0; k < erosion_px; ++k) {
       deconv_erode_kernel<<<grid, 256, 0, st>>>(m0, m1, shape[0], shape[1], shape[2], ndim);

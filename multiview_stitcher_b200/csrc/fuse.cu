@@ -1088,7 +1088,7 @@ extern "C" int mvs_fuse_finalize_boxes(const mvs_chunk* boxes, int n_boxes, void
   if (biggest == 0) return MVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   mvs_chunk* d_boxes = nullptr;
-  MVS_CHECK_CUDA(cudaMallocAsync((void**)&d_boxes, sizeof(mvs_chunk) * n_boxes, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc((void**)&d_boxes, sizeof(mvs_chunk) * n_boxes, st));
   // pageable source: staged before the call returns
   MVS_CHECK_CUDA(cudaMemcpyAsync(d_boxes, boxes, sizeof(mvs_chunk) * n_boxes,
                                  cudaMemcpyHostToDevice, st));
@@ -1126,7 +1126,7 @@ extern "C" int mvs_resample_views(const mvs_view_xform* xforms, int n_views, con
   const size_t xbytes = ((sizeof(mvs_view_xform) * n_views + 255) / 256) * 256;
   const size_t tbytes = d_weights ? sizeof(float) * 125 * n_tables : 0;
   void* d_buf = nullptr;
-  MVS_CHECK_CUDA(cudaMallocAsync(&d_buf, xbytes + tbytes, st));
+  MVS_CHECK_CUDA(mvs::pool_malloc(&d_buf, xbytes + tbytes, st));
   mvs_view_xform* d_x = (mvs_view_xform*)d_buf;
   float* d_t = d_weights ? (float*)((char*)d_buf + xbytes) : nullptr;
   if (d_weights)

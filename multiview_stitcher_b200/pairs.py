@@ -327,6 +327,7 @@ class PairPlan:
         planned = [plan_one(k) for k in range(len(self.pairs))]
         self.items = [p for p, _ in planned]
         self.bbox = [b for _, b in planned]
+        self._stacks = {}  # crop shape -> (2P, *crop) float32 stack kept for reuse_buffers
         self.groups = {}
         for k, pl in enumerate(self.items):
             self.groups.setdefault(pl["shape"], []).append(k)
@@ -340,9 +341,12 @@ class PairPlan:
         pl = self.items[k]
         return {"origin": pl["origin"], "spacing": pl["spacing"], "shape": pl["shape"]}
 
-    def prepare(self, views):
+    def prepare(self, views, reuse_buffers=False):
         """Device half: bin (one kernel per view and binning), window, and ONE resample
-        launch per crop-shape group.  Returns ``PreparedPairs``."""
+        launch per crop-shape group.  Returns ``PreparedPairs``.  ``reuse_buffers``: the crop
+        stacks live in the plan and are overwritten by the next call (time lapses: several GB per
+        crop shape for 3-D tiles, and a fresh ``cudaMalloc`` of that size costs more than the
+        registration itself -- measured 200 ms vs 500-900 ms per call on C3)."""
         import torch
 
         from .fusion import DeviceView, to_device_view
@@ -384,7 +388,11 @@ class PairPlan:
                     x["stride"] = [0] * (3 - ndim) + [int(s) for s in win.stride()]
                     x["matrix"], x["offset"] = geometry.embed3(*pl["xforms"][side])
                     x["wmatrix"], x["woffset"] = geometry.embed3(np.eye(ndim), np.zeros(ndim))
-            stack = torch.empty((2 * len(idx),) + tuple(shape), dtype=torch.float32, device="cuda")
+            stack = self._stacks.get(shape) if reuse_buffers else None
+            if stack is None or stack.shape[0] != 2 * len(idx):
+                stack = torch.empty((2 * len(idx),) + tuple(shape), dtype=torch.float32, device="cuda")
+                if reuse_buffers:
+                    self._stacks[shape] = stack
             _lib.check(
                 lib.mvs_resample_views(
                     xarr.ctypes.data_as(ctypes.c_void_p), len(xarr), None, 0,
@@ -434,9 +442,10 @@ def register_views(views, affines=None, pairs=None, overlap_tolerance=None, regi
     plan's); ``pc_plans``: dict that keeps the phase-correlation buffers across calls."""
     from . import registration
 
+    reuse = plan is not None and not return_prepared  # a plan the caller keeps: its crop stacks stay too
     if plan is None:
         plan = PairPlan(views, affines, pairs, overlap_tolerance, registration_binning)
-    prep = plan.prepare(views)
+    prep = plan.prepare(views, reuse_buffers=reuse)
     kw = dict(pairwise_reg_func_kwargs or {})
     res = registration.register_pairs(
         prep.fixed, prep.moving, kw.pop("disambiguate_region_mode", None), kw.pop("upsample_factor", None),
