@@ -11,6 +11,6 @@ hf = [np.ascontiguousarray(a) for a in hf]; hm = [np.ascontiguousarray(a) for a 
 plans = {}
 for _ in range(2): registration.register_pairs(hf, hm, plans=plans)
 ts = []
-for _ in range(5):
+for _ in range(16):
     t0 = time.perf_counter(); registration.register_pairs(hf, hm, plans=plans); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
 print(os.environ.get("MVS_REG_UPLOAD_EARLY"), " ".join(f"{t:.1f}" for t in ts))
