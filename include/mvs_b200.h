@@ -286,9 +286,10 @@ int mvs_pc_spearman_batch(mvs_pc_plan* plan, int n, const int32_t* pairs, const 
  * Host <-> device movement of PAGEABLE host arrays: what the reference's hooks hand
  * over are plain numpy arrays (view slices, fusion/_core.py:1579-1587; the zarr
  * region a fused block is written to, :2130-2150).  `rows` rows of `width` bytes
- * are cut into 2 MiB pieces; every thread of a small pool moves its pieces end to end
- * through its own two pinned buffers and its own stream (fill + DMA, or DMA + drain with
- * cache-bypassing stores), so uploads, downloads and the host copies all overlap.
+ * are cut into 1 MiB pieces that rotate through a ring of pinned slots per direction: a small
+ * pool of threads copies between the user's array and the slots (downloads with
+ * cache-bypassing stores) while the calling thread alone enqueues the DMAs on `stream` and
+ * waits for their events, so uploads, downloads and the host copies all overlap.
  * mvs_copy_h2d_2d returns once h_src has been staged (the device copy is ordered on
  * `stream`); mvs_copy_d2h_2d returns once h_dst is filled (work on `stream` enqueued
  * before the call is waited for).  Pitches in bytes.
