@@ -207,9 +207,14 @@ static void copy_stream_stores(char* dst, const char* src, size_t n) {
 // report back through a flag per slot.  (Measured on the B200 box: letting every worker
 // enqueue its own DMAs and poll its own events makes an upload and a download that run side
 // by side 8x slower than either alone -- the driver serialises the calls.)
-constexpr int kSlots = 16;
-constexpr int kFillAhead = 12;  // upload: pieces being filled by the pool (the other slots hold DMAs in flight)
-constexpr int kDmaAhead = 6;    // download: DMAs in flight (the other slots are being drained by the pool)
+#ifndef MVS_COPY_SLOTS
+#define MVS_COPY_SLOTS 16
+#define MVS_COPY_FILL 12
+#define MVS_COPY_DMA 6
+#endif
+constexpr int kSlots = MVS_COPY_SLOTS;
+constexpr int kFillAhead = MVS_COPY_FILL;  // upload: pieces being filled by the pool (the other slots hold DMAs in flight)
+constexpr int kDmaAhead = MVS_COPY_DMA;    // download: DMAs in flight (the other slots are being drained by the pool)
 
 struct Ring {
   std::mutex mtx;  // one transfer per direction at a time
