@@ -298,6 +298,10 @@ int mvs_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pit
                     size_t width, size_t rows, void* stream);
 int mvs_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
                     size_t width, size_t rows, void* stream);
+/* n contiguous host arrays -> n device buffers as one pipelined transfer (the crops a
+ * pairwise_reg_func batch is handed, registration.py:1926-1941). */
+int mvs_copy_h2d_many(int n, void* const* d_dst, const void* const* h_src, const size_t* bytes,
+                      void* stream);
 /* The same for `planes` planes `*_plane` bytes apart (3-D windows of tiles and fused blocks). */
 int mvs_copy_h2d_3d(void* d_dst, size_t d_pitch, size_t d_plane, const void* h_src, size_t h_pitch,
                     size_t h_plane, size_t width, size_t rows, size_t planes, void* stream);

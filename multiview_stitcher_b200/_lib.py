@@ -126,6 +126,7 @@ _SIGNATURES = {
     ),
     "mvs_copy_h2d_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_copy_d2h_2d": (ctypes.c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
+    "mvs_copy_h2d_many": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P]),
     "mvs_copy_h2d_3d": (ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_copy_d2h_3d": (ctypes.c_int, [_P, ctypes.c_size_t, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),
     "mvs_io_files": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int]),
@@ -260,3 +261,24 @@ def copy_d2h(dst_array, src_tensor, stream_ptr=None):
     if not dst_array.flags.writeable:
         raise EngineError("copy_d2h: destination is read-only")
     return _staged("mvs_copy_d2h_3d", src_tensor, dst_array, stream_ptr)
+
+
+def copy_h2d_many(dst_tensors, src_arrays, stream_ptr=None):
+    """Contiguous numpy arrays -> CUDA tensors of the same size, as ONE pipelined transfer through the
+    staging ring (per-array calls leave the copy pool idle between arrays).  Returns the bytes moved."""
+    lib = load(require_device=True)
+    n = len(dst_tensors)
+    if n != len(src_arrays):
+        raise EngineError("copy_h2d_many: list lengths differ")
+    if n == 0:
+        return 0
+    d = (ctypes.c_void_p * n)()
+    h = (ctypes.c_void_p * n)()
+    b = (ctypes.c_size_t * n)()
+    for i, (t, a) in enumerate(zip(dst_tensors, src_arrays)):
+        if not a.flags.c_contiguous or not t.is_contiguous() or t.numel() * t.element_size() != a.nbytes:
+            raise EngineError("copy_h2d_many: arrays must be contiguous and of equal size")
+        d[i], h[i], b[i] = t.data_ptr(), a.ctypes.data, a.nbytes
+    st = stream_ptr if stream_ptr is not None else current_stream_ptr()
+    check(lib.mvs_copy_h2d_many(n, d, h, b, st), "mvs_copy_h2d_many")
+    return int(sum(b))

@@ -383,6 +383,58 @@ static int staged_upload(char* d_dst, size_t d_pitch, size_t d_plane, const char
   return MVS_OK;
 }
 
+// Many contiguous host arrays -> device buffers as ONE pipelined transfer (the crops of a batch of
+// pairs: per-array calls leave the pool idle between arrays; measured 2 x 40 crops of 2.5 MB:
+// ~10 ms array by array).
+static int staged_upload_many(int n, char* const* d_dst, const char* const* h_src, const size_t* bytes,
+                              cudaStream_t st) {
+  struct Seg { char* d; const char* h; size_t n; };
+  std::vector<Seg> segs;
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) total += bytes[i];
+  if (total == 0) return MVS_OK;
+  const size_t piece = std::min<size_t>(kPiece, std::max<size_t>((size_t)256 << 10, ((total / 64) + 65535) & ~(size_t)65535));
+  for (int i = 0; i < n; ++i) {
+    MVS_REQUIRE(bytes[i] == 0 || (d_dst[i] && h_src[i]), MVS_ERR_INVALID, "array %d: NULL pointer", i);
+    for (size_t a = 0; a < bytes[i]; a += piece) segs.push_back({d_dst[i] + a, h_src[i] + a, std::min(piece, bytes[i] - a)});
+  }
+  int dev = 0;
+  MVS_CHECK_CUDA(cudaGetDevice(&dev));
+  Ring& R = ring(0);
+  std::lock_guard<std::mutex> lock(R.mtx);
+  MVS_CHECK_CUDA(R.prepare(dev, kPiece));
+  const size_t N = segs.size(), base = R.pos;
+  R.pos = (R.pos + N) % kSlots;
+  size_t dispatched = 0, issued = 0;
+  cudaError_t e = cudaSuccess;
+  const Seg* S = segs.data();
+  while (issued < N && e == cudaSuccess) {
+    while (dispatched < N && dispatched < issued + kFillAhead) {
+      const int k = (int)((base + dispatched) % kSlots);
+      if (R.dma_pending[k]) {
+        if ((e = cudaEventSynchronize(R.ev[k])) != cudaSuccess) break;
+        R.dma_pending[k] = false;
+      }
+      R.clear(k);
+      const size_t p = dispatched++;
+      pool().submit([&R, S, k, p] {
+        memcpy(R.at(k, S[p].h), S[p].h, S[p].n);
+        R.mark(k);
+      });
+    }
+    if (e != cudaSuccess) break;
+    const int k = (int)((base + issued) % kSlots);
+    R.wait_host(k);
+    e = cudaMemcpyAsync(S[issued].d, R.at(k, S[issued].h), S[issued].n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(R.ev[k], st);
+    R.dma_pending[k] = true;
+    ++issued;
+  }
+  for (size_t p = issued; p < dispatched; ++p) R.wait_host((int)((base + p) % kSlots));
+  MVS_REQUIRE(e == cudaSuccess, MVS_ERR_CUDA, "staged upload failed: %s", cudaGetErrorString(e));
+  return MVS_OK;
+}
+
 static int staged_download(char* h_dst, size_t h_pitch, size_t h_plane, const char* d_src, size_t d_pitch,
                            size_t d_plane, size_t width, size_t rows, size_t planes, cudaStream_t st) {
   if (width == 0 || rows == 0 || planes == 0) return MVS_OK;
@@ -453,6 +505,13 @@ extern "C" int mvs_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, s
 extern "C" int mvs_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
                                size_t width, size_t rows, void* stream) {
   return staged_download((char*)h_dst, h_pitch, 0, (const char*)d_src, d_pitch, 0, width, rows, 1, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_copy_h2d_many(int n, void* const* d_dst, const void* const* h_src, const size_t* bytes,
+                                 void* stream) {
+  if (n <= 0) return MVS_OK;
+  MVS_REQUIRE(d_dst && h_src && bytes, MVS_ERR_INVALID, "NULL pointer");
+  return staged_upload_many(n, (char* const*)d_dst, (const char* const*)h_src, bytes, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_copy_h2d_3d(void* d_dst, size_t d_pitch, size_t d_plane, const void* h_src, size_t h_pitch,

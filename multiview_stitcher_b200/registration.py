@@ -422,6 +422,27 @@ def _to_device_f32(a):
     return t
 
 
+def _to_device_many(arrays, n):
+    """Device float32 tensors of all crops: host arrays travel as ONE staged transfer."""
+    import torch
+
+    out, host_idx, host_arr = [None] * len(arrays), [], []
+    for i, a in enumerate(arrays):
+        if not isinstance(a, torch.Tensor) and hasattr(a, "data") and not isinstance(a, np.ndarray):
+            a = a.data  # xr.DataArray-like (registration.py:377-378)
+        if isinstance(a, torch.Tensor) or hasattr(a, "__cuda_array_interface__"):
+            out[i] = _to_device_f32(a)
+        else:
+            host_idx.append(i)
+            host_arr.append(np.ascontiguousarray(a, dtype=np.float32))
+    if host_arr:
+        tens = [torch.empty(a.shape, dtype=torch.float32, device="cuda") for a in host_arr]
+        _lib.copy_h2d_many(tens, host_arr)
+        for i, t in zip(host_idx, tens):
+            out[i] = t
+    return out[:n], out[n:]
+
+
 _SPLIT = int(os.environ.get("MVS_REG_SPLIT", "1"))
 
 
@@ -451,8 +472,7 @@ def register_pairs(fixed_list, moving_list, disambiguate_region_mode=None, upsam
     # another's kernels is slower -- 24-57 ms when the group threads upload, 23-24 ms when this thread
     # uploads group by group -- against 21.6 ms for C2's 40 pairs: the registration threads, the
     # interpreter and the copy pool fight over the host's cores)
-    fixed = [_to_device_f32(a) for a in fixed_list]
-    moving = [_to_device_f32(a) for a in moving_list]
+    fixed, moving = _to_device_many(list(fixed_list) + list(moving_list), n)
 
     def run_group(shape, idx, part=0):
         ndim = len(shape)
