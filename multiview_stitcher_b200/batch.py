@@ -196,6 +196,27 @@ class BatchFuser:
                 zarr_out[region] = data.reshape((1,) * len(nsdims) + tuple(shape))
                 self.blocks_written += 1
 
+    def _upload_many(self, vis, h2d):
+        """Enqueue the upload of all still-pending views of ``vis`` as ONE staged transfer (the copy
+        pool keeps working across tiles); they share one completion event."""
+        import torch
+
+        from . import _lib
+
+        todo = [vi for vi in vis if self._host[vi] is not None and self._events[vi] is None]
+        if not todo:
+            return
+        if len(todo) == 1 or not all(self._host[vi].flags.c_contiguous and self._views[vi].tensor.is_contiguous() for vi in todo):
+            for vi in todo:
+                self._upload(vi, h2d)
+            return
+        self.h2d_bytes += _lib.copy_h2d_many([self._views[vi].tensor for vi in todo], [self._host[vi] for vi in todo],
+                                             ctypes.c_void_p(h2d.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(h2d)
+        for vi in todo:
+            self._events[vi] = ev
+
     def _upload_now(self, vi):
         import torch
 
@@ -281,8 +302,8 @@ class BatchFuser:
 
         pos = 0
         for first, n, row0, nrows, vidx in plan.bands():
+            self._upload_many(vidx, h2d)
             for vi in vidx:
-                self._upload(vi, h2d)
                 if self._events[vi] is not None:
                     cur.wait_event(self._events[vi])
             plan.run_chunks(first, n)
