@@ -28,6 +28,12 @@ from ._lib import EngineError
 _BUILTIN = ("weighted_average_fusion", "max_fusion", "simple_average_fusion")
 
 
+def _lib_copy_d2h(dst_array, src_tensor):
+    from . import _lib
+
+    return _lib.copy_d2h(dst_array, src_tensor)
+
+
 def _select_ns(sim, ns_coord):
     """The spatial image at one non-spatial coordinate (the reference's
     ``sim_sel_coords(sim, {dim: sim.coords[dim][[ic]]})``, _core.py:2105-2111)."""
@@ -190,10 +196,20 @@ class BatchFuser:
                 continue
             for vi in range(len(views)):  # multi-pass path: everything resident first
                 self._upload_now(vi)
-            fused = self._fuse_blocks_multipass(views, params, osp, fk, blocks, dims)
+            fused = self._fuse_blocks_multipass(views, params, osp, fk, blocks, dims)  # device tensors
+            from .ngff_io import ZarrArray
+
+            dev_store = (isinstance(zarr_out, ZarrArray) and zarr_out._codec is None
+                         and tuple(zarr_out.chunks) == (1,) * len(nsdims) + tuple(int(chunksize[d]) for d in dims))
             for (lin, start, shape), data in zip(blocks, fused):
-                region = tuple(slice(i, i + 1) for i in ns_idx) + tuple(slice(int(a), int(a) + int(n)) for a, n in zip(start, shape))
-                zarr_out[region] = data.reshape((1,) * len(nsdims) + tuple(shape))
+                if isinstance(zarr_out, np.ndarray):
+                    region = tuple(int(i) for i in ns_idx) + tuple(slice(int(a), int(a) + int(n)) for a, n in zip(start, shape))
+                    self.d2h_bytes += _lib_copy_d2h(zarr_out[region], data)
+                elif dev_store:
+                    self.d2h_bytes += zarr_out.write_device(data, lead=ns_idx, start=start)
+                else:
+                    region = tuple(slice(i, i + 1) for i in ns_idx) + tuple(slice(int(a), int(a) + int(n)) for a, n in zip(start, shape))
+                    zarr_out[region] = data.cpu().numpy().reshape((1,) * len(nsdims) + tuple(shape))
                 self.blocks_written += 1
 
     def _upload_many(self, vis, h2d):
@@ -317,9 +333,12 @@ class BatchFuser:
         self.blocks_written += len(blocks)
 
     def _fuse_blocks_multipass(self, views, params, osp, fk, blocks, dims):
-        """Host arrays of the fused blocks, in order: any other fusion_func / a weights_func
+        """Device tensors of the fused blocks, in order: any other fusion_func / a weights_func
         runs the multi-pass device path, one output stack per block exactly like the
-        reference's per-chunk fuse() (_core.py:2118-2128)."""
+        reference's per-chunk fuse() (_core.py:2118-2128).  Consecutive blocks alternate between
+        two streams (see content.fuse_with_weights); nothing returns to the host in between."""
+        import torch
+
         from . import content
 
         fusion_func, weights_func = fk.get("fusion_func"), fk.get("weights_func")
@@ -327,16 +346,23 @@ class BatchFuser:
         widths = fk.get("blending_widths")
         o_org = np.array([osp["origin"][d] for d in dims], dtype=np.float64)
         o_sp = np.array([osp["spacing"][d] for d in dims], dtype=np.float64)
+        cur = torch.cuda.current_stream()
+        streams = content._side_streams() if len(blocks) > 1 and content._TWO_STREAMS else [cur]
+        for st in streams:
+            st.wait_stream(cur)
         res = []
-        for _, start, shape in blocks:
+        for k, (_, start, shape) in enumerate(blocks):
             c_org = np.array(start) * o_sp + o_org  # _core.py:2083-2086
             sub = {"origin": dict(zip(dims, map(float, c_org))), "spacing": dict(osp["spacing"]),
                    "shape": {d: int(n) for d, n in zip(dims, shape)}}
-            out = content.fuse_with_weights(
-                views, params, sub, {d: int(n) for d, n in zip(dims, shape)}, fusion_func, weights_func,
-                fk.get("weights_func_kwargs"), order, widths, fk.get("overlap_in_pixels"),
-            )
-            res.append(out.cpu().numpy())
+            with torch.cuda.stream(streams[k % len(streams)]):
+                out = content.fuse_with_weights(
+                    views, params, sub, {d: int(n) for d, n in zip(dims, shape)}, fusion_func, weights_func,
+                    fk.get("weights_func_kwargs"), order, widths, fk.get("overlap_in_pixels"),
+                )
+            res.append(out)
+        for st in streams:
+            cur.wait_stream(st)
         return res
 
     def close(self):

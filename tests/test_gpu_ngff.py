@@ -193,3 +193,47 @@ def test_fuse_to_ome_zarr_and_hook_c_into_engine_array(tmp_path):
         bf(fuse_chunk, ids[i:i + 3])
     assert bf.blocks_written == len(ids) and dest.bytes_written == len(ids) * dest.chunk_bytes
     assert np.array_equal(ngff_io.ZarrArray.open(tmp_path / "c.zarr")[...], fused)
+
+
+def test_hook_c_content_weighted_into_engine_array(tmp_path):
+    """The multi-pass path of hook C (a weights_func: one output stack per block, blocks alternating
+    between two streams) writes the engine's ZarrArray from the device and equals the numpy
+    destination of the same call sequence."""
+    from multiview_stitcher_b200 import fusion as efusion, ngff_io
+    from multiview_stitcher_b200.batch import BatchFuser, block_geometry
+
+    rng = np.random.default_rng(10)
+    base = cases._smooth(rng, (90, 150), 1.2).astype(np.float32)
+    views = [cases._view(base[:, :90].copy(), (0, 0), (1, 1)), cases._view(base[:, 60:].copy(), (0, 0), (1, 1))]
+    params = [cases._translation((0, 0)), cases._translation((0.3, 60.2))]
+    wkw = {"sigma_1": 2, "sigma_2": 3}
+    osp = of.calc_stack_properties([of.view_bb(v) for v in views], params, views[0]["spacing"])
+    chunksize = {"y": 48, "x": 64}
+    ref, _ = of.fuse(views, params, output_stack_properties=osp, output_chunksize=chunksize,
+                     weights_func=of.content_based, weights_func_kwargs=wkw)
+    msims = [dict(v, transforms={"reg": p}) for v, p in zip(views, params)]
+    ids = sorted(block_geometry(osp, chunksize))
+
+    def run(dest):
+        fk = {"images": msims, "transform_key": "reg", "fusion_func": efusion.weighted_average_fusion,
+              "weights_func": efusion.content_based, "weights_func_kwargs": wkw, "interpolation_order": 1,
+              "blending_widths": None, "backend": None, "output_chunksize": chunksize}
+
+        def never(block_id, **kw):
+            raise AssertionError("fuse_chunk called")
+
+        part = functools.partial(never, output_stack_properties=osp, ns_shape={}, nsdims=[], fuse_kwargs=fk,
+                                 output_chunksize=chunksize, output_zarr_array=dest)
+        bf = BatchFuser()
+        for i in range(0, len(ids), 4):
+            bf(part, ids[i:i + 4])
+        assert bf.blocks_written == len(ids)
+
+    host = np.zeros(ref.shape, np.float32)
+    run(host)
+    tol = 1e-4 * np.abs(ref) + 1e-6 * np.abs(ref).max()
+    assert np.all(np.abs(host - ref) <= tol)
+    dest = ngff_io.ZarrArray.create(tmp_path / "cw.zarr", ref.shape, [chunksize[d] for d in "yx"], np.float32)
+    run(dest)
+    assert dest.bytes_written == len(ids) * dest.chunk_bytes
+    assert np.array_equal(ngff_io.ZarrArray.open(tmp_path / "cw.zarr")[...], host)
