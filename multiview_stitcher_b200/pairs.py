@@ -328,6 +328,7 @@ class PairPlan:
         self.items = [p for p, _ in planned]
         self.bbox = [b for _, b in planned]
         self._stacks = {}  # crop shape -> (2P, *crop) float32 stack kept for reuse_buffers
+        self._xarr, self._xarr_key = {}, None  # crop shape -> resample records of the current view tensors
         self.groups = {}
         for k, pl in enumerate(self.items):
             self.groups.setdefault(pl["shape"], []).append(k)
@@ -374,20 +375,30 @@ class PairPlan:
 
         out = PreparedPairs(len(self.pairs))
         halo = (ctypes.c_int32 * 3)(0, 0, 0)
+        # the per-crop records depend only on the plan and on where the views live: kept while the same
+        # un-binned tensors come back (time lapses re-fill them; binned views are new tensors every call)
+        ptr_key = tuple((i, v.tensor.data_ptr(), tuple(v.tensor.stride())) for i, v in sorted(dviews.items()))
+        unbinned = all(max(pl["binning"]) <= 1 for pl in self.items)
+        if not unbinned or self._xarr_key != ptr_key:
+            self._xarr, self._xarr_key = {}, ptr_key if unbinned else None
         for shape, idx in self.groups.items():
-            xarr = np.zeros(2 * len(idx), dtype=_lib.VIEW_XFORM_DTYPE)
-            for r, k in enumerate(idx):
-                pl = self.items[k]
-                for side in (0, 1):
-                    dv = view_at(self.pairs[k][side], pl["binning"])
-                    win = dv.tensor[tuple(slice(i0, i1) for i0, i1 in pl["ranges"][side])]
-                    x = xarr[2 * r + side]
-                    x["data"] = win.data_ptr()
-                    x["dtype"] = dv.mvs_dtype
-                    x["shape"] = [1] * (3 - ndim) + list(map(int, win.shape))
-                    x["stride"] = [0] * (3 - ndim) + [int(s) for s in win.stride()]
-                    x["matrix"], x["offset"] = geometry.embed3(*pl["xforms"][side])
-                    x["wmatrix"], x["woffset"] = geometry.embed3(np.eye(ndim), np.zeros(ndim))
+            xarr = self._xarr.get(shape)
+            if xarr is None:
+                xarr = np.zeros(2 * len(idx), dtype=_lib.VIEW_XFORM_DTYPE)
+                for r, k in enumerate(idx):
+                    pl = self.items[k]
+                    for side in (0, 1):
+                        dv = view_at(self.pairs[k][side], pl["binning"])
+                        win = dv.tensor[tuple(slice(i0, i1) for i0, i1 in pl["ranges"][side])]
+                        x = xarr[2 * r + side]
+                        x["data"] = win.data_ptr()
+                        x["dtype"] = dv.mvs_dtype
+                        x["shape"] = [1] * (3 - ndim) + list(map(int, win.shape))
+                        x["stride"] = [0] * (3 - ndim) + [int(s) for s in win.stride()]
+                        x["matrix"], x["offset"] = geometry.embed3(*pl["xforms"][side])
+                        x["wmatrix"], x["woffset"] = geometry.embed3(np.eye(ndim), np.zeros(ndim))
+                if unbinned:
+                    self._xarr[shape] = xarr
             stack = self._stacks.get(shape) if reuse_buffers else None
             if stack is None or stack.shape[0] != 2 * len(idx):
                 stack = torch.empty((2 * len(idx),) + tuple(shape), dtype=torch.float32, device="cuda")
